@@ -1,0 +1,151 @@
+/*
+ * inf_field.h -- C ABI of the B200-native intrinsic-neural-field evaluation path.
+ *
+ * One shared library (libinf_field.so, built from intrinsic-neural-fields_b200/csrc) exports
+ * exactly the entry points below.  They replace, for the one hot path
+ *
+ *     gather 3 eigenfunction rows per ray -> barycentric interpolation -> MLP -> RGB
+ *     (+ the L1-loss training backward pass producing the MLP weight gradients)
+ *
+ * the following reference interfaces (paths relative to tum-vision/intrinsic-neural-fields):
+ *
+ *   inf_forward            mesh.py:313-324  get_k_eigenfunc_vec_vals(E, vids, bary)
+ *                          model.py:98-112  TextureField.forward(batch)
+ *                          layers.py:60-62  LinearWithConcatAndActivation.forward
+ *                          renderer.py:113-118 per-chunk model(batch) of Renderer.render
+ *   inf_forward_backward   trainer.py:71-84 Trainer._train_step (forward, loss, backward; Adam
+ *                          stays torch.optim.Adam), config.py:117-118 (L1 = F.l1_loss, mean)
+ *   inf_relayout_table     mesh.py:53-108   tail of load_first_k_eigenfunctions (dense (V,k) f32
+ *                          table -> device-resident padded table the kernels gather from)
+ *   inf_pack_weights       model.py:42-96   parameter tensors of TextureField (state_dict order)
+ *                          -> tensor-core operand images
+ *
+ * The reference has no FFI layer of its own (pure PyTorch); the binding a
+ * maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer owned by the caller unless stated otherwise; the
+ *     library never frees or retains a buffer past the call and allocates nothing persistent;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no hidden
+ *     device synchronisation; safe to call from any host thread (no thread-local CUDA state);
+ *   - return value 0 = success, negative = error (INF_ERR_*); the message of the last error on
+ *     the calling thread is returned by inf_last_error();
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef INF_FIELD_H_
+#define INF_FIELD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INF_ABI_VERSION 1
+
+/* error codes */
+#define INF_OK 0
+#define INF_ERR_BAD_ARG (-1)      /* null pointer, bad shape, misaligned buffer            */
+#define INF_ERR_UNSUPPORTED (-2)  /* config outside the compiled set (hidden!=128, ...)     */
+#define INF_ERR_WORKSPACE (-3)    /* workspace too small                                   */
+#define INF_ERR_CUDA (-4)         /* CUDA runtime error (message has cudaGetErrorString)   */
+
+/* InfDesc.idx_dtype */
+#define INF_IDX_I32 0
+#define INF_IDX_I64 1
+/* InfDesc.table_dtype */
+#define INF_TABLE_F32 0
+#define INF_TABLE_F16 1
+/* InfDesc.input_mode */
+#define INF_INPUT_GATHER 0 /* table (V,k_pad) + vids (B,3) + bary (B,3): the fused path          */
+#define INF_INPUT_DENSE 1  /* table IS the materialised embedding (B,k_pad), no vids/bary        */
+/* InfDesc.view_strategy */
+#define INF_VIEW_NONE 0
+#define INF_VIEW_INTRINSIC 1 /* model.py:176-182 */
+#define INF_VIEW_EXTRINSIC 2 /* model.py:183-184 */
+
+#define INF_MAX_LAYERS 8
+#define INF_MAX_PARAMS 20
+
+/* Shape / mode descriptor of one call (plain data, passed by pointer from host memory). */
+typedef struct InfDesc {
+  int32_t abi_version;   /* INF_ABI_VERSION                                                   */
+  int32_t idx_dtype;     /* dtype of vids / face_idxs                                         */
+  int64_t n_rays;        /* B: rays in this call (any value >= 0; ragged tail tiles handled)  */
+  int64_t n_rows;        /* V: rows of the table (GATHER) -- unused for DENSE                 */
+  int32_t k;             /* embedding dim = in_dim of layer 0 (model.py:211-215)              */
+  int32_t k_pad;         /* row stride of the table in elements, multiple of 64, >= k         */
+  int32_t hidden;        /* mlp_hidden_dim; compiled set: 128                                 */
+  int32_t num_layers;    /* 3..INF_MAX_LAYERS (model.py:27)                                   */
+  int32_t skip;          /* skip_layer_idx, 0 < skip < num_layers-1                           */
+  int32_t table_dtype;   /* INF_TABLE_F32 | INF_TABLE_F16                                     */
+  int32_t input_mode;    /* INF_INPUT_GATHER | INF_INPUT_DENSE                                */
+  int32_t view_strategy; /* INF_VIEW_*                                                        */
+  int32_t view_embed;    /* embed_size of the view-direction Fourier features                 */
+  int32_t view_include;  /* include_view_dir (0/1)                                            */
+  int32_t view_bneck;    /* bottleneck_vec_dim; compiled set: 128                             */
+  int32_t view_hidden;   /* directional_hidden_dim; compiled set: 64                          */
+  int64_t n_faces;       /* rows of face_normals (intrinsic view strategy)                    */
+  float grad_scale;      /* multiplies every summed gradient; 1/(3*B_global) for the L1 mean  */
+  float reserved0;
+} InfDesc;
+
+/* Device buffers of one call. */
+typedef struct InfTensors {
+  const void* table;          /* (V,k_pad) f32|f16 row-major, 16-byte aligned (inf_relayout_table) */
+  const void* vids;           /* (B,3) i32|i64 vertex ids of the hit faces (bit-exact pass-through) */
+  const float* bary;          /* (B,3) f32 barycentric weights                                      */
+  const float* target;        /* (B,3) f32 expected_rgbs, training with the built-in L1 loss        */
+  const float* grad_pred;     /* (B,3) f32 dLoss/dpred supplied by autograd (exclusive with target) */
+  const float* unit_ray_dirs; /* (B,3) f32, view branch                                             */
+  const void* face_idxs;      /* (B,)  i32|i64, intrinsic view branch                               */
+  const float* face_normals;  /* (F,3) f32, intrinsic view branch                                   */
+  const void* packed;         /* operand images written by inf_pack_weights                         */
+  float* pred;                /* (B,3) f32 out                                                      */
+  void* workspace;            /* >= inf_workspace_bytes(desc, training)                             */
+  size_t workspace_bytes;
+} InfTensors;
+
+/* Gradient outputs of inf_forward_backward. */
+typedef struct InfGrads {
+  float* flat;       /* inf_num_params(desc) f32: all parameter gradients, state_dict order   */
+  float* loss_sums;  /* 2 f32: sum|pred-target| and sum (pred-target)^2 over this call's rays */
+} InfGrads;
+
+/* version / errors */
+int inf_version(void);
+const char* inf_last_error(void);
+
+/* sizes (host-only, no CUDA calls) */
+int64_t inf_num_params(const InfDesc* desc);  /* number of f32 in the flat parameter vector   */
+int32_t inf_num_param_tensors(const InfDesc* desc);
+/* offset (in f32 elements) and shape of parameter tensor `i` (state_dict order,
+ * model.py:42-96: layers.0.0.weight, layers.0.0.bias, ..., layers.<skip>.Lx.weight, .Lx.bias,
+ * .Ly.weight, .Ly.bias, ..., then directional_mlp.0/.2 for the view branch). */
+int inf_param_info(const InfDesc* desc, int32_t i, int64_t* offset, int32_t* rows, int32_t* cols);
+size_t inf_packed_bytes(const InfDesc* desc);
+size_t inf_workspace_bytes(const InfDesc* desc, int training);
+
+/* (V,k) f32 table with arbitrary row stride -> (V,k_pad) f32|f16, zero padded columns. */
+int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride,
+                       void* dst, int32_t k_pad, int32_t dst_dtype, void* stream);
+
+/* fp32 master parameters -> operand images.  `params[i]` = device pointer of tensor i. */
+int inf_pack_weights(const InfDesc* desc, const float* const* params, void* packed, void* stream);
+
+/* gather -> interpolate -> MLP -> RGB (inference; no gradients, no workspace needed). */
+int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream);
+
+/* fused training pass: pred, loss sums and all parameter gradients (scaled by grad_scale). */
+int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, void* stream);
+
+/* Self-test hook used by tests/: D(128,n) = A(128,k) * B(n,k)^T on the tensor cores with the
+ * operand-layout variant `mode` (0: A,B K-major; 1: A MN-major; 2: A,B MN-major).  A and B are
+ * f32 row-major on the device ((128,k)/(n,k) for K-major, (k,128)/(k,n) for MN-major). */
+int inf_debug_umma(int mode, int n, int k, const float* a, const float* b, float* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INF_FIELD_H_ */

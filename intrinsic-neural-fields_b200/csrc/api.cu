@@ -1,0 +1,327 @@
+// C ABI of libinf_field.so (see include/inf_field.h).  Validation, workspace carving, launches.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace inf {
+
+// kernels / launchers defined in the other translation units
+cudaError_t launch_field_main(const FieldParams& p, bool train, bool table_f16, int grid, cudaStream_t stream);
+cudaError_t launch_field_wgrad(const FieldParams& p, bool table_f16, int groups, int grid, cudaStream_t stream);
+cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream);
+
+void launch_pack_weights(const PackParams& pp, cudaStream_t stream);
+void launch_relayout(const float* src, int64_t n_rows, int k, int64_t src_stride, void* dst, int k_pad, int dst_dtype,
+                     cudaStream_t stream);
+void launch_umma_probe(int mode, int n, int k, const float* a, const float* b, float* d, cudaStream_t stream);
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_desc(const InfDesc* d) {
+  if (d == nullptr) return fail(INF_ERR_BAD_ARG, "desc is null");
+  if (d->abi_version != INF_ABI_VERSION)
+    return fail(INF_ERR_BAD_ARG, "abi_version %d != %d", d->abi_version, INF_ABI_VERSION);
+  if (d->hidden != HID)
+    return fail(INF_ERR_UNSUPPORTED, "mlp_hidden_dim=%d outside the compiled set {128}", d->hidden);
+  if (d->num_layers < 3 || d->num_layers > INF_MAX_LAYERS)
+    return fail(INF_ERR_UNSUPPORTED, "num_layers=%d outside [3,%d]", d->num_layers, INF_MAX_LAYERS);
+  if (!(d->skip > 0 && d->skip < d->num_layers - 1))
+    return fail(INF_ERR_BAD_ARG, "skip_layer_idx=%d must satisfy 0 < skip < num_layers-1 (model.py:27)", d->skip);
+  if (d->k < 1 || d->k_pad < d->k || d->k_pad % KC != 0 || d->k_pad > 16384)
+    return fail(INF_ERR_BAD_ARG, "k=%d k_pad=%d: k_pad must be a multiple of 64, >= k, <= 16384", d->k, d->k_pad);
+  if (d->n_rays < 0 || d->n_rays > (int64_t(1) << 31) - TILE_M)
+    return fail(INF_ERR_BAD_ARG, "n_rays=%lld out of range", static_cast<long long>(d->n_rays));
+  if (d->idx_dtype != INF_IDX_I32 && d->idx_dtype != INF_IDX_I64) return fail(INF_ERR_BAD_ARG, "bad idx_dtype");
+  if (d->table_dtype != INF_TABLE_F32 && d->table_dtype != INF_TABLE_F16) return fail(INF_ERR_BAD_ARG, "bad table_dtype");
+  if (d->input_mode != INF_INPUT_GATHER && d->input_mode != INF_INPUT_DENSE) return fail(INF_ERR_BAD_ARG, "bad input_mode");
+  if (d->view_strategy != INF_VIEW_NONE)
+    return fail(INF_ERR_UNSUPPORTED, "view-direction branch is not compiled into this build");
+  if (d->input_mode == INF_INPUT_GATHER && d->n_rows > (int64_t(1) << 32) - 1)
+    return fail(INF_ERR_BAD_ARG, "n_rows exceeds 2^32-1");
+  return INF_OK;
+}
+
+Geo geo_of(const InfDesc* d) { return make_geo(d->k, d->k_pad, d->num_layers, d->skip); }
+
+struct ParamInfo {
+  int64_t off;
+  int rows, cols;
+  int kind, a;  // ReduceSeg kind / argument
+};
+
+// state_dict order (model.py:42-96, layers.py:50-58)
+int build_param_table(const InfDesc* d, ParamInfo* out, int64_t* total) {
+  int n = 0;
+  int64_t off = 0;
+  const int L = d->num_layers;
+  auto add = [&](int rows, int cols, int kind, int a) {
+    out[n++] = ParamInfo{off, rows, cols, kind, a};
+    off += static_cast<int64_t>(rows) * cols;
+  };
+  for (int i = 0; i < L; ++i) {
+    if (i == d->skip) {
+      add(HID, HID, 1, i);      // Lx.weight
+      add(HID, 1, 2, i);        // Lx.bias
+      add(HID, d->k, 0, 1);     // Ly.weight
+      add(HID, 1, 2, i);        // Ly.bias (same gradient as Lx.bias)
+    } else if (i == 0) {
+      add(HID, d->k, 0, 0);
+      add(HID, 1, 2, 0);
+    } else if (i == L - 1) {
+      add(OUT_DIM, HID, 3, 0);
+      add(OUT_DIM, 1, 4, 0);
+    } else {
+      add(HID, HID, 1, i);
+      add(HID, 1, 2, i);
+    }
+  }
+  if (total) *total = off;
+  return n;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(INF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int sm_count(int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+  *out = n < MAX_CTAS ? n : MAX_CTAS;
+  return INF_OK;
+}
+
+int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
+  if (t == nullptr) return fail(INF_ERR_BAD_ARG, "tensors is null");
+  if (d->n_rays == 0) return INF_OK;
+  if (t->table == nullptr || t->packed == nullptr || t->pred == nullptr)
+    return fail(INF_ERR_BAD_ARG, "table / packed / pred must be non-null");
+  if ((reinterpret_cast<uintptr_t>(t->table) & 15) != 0) return fail(INF_ERR_BAD_ARG, "table must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(t->packed) & 127) != 0) return fail(INF_ERR_BAD_ARG, "packed must be 128-byte aligned");
+  if (d->input_mode == INF_INPUT_GATHER && (t->vids == nullptr || t->bary == nullptr))
+    return fail(INF_ERR_BAD_ARG, "vids / bary must be non-null in gather mode");
+  if (training) {
+    if ((t->target == nullptr) == (t->grad_pred == nullptr))
+      return fail(INF_ERR_BAD_ARG, "exactly one of target / grad_pred must be given");
+    const WorkspaceLayout w = workspace_layout(geo_of(d), d->n_rays, true);
+    if (t->workspace == nullptr || t->workspace_bytes < w.total)
+      return fail(INF_ERR_WORKSPACE, "workspace %zu B < required %zu B", t->workspace_bytes, w.total);
+    if ((reinterpret_cast<uintptr_t>(t->workspace) & 255) != 0)
+      return fail(INF_ERR_BAD_ARG, "workspace must be 256-byte aligned");
+  }
+  return INF_OK;
+}
+
+FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
+  FieldParams p{};
+  p.table = t->table;
+  p.row_stride = d->k_pad;
+  p.vids = t->vids;
+  p.bary = t->bary;
+  p.target = t->target;
+  p.grad_pred = t->grad_pred;
+  p.pred = t->pred;
+  p.packed = reinterpret_cast<const uint8_t*>(t->packed);
+  p.n_rays = d->n_rays;
+  p.ntiles = static_cast<int>((d->n_rays + TILE_M - 1) / TILE_M);
+  p.idx64 = d->idx_dtype == INF_IDX_I64;
+  p.dense = d->input_mode == INF_INPUT_DENSE;
+  p.ext_scale = 1.f;
+  p.geo = geo_of(d);
+  if (t->workspace != nullptr && t->workspace_bytes >= 256) {
+    const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(t->workspace);
+    p.err = reinterpret_cast<unsigned int*>(ws + w.err_off);
+    if (training) {
+      p.stash = ws + w.stash_off;
+      p.partw = reinterpret_cast<float*>(ws + w.partw_off);
+      p.part1 = reinterpret_cast<float*>(ws + w.part1_off);
+    }
+  }
+  return p;
+}
+
+}  // namespace
+}  // namespace inf
+
+using namespace inf;
+
+extern "C" {
+
+int inf_version(void) { return INF_ABI_VERSION; }
+
+const char* inf_last_error(void) { return g_err; }
+
+int64_t inf_num_params(const InfDesc* desc) {
+  if (check_desc(desc) != INF_OK) return -1;
+  ParamInfo pi[INF_MAX_PARAMS];
+  int64_t total = 0;
+  build_param_table(desc, pi, &total);
+  return total;
+}
+
+int32_t inf_num_param_tensors(const InfDesc* desc) {
+  if (check_desc(desc) != INF_OK) return -1;
+  ParamInfo pi[INF_MAX_PARAMS];
+  return build_param_table(desc, pi, nullptr);
+}
+
+int inf_param_info(const InfDesc* desc, int32_t i, int64_t* offset, int32_t* rows, int32_t* cols) {
+  int rc = check_desc(desc);
+  if (rc != INF_OK) return rc;
+  ParamInfo pi[INF_MAX_PARAMS];
+  const int n = build_param_table(desc, pi, nullptr);
+  if (i < 0 || i >= n) return fail(INF_ERR_BAD_ARG, "parameter index %d out of range [0,%d)", i, n);
+  if (offset) *offset = pi[i].off;
+  if (rows) *rows = pi[i].rows;
+  if (cols) *cols = pi[i].cols;
+  return INF_OK;
+}
+
+size_t inf_packed_bytes(const InfDesc* desc) {
+  if (check_desc(desc) != INF_OK) return 0;
+  return packed_total_bytes(geo_of(desc));
+}
+
+size_t inf_workspace_bytes(const InfDesc* desc, int training) {
+  if (check_desc(desc) != INF_OK) return 0;
+  return workspace_layout(geo_of(desc), desc->n_rays, training != 0).total;
+}
+
+int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, void* dst, int32_t k_pad,
+                       int32_t dst_dtype, void* stream) {
+  if (src == nullptr || dst == nullptr) return fail(INF_ERR_BAD_ARG, "src / dst must be non-null");
+  if (n_rows < 0 || k < 1 || k_pad < k || k_pad % KC != 0 || src_row_stride < k)
+    return fail(INF_ERR_BAD_ARG, "bad table shape: rows=%lld k=%d k_pad=%d stride=%lld", static_cast<long long>(n_rows), k,
+                k_pad, static_cast<long long>(src_row_stride));
+  if (dst_dtype != INF_TABLE_F32 && dst_dtype != INF_TABLE_F16) return fail(INF_ERR_BAD_ARG, "bad dst_dtype");
+  launch_relayout(src, n_rows, k, src_row_stride, dst, k_pad, dst_dtype, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "relayout_table launch");
+  return INF_OK;
+}
+
+int inf_pack_weights(const InfDesc* desc, const float* const* params, void* packed, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != INF_OK) return rc;
+  if (params == nullptr || packed == nullptr) return fail(INF_ERR_BAD_ARG, "params / packed must be non-null");
+  PackParams pp{};
+  pp.geo = geo_of(desc);
+  pp.packed = reinterpret_cast<uint8_t*>(packed);
+  int idx = 0;
+  for (int i = 0; i < desc->num_layers; ++i) {
+    pp.w[i] = params[idx++];
+    pp.b[i] = params[idx++];
+    if (i == desc->skip) {
+      pp.wy = params[idx++];
+      pp.by = params[idx++];
+    }
+  }
+  for (int i = 0; i < idx; ++i)
+    if (params[i] == nullptr) return fail(INF_ERR_BAD_ARG, "params[%d] is null", i);
+  launch_pack_weights(pp, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pack_weights launch");
+  return INF_OK;
+}
+
+int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != INF_OK) return rc;
+  rc = check_tensors(desc, t, false);
+  if (rc != INF_OK) return rc;
+  if (desc->n_rays == 0) return INF_OK;
+  int nsm = 0;
+  rc = sm_count(&nsm);
+  if (rc != INF_OK) return rc;
+  FieldParams p = make_params(desc, t, false);
+  const int grid = p.ntiles < nsm ? p.ntiles : nsm;
+  cudaError_t e = launch_field_main(p, false, desc->table_dtype == INF_TABLE_F16, grid, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<inference> launch");
+  return INF_OK;
+}
+
+int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != INF_OK) return rc;
+  rc = check_tensors(desc, t, true);
+  if (rc != INF_OK) return rc;
+  if (g == nullptr || g->flat == nullptr) return fail(INF_ERR_BAD_ARG, "grads.flat must be non-null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ParamInfo pi[INF_MAX_PARAMS];
+  int64_t total = 0;
+  const int nparam = build_param_table(desc, pi, &total);
+  if (desc->n_rays == 0) {
+    cudaError_t e = cudaMemsetAsync(g->flat, 0, static_cast<size_t>(total) * 4, st);
+    if (e == cudaSuccess && g->loss_sums) e = cudaMemsetAsync(g->loss_sums, 0, 8, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    return INF_OK;
+  }
+  int nsm = 0;
+  rc = sm_count(&nsm);
+  if (rc != INF_OK) return rc;
+  FieldParams p = make_params(desc, t, true);
+  // External upstream gradients are typically O(1/(3B)); bring them to O(1) for the fp16 chain.
+  const float ext = (t->grad_pred != nullptr) ? 3.f * static_cast<float>(desc->n_rays) : 1.f;
+  p.ext_scale = ext;
+  const Geo geo = p.geo;
+  const int grid1 = p.ntiles < nsm ? p.ntiles : nsm;
+  const int nslices = geo.nbig + geo.nhid;
+  int groups = nsm / nslices;
+  if (groups < 1) groups = 1;
+  if (groups > p.ntiles) groups = p.ntiles;
+  const int grid2 = nslices * groups;
+  if (grid2 > MAX_CTAS) return fail(INF_ERR_UNSUPPORTED, "k_pad=%d needs %d wgrad CTAs > %d", desc->k_pad, grid2, MAX_CTAS);
+
+  const bool f16 = desc->table_dtype == INF_TABLE_F16;
+  cudaError_t e = launch_field_main(p, true, f16, grid1, st);
+  if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<train> launch");
+  e = launch_field_wgrad(p, f16, groups, grid2, st);
+  if (e != cudaSuccess) return cuda_fail(e, "field_wgrad_kernel launch");
+
+  ReduceParams rp{};
+  rp.nseg = nparam;
+  for (int i = 0; i < nparam; ++i) rp.seg[i] = ReduceSeg{pi[i].off, pi[i].rows, pi[i].cols, pi[i].kind, pi[i].a};
+  rp.total = total;
+  rp.partw = p.partw;
+  rp.part1 = p.part1;
+  rp.flat = g->flat;
+  rp.loss_sums = (t->target != nullptr) ? g->loss_sums : nullptr;
+  rp.ncta1 = grid1;
+  rp.groups = groups;
+  rp.scale = desc->grad_scale / (DZ_SCALE * ext);
+  rp.geo = geo;
+  e = launch_field_reduce(rp, st);
+  if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel launch");
+  return INF_OK;
+}
+
+int inf_debug_umma(int mode, int n, int k, const float* a, const float* b, float* d, void* stream) {
+  if (mode < 0 || mode > 2 || n < 16 || n > 256 || n % 16 != 0 || (k != 64 && k != 128) || !a || !b || !d)
+    return fail(INF_ERR_BAD_ARG, "inf_debug_umma: mode in [0,2], n in {16..256 step 16}, k in {64,128}");
+  if (mode == 2 && n % 64 != 0) return fail(INF_ERR_BAD_ARG, "inf_debug_umma: MN-major B needs n %% 64 == 0");
+  launch_umma_probe(mode, n, k, a, b, d, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "umma_probe launch");
+  return INF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+// Operand preparation kernels: fp32 master weights -> swizzled fp16 operand images, and the
+// eigenfunction-table re-layout (pad k -> k_pad, optional fp16 storage).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace inf {
+
+
+// One thread per 16-bit element of the blob section + one per f32 of the tail section.
+__global__ void pack_weights_kernel(const PackParams pp) {
+  const Geo g = pp.geo;
+  const int L = g.L;
+  const int64_t nhalf = static_cast<int64_t>(g.nblobs_train) * (BLOB_BYTES / 2);
+  const int nf32 = (L - 1) * HID + OUT_DIM * HID + 4;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < nhalf) {
+    const int blob = static_cast<int>(i / (BLOB_BYTES / 2));
+    const int e = static_cast<int>(i % (BLOB_BYTES / 2));
+    float v = 0.f;
+    uint32_t off;
+    if (blob < g.nchunks) {
+      // [256 rows][64 k]: row < 128 -> W0, else Wy
+      const int row = e >> 6, c = e & 63;
+      const int kcol = blob * KC + c;
+      if (kcol < g.k) v = (row < HID) ? pp.w[0][static_cast<size_t>(row) * g.k + kcol]
+                                      : pp.wy[static_cast<size_t>(row - HID) * g.k + kcol];
+      off = sw128_off(row, c);
+    } else {
+      // [128 rows][128 cols] as two 64-column panels
+      const int row = e >> 7, col = e & 127;
+      const int hb = blob - g.nchunks;
+      if (hb < L - 2) {
+        const int l = hb + 1;                       // W_l[n=row][k=col]
+        v = pp.w[l][row * HID + col];
+      } else {
+        const int l = (L - 2) - (hb - (L - 2));     // W_l^T: [j=row][n=col] = W_l[col][row]
+        v = pp.w[l][col * HID + row];
+      }
+      off = static_cast<uint32_t>(col >> 6) * PANEL_BYTES + sw128_off(row, col & 63);
+    }
+    *reinterpret_cast<__half*>(pp.packed + static_cast<size_t>(blob) * BLOB_BYTES + off) = __float2half_rn(v);
+  } else if (i < nhalf + nf32) {
+    const int e = static_cast<int>(i - nhalf);
+    float v;
+    if (e < (L - 1) * HID) {
+      const int l = e / HID, n = e % HID;
+      v = pp.b[l][n];
+      if (l == g.skip) v += pp.by[n];
+    } else if (e < (L - 1) * HID + OUT_DIM * HID) {
+      v = pp.w[L - 1][e - (L - 1) * HID];
+    } else {
+      const int c = e - (L - 1) * HID - OUT_DIM * HID;
+      v = (c < OUT_DIM) ? pp.b[L - 1][c] : 0.f;
+    }
+    reinterpret_cast<float*>(pp.packed + packed_f32_offset(g))[e] = v;
+  }
+}
+
+void launch_pack_weights(const PackParams& pp, cudaStream_t stream) {
+  const Geo g = pp.geo;
+  const int64_t n = static_cast<int64_t>(g.nblobs_train) * (BLOB_BYTES / 2) + (g.L - 1) * HID + OUT_DIM * HID + 4;
+  const int threads = 256;
+  pack_weights_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0, stream>>>(pp);
+}
+
+template <typename OutT>
+__global__ void relayout_table_kernel(const float* __restrict__ src, int64_t n_rows, int k, int64_t src_stride,
+                                      OutT* __restrict__ dst, int k_pad) {
+  const int64_t total = n_rows * k_pad;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / k_pad;
+    const int c = static_cast<int>(i % k_pad);
+    const float v = (c < k) ? src[r * src_stride + c] : 0.f;
+    if constexpr (sizeof(OutT) == 2) dst[i] = __float2half_rn(v);
+    else dst[i] = v;
+  }
+}
+
+void launch_relayout(const float* src, int64_t n_rows, int k, int64_t src_stride, void* dst, int k_pad, int dst_dtype,
+                     cudaStream_t stream) {
+  const int64_t total = n_rows * k_pad;
+  if (total == 0) return;
+  const int threads = 256;
+  const int64_t want = (total + threads - 1) / threads;
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
+  if (dst_dtype == INF_TABLE_F16)
+    relayout_table_kernel<__half><<<blocks, threads, 0, stream>>>(src, n_rows, k, src_stride, reinterpret_cast<__half*>(dst), k_pad);
+  else
+    relayout_table_kernel<float><<<blocks, threads, 0, stream>>>(src, n_rows, k, src_stride, reinterpret_cast<float*>(dst), k_pad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// UMMA self-test (inf_debug_umma): one CTA, D(128,n) = A(128,k) * B(n,k)^T for the three operand
+// layout variants the field kernels rely on.  k multiple of 64 (<= 128), n multiple of 64 or 16.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(int mode, int n, int k, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  // layout: A image 32 KB | B image 64 KB | bar | tmem ptr
+  const uint32_t SA = 0, SB = 32768, SBAR = 32768 + 65536, SPTR = SBAR + 8;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool a_mn = mode >= 1, b_mn = mode >= 2;
+  __half* sa = reinterpret_cast<__half*>(smem + SA);
+  __half* sb = reinterpret_cast<__half*>(smem + SB);
+  // K-major image: element (row m, col kk) -> panel kk/64 (stride rows*128 B), sw128(row, kk%64)
+  // MN-major image: element (m, kk) stored at "row" kk, "col" m: panel m/64 (stride k*128 B), sw128(kk, m%64)
+  for (int i = tid; i < 128 * k; i += 128) {
+    const int m = a_mn ? i % 128 : i / k, kk = a_mn ? i / 128 : i % k;
+    const float v = a[i];  // K-major source (128,k); MN-major source (k,128)
+    uint32_t off = a_mn ? static_cast<uint32_t>(m >> 6) * (k * 128u) + sw128_off(kk, m & 63)
+                        : static_cast<uint32_t>(kk >> 6) * (128u * 128u) + sw128_off(m, kk & 63);
+    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(sa) + off) = __float2half_rn(v);
+  }
+  for (int i = tid; i < n * k; i += 128) {
+    const int m = b_mn ? i % n : i / k, kk = b_mn ? i / n : i % k;
+    const float v = b[i];
+    uint32_t off = b_mn ? static_cast<uint32_t>(m >> 6) * (k * 128u) + sw128_off(kk, m & 63)
+                        : static_cast<uint32_t>(kk >> 6) * (n * 128u) + sw128_off(m, kk & 63);
+    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(sb) + off) = __float2half_rn(v);
+  }
+  if (tid == 0) { mbar_init(smem_base + SBAR, 1); mbar_fence_init(); }
+  if (warp == 0) { tmem_alloc(smem_base + SPTR, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SPTR);
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, n, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    for (int kk = 0; kk < k / 16; ++kk) {
+      uint64_t ad, bd;
+      if (a_mn) ad = umma_desc_sw128(smem_base + SA + kk * 2048u, k * 128u, 1024);
+      else ad = umma_desc_sw128(smem_base + SA + (kk >> 2) * (128u * 128u) + (kk & 3) * 32u, 0, 1024);
+      if (b_mn) bd = umma_desc_sw128(smem_base + SB + kk * 2048u, k * 128u, 1024);
+      else bd = umma_desc_sw128(smem_base + SB + (kk >> 2) * (n * 128u) + (kk & 3) * 32u, 0, 1024);
+      umma_f16(tmem_base, ad, bd, idesc, kk > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_base + SBAR);
+  }
+  mbar_wait(smem_base + SBAR, 0, nullptr, 0x90);
+  tc_fence_after();
+  const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c = 0; c < n; ++c) {
+    uint32_t v;
+    tmem_ld1(tlane + c, v);
+    tmem_ld_wait();
+    d[tid * n + c] = __uint_as_float(v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+void launch_umma_probe(int mode, int n, int k, const float* a, const float* b, float* d, cudaStream_t stream) {
+  const size_t smem = 32768 + 65536 + 64 + 1024;
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  umma_probe_kernel<<<1, 128, smem, stream>>>(mode, n, k, a, b, d);
+}
+
+}  // namespace inf

@@ -1,0 +1,209 @@
+"""Drop-in model surface of the reference's ``model.py`` for the intrinsic (eigenfunction) path.
+
+``make_model(model_config, mesh=None)`` returns a module with the same constructor config, the same
+``state_dict`` keys/shapes (``layers.0.0.weight``, ``layers.<skip>.Lx.weight``, ``layers.<skip>.Ly.weight``
+..., model.py:42-96 / layers.py:50-58 of the reference) and the same ``forward(batch) -> (B,3)``
+contract (model.py:98-112), but the arithmetic runs in the fused sm_100a kernels:
+
+* fused path  -- the batch carries ``"vertex_idxs_of_hit_faces"`` (B,3), ``"barycentric_coords"`` (B,3)
+  and ``"eigenfunction_table"`` (an :class:`EigenTable`); the interpolated embedding is never built;
+* dense path  -- the batch carries the reference's ``"eigenfunctions"`` (B,k) tensor; the same kernels
+  read it as the A operand (it is padded to a 16-byte aligned row stride first).
+
+Training: ``forward`` is differentiable w.r.t. the parameters (the backward pass re-runs the fused
+forward+backward kernel with the upstream gradient), and :meth:`TextureField.l1_step` is the fast path
+used by the trainer for ``loss_type: L1`` (forward + L1 loss + backward in one fused pass,
+trainer.py:71-84).  Unsupported reference options (batchnorm, sine, ff/rff/xyz features) raise.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import EigenTable, FieldConfig
+
+RGB_COLOR_DIM = 3  # model.py:9
+
+
+class _SkipLinear(nn.Module):
+    """Parameter container with the reference's key names (layers.py:50-58)."""
+
+    def __init__(self, x_in_dim: int, y_in_dim: int, out_dim: int):
+        super().__init__()
+        self.Lx = nn.Linear(x_in_dim, out_dim)
+        self.Ly = nn.Linear(y_in_dim, out_dim)
+
+
+def _linear_block(in_dim: int, out_dim: int) -> nn.Sequential:
+    # index 0 holds the Linear exactly as in the reference's nn.Sequential(Linear, activation)
+    return nn.Sequential(nn.Linear(in_dim, out_dim))
+
+
+class _FieldFunction(torch.autograd.Function):
+    """pred = field(table, vids, bary; params).  No gradient flows into table / vids / bary
+    (none requires grad in the reference either)."""
+
+    @staticmethod
+    def forward(ctx, module, table, vids, bary, dense, *params):
+        cfg = module.cfg
+        packed = module._packed_weights()
+        ctx.module, ctx.dense = module, dense
+        ctx.save_for_backward(table, vids, bary)
+        return torch.ops.inf_b200.field_forward(table, vids, bary, packed, cfg.k, cfg.num_layers, cfg.skip, dense)
+
+    @staticmethod
+    def backward(ctx, grad_pred):
+        module = ctx.module
+        cfg = module.cfg
+        table, vids, bary = ctx.saved_tensors
+        _, flat, _ = torch.ops.inf_b200.field_forward_backward(
+            table, vids, bary, module._packed_weights(), None, grad_pred.contiguous().float(), cfg.k, cfg.num_layers,
+            cfg.skip, ctx.dense, 1.0)
+        grads = [flat[off:off + r * c].view(p.shape) for (off, r, c), p in zip(module._layout, module._ordered_params())]
+        return (None, None, None, None, None, *grads)
+
+
+class TextureField(nn.Module):
+    """6-layer/128-wide ReLU MLP with an input skip connection, RGB sigmoid head (model.py:12-112)."""
+
+    def __init__(self, num_layers, in_dim, hidden_dim, skip_layer_idx, input_feature_embed=None, embed_dim=None,
+                 embed_include_input=True, embed_std=1., return_rgb=True, out_dim=RGB_COLOR_DIM, batchnorm=False,
+                 activation=nn.ReLU, table_dtype: str = "f32"):
+        super().__init__()
+        assert num_layers > 2 and 0 < skip_layer_idx and skip_layer_idx < num_layers - 1   # model.py:27
+        if input_feature_embed not in (None, "efuncs"):
+            raise NotImplementedError(f"feature_strategy={input_feature_embed!r}: only the intrinsic 'efuncs' path is "
+                                      "implemented by the B200 kernels (extrinsic ff/rff/xyz baselines are out of scope)")
+        if batchnorm:
+            raise NotImplementedError("batchnorm=True is not supported by the B200 kernels (no shipped config uses it)")
+        if activation is not nn.ReLU:
+            raise NotImplementedError("only activation='relu' is supported by the B200 kernels")
+        if not return_rgb or out_dim != RGB_COLOR_DIM:
+            raise NotImplementedError("spatial MLP with a bottleneck head (view-direction branch) is not built yet")
+        if hidden_dim != ops.HIDDEN:
+            raise NotImplementedError(f"mlp_hidden_dim={hidden_dim}: compiled set is {{{ops.HIDDEN}}}")
+        self.skip_layer_idx = skip_layer_idx
+        self.cfg = FieldConfig(k=in_dim, num_layers=num_layers, skip=skip_layer_idx, hidden=hidden_dim)
+        self.table_dtype = table_dtype
+        layers: List[nn.Module] = [_linear_block(in_dim, hidden_dim)]
+        for i in range(1, num_layers - 1):
+            layers.append(_SkipLinear(hidden_dim, in_dim, hidden_dim) if i == skip_layer_idx
+                          else _linear_block(hidden_dim, hidden_dim))
+        layers.append(_linear_block(hidden_dim, out_dim))
+        self.layers = nn.ModuleList(layers)
+        self._layout = None
+        self._packed = None
+        self._packed_key = None
+
+    # ---- parameters in the flat / state_dict order the C ABI expects -------------------------------
+    def _ordered_params(self) -> List[torch.Tensor]:
+        out = []
+        for i, layer in enumerate(self.layers):
+            if i == self.skip_layer_idx:
+                out += [layer.Lx.weight, layer.Lx.bias, layer.Ly.weight, layer.Ly.bias]
+            else:
+                out += [layer[0].weight, layer[0].bias]
+        return out
+
+    def _packed_weights(self) -> torch.Tensor:
+        """Operand images of the current parameter values (re-packed when any parameter changed)."""
+        params = self._ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed_key != key or self._packed.device != params[0].device:
+            with torch.no_grad():
+                self._packed = ops.pack_weights(self.cfg, [p.detach().contiguous() for p in params], None)
+            self._packed_key = key
+        if self._layout is None:
+            self._layout = ops.param_layout(self.cfg)
+        return self._packed
+
+    def __deepcopy__(self, memo):
+        # trainer.py:67,274 deep-copies the model; cached device buffers are rebuilt lazily
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, None if k in ("_packed", "_packed_key") else copy.deepcopy(v, memo))
+        return new
+
+    # ---- batch decoding ----------------------------------------------------------------------------
+    def _inputs(self, batch: Dict[str, torch.Tensor]):
+        table = batch.get("eigenfunction_table")
+        if table is not None and "vertex_idxs_of_hit_faces" in batch:
+            if not isinstance(table, EigenTable):
+                raise TypeError("batch['eigenfunction_table'] must be an inf_b200.EigenTable")
+            if table.k != self.cfg.k:
+                raise ValueError(f"table has k={table.k}, model expects {self.cfg.k}")
+            return table.data, batch["vertex_idxs_of_hit_faces"].contiguous(), batch["barycentric_coords"].contiguous(), False
+        if "eigenfunctions" in batch:
+            x = batch["eigenfunctions"]
+            if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.cfg.k:
+                raise ValueError(f"batch['eigenfunctions'] must be (B,{self.cfg.k}) float32")
+            return EigenTable.from_dense(x, device=x.device, dtype="f32").data, None, None, True
+        raise KeyError("batch needs 'eigenfunction_table' + 'vertex_idxs_of_hit_faces' + 'barycentric_coords' "
+                       "(fused path) or 'eigenfunctions' (dense path)")
+
+    def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        table, vids, bary, dense = self._inputs(batch)
+        params = self._ordered_params()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _FieldFunction.apply(self, table, vids, bary, dense, *params)
+        cfg = self.cfg
+        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(), cfg.k, cfg.num_layers,
+                                                cfg.skip, dense)
+
+    # ---- fused training pass -----------------------------------------------------------------------
+    def l1_step(self, batch: Dict[str, torch.Tensor], global_rays: Optional[int] = None,
+                flat_grad: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Forward + mean-L1 loss + backward in one fused pass (trainer.py:75-81, config.py:117-118).
+
+        Sets ``.grad`` of every parameter (views into one flat buffer, ready for a single allreduce) and
+        returns ``(loss_sums, pred, flat_grad)`` where ``loss_sums = [sum|pred-target|, sum (pred-target)^2]``
+        over this call's rays; the mean L1 loss is ``loss_sums[0] / (3 * global_rays)``.
+        ``global_rays`` is the number of rays of the whole (all-rank) batch; it defaults to this call's B.
+        """
+        table, vids, bary, dense = self._inputs(batch)
+        target = batch["expected_rgbs"].contiguous()
+        B = target.shape[0]
+        cfg = self.cfg
+        scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
+        pred, flat, sums = torch.ops.inf_b200.field_forward_backward(
+            table, vids, bary, self._packed_weights(), target, None, cfg.k, cfg.num_layers, cfg.skip, dense, scale)
+        if flat_grad is not None:
+            flat_grad.copy_(flat)
+            flat = flat_grad
+        for (off, r, c), p in zip(self._layout, self._ordered_params()):
+            p.grad = flat[off:off + r * c].view(p.shape)
+        return sums, pred, flat
+
+
+def init_weights(m):
+    if isinstance(m, nn.Linear):
+        torch.nn.init.xavier_uniform_(m.weight.data)   # model.py:194-196
+
+
+def make_model(model_config: dict, mesh=None) -> nn.Module:
+    """Same contract as the reference's make_model (model.py:199-258) for the intrinsic path."""
+    view_cfg = model_config.get("view_dependence")
+    feature_strategy = model_config.get("feature_strategy", "efuncs")
+    if model_config.get("type") == "neutex":
+        raise NotImplementedError("the NeuTex baseline is a different model and is out of scope of the B200 path")
+    if feature_strategy != "efuncs":
+        raise NotImplementedError(f"feature_strategy={feature_strategy!r}: only 'efuncs' is implemented")
+    k = model_config["k"]
+    in_dim = k if isinstance(k, int) else len(k)                       # model.py:211-215
+    act = model_config.get("activation", "relu")
+    if act != "relu":
+        raise NotImplementedError(f"Activation function {act} is not implemented by the B200 kernels.")
+    if view_cfg is not None:
+        raise NotImplementedError("view_dependence branch is not built yet")
+    model = TextureField(model_config["num_layers"], in_dim, model_config["mlp_hidden_dim"],
+                         model_config["skip_layer_idx"], input_feature_embed=feature_strategy,
+                         batchnorm=model_config.get("batchnorm", False),
+                         table_dtype=model_config.get("table_dtype", "f32"))
+    model.apply(init_weights)                                           # model.py:257
+    return model

@@ -1,0 +1,296 @@
+"""Torch-facing operators of the fused gather -> interpolate -> MLP path.
+
+Everything here is plumbing: device buffers are torch CUDA tensors, kernels are launched through the
+C ABI of ``libinf_field.so`` on torch's current stream.  The path is registered as PyTorch custom ops
+(``torch.ops.inf_b200.field_forward`` / ``field_forward_backward``); the drop-in modules in
+``model.py`` build their autograd on top of them.  No CPU implementation exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+HIDDEN = 128
+KC = 64
+
+
+def pad_k(k: int) -> int:
+    return (k + KC - 1) // KC * KC
+
+
+@dataclass(frozen=True)
+class FieldConfig:
+    """Static shape of the spatial MLP (model.py:12-96 of the reference)."""
+    k: int
+    num_layers: int = 6
+    skip: int = 3
+    hidden: int = HIDDEN
+
+    @property
+    def k_pad(self) -> int:
+        return pad_k(self.k)
+
+
+def _desc(cfg: FieldConfig, n_rays: int, n_rows: int, *, idx64: bool = True, table_f16: bool = False,
+          dense: bool = False, grad_scale: float = 1.0) -> _lib.InfDesc:
+    d = _lib.InfDesc()
+    d.abi_version = _lib.ABI_VERSION
+    d.idx_dtype = _lib.IDX_I64 if idx64 else _lib.IDX_I32
+    d.n_rays = n_rays
+    d.n_rows = n_rows
+    d.k = cfg.k
+    d.k_pad = cfg.k_pad
+    d.hidden = cfg.hidden
+    d.num_layers = cfg.num_layers
+    d.skip = cfg.skip
+    d.table_dtype = _lib.TABLE_F16 if table_f16 else _lib.TABLE_F32
+    d.input_mode = _lib.INPUT_DENSE if dense else _lib.INPUT_GATHER
+    d.view_strategy = _lib.VIEW_NONE
+    d.grad_scale = grad_scale
+    return d
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# sizes / layout (host only)
+# ------------------------------------------------------------------------------------------------
+def num_params(cfg: FieldConfig) -> int:
+    return int(_lib.load().inf_num_params(C.byref(_desc(cfg, 0, 0))))
+
+
+def param_layout(cfg: FieldConfig) -> List[Tuple[int, int, int]]:
+    """[(offset, rows, cols)] of every parameter tensor in the flat vector (state_dict order)."""
+    lib = _lib.load()
+    d = _desc(cfg, 0, 0)
+    out = []
+    for i in range(lib.inf_num_param_tensors(C.byref(d))):
+        off, r, c = C.c_int64(), C.c_int32(), C.c_int32()
+        _lib.check(lib.inf_param_info(C.byref(d), i, C.byref(off), C.byref(r), C.byref(c)), "inf_param_info")
+        out.append((off.value, r.value, c.value))
+    return out
+
+
+def packed_bytes(cfg: FieldConfig) -> int:
+    return int(_lib.load().inf_packed_bytes(C.byref(_desc(cfg, 0, 0))))
+
+
+def workspace_bytes(cfg: FieldConfig, n_rays: int, training: bool) -> int:
+    return int(_lib.load().inf_workspace_bytes(C.byref(_desc(cfg, n_rays, 0)), 1 if training else 0))
+
+
+# ------------------------------------------------------------------------------------------------
+# eigenfunction table
+# ------------------------------------------------------------------------------------------------
+class EigenTable:
+    """Device-resident, padded (V, k_pad) copy of the eigenfunction table the kernels gather from.
+
+    Built once where the reference moves ``features`` to the device (ray_dataloader.py:73,
+    renderer.py:43).  ``dtype`` "f32" keeps the reference's values bit-for-bit; "f16" halves the
+    gather traffic (values are rounded once, before interpolation).
+    """
+
+    def __init__(self, data: torch.Tensor, k: int, dtype: str):
+        self.data, self.k, self.dtype = data, k, dtype
+
+    @property
+    def n_rows(self) -> int:
+        return self.data.shape[0]
+
+    @property
+    def k_pad(self) -> int:
+        return self.data.shape[1]
+
+    @property
+    def device(self):
+        return self.data.device
+
+    @staticmethod
+    def from_dense(E: torch.Tensor, device=None, dtype: str = "f32") -> "EigenTable":
+        if E.dim() != 2 or E.dtype != torch.float32:
+            raise ValueError("eigenfunction table must be a 2-D float32 tensor (mesh.py:105-108)")
+        device = torch.device(device if device is not None else E.device)
+        if device.type != "cuda":
+            raise RuntimeError("EigenTable needs a CUDA device: the B200 path has no CPU fallback")
+        src = E.to(device)
+        if src.stride(1) != 1:
+            src = src.contiguous()
+        V, k = src.shape
+        kp = pad_k(k)
+        out = torch.empty((V, kp), device=device, dtype=torch.float16 if dtype == "f16" else torch.float32)
+        with torch.cuda.device(device):
+            rc = _lib.load().inf_relayout_table(C.c_void_p(src.data_ptr()), V, k, src.stride(0), C.c_void_p(out.data_ptr()),
+                                                kp, _lib.TABLE_F16 if dtype == "f16" else _lib.TABLE_F32, _stream(device))
+        _lib.check(rc, "inf_relayout_table")
+        return EigenTable(out, k, dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# workspace cache (one growing buffer per device; the first 256 bytes hold the kernel error word)
+# ------------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def kernel_error_word(device) -> int:
+    """Non-zero if a kernel watchdog fired (pipeline stall); 0 otherwise.  Synchronises."""
+    key = (torch.device(device).type, torch.device(device).index if torch.device(device).index is not None
+           else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None:
+        return 0
+    return int(ws[:4].view(torch.int32).item())
+
+
+# ------------------------------------------------------------------------------------------------
+# raw operators
+# ------------------------------------------------------------------------------------------------
+def pack_weights(cfg: FieldConfig, params: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 master parameters (state_dict order) -> tensor-core operand images."""
+    lib = _lib.load()
+    layout = param_layout(cfg)
+    if len(params) != len(layout):
+        raise ValueError(f"expected {len(layout)} parameter tensors, got {len(params)}")
+    for p, (_, r, c) in zip(params, layout):
+        _require_cuda(p, "parameter")
+        if p.dtype != torch.float32 or p.numel() != r * c:
+            raise ValueError(f"parameter shape {tuple(p.shape)} does not match ({r},{c}) float32")
+    device = params[0].device
+    if out is None:
+        out = torch.empty(packed_bytes(cfg), dtype=torch.uint8, device=device)
+    arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    with torch.cuda.device(device):
+        rc = lib.inf_pack_weights(C.byref(_desc(cfg, 0, 0)), arr, C.c_void_p(out.data_ptr()), _stream(device))
+    _lib.check(rc, "inf_pack_weights")
+    return out
+
+
+def _check_inputs(cfg, table, vids, bary, dense):
+    _require_cuda(table, "table")
+    if table.dim() != 2 or table.shape[1] != cfg.k_pad or table.dtype not in (torch.float32, torch.float16):
+        raise ValueError(f"table must be (V,{cfg.k_pad}) float32/float16 (use EigenTable.from_dense)")
+    if dense:
+        return table.shape[0]
+    _require_cuda(vids, "vertex_idxs_of_hit_faces")
+    _require_cuda(bary, "barycentric_coords")
+    if vids.dtype not in (torch.int64, torch.int32) or vids.dim() != 2 or vids.shape[1] != 3:
+        raise ValueError("vertex_idxs_of_hit_faces must be (B,3) int64/int32")
+    if bary.dtype != torch.float32 or bary.shape != vids.shape:
+        raise ValueError("barycentric_coords must be (B,3) float32")
+    return vids.shape[0]
+
+
+def _field_forward_impl(table, vids, bary, packed, k: int, num_layers: int, skip: int, dense: bool) -> torch.Tensor:
+    cfg = FieldConfig(k, num_layers, skip)
+    B = _check_inputs(cfg, table, vids, bary, dense)
+    device = table.device
+    pred = torch.empty((B, 3), dtype=torch.float32, device=device)
+    if B == 0:
+        return pred
+    ws = _workspace(device, workspace_bytes(cfg, B, False))
+    d = _desc(cfg, B, table.shape[0], idx64=(vids is None or vids.dtype == torch.int64),
+              table_f16=table.dtype == torch.float16, dense=dense)
+    t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), packed=packed.data_ptr(),
+                        pred=pred.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+    with torch.cuda.device(device):
+        rc = _lib.load().inf_forward(C.byref(d), C.byref(t), _stream(device))
+    _lib.check(rc, "inf_forward")
+    return pred
+
+
+def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, k: int, num_layers: int, skip: int,
+                                 dense: bool, grad_scale: float):
+    cfg = FieldConfig(k, num_layers, skip)
+    B = _check_inputs(cfg, table, vids, bary, dense)
+    device = table.device
+    pred = torch.empty((B, 3), dtype=torch.float32, device=device)
+    flat = torch.empty(num_params(cfg), dtype=torch.float32, device=device)
+    sums = torch.zeros(2, dtype=torch.float32, device=device)
+    for name, x in (("target", target), ("grad_pred", grad_pred)):
+        if x is not None:
+            _require_cuda(x, name)
+            if x.dtype != torch.float32 or tuple(x.shape) != (B, 3):
+                raise ValueError(f"{name} must be ({B},3) float32")
+    ws = _workspace(device, workspace_bytes(cfg, B, True))
+    d = _desc(cfg, B, table.shape[0], idx64=(vids is None or vids.dtype == torch.int64),
+              table_f16=table.dtype == torch.float16, dense=dense, grad_scale=grad_scale)
+    t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), target=_ptr(target),
+                        grad_pred=_ptr(grad_pred), packed=packed.data_ptr(), pred=pred.data_ptr(),
+                        workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+    g = _lib.InfGrads(flat=flat.data_ptr(), loss_sums=sums.data_ptr())
+    with torch.cuda.device(device):
+        rc = _lib.load().inf_forward_backward(C.byref(d), C.byref(t), C.byref(g), _stream(device))
+    _lib.check(rc, "inf_forward_backward")
+    return pred, flat, sums
+
+
+# ------------------------------------------------------------------------------------------------
+# PyTorch custom-op registration (torch.library)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("inf_b200::field_forward", mutates_args=())
+def field_forward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor],
+                  packed: torch.Tensor, k: int, num_layers: int, skip: int, dense: bool) -> torch.Tensor:
+    return _field_forward_impl(table, vids, bary, packed, k, num_layers, skip, dense)
+
+
+@field_forward.register_fake
+def _(table, vids, bary, packed, k, num_layers, skip, dense):
+    B = table.shape[0] if dense else vids.shape[0]
+    return table.new_empty((B, 3), dtype=torch.float32)
+
+
+@torch.library.custom_op("inf_b200::field_forward_backward", mutates_args=())
+def field_forward_backward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor],
+                           packed: torch.Tensor, target: Optional[torch.Tensor], grad_pred: Optional[torch.Tensor],
+                           k: int, num_layers: int, skip: int, dense: bool,
+                           grad_scale: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, k, num_layers, skip, dense,
+                                        grad_scale)
+
+
+@field_forward_backward.register_fake
+def _(table, vids, bary, packed, target, grad_pred, k, num_layers, skip, dense, grad_scale):
+    B = table.shape[0] if dense else vids.shape[0]
+    n = num_params(FieldConfig(k, num_layers, skip))
+    return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n,), dtype=torch.float32),
+            table.new_empty((2,), dtype=torch.float32))
+
+
+def debug_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Tensor-core self test: D(128,n) = A(128,k) B(n,k)^T with the operand-layout variant `mode`."""
+    _require_cuda(a, "a")
+    _require_cuda(b, "b")
+    k = a.shape[1] if mode == 0 else a.shape[0]
+    n = b.shape[1] if mode == 2 else b.shape[0]
+    d = torch.empty((128, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().inf_debug_umma(mode, n, k, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),
+                                        C.c_void_p(d.data_ptr()), _stream(a.device))
+    _lib.check(rc, "inf_debug_umma")
+    return d

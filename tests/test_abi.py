@@ -1,0 +1,96 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol declared in
+include/inf_field.h, and the host-only size/layout queries agree with the reference's state_dict."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, load_golden
+
+import inf_b200
+from inf_b200 import _lib, ops
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "inf_field.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(inf_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 11
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.EXPORTS) == names
+    assert lib.inf_version() == _lib.ABI_VERSION
+
+
+@pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1"])
+def test_param_layout_matches_reference_state_dict(name):
+    c = load_golden(name)
+    cfg = ops.FieldConfig(k=c["k"], num_layers=c["num_layers"], skip=c["skip"])
+    layout = ops.param_layout(cfg)
+    assert len(layout) == len(c["param_names"])
+    off = 0
+    for (o, r, cc), n in zip(layout, c["param_names"]):
+        shp = tuple(c["params"][n].shape)
+        assert o == off, n
+        assert r * cc == c["params"][n].numel(), n
+        assert r == shp[0], n
+        off += r * cc
+    assert ops.num_params(cfg) == off
+
+
+def test_production_config_sizes():
+    cfg = ops.FieldConfig(k=1023, num_layers=6, skip=3)
+    assert cfg.k_pad == 1024
+    assert ops.num_params(cfg) == 328579
+    assert ops.packed_bytes(cfg) == (16 + 8) * 32768 + (5 * 128 + 3 * 128 + 4) * 4
+    assert ops.workspace_bytes(cfg, 4096, False) == 256
+    assert ops.workspace_bytes(cfg, 4096, True) > 32 * 9 * 32768
+
+
+def test_bad_descriptors_are_rejected():
+    with pytest.raises(NotImplementedError):
+        ops.num_params(ops.FieldConfig(k=64, hidden=256)) if False else _raise_for(ops.FieldConfig(k=64, hidden=256))
+    with pytest.raises(RuntimeError):
+        _raise_for(ops.FieldConfig(k=64, num_layers=6, skip=5))
+    with pytest.raises(NotImplementedError):
+        _raise_for(ops.FieldConfig(k=64, num_layers=12, skip=3))
+
+
+def _raise_for(cfg):
+    lib = _lib.load()
+    d = ops._desc(cfg, 0, 0)
+    off, r, c = C.c_int64(), C.c_int32(), C.c_int32()
+    _lib.check(lib.inf_param_info(C.byref(d), 0, C.byref(off), C.byref(r), C.byref(c)), "inf_param_info")
+
+
+def test_model_state_dict_keys_match_reference():
+    c = load_golden("tf_k1023")
+    m = inf_b200.make_model(dict(k=list(range(c["k"])), num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3,
+                                 batchnorm=False))
+    sd = m.state_dict()
+    assert list(sd.keys()) == c["param_names"]
+    for n in sd:
+        assert tuple(sd[n].shape) == tuple(c["params"][n].shape)
+    m.load_state_dict(c["params"])       # reference-trained weights load unchanged
+    import copy
+    copy.deepcopy(m)                      # trainer.py:67
+
+
+def test_unsupported_options_raise():
+    base = dict(k=64, num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3)
+    for bad in (dict(batchnorm=True), dict(activation="sine"), dict(feature_strategy="rff"), dict(mlp_hidden_dim=64)):
+        with pytest.raises(NotImplementedError):
+            inf_b200.make_model({**base, **bad})
+
+
+def test_cpu_tensors_fail_loudly():
+    import torch
+    m = inf_b200.make_model(dict(k=64, num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3))
+    with pytest.raises(RuntimeError):
+        m({"eigenfunctions": torch.zeros(4, 64)})
