@@ -140,6 +140,20 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream);
 /* fused training pass: pred, loss sums and all parameter gradients (scaled by grad_scale). */
 int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, void* stream);
 
+/* Materialising gather, mesh.py:313-324 get_k_eigenfunc_vec_vals as one kernel:
+ * out (B,k) f32 = sum_j bary[:,j] * table[vids[:,j], :k].  For callers that need the dense embedding
+ * (UV baking, notebooks); the fused path above never builds it. */
+int inf_gather_interpolate(const void* table, int32_t table_dtype, int32_t k, int32_t k_pad,
+                           const void* vids, int32_t idx_dtype, const float* bary, int64_t n_rays,
+                           float* out, void* stream);
+
+/* Measurement hooks (bench.py): while enabled, inf_forward / inf_forward_backward bracket their
+ * kernels with library-owned CUDA events on the launching stream (up to 256 calls, no sync);
+ * inf_profile_read synchronises on those events and returns the average device time per call of the
+ * forward/backward kernel, the wgrad kernel and the reduction.  Single-threaded use only. */
+int inf_profile_enable(int on);
+int inf_profile_read(float* main_ms, float* wgrad_ms, float* reduce_ms, int* calls);
+
 /* Self-test hook used by tests/: D(128,n) = A(128,k) * B(n,k)^T on the tensor cores with the
  * operand-layout variant `mode` (0: A,B K-major; 1: A MN-major; 2: A,B MN-major).  A and B are
  * f32 row-major on the device ((128,k)/(n,k) for K-major, (k,128)/(k,n) for MN-major). */

@@ -61,6 +61,11 @@ EXPORTS = {
     "inf_pack_weights": (C.c_int, [C.POINTER(InfDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "inf_forward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p]),
     "inf_forward_backward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.POINTER(InfGrads), C.c_void_p]),
+    "inf_gather_interpolate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p]),
+    "inf_profile_enable": (C.c_int, [C.c_int]),
+    "inf_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                   C.POINTER(C.c_int)]),
     "inf_debug_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

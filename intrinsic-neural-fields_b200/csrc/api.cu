@@ -18,6 +18,8 @@ cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream);
 void launch_pack_weights(const PackParams& pp, cudaStream_t stream);
 void launch_relayout(const float* src, int64_t n_rows, int k, int64_t src_stride, void* dst, int k_pad, int dst_dtype,
                      cudaStream_t stream);
+void launch_gather_interpolate(const void* table, int table_f16, int k, int k_pad, const void* vids, int idx64,
+                               const float* bary, int64_t n_rays, float* out, cudaStream_t stream);
 void launch_umma_probe(int mode, int n, int k, const float* a, const float* b, float* d, cudaStream_t stream);
 
 namespace {
@@ -92,6 +94,19 @@ int build_param_table(const InfDesc* d, ParamInfo* out, int64_t* total) {
   }
   if (total) *total = off;
   return n;
+}
+
+// ---- optional per-kernel timing (inf_profile_*): library-owned CUDA events around the launches ----
+constexpr int PROF_SLOTS = 256;
+struct Profile {
+  bool on = false;
+  int n = 0;                       // recorded calls since inf_profile_enable(1)
+  cudaEvent_t ev[PROF_SLOTS][4];   // before main, after main, after wgrad, after reduce
+  bool created = false;
+} g_prof;
+
+void prof_record(int slot, int i, cudaStream_t st) {
+  if (g_prof.on && slot < PROF_SLOTS) cudaEventRecord(g_prof.ev[slot][i], st);
 }
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -254,8 +269,12 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream) {
   if (rc != INF_OK) return rc;
   FieldParams p = make_params(desc, t, false);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
+  const int slot = g_prof.n;
+  prof_record(slot, 0, static_cast<cudaStream_t>(stream));
   cudaError_t e = launch_field_main(p, false, desc->table_dtype == INF_TABLE_F16, grid, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<inference> launch");
+  for (int i = 1; i < 4; ++i) prof_record(slot, i, static_cast<cudaStream_t>(stream));
+  if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
   return INF_OK;
 }
 
@@ -292,9 +311,13 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   if (grid2 > MAX_CTAS) return fail(INF_ERR_UNSUPPORTED, "k_pad=%d needs %d wgrad CTAs > %d", desc->k_pad, grid2, MAX_CTAS);
 
   const bool f16 = desc->table_dtype == INF_TABLE_F16;
+  const int slot = g_prof.n;
+  prof_record(slot, 0, st);
   cudaError_t e = launch_field_main(p, true, f16, grid1, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<train> launch");
+  prof_record(slot, 1, st);
   e = launch_field_wgrad(p, f16, groups, grid2, st);
+  prof_record(slot, 2, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_wgrad_kernel launch");
 
   ReduceParams rp{};
@@ -310,7 +333,53 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
   rp.geo = geo;
   e = launch_field_reduce(rp, st);
+  prof_record(slot, 3, st);
+  if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
   if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel launch");
+  return INF_OK;
+}
+
+int inf_gather_interpolate(const void* table, int32_t table_dtype, int32_t k, int32_t k_pad, const void* vids,
+                           int32_t idx_dtype, const float* bary, int64_t n_rays, float* out, void* stream) {
+  if (n_rays < 0 || k < 1 || k_pad < k || k_pad % KC != 0) return fail(INF_ERR_BAD_ARG, "bad shape");
+  if (n_rays > 0 && (!table || !vids || !bary || !out)) return fail(INF_ERR_BAD_ARG, "null pointer");
+  launch_gather_interpolate(table, table_dtype == INF_TABLE_F16, k, k_pad, vids, idx_dtype == INF_IDX_I64, bary, n_rays, out,
+                            static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gather_interpolate launch");
+  return INF_OK;
+}
+
+int inf_profile_enable(int on) {
+  if (on && !g_prof.created) {
+    for (int s = 0; s < PROF_SLOTS; ++s)
+      for (int i = 0; i < 4; ++i) {
+        cudaError_t e = cudaEventCreate(&g_prof.ev[s][i]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+      }
+    g_prof.created = true;
+  }
+  g_prof.on = on != 0;
+  g_prof.n = 0;
+  return INF_OK;
+}
+
+int inf_profile_read(float* main_ms, float* wgrad_ms, float* reduce_ms, int* calls) {
+  const int n = g_prof.n < PROF_SLOTS ? g_prof.n : PROF_SLOTS;
+  double a = 0, b = 0, c = 0;
+  for (int s = 0; s < n; ++s) {
+    cudaError_t e = cudaEventSynchronize(g_prof.ev[s][3]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+    float t0 = 0, t1 = 0, t2 = 0;
+    cudaEventElapsedTime(&t0, g_prof.ev[s][0], g_prof.ev[s][1]);
+    cudaEventElapsedTime(&t1, g_prof.ev[s][1], g_prof.ev[s][2]);
+    cudaEventElapsedTime(&t2, g_prof.ev[s][2], g_prof.ev[s][3]);
+    a += t0; b += t1; c += t2;
+  }
+  if (main_ms) *main_ms = n ? static_cast<float>(a / n) : 0.f;
+  if (wgrad_ms) *wgrad_ms = n ? static_cast<float>(b / n) : 0.f;
+  if (reduce_ms) *reduce_ms = n ? static_cast<float>(c / n) : 0.f;
+  if (calls) *calls = n;
   return INF_OK;
 }
 

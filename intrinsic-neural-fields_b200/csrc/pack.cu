@@ -161,3 +161,65 @@ void launch_umma_probe(int mode, int n, int k, const float* a, const float* b, f
 }
 
 }  // namespace inf
+
+namespace inf {
+
+// ---------------------------------------------------------------------------------------------
+// Materialising gather (mesh.py:313-324 as one kernel): x[b,:] = sum_j bary[b,j] * E[vids[b,j],:].
+// Kept for callers that need the dense (B,k) embedding (baking, notebooks); the hot path never
+// builds it.  One warp per ray, 16-byte loads along the row.
+// ---------------------------------------------------------------------------------------------
+template <typename TableT>
+__global__ void gather_interpolate_kernel(const TableT* __restrict__ table, int k, int k_pad, const void* __restrict__ vids,
+                                          int idx64, const float* __restrict__ bary, int64_t n_rays, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t b = warp; b < n_rays; b += nwarps) {
+    int64_t v[3];
+    float w[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      v[j] = idx64 ? reinterpret_cast<const long long*>(vids)[b * 3 + j] : reinterpret_cast<const int*>(vids)[b * 3 + j];
+      w[j] = bary[b * 3 + j];
+    }
+    for (int c0 = lane * 4; c0 < k_pad; c0 += 128) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const TableT* row = table + v[j] * k_pad + c0;
+        float e[4];
+        if constexpr (sizeof(TableT) == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(row);
+          e[0] = q.x; e[1] = q.y; e[2] = q.z; e[3] = q.w;
+        } else {
+          const uint2 q = *reinterpret_cast<const uint2*>(row);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+          e[0] = lo.x; e[1] = lo.y; e[2] = hi.x; e[3] = hi.y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = (j == 0) ? w[0] * e[i] : fmaf(w[j], e[i], acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c0 + i < k) out[b * k + c0 + i] = acc[i];
+    }
+  }
+}
+
+void launch_gather_interpolate(const void* table, int table_f16, int k, int k_pad, const void* vids, int idx64,
+                               const float* bary, int64_t n_rays, float* out, cudaStream_t stream) {
+  if (n_rays == 0) return;
+  const int threads = 256;
+  const int64_t want = (n_rays * 32 + threads - 1) / threads;
+  const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
+  if (table_f16)
+    gather_interpolate_kernel<__half><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(table), k, k_pad, vids,
+                                                                     idx64, bary, n_rays, out);
+  else
+    gather_interpolate_kernel<float><<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(table), k, k_pad, vids, idx64,
+                                                                    bary, n_rays, out);
+}
+
+}  // namespace inf

@@ -282,6 +282,26 @@ def _(table, vids, bary, packed, target, grad_pred, k, num_layers, skip, dense, 
             table.new_empty((2,), dtype=torch.float32))
 
 
+def gather_interpolate_dense(table: "EigenTable", vids: torch.Tensor, bary: torch.Tensor) -> torch.Tensor:
+    """get_k_eigenfunc_vec_vals (mesh.py:313-324) as one CUDA kernel: the materialised (B,k) f32 embedding.
+    Only for callers that need the dense tensor; the fused path never builds it."""
+    _require_cuda(table.data, "table")
+    vids, bary = vids.contiguous(), bary.contiguous()
+    _require_cuda(vids, "vertex_idxs_of_hit_faces")
+    _require_cuda(bary, "barycentric_coords")
+    if vids.dtype not in (torch.int64, torch.int32) or bary.dtype != torch.float32:
+        raise ValueError("vids must be int64/int32 and bary float32")
+    B = vids.shape[0]
+    out = torch.empty((B, table.k), dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        rc = _lib.load().inf_gather_interpolate(
+            C.c_void_p(table.data.data_ptr()), _lib.TABLE_F16 if table.data.dtype == torch.float16 else _lib.TABLE_F32,
+            table.k, table.k_pad, C.c_void_p(vids.data_ptr()), _lib.IDX_I64 if vids.dtype == torch.int64 else _lib.IDX_I32,
+            C.c_void_p(bary.data_ptr()), B, C.c_void_p(out.data_ptr()), _stream(table.device))
+    _lib.check(rc, "inf_gather_interpolate")
+    return out
+
+
 def debug_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Tensor-core self test: D(128,n) = A(128,k) B(n,k)^T with the operand-layout variant `mode`."""
     _require_cuda(a, "a")

@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing: one process per GPU, rays sharded by rank, table + weights replicated, and ONE
+allreduce(SUM) per step over the flat fp32 gradient buffer the kernels write (replaces the reference's
+``nn.DataParallel``, train.py:46-48).  Gradients are already scaled by 1/(3*B_global) on every rank, so
+SUM reproduces the reference's global-mean L1 gradient and Adam stays bit-identical across ranks."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank(group=None) -> int:
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_range(n: int, group=None):
+    """Contiguous 1/W slice of n rays owned by this rank (ragged tail goes to the last ranks evenly)."""
+    w, r = world_size(group), rank(group)
+    base, rem = divmod(n, w)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+def allreduce_flat(flat: torch.Tensor, sums: torch.Tensor, group=None):
+    """Sum the flat gradient vector (and the two loss sums) over ranks with a single collective each."""
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+
+
+def allreduce_module_grads(model, group=None):
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def broadcast_parameters(model, src: int = 0, group=None):
+    for p in model.parameters():
+        dist.broadcast(p.data, src=src, group=group)

@@ -1,0 +1,69 @@
+"""Inference data path of the reference's ``Renderer.render`` (renderer.py:64-146), minus ray casting.
+
+Ray generation and ray-mesh intersection stay the reference's CPU preprocessing (trimesh/pyembree,
+mesh.py:171-310); they produce, per hit, the vertex-id triplet, the barycentric weights, the hit-ray
+index (and optionally ray direction / face id).  ``FieldRenderer.render_hits`` is everything after that:
+instead of gathering on the CPU and uploading a 4 KB/ray embedding (mesh.py:327-339, renderer.py:116) it
+uploads the 36 B/ray gather inputs, runs the fused kernel in chunks against the resident table, and
+scatters the RGB into the canvas by ``hit_ray_idxs`` exactly as renderer.py:119-142 does.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .ops import EigenTable
+
+
+class FieldRenderer:
+    def __init__(self, model, eigenfunctions, H: int, W: int, background: str = "white", device="cuda",
+                 chunk: int = 1 << 20, table_dtype: str = "f32"):
+        assert background in ("white", "black")
+        self.model, self.H, self.W, self.background = model, H, W, background
+        self.device = torch.device(device)
+        self.chunk = chunk
+        self.set_eigenfunctions(eigenfunctions, table_dtype)
+
+    def set_eigenfunctions(self, eigenfunctions, table_dtype: str = "f32"):
+        """Swap the table under a fixed model (texture transfer passes a mapped table per renderer)."""
+        self.table = eigenfunctions if isinstance(eigenfunctions, EigenTable) else EigenTable.from_dense(
+            eigenfunctions.to(torch.float32), device=self.device, dtype=table_dtype)
+
+    @torch.no_grad()
+    def predict_hits(self, vertex_idxs_of_hit_faces: torch.Tensor, barycentric_coords: torch.Tensor,
+                     unit_ray_dirs: Optional[torch.Tensor] = None, face_idxs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(M,3) vids + (M,3) bary on the host or device -> (M,3) RGB on the device, chunked."""
+        self.model.eval()
+        M = vertex_idxs_of_hit_faces.shape[0]
+        out = torch.empty((M, 3), dtype=torch.float32, device=self.device)
+        for lo in range(0, M, self.chunk):
+            hi = min(M, lo + self.chunk)
+            batch = {"eigenfunction_table": self.table,
+                     "vertex_idxs_of_hit_faces": vertex_idxs_of_hit_faces[lo:hi].to(self.device, non_blocking=True),
+                     "barycentric_coords": barycentric_coords[lo:hi].to(self.device, non_blocking=True)}
+            if unit_ray_dirs is not None:
+                batch["unit_ray_dirs"] = unit_ray_dirs[lo:hi].to(self.device, non_blocking=True)
+                batch["hit_face_idxs"] = face_idxs[lo:hi].to(self.device, non_blocking=True)
+            out[lo:hi] = self.model(batch)
+        return out
+
+    @torch.no_grad()
+    def render_hits(self, vertex_idxs_of_hit_faces, barycentric_coords, hit_ray_idxs, obj_mask_1d=None,
+                    unit_ray_dirs=None, face_idxs=None, eval_render: bool = False):
+        """Canvas assembly of renderer.py:119-146 on the device; returns (H,W,3) numpy (or torch + hit idxs)."""
+        assert obj_mask_1d is None or obj_mask_1d.size()[0] == self.H * self.W
+        pred = self.predict_hits(vertex_idxs_of_hit_faces, barycentric_coords, unit_ray_dirs, face_idxs)
+        fill = 1.0 if self.background == "white" else 0.0
+        N = self.H * self.W if obj_mask_1d is None else int(obj_mask_1d.sum())
+        img = torch.full((N, 3), fill, dtype=torch.float32, device=self.device)
+        img[hit_ray_idxs.to(self.device)] = pred
+        if obj_mask_1d is not None:
+            assert obj_mask_1d.dtype == torch.bool
+            full = torch.full((self.H * self.W, 3), fill, dtype=torch.float32, device=self.device)
+            full[obj_mask_1d.to(self.device)] = img
+            img = full
+        img = img.reshape(self.H, self.W, 3).cpu()
+        if eval_render:
+            return img, hit_ray_idxs
+        return img.numpy()

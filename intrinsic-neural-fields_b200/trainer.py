@@ -1,0 +1,75 @@
+"""Training-step surface of the reference's ``Trainer`` (trainer.py:71-84, 158-187) on the fused path.
+
+``train_step`` keeps ``_train_step``'s contract -- ``(loss.item(), pred_rgbs)`` after forward, loss,
+zero_grad, backward and ``optim.step()`` -- and uses the fused forward+backward kernel when the loss is
+the config's L1 (config.py:117-118); any other loss callable goes through autograd into the same
+backward kernels.  Epoch loops, TensorBoard, checkpoints stay the reference's host code.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import parallel
+
+
+def get_loss_fn(loss_type: str) -> Callable:
+    """config.py:113-122."""
+    if loss_type == "L2":
+        return F.mse_loss
+    if loss_type == "L1":
+        return F.l1_loss
+    if loss_type == "cauchy":
+        return lambda rgb_pred, rgb_gt: ((20 / 255) * (20 / 255) * torch.log(
+            1 + (rgb_pred - rgb_gt) ** 2 / ((20 / 255) * (20 / 255)))).mean()
+    raise RuntimeError(f"Unknown loss function: {loss_type}. Please use either 'L1', 'L2' or 'cauchy'")
+
+
+def train_step_async(model, optim, batch, loss_fn=F.l1_loss, group=None, flat_grad=None):
+    """One optimisation step without a host sync; returns (loss tensor (0-dim, device), pred)."""
+    world = parallel.world_size(group)
+    B = batch["expected_rgbs"].shape[0]
+    if loss_fn is F.l1_loss:
+        optim.zero_grad(set_to_none=True)
+        sums, pred, flat = model.l1_step(batch, global_rays=B * world, flat_grad=flat_grad)
+        if world > 1:
+            parallel.allreduce_flat(flat, sums, group)
+        loss = sums[0] / (3.0 * B * world)
+    else:
+        pred = model(batch)
+        loss = loss_fn(pred, batch["expected_rgbs"])
+        optim.zero_grad(set_to_none=True)
+        (loss / world).backward()
+        if world > 1:
+            parallel.allreduce_module_grads(model, group)
+    optim.step()
+    return loss, pred
+
+
+def train_step(model, optim, batch, loss_fn=F.l1_loss, group=None) -> Tuple[float, torch.Tensor]:
+    """trainer.py:71-84: returns (loss.item(), pred_rgbs)."""
+    loss, pred = train_step_async(model, optim, batch, loss_fn, group)
+    return loss.item(), pred
+
+
+@torch.no_grad()
+def evaluate(model, data_loader, loss_fn=F.l1_loss):
+    """trainer.py:164-187 without the TensorBoard writes: (val_loss, epoch PSNR)."""
+    model.eval()
+    acc_loss = acc_l2 = 0.0
+    total = 0
+    for batch in data_loader:
+        pred = model(batch)
+        n = batch["expected_rgbs"].size()[0]
+        acc_l2 += F.mse_loss(pred, batch["expected_rgbs"], reduction="sum").item()
+        acc_loss += loss_fn(pred, batch["expected_rgbs"]).item() * n
+        total += n
+    return acc_loss / total, epoch_psnr(acc_l2 / total)
+
+
+def epoch_psnr(x: float) -> float:
+    """evaluation_metrics.py:25-26."""
+    return -10.0 * math.log10(x)

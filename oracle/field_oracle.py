@@ -260,6 +260,78 @@ def manual_grads_texture_field(p, E, vids, bary, target, num_layers=6, skip=3):
     return loss, y, g
 
 
+def _r16(a: np.ndarray) -> np.ndarray:
+    """Round to fp16 and back (the operand precision of the CUDA path's tensor-core GEMMs)."""
+    return a.astype(np.float16).astype(np.float64)
+
+
+def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale=32.0, table_f16=False):
+    """The reference's forward/backward (model.py:98-112, trainer.py:76-81) restated in float64 with the
+    CUDA path's rounding points: table (optionally), interpolated embedding, weights, hidden activations
+    and backward signals are rounded to fp16 before each matrix product; accumulation is exact.
+
+    Purpose: ReLU masks of a reduced-precision forward differ from the fp32 reference wherever |z| is
+    below the rounding noise, which alone moves each gradient tensor by a few percent in Frobenius
+    norm.  Against THIS restatement the masks agree, so the kernels' arithmetic can be checked tightly.
+    Returns (loss, pred, grads) with grads of the mean L1 loss.
+    """
+    P = {n: t.double().numpy() for n, t in p.items()}
+    Ed = E.double().numpy()
+    if table_f16:
+        Ed = _r16(Ed)
+    b = bary.numpy().astype(np.float32)
+    rows = Ed[vids.numpy().reshape(-1)].reshape(vids.shape[0], 3, -1)
+    # fp32 interpolation (w0*e0, then two fma) as the producer warps do, then one fp16 rounding
+    x32 = (b[:, 0:1] * rows[:, 0].astype(np.float32)).astype(np.float32)
+    x32 = (b[:, 1:2].astype(np.float64) * rows[:, 1] + x32).astype(np.float32)
+    x32 = (b[:, 2:3].astype(np.float64) * rows[:, 2] + x32).astype(np.float32)
+    x = _r16(x32)
+    t = target.double().numpy()
+    L = num_layers
+
+    def W(i):
+        return P[f"layers.{i}.Lx.weight" if i == skip else f"layers.{i}.0.weight"]
+
+    def bias(i):
+        if i == skip:
+            return (P[f"layers.{i}.Lx.bias"].astype(np.float32) + P[f"layers.{i}.Ly.bias"].astype(np.float32)).astype(np.float64)
+        return P[f"layers.{i}.0.bias"]
+
+    hs, masks = [], []
+    h16 = x
+    for i in range(L - 1):
+        z = h16 @ _r16(W(i)).T + bias(i)
+        if i == skip:
+            z = z + x @ _r16(P[f"layers.{i}.Ly.weight"]).T
+        masks.append(z > 0)
+        h = np.maximum(z, 0.0)
+        hs.append(h)
+        h16 = _r16(h)
+    z = hs[-1] @ W(L - 1).T + bias(L - 1)            # output layer runs in fp32 on CUDA cores
+    y = 1.0 / (1.0 + np.exp(-z))
+    B = y.shape[0]
+    loss = np.abs(y - t).mean()
+    dzl = np.sign(y - t) * y * (1.0 - y) * dz_scale
+    g = {}
+    g[f"layers.{L-1}.0.weight"] = dzl.T @ _r16(hs[-1])
+    g[f"layers.{L-1}.0.bias"] = dzl.sum(0)
+    dz = _r16((dzl @ W(L - 1)) * masks[L - 2])
+    for i in range(L - 2, -1, -1):
+        hin = x if i == 0 else _r16(hs[i - 1])
+        if i == skip:
+            g[f"layers.{i}.Lx.weight"] = dz.T @ hin
+            g[f"layers.{i}.Lx.bias"] = dz.sum(0)
+            g[f"layers.{i}.Ly.weight"] = dz.T @ x
+            g[f"layers.{i}.Ly.bias"] = dz.sum(0)
+        else:
+            g[f"layers.{i}.0.weight"] = dz.T @ hin
+            g[f"layers.{i}.0.bias"] = dz.sum(0)
+        if i > 0:
+            dz = _r16((dz @ _r16(W(i))) * masks[i - 1])
+    s = 1.0 / (3.0 * B * dz_scale)
+    return loss, y, {n: v * s for n, v in g.items()}
+
+
 def adam_train_steps(p, E, vids, bary, target, batch_index_lists, lr=1e-4, **kw):
     """Fixed-step Adam training as trainer.py:71-84 + config.py:108 (Adam(lr), defaults).
 

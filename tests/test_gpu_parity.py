@@ -14,7 +14,13 @@ from inf_b200 import ops
 pytestmark = pytest.mark.gpu
 
 RGB_MAX, RGB_MEAN = 2e-2, 1e-3      # BASELINE.json north_star tolerances
-GRAD_REL = 2e-2                     # relative Frobenius error of each gradient tensor (fp16 operands)
+# Gradients.  A reduced-precision forward flips the ReLU mask wherever |z| is below the rounding noise;
+# those few elements alone move every gradient tensor by 1-4 % in Frobenius norm against the fp32
+# reference (measured; identical for tf32).  So: a loose bound + cosine against the reference, and a
+# tight bound against the oracle's restatement with the kernels' rounding points (masks then agree).
+GRAD_REL = 6e-2
+GRAD_COS = 0.997
+GRAD_REL_EMULATED = 5e-3
 
 DEV = "cuda:0"
 
@@ -124,14 +130,25 @@ def test_empty_batch():
 # ---------------------------------------------------------------------------------------------
 # training: fused L1 step and autograd path
 # ---------------------------------------------------------------------------------------------
-def _check_grads(m, ref_grads, tol=GRAD_REL):
+def _check_grads(m, ref_grads, tol=GRAD_REL, cos_min=GRAD_COS):
     worst = 0.0
     for n, p in m.named_parameters():
         ref = ref_grads[n]
-        rel = (p.grad.detach().cpu() - ref).norm().item() / (ref.norm().item() + 1e-12)
+        if not torch.is_tensor(ref):
+            ref = torch.from_numpy(np.asarray(ref)).float()
+        ref = ref.reshape(p.shape).float()
+        g = p.grad.detach().cpu()
+        rel = (g - ref).norm().item() / (ref.norm().item() + 1e-12)
+        cos = (g * ref).sum().item() / (g.norm().item() * ref.norm().item() + 1e-30)
         worst = max(worst, rel)
-        assert rel <= tol, (n, rel)
+        assert rel <= tol and cos >= cos_min, (n, rel, cos)
     return worst
+
+
+def _check_grads_emulated(m, case, table_f16=False):
+    _, _, g = O.emulated_fp16_grads(case["params"], case["table"], case["vids"], case["bary"], case["target"],
+                                    case["num_layers"], case["skip"], table_f16=table_f16)
+    return _check_grads(m, g, tol=GRAD_REL_EMULATED, cos_min=0.9999)
 
 
 @pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1"])
@@ -148,6 +165,7 @@ def test_fused_l1_step_matches_reference_golden(name, table_dtype):
     assert abs(sums[1].item() - sse_ref) <= 2e-2 * max(1.0, sse_ref)
     assert (pred.cpu() - c["pred"]).abs().max().item() <= RGB_MAX
     _check_grads(m, c["grads"])
+    _check_grads_emulated(m, c, table_f16=(table_dtype == "f16"))
 
 
 def test_autograd_path_matches_fused_step_and_reference():
