@@ -20,7 +20,7 @@ RGB_MAX, RGB_MEAN = 2e-2, 1e-3      # BASELINE.json north_star tolerances
 # tight bound against the oracle's restatement with the kernels' rounding points (masks then agree).
 GRAD_REL = 6e-2
 GRAD_COS = 0.997
-GRAD_REL_EMULATED = 5e-3
+GRAD_REL_EMULATED = 1e-2
 
 DEV = "cuda:0"
 
