@@ -325,7 +325,10 @@ def main():
     ap.add_argument("--batch", type=int, default=131072, help="rays per GPU per step")
     ap.add_argument("--table-dtype", default="f32", choices=["f32", "f16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid", type=int, default=224, help="torus grid side: V = grid^2 vertices (default: config 2)")
     args = ap.parse_args()
+    global GRID
+    GRID = args.grid
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -12,7 +13,7 @@ namespace inf {
 
 // kernels / launchers defined in the other translation units
 cudaError_t launch_field_main(const FieldParams& p, bool train, bool table_f16, int grid, cudaStream_t stream);
-cudaError_t launch_field_wgrad(const FieldParams& p, bool table_f16, int groups, int grid, cudaStream_t stream);
+cudaError_t launch_field_wgrad(const FieldParams& p, bool table_f16, int grid, cudaStream_t stream);
 cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream);
 
 void launch_pack_weights(const PackParams& pp, cudaStream_t stream);
@@ -161,6 +162,12 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   p.dense = d->input_mode == INF_INPUT_DENSE;
   p.ext_scale = 1.f;
   p.geo = geo_of(d);
+  {
+    // tuning knob (measurement only): INF_PREFETCH=<k-chunks ahead>, default off
+    const char* e = getenv("INF_PREFETCH");
+    p.prefetch = e ? atoi(e) : 0;
+    if (p.prefetch < 0 || p.prefetch > 8) p.prefetch = 0;
+  }
   if (t->workspace != nullptr && t->workspace_bytes >= 256) {
     const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training);
     uint8_t* ws = reinterpret_cast<uint8_t*>(t->workspace);
@@ -304,10 +311,17 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   const Geo geo = p.geo;
   const int grid1 = p.ntiles < nsm ? p.ntiles : nsm;
   const int nslices = geo.nbig + geo.nhid;
-  int groups = nsm / nslices;
-  if (groups < 1) groups = 1;
-  if (groups > p.ntiles) groups = p.ntiles;
-  const int grid2 = nslices * groups;
+  // hidden slices move ~1/8 of the wgrad bytes (bulk loads only); big slices also re-gather x
+  int gh = (nsm / 8) / geo.nhid;
+  if (gh < 1) gh = 1;
+  if (gh > p.ntiles) gh = p.ntiles;
+  int gb = (nsm - geo.nhid * gh) / geo.nbig;
+  if (gb < 1) gb = 1;
+  if (gb > p.ntiles) gb = p.ntiles;
+  p.groups_big = gb;
+  p.groups_hid = gh;
+  const int grid2 = geo.nbig * gb + geo.nhid * gh;
+  (void)nslices;
   if (grid2 > MAX_CTAS) return fail(INF_ERR_UNSUPPORTED, "k_pad=%d needs %d wgrad CTAs > %d", desc->k_pad, grid2, MAX_CTAS);
 
   const bool f16 = desc->table_dtype == INF_TABLE_F16;
@@ -316,7 +330,7 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   cudaError_t e = launch_field_main(p, true, f16, grid1, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<train> launch");
   prof_record(slot, 1, st);
-  e = launch_field_wgrad(p, f16, groups, grid2, st);
+  e = launch_field_wgrad(p, f16, grid2, st);
   prof_record(slot, 2, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_wgrad_kernel launch");
 
@@ -329,7 +343,8 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   rp.flat = g->flat;
   rp.loss_sums = (t->target != nullptr) ? g->loss_sums : nullptr;
   rp.ncta1 = grid1;
-  rp.groups = groups;
+  rp.groups_big = gb;
+  rp.groups_hid = gh;
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
   rp.geo = geo;
   e = launch_field_reduce(rp, st);

@@ -109,6 +109,9 @@ struct FieldParams {
   int idx64;
   int dense;
   float ext_scale;  // multiplies grad_pred before it enters the fp16 backward chain
+  int prefetch;     // L2 prefetch distance of the gather (k-chunks / units ahead); 0 = off
+  int groups_big;   // wgrad: ray groups (CTAs) per big slice
+  int groups_hid;   // wgrad: ray groups (CTAs) per hidden slice
   Geo geo;
 };
 
@@ -136,7 +139,7 @@ struct ReduceParams {
   float* flat;
   float* loss_sums;
   int ncta1;   // CTAs of the forward/backward kernel
-  int groups;  // ray groups per wgrad slice
+  int groups_big, groups_hid;  // ray groups per wgrad slice (big / hidden)
   float scale;
   Geo geo;
 };

@@ -30,9 +30,9 @@ constexpr uint32_t SM_ONES = SM_H + 2 * BLOB_BYTES;               // 196608
 constexpr uint32_t SM_BIAS = SM_ONES + 2048;                      // f32 [L-1][128]
 constexpr uint32_t SM_WLAST = SM_BIAS + (INF_MAX_LAYERS - 1) * HID * 4;
 constexpr uint32_t SM_BLAST = SM_WLAST + OUT_DIM * HID * 4;
-constexpr uint32_t SM_VID = SM_BLAST + 16;                        // u32 [2][384]
-constexpr uint32_t SM_BARY = SM_VID + 2 * 384 * 4;                // f32 [2][384]
-constexpr uint32_t SM_DZL = SM_BARY + 2 * 384 * 4;                // f32 [128][4]
+constexpr uint32_t SM_VID = SM_BLAST + 16;                        // u32 [3][384]
+constexpr uint32_t SM_BARY = SM_VID + 3 * 384 * 4;                // f32 [3][384]
+constexpr uint32_t SM_DZL = SM_BARY + 3 * 384 * 4;                // f32 [128][4]
 constexpr uint32_t SM_RED = SM_DZL + TILE_M * 16;                 // f32 [8]
 constexpr uint32_t SM_MASK = SM_RED + 32;                         // u32x4 [L-1][128]
 constexpr uint32_t SM_BARS = SM_MASK + (INF_MAX_LAYERS - 1) * TILE_M * 16;
@@ -194,9 +194,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
     float* s_bary = reinterpret_cast<float*>(smem + SM_BARY);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int mb = (it & 1) * 384;
+    // tile metadata ring (3 deep): entry i = (ray i/3, vertex i%3) -> vertex id, barycentric weight
+    auto load_meta = [&](int tile, int slot) {
       const int64_t ray0 = static_cast<int64_t>(tile) * TILE_M;
       for (int i = pt; i < 384; i += PROD_THREADS) {
         const int64_t e = ray0 * 3 + i;
@@ -210,35 +209,56 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
             w = p.bary[e];
           }
         }
-        s_vid[mb + i] = v;
-        s_bary[mb + i] = w;
+        s_vid[slot * 384 + i] = v;
+        s_bary[slot * 384 + i] = w;
       }
+    };
+    // Software-pipelined gather.  A "pass" = 4 rays per warp (8 lanes per ray) of one k-chunk.  Two passes
+    // are always in flight: the loads of pass n+2 are issued right after pass n has been consumed -- also
+    // across k-chunk and tile boundaries, because a load needs registers only, not a free ring slot.
+    struct Cursor { int tile, slot, c, q; };
+    auto advance = [&](Cursor& k) {
+      if (++k.q == 4) {
+        k.q = 0;
+        if (++k.c == nchunks) { k.c = 0; k.tile += gridDim.x; k.slot = (k.slot + 1) % 3; }
+      }
+    };
+    // rows of a pass: lanes 8g..8g+7 take row base + {0,4,1,5}[g] so that 64-bit stores are bank-conflict free
+    auto pass_row = [&](int q) { return 16 * pw + 8 * (q >> 1) + 2 * (q & 1) + (gq >> 1) + 4 * (gq & 1); };
+    auto issue = [&](const Cursor& k, RowLoader<TableT>& ld) {
+      if (k.tile >= ntiles) return;
+      const int e = k.slot * 384 + 3 * pass_row(k.q);
+      int64_t roff[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) roff[j] = static_cast<int64_t>(s_vid[e + j]) * p.row_stride;
+      ld.load(table, roff, k.c * KC, s);
+    };
+    auto consume = [&](int slot, int q, const RowLoader<TableT>& ld, uint32_t panel) {
+      const int r = pass_row(q);
+      const float w[3] = {s_bary[slot * 384 + 3 * r], s_bary[slot * 384 + 3 * r + 1], s_bary[slot * 384 + 3 * r + 2]};
+      ld.store(panel, r, s, w);
+    };
+    RowLoader<TableT> ld0, ld1;
+    Cursor L{static_cast<int>(blockIdx.x), 0, 0, 0};
+    if (static_cast<int>(blockIdx.x) < ntiles) {
+      load_meta(blockIdx.x, 0);
+      named_bar_sync(2, PROD_THREADS);
+      issue(L, ld0); advance(L);
+      issue(L, ld1); advance(L);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int slot = it % 3;
+      const int next_tile = tile + gridDim.x;
+      if (next_tile < ntiles) load_meta(next_tile, (it + 1) % 3);   // the load cursor enters it 2 passes early
       named_bar_sync(2, PROD_THREADS);
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(bar(BAR_A_EMPTY + stage), phase ^ 1u, p.err, 0x10);
         const uint32_t panel = smem_base + SM_A + static_cast<uint32_t>(stage) * PANEL_BYTES;
-        const int koff = c * KC;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          RowLoader<TableT> ld[2];
-          int rr[2];
-          float ww[2][3];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int q = half * 2 + u;
-            const int r = 16 * pw + 8 * (q >> 1) + 2 * (q & 1) + (gq >> 1) + 4 * (gq & 1);
-            rr[u] = r;
-            int64_t roff[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              roff[j] = static_cast<int64_t>(s_vid[mb + 3 * r + j]) * p.row_stride;
-              ww[u][j] = s_bary[mb + 3 * r + j];
-            }
-            ld[u].load(table, roff, koff, s);
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) ld[u].store(panel, rr[u], s, ww[u]);
-        }
+        consume(slot, 0, ld0, panel); issue(L, ld0); advance(L);
+        consume(slot, 1, ld1, panel); issue(L, ld1); advance(L);
+        consume(slot, 2, ld0, panel); issue(L, ld0); advance(L);
+        consume(slot, 3, ld1, panel); issue(L, ld1); advance(L);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_A_FULL + stage));

@@ -22,9 +22,9 @@ namespace {
 constexpr int NSTAGE = 3;
 constexpr uint32_t STAGE_BYTES = 2 * BLOB_BYTES;  // [A 32 KB][B 32 KB]
 constexpr uint32_t SM_STAGES = 0;
-constexpr uint32_t SM_VID = SM_STAGES + NSTAGE * STAGE_BYTES;  // u32 [2][192]
-constexpr uint32_t SM_BARY = SM_VID + 2 * 192 * 4;
-constexpr uint32_t SM_BARS = SM_BARY + 2 * 192 * 4;
+constexpr uint32_t SM_VID = SM_STAGES + NSTAGE * STAGE_BYTES;  // u32 [4][192]
+constexpr uint32_t SM_BARY = SM_VID + 4 * 192 * 4;
+constexpr uint32_t SM_BARS = SM_BARY + 4 * 192 * 4;
 constexpr uint32_t SM_TMEMPTR = SM_BARS + 16 * 8;
 constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
 constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;
@@ -98,7 +98,7 @@ struct SliceLoader<__half> {
 }  // namespace
 
 template <typename TableT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) field_wgrad_kernel(const FieldParams p, const int groups) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) field_wgrad_kernel(const FieldParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -108,9 +108,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_wgrad_kernel(const Field
   const int lane = tid & 31;
   const Geo g = p.geo;
   const int L = g.L;
-  const int slice = blockIdx.x / groups;
-  const int grp = blockIdx.x % groups;
-  const bool big = slice < g.nbig;
+  // CTA -> (slice, ray group): big slices first (groups_big CTAs each), then hidden slices
+  const int nbig_ctas = g.nbig * p.groups_big;
+  const bool big = static_cast<int>(blockIdx.x) < nbig_ctas;
+  const int groups = big ? p.groups_big : p.groups_hid;
+  const int rel = big ? blockIdx.x : blockIdx.x - nbig_ctas;
+  const int slice = (big ? 0 : g.nbig) + rel / groups;
+  const int grp = rel % groups;
   const int ncols = big ? min(256, g.k_pad - 256 * slice) : 0;        // big: columns of this slice
   const int hl0 = big ? 0 : 1 + 4 * (slice - g.nbig);                  // hidden: first layer
   const int hn = big ? 0 : min(4, (L - 2) - 4 * (slice - g.nbig));    // hidden: layer count
@@ -151,12 +155,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_wgrad_kernel(const Field
       const int npanels = ncols / KC;
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = 0; u < nunits; ++u) {
-        const int tile = grp + (u >> 1) * groups;
-        const int hh = u & 1;
-        const int mb = (u & 1) * 192;
-        const int64_t ray0 = static_cast<int64_t>(tile) * TILE_M + 64 * hh;
-        if (pt < 192) {
+      // unit metadata ring (4 deep), filled two units ahead of the consumer
+      auto load_meta = [&](int u) {
+        if (u < nunits && pt < 192) {
+          const int tile = grp + (u >> 1) * groups;
+          const int64_t ray0 = static_cast<int64_t>(tile) * TILE_M + 64 * (u & 1);
           const int64_t e = ray0 * 3 + pt;
           uint32_t v = 0;
           float w = 0.f;
@@ -168,32 +171,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_wgrad_kernel(const Field
               w = p.bary[e];
             }
           }
-          s_vid[mb + pt] = v;
-          s_bary[mb + pt] = w;
+          s_vid[(u & 3) * 192 + pt] = v;
+          s_bary[(u & 3) * 192 + pt] = w;
         }
+      };
+      // software-pipelined gather (see field_main.cu): pass = 4 rays per warp of one 64-column panel;
+      // the loads of pass n+2 are issued as soon as pass n is consumed, across panels and units.
+      struct Cursor { int u, pn, q; };
+      auto advance = [&](Cursor& k) {
+        if (++k.q == 2) { k.q = 0; if (++k.pn == npanels) { k.pn = 0; ++k.u; } }
+      };
+      auto pass_row = [&](int q) { return 8 * pw + 2 * q + (gq >> 1) + 4 * (gq & 1); };
+      auto issue = [&](const Cursor& k, SliceLoader<TableT>& ld) {
+        if (k.u >= nunits) return;
+        const int e = (k.u & 3) * 192 + 3 * pass_row(k.q);
+        int64_t roff[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) roff[j] = static_cast<int64_t>(s_vid[e + j]) * p.row_stride;
+        ld.load(table, roff, 256 * slice + KC * k.pn, s);
+      };
+      auto consume = [&](int u, int q, const SliceLoader<TableT>& ld, uint32_t panel) {
+        const int r = pass_row(q);
+        const int e = (u & 3) * 192 + 3 * r;
+        const float w[3] = {s_bary[e], s_bary[e + 1], s_bary[e + 2]};
+        ld.store(panel, r, s, w);
+      };
+      SliceLoader<TableT> ld0, ld1;
+      Cursor Lc{0, 0, 0};
+      load_meta(0);
+      load_meta(1);
+      named_bar_sync(2, PROD_THREADS);
+      issue(Lc, ld0); advance(Lc);
+      issue(Lc, ld1); advance(Lc);
+      for (int u = 0; u < nunits; ++u) {
+        load_meta(u + 2);
         named_bar_sync(2, PROD_THREADS);
         mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1u, p.err, 0x50);
         const uint32_t bpart = smem_base + SM_STAGES + static_cast<uint32_t>(stage) * STAGE_BYTES + BLOB_BYTES;
-        int rr[2];
-        float ww[2][3];
-        int64_t roff[2][3];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int r = 8 * pw + 2 * q + (gq >> 1) + 4 * (gq & 1);
-          rr[q] = r;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            roff[q][j] = static_cast<int64_t>(s_vid[mb + 3 * r + j]) * p.row_stride;
-            ww[q][j] = s_bary[mb + 3 * r + j];
-          }
-        }
         for (int pn = 0; pn < npanels; ++pn) {
-          const int koff = 256 * slice + KC * pn;
-          SliceLoader<TableT> ld[2];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) ld[q].load(table, roff[q], koff, s);
-#pragma unroll
-          for (int q = 0; q < 2; ++q) ld[q].store(bpart + static_cast<uint32_t>(pn) * HALF_PANEL, rr[q], s, ww[q]);
+          const uint32_t panel = bpart + static_cast<uint32_t>(pn) * HALF_PANEL;
+          consume(u, 0, ld0, panel); issue(Lc, ld0); advance(Lc);
+          consume(u, 1, ld1, panel); issue(Lc, ld1); advance(Lc);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -300,16 +318,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_wgrad_kernel(const Field
 size_t field_wgrad_smem_bytes() { return SM_ALLOC; }
 
 template <typename TableT>
-static cudaError_t launch_wgrad_one(const FieldParams& p, int groups, int grid, cudaStream_t stream) {
+static cudaError_t launch_wgrad_one(const FieldParams& p, int grid, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(field_wgrad_kernel<TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(SM_ALLOC));
   if (e != cudaSuccess) return e;
-  field_wgrad_kernel<TableT><<<grid, NUM_THREADS, SM_ALLOC, stream>>>(p, groups);
+  field_wgrad_kernel<TableT><<<grid, NUM_THREADS, SM_ALLOC, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_field_wgrad(const FieldParams& p, bool table_f16, int groups, int grid, cudaStream_t stream) {
-  return table_f16 ? launch_wgrad_one<__half>(p, groups, grid, stream) : launch_wgrad_one<float>(p, groups, grid, stream);
+cudaError_t launch_field_wgrad(const FieldParams& p, bool table_f16, int grid, cudaStream_t stream) {
+  return table_f16 ? launch_wgrad_one<__half>(p, grid, stream) : launch_wgrad_one<float>(p, grid, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -339,13 +357,13 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   if (sg.kind == 0) {  // W0 / Wy: row n, column j
     const int slice = col >> 8;
     const int c = (col & 255) + (sg.a ? 256 : 0);
-    for (int gI = 0; gI < rp.groups; ++gI)
-      acc += rp.partw[(static_cast<size_t>(slice * rp.groups + gI) * HID + row) * WG_COLS + c];
+    for (int gI = 0; gI < rp.groups_big; ++gI)
+      acc += rp.partw[(static_cast<size_t>(slice * rp.groups_big + gI) * HID + row) * WG_COLS + c];
   } else if (sg.kind == 1) {  // hidden W_l
     const int hs = (sg.a - 1) >> 2;
     const int c = 128 * ((sg.a - 1) & 3) + col;
-    for (int gI = 0; gI < rp.groups; ++gI)
-      acc += rp.partw[(static_cast<size_t>((rp.geo.nbig + hs) * rp.groups + gI) * HID + row) * WG_COLS + c];
+    for (int gI = 0; gI < rp.groups_hid; ++gI)
+      acc += rp.partw[(static_cast<size_t>(rp.geo.nbig * rp.groups_big + hs * rp.groups_hid + gI) * HID + row) * WG_COLS + c];
   } else if (sg.kind == 2) {  // bias of layer a (rows == HID entries, cols == 1)
     for (int c = 0; c < rp.ncta1; ++c) acc += rp.part1[static_cast<size_t>(c) * K1_PART_FLOATS + sg.a * HID + row];
   } else if (sg.kind == 3) {  // output-layer weight [3][128]

@@ -82,6 +82,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint
                "r"(src_smem), "r"(bytes)
                : "memory");
 }
+// DRAM -> L2 prefetch through the bulk-copy engine (no destination: costs neither registers nor smem).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
