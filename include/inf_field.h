@@ -12,6 +12,8 @@
  *   inf_forward            mesh.py:313-324  get_k_eigenfunc_vec_vals(E, vids, bary)
  *                          model.py:98-112  TextureField.forward(batch)
  *                          layers.py:60-62  LinearWithConcatAndActivation.forward
+ *                          model.py:175-191 TextureFieldWithViewDependency.forward (view-direction branch:
+ *                          face-normal angle / raw direction -> layers.py:21-25 FourierFeatEnc -> directional_mlp)
  *                          renderer.py:113-118 per-chunk model(batch) of Renderer.render
  *   inf_forward_backward   trainer.py:71-84 Trainer._train_step (forward, loss, backward; Adam
  *                          stays torch.optim.Adam), config.py:117-118 (L1 = F.l1_loss, mean)
@@ -42,7 +44,7 @@
 extern "C" {
 #endif
 
-#define INF_ABI_VERSION 1
+#define INF_ABI_VERSION 2
 
 /* error codes */
 #define INF_OK 0
@@ -77,15 +79,16 @@ typedef struct InfDesc {
   int32_t k;             /* embedding dim = in_dim of layer 0 (model.py:211-215)              */
   int32_t k_pad;         /* row stride of the table in elements, multiple of 64, >= k         */
   int32_t hidden;        /* mlp_hidden_dim; compiled set: 128                                 */
-  int32_t num_layers;    /* 3..INF_MAX_LAYERS (model.py:27)                                   */
+  int32_t num_layers;    /* 3..INF_MAX_LAYERS (model.py:27); <= 7 with the view branch        */
   int32_t skip;          /* skip_layer_idx, 0 < skip < num_layers-1                           */
   int32_t table_dtype;   /* INF_TABLE_F32 | INF_TABLE_F16                                     */
   int32_t input_mode;    /* INF_INPUT_GATHER | INF_INPUT_DENSE                                */
   int32_t view_strategy; /* INF_VIEW_*                                                        */
-  int32_t view_embed;    /* embed_size of the view-direction Fourier features                 */
+  int32_t view_embed;    /* embed_size of the view-direction Fourier features; the embedding  */
+                         /* d*embed*2 (+d) must fit 64 dims (d = 1 intrinsic, 3 extrinsic)     */
   int32_t view_include;  /* include_view_dir (0/1)                                            */
-  int32_t view_bneck;    /* bottleneck_vec_dim; compiled set: 128                             */
-  int32_t view_hidden;   /* directional_hidden_dim; compiled set: 64                          */
+  int32_t view_bneck;    /* bottleneck_vec_dim, 1..128 (zero-padded to 128 inside)            */
+  int32_t view_hidden;   /* directional_hidden_dim, 1..128 (zero-padded to 128 inside)        */
   int64_t n_faces;       /* rows of face_normals (intrinsic view strategy)                    */
   float grad_scale;      /* multiplies every summed gradient; 1/(3*B_global) for the L1 mean  */
   float reserved0;
@@ -155,8 +158,8 @@ int inf_profile_enable(int on);
 int inf_profile_read(float* main_ms, float* wgrad_ms, float* reduce_ms, int* calls);
 
 /* Self-test hook used by tests/: D(128,n) = A(128,k) * B(n,k)^T on the tensor cores with the
- * operand-layout variant `mode` (0: A,B K-major; 1: A MN-major; 2: A,B MN-major).  A and B are
- * f32 row-major on the device ((128,k)/(n,k) for K-major, (k,128)/(k,n) for MN-major). */
+ * operand-layout variant `mode` (0: A,B K-major; 1: A MN-major; 2: A,B MN-major; 3: B MN-major).  A and
+ * B are f32 row-major on the device ((128,k)/(n,k) for K-major, (k,128)/(k,n) for MN-major). */
 int inf_debug_umma(int mode, int n, int k, const float* a, const float* b, float* d, void* stream);
 
 #ifdef __cplusplus

@@ -4,7 +4,7 @@ training backward, behind the call surface of tum-vision/intrinsic-neural-fields
 (model.py / ray_dataloader.py / renderer.py / trainer.py).  Import as ``inf_b200``."""
 from . import _lib
 from .ops import EigenTable, FieldConfig, pack_weights, param_layout, num_params, debug_umma, kernel_error_word
-from .model import TextureField, make_model, init_weights
+from .model import TextureField, TextureFieldWithViewDependency, make_model, init_weights
 
-__all__ = ["EigenTable", "FieldConfig", "TextureField", "make_model", "init_weights", "pack_weights",
+__all__ = ["EigenTable", "FieldConfig", "TextureField", "TextureFieldWithViewDependency", "make_model", "init_weights", "pack_weights",
            "param_layout", "num_params", "debug_umma", "kernel_error_word"]

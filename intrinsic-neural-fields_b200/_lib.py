@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libinf_field.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 IDX_I32, IDX_I64 = 0, 1
 TABLE_F32, TABLE_F16 = 0, 1
 INPUT_GATHER, INPUT_DENSE = 0, 1

@@ -13,7 +13,7 @@ namespace inf {
 
 // kernels / launchers defined in the other translation units
 cudaError_t launch_field_main(const FieldParams& p, bool train, bool table_f16, int grid, cudaStream_t stream);
-cudaError_t launch_field_wgrad(const FieldParams& p, bool table_f16, int grid, cudaStream_t stream);
+cudaError_t launch_field_wgrad(const FieldParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream);
 
 void launch_pack_weights(const PackParams& pp, cudaStream_t stream);
@@ -52,46 +52,76 @@ int check_desc(const InfDesc* d) {
   if (d->idx_dtype != INF_IDX_I32 && d->idx_dtype != INF_IDX_I64) return fail(INF_ERR_BAD_ARG, "bad idx_dtype");
   if (d->table_dtype != INF_TABLE_F32 && d->table_dtype != INF_TABLE_F16) return fail(INF_ERR_BAD_ARG, "bad table_dtype");
   if (d->input_mode != INF_INPUT_GATHER && d->input_mode != INF_INPUT_DENSE) return fail(INF_ERR_BAD_ARG, "bad input_mode");
-  if (d->view_strategy != INF_VIEW_NONE)
-    return fail(INF_ERR_UNSUPPORTED, "view-direction branch is not compiled into this build");
+  if (d->view_strategy != INF_VIEW_NONE) {
+    if (d->view_strategy != INF_VIEW_INTRINSIC && d->view_strategy != INF_VIEW_EXTRINSIC)
+      return fail(INF_ERR_BAD_ARG, "bad view_strategy %d", d->view_strategy);
+    if (d->num_layers > MAX_MMA_LAYERS - 1)
+      return fail(INF_ERR_UNSUPPORTED, "num_layers=%d with the view branch exceeds %d", d->num_layers, MAX_MMA_LAYERS - 1);
+    if (d->view_bneck < 1 || d->view_bneck > HID || d->view_hidden < 1 || d->view_hidden > HID)
+      return fail(INF_ERR_UNSUPPORTED, "bottleneck_vec_dim=%d / directional_hidden_dim=%d outside [1,%d]", d->view_bneck,
+                  d->view_hidden, HID);
+    const int dd = d->view_strategy == INF_VIEW_EXTRINSIC ? 3 : 1;
+    const int e = dd * d->view_embed * 2 + (d->view_include ? dd : 0);
+    if (d->view_embed < 0 || d->view_embed > 24 || e < 1 || e > KC)
+      return fail(INF_ERR_UNSUPPORTED, "view embedding of %d dims (embed_size=%d) outside [1,%d]", e, d->view_embed, KC);
+  } else if (d->num_layers - 2 > MAX_MMA_LAYERS - 1) {
+    return fail(INF_ERR_UNSUPPORTED, "num_layers=%d outside the compiled set", d->num_layers);
+  }
   if (d->input_mode == INF_INPUT_GATHER && d->n_rows > (int64_t(1) << 32) - 1)
     return fail(INF_ERR_BAD_ARG, "n_rows exceeds 2^32-1");
   return INF_OK;
 }
 
-Geo geo_of(const InfDesc* d) { return make_geo(d->k, d->k_pad, d->num_layers, d->skip); }
+Geo geo_of(const InfDesc* d) {
+  return make_geo(d->k, d->k_pad, d->num_layers, d->skip, d->view_strategy, d->view_embed, d->view_include, d->view_bneck,
+                  d->view_hidden);
+}
 
 struct ParamInfo {
   int64_t off;
   int rows, cols;
-  int kind, a;  // ReduceSeg kind / argument
+  int kind, a, b, split;  // ReduceSeg fields
 };
 
-// state_dict order (model.py:42-96, layers.py:50-58)
+// state_dict order (model.py:42-96, layers.py:50-58; with the view branch the spatial MLP comes first under
+// "spatial_mlp." followed by directional_mlp.0 / directional_mlp.2, model.py:134-173)
 int build_param_table(const InfDesc* d, ParamInfo* out, int64_t* total) {
+  const Geo g = geo_of(d);
+  const WPlan plan = make_wplan(g);
   int n = 0;
   int64_t off = 0;
   const int L = d->num_layers;
-  auto add = [&](int rows, int cols, int kind, int a) {
-    out[n++] = ParamInfo{off, rows, cols, kind, a};
+  auto add = [&](int rows, int cols, int kind, int a, int b = -1, int split = 1 << 30) {
+    out[n++] = ParamInfo{off, rows, cols, kind, a, b, split};
     off += static_cast<int64_t>(rows) * cols;
   };
   for (int i = 0; i < L; ++i) {
     if (i == d->skip) {
-      add(HID, HID, 1, i);      // Lx.weight
-      add(HID, 1, 2, i);        // Lx.bias
-      add(HID, d->k, 0, 1);     // Ly.weight
-      add(HID, 1, 2, i);        // Ly.bias (same gradient as Lx.bias)
+      add(HID, HID, 1, plan.unit_w[i]);         // Lx.weight
+      add(HID, 1, 2, plan.unit_bias[i]);        // Lx.bias
+      add(HID, d->k, 0, 1);                     // Ly.weight
+      add(HID, 1, 2, plan.unit_bias[i]);        // Ly.bias (same gradient as Lx.bias)
     } else if (i == 0) {
       add(HID, d->k, 0, 0);
-      add(HID, 1, 2, 0);
+      add(HID, 1, 2, plan.unit_bias[0]);
     } else if (i == L - 1) {
-      add(OUT_DIM, HID, 3, 0);
-      add(OUT_DIM, 1, 4, 0);
+      if (g.view) {                             // bottleneck layer (ReLU), an MMA layer
+        add(g.bneck, HID, 1, plan.unit_w[i]);
+        add(g.bneck, 1, 2, plan.unit_bias[i]);
+      } else {
+        add(OUT_DIM, HID, 3, plan.unit_last);
+        add(OUT_DIM, 1, 4, 0);
+      }
     } else {
-      add(HID, HID, 1, i);
-      add(HID, 1, 2, i);
+      add(HID, HID, 1, plan.unit_w[i]);
+      add(HID, 1, 2, plan.unit_bias[i]);
     }
+  }
+  if (g.view) {
+    add(g.dh, g.bneck + g.edim, 1, plan.unit_w[g.nb], plan.unit_e, g.bneck);   // directional_mlp.0.weight
+    add(g.dh, 1, 2, plan.unit_bias[g.nb]);
+    add(OUT_DIM, g.dh, 3, plan.unit_last);                                      // directional_mlp.2.weight
+    add(OUT_DIM, 1, 4, 0);
   }
   if (total) *total = off;
   return n;
@@ -134,6 +164,11 @@ int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
   if ((reinterpret_cast<uintptr_t>(t->packed) & 127) != 0) return fail(INF_ERR_BAD_ARG, "packed must be 128-byte aligned");
   if (d->input_mode == INF_INPUT_GATHER && (t->vids == nullptr || t->bary == nullptr))
     return fail(INF_ERR_BAD_ARG, "vids / bary must be non-null in gather mode");
+  if (d->view_strategy != INF_VIEW_NONE) {
+    if (t->unit_ray_dirs == nullptr) return fail(INF_ERR_BAD_ARG, "unit_ray_dirs must be non-null with the view branch");
+    if (d->view_strategy == INF_VIEW_INTRINSIC && (t->face_idxs == nullptr || t->face_normals == nullptr))
+      return fail(INF_ERR_BAD_ARG, "face_idxs / face_normals must be non-null for the intrinsic view strategy");
+  }
   if (training) {
     if ((t->target == nullptr) == (t->grad_pred == nullptr))
       return fail(INF_ERR_BAD_ARG, "exactly one of target / grad_pred must be given");
@@ -154,6 +189,9 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   p.bary = t->bary;
   p.target = t->target;
   p.grad_pred = t->grad_pred;
+  p.dirs = t->unit_ray_dirs;
+  p.face_idxs = t->face_idxs;
+  p.face_normals = t->face_normals;
   p.pred = t->pred;
   p.packed = reinterpret_cast<const uint8_t*>(t->packed);
   p.n_rays = d->n_rays;
@@ -162,12 +200,7 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   p.dense = d->input_mode == INF_INPUT_DENSE;
   p.ext_scale = 1.f;
   p.geo = geo_of(d);
-  {
-    // tuning knob (measurement only): INF_PREFETCH=<k-chunks ahead>, default off
-    const char* e = getenv("INF_PREFETCH");
-    p.prefetch = e ? atoi(e) : 0;
-    if (p.prefetch < 0 || p.prefetch > 8) p.prefetch = 0;
-  }
+  p.plan = make_wplan(p.geo);
   if (t->workspace != nullptr && t->workspace_bytes >= 256) {
     const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training);
     uint8_t* ws = reinterpret_cast<uint8_t*>(t->workspace);
@@ -248,14 +281,24 @@ int inf_pack_weights(const InfDesc* desc, const float* const* params, void* pack
   PackParams pp{};
   pp.geo = geo_of(desc);
   pp.packed = reinterpret_cast<uint8_t*>(packed);
+  const int L = desc->num_layers;
+  const bool view = desc->view_strategy != INF_VIEW_NONE;
   int idx = 0;
-  for (int i = 0; i < desc->num_layers; ++i) {
-    pp.w[i] = params[idx++];
-    pp.b[i] = params[idx++];
+  for (int i = 0; i < L; ++i) {
+    const float* w = params[idx++];
+    const float* b = params[idx++];
+    if (i == L - 1 && !view) { pp.wlast = w; pp.blast = b; }
+    else { pp.w[i] = w; pp.b[i] = b; }
     if (i == desc->skip) {
       pp.wy = params[idx++];
       pp.by = params[idx++];
     }
+  }
+  if (view) {
+    pp.w[pp.geo.nb] = params[idx++];
+    pp.b[pp.geo.nb] = params[idx++];
+    pp.wlast = params[idx++];
+    pp.blast = params[idx++];
   }
   for (int i = 0; i < idx; ++i)
     if (params[i] == nullptr) return fail(INF_ERR_BAD_ARG, "params[%d] is null", i);
@@ -310,18 +353,25 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   p.ext_scale = ext;
   const Geo geo = p.geo;
   const int grid1 = p.ntiles < nsm ? p.ntiles : nsm;
-  const int nslices = geo.nbig + geo.nhid;
-  // hidden slices move ~1/8 of the wgrad bytes (bulk loads only); big slices also re-gather x
-  int gh = (nsm / 8) / geo.nhid;
-  if (gh < 1) gh = 1;
-  if (gh > p.ntiles) gh = p.ntiles;
-  int gb = (nsm - geo.nhid * gh) / geo.nbig;
+  // wgrad CTAs: every slice gets ray groups in proportion to the bytes it moves per tile
+  const WPlan& plan = p.plan;
+  double wsum = static_cast<double>(geo.nbig) * BIG_BYTES_PER_TILE;
+  for (int s = 0; s < plan.nslice; ++s) wsum += plan.bytes_per_tile[s];
+  int used = 0;
+  int gh[MAX_HID_SLICES] = {0, 0, 0, 0};
+  for (int s = 0; s < plan.nslice; ++s) {
+    int v = static_cast<int>(nsm * (plan.bytes_per_tile[s] / wsum));
+    if (v < 1) v = 1;
+    if (v > p.ntiles) v = p.ntiles;
+    gh[s] = v;
+    used += v;
+  }
+  int gb = (nsm - used) / geo.nbig;
   if (gb < 1) gb = 1;
   if (gb > p.ntiles) gb = p.ntiles;
   p.groups_big = gb;
-  p.groups_hid = gh;
-  const int grid2 = geo.nbig * gb + geo.nhid * gh;
-  (void)nslices;
+  for (int s = 0; s < MAX_HID_SLICES; ++s) p.groups_hid[s] = gh[s];
+  const int grid2 = geo.nbig * gb + used;
   if (grid2 > MAX_CTAS) return fail(INF_ERR_UNSUPPORTED, "k_pad=%d needs %d wgrad CTAs > %d", desc->k_pad, grid2, MAX_CTAS);
 
   const bool f16 = desc->table_dtype == INF_TABLE_F16;
@@ -330,13 +380,14 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   cudaError_t e = launch_field_main(p, true, f16, grid1, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<train> launch");
   prof_record(slot, 1, st);
-  e = launch_field_wgrad(p, f16, grid2, st);
+  e = launch_field_wgrad(p, grid2, st);
   prof_record(slot, 2, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_wgrad_kernel launch");
 
   ReduceParams rp{};
   rp.nseg = nparam;
-  for (int i = 0; i < nparam; ++i) rp.seg[i] = ReduceSeg{pi[i].off, pi[i].rows, pi[i].cols, pi[i].kind, pi[i].a};
+  for (int i = 0; i < nparam; ++i)
+    rp.seg[i] = ReduceSeg{pi[i].off, pi[i].rows, pi[i].cols, pi[i].kind, pi[i].a, pi[i].b, pi[i].split};
   rp.total = total;
   rp.partw = p.partw;
   rp.part1 = p.part1;
@@ -344,9 +395,15 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   rp.loss_sums = (t->target != nullptr) ? g->loss_sums : nullptr;
   rp.ncta1 = grid1;
   rp.groups_big = gb;
-  rp.groups_hid = gh;
+  int base = geo.nbig * gb;
+  for (int s = 0; s < MAX_HID_SLICES; ++s) {
+    rp.groups_hid[s] = gh[s];
+    rp.cta_base_hid[s] = base;
+    base += gh[s];
+  }
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
   rp.geo = geo;
+  rp.plan = plan;
   e = launch_field_reduce(rp, st);
   prof_record(slot, 3, st);
   if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
@@ -399,9 +456,9 @@ int inf_profile_read(float* main_ms, float* wgrad_ms, float* reduce_ms, int* cal
 }
 
 int inf_debug_umma(int mode, int n, int k, const float* a, const float* b, float* d, void* stream) {
-  if (mode < 0 || mode > 2 || n < 16 || n > 256 || n % 16 != 0 || (k != 64 && k != 128) || !a || !b || !d)
-    return fail(INF_ERR_BAD_ARG, "inf_debug_umma: mode in [0,2], n in {16..256 step 16}, k in {64,128}");
-  if (mode == 2 && n % 64 != 0) return fail(INF_ERR_BAD_ARG, "inf_debug_umma: MN-major B needs n %% 64 == 0");
+  if (mode < 0 || mode > 3 || n < 16 || n > 256 || n % 16 != 0 || (k != 64 && k != 128) || !a || !b || !d)
+    return fail(INF_ERR_BAD_ARG, "inf_debug_umma: mode in [0,3], n in {16..256 step 16}, k in {64,128}");
+  if (mode >= 2 && n % 64 != 0) return fail(INF_ERR_BAD_ARG, "inf_debug_umma: MN-major B needs n %% 64 == 0");
   launch_umma_probe(mode, n, k, a, b, d, static_cast<cudaStream_t>(stream));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "umma_probe launch");

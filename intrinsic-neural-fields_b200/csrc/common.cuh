@@ -1,5 +1,5 @@
 // Shared geometry of the field kernels: tile sizes, operand-image ("blob") layout in HBM,
-// activation stash layout, partial-gradient workspace layout.  Host + device.
+// activation stash layout, wgrad work plan, partial-gradient workspace layout.  Host + device.
 #pragma once
 #include <stdint.h>
 
@@ -7,71 +7,104 @@
 
 namespace inf {
 
-constexpr int HID = 128;         // mlp_hidden_dim (compiled set)
+constexpr int HID = 128;         // mlp_hidden_dim (compiled set); narrower view layers are zero-padded to it
 constexpr int TILE_M = 128;      // rays per tile = UMMA M = TMEM lanes
 constexpr int KC = 64;           // k elements per chunk: 64 x fp16 = one 128-byte swizzle row
 constexpr int PANEL_BYTES = TILE_M * KC * 2;  // 16 KB: [128 rows][64 fp16], SWIZZLE_128B
 constexpr int BLOB_BYTES = 2 * PANEL_BYTES;   // 32 KB: [256 x 64] (GEMM1 weight chunk) or
                                               //        [128 x 128] as two k-panels (hidden operand)
+constexpr int HALF_PANEL = 64 * 128;          // 8 KB: 64 rows of a panel
+constexpr int DZLT_BYTES = 4096;              // [16 x 128 rays] fp16, K-major: two [16 x 64] panels
 constexpr int OUT_DIM = 3;       // RGB_COLOR_DIM, model.py:9
 constexpr float DZ_SCALE = 32.f; // backward signals are carried x32 in fp16 (range centring)
 constexpr int MAX_CTAS = 160;    // sizing bound for per-CTA partials (B200: 148 SMs)
-constexpr int K1_PART_FLOATS = 1536;  // per-CTA partials of the forward/backward kernel
+constexpr int MAX_MMA_LAYERS = 8;  // MMA layers 0..nb, nb <= 7
+constexpr int K1_PART_FLOATS = 8;  // per-CTA partials of the forward/backward kernel: gb[3], pad, loss sums[2]
 constexpr int WG_COLS = 512;     // TMEM columns = accumulator columns of a wgrad CTA
+constexpr int MAX_UNITS = 16;    // wgrad work units of the hidden slices
+constexpr int MAX_HID_SLICES = 4;
 
-// Block shape shared by the forward/backward kernel and the wgrad kernel.
-constexpr int EPI_WARPS = 4;     // warps 0..3: TMEM epilogue (warp w owns TMEM lanes 32w..32w+31)
-constexpr int PROD_WARPS = 8;    // warps 4..11: gather producers
-constexpr int MMA_WARP = 12;     // warp 12: tcgen05.mma issuer + TMEM allocator
-constexpr int LOAD_WARP = 13;    // warp 13: bulk-copy (TMA engine) loader
-constexpr int NUM_THREADS = 14 * 32;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int PROD_THREADS = PROD_WARPS * 32;
-
+// Model geometry.  MMA "layers" are numbered 0..nb:
+//   layer 0            x (k_pad) -> 128, fused with the skip branch Ly in GEMM1
+//   layers 1..nhid     128 -> 128 ReLU layers.  nhid = L-2, or L-1 with the view branch: its spatial MLP ends
+//                      in a ReLU bottleneck (model.py:92,156-157), zero-padded to 128 outputs
+//   layer nb = nhid+1  view branch only: [bottleneck | Fourier(view dir)] (128 + 64 padded) -> dh (padded to 128),
+//                      ReLU (model.py:168-170)
+// The output layer (-> 3, sigmoid) runs on CUDA cores from the registers of layer nb's epilogue.
 struct Geo {
   int k, k_pad, nchunks;  // nchunks = k_pad / 64
   int L, skip;
+  int view;               // INF_VIEW_*
+  int emb, include;       // Fourier bands per input dim, include raw input
+  int vdim;               // d: 1 (intrinsic: angle) or 3 (extrinsic: direction)
+  int edim;               // E = 2*d*emb (+ d) <= 64
+  int bneck, dh;          // true widths (<= 128) of the bottleneck / directional hidden layer
+  int nhid;               // number of 128->128 MMA layers
+  int nb;                 // index of the last MMA layer
+  int wout;               // true input width of the output layer (128 or dh)
   int nbig;               // wgrad slices over k_pad, 256 columns each
-  int nhid;               // wgrad slices over the hidden layers, 4 layers each
-  int nslots;             // stash blobs per tile: dz_0..dz_{L-2}, h_0..h_{L-3}
-  int nblobs_fwd, nblobs_train;
+  int nblobs;             // packed operand blobs: nchunks + nhid (+2 view)
+  int stash_blobs;        // 32 KB stash blobs per tile before the x panels
 };
 
-__host__ __device__ inline Geo make_geo(int k, int k_pad, int L, int skip) {
+__host__ __device__ inline Geo make_geo(int k, int k_pad, int L, int skip, int view = 0, int emb = 0, int include = 0,
+                                        int bneck = 0, int dh = 0) {
   Geo g;
   g.k = k; g.k_pad = k_pad; g.nchunks = k_pad / KC;
   g.L = L; g.skip = skip;
+  g.view = view; g.emb = view ? emb : 0; g.include = view ? include : 0;
+  g.vdim = (view == INF_VIEW_EXTRINSIC) ? 3 : 1;
+  g.edim = view ? g.vdim * emb * 2 + (include ? g.vdim : 0) : 0;
+  g.bneck = view ? bneck : 0; g.dh = view ? dh : 0;
+  g.nhid = (L - 2) + (view ? 1 : 0);
+  g.nb = g.nhid + (view ? 1 : 0);
+  g.wout = view ? dh : HID;
   g.nbig = (k_pad + 255) / 256;
-  g.nhid = (L - 2 + 3) / 4;
-  g.nslots = 2 * L - 3;
-  g.nblobs_fwd = g.nchunks + (L - 2);
-  g.nblobs_train = g.nchunks + 2 * (L - 2);
+  g.nblobs = g.nchunks + g.nhid + (view ? 2 : 0);
+  g.stash_blobs = 2 * (g.nb + 1) + 1;
   return g;
 }
 
 // ---- packed operand images (inf_pack_weights) -------------------------------------------------
-// blob b (32 KB each), in the order the forward/backward kernel consumes them per tile:
-//   [0, nchunks)                 chunk c of [W0;Wy]: rows 0..127 = W0[:, 64c..], 128..255 = Wy
-//   nchunks + (l-1), l=1..L-2    W_l  (Lx for the skip layer): [n][k]
-//   nchunks + (L-2) + i          W_l^T for l = L-2-i (i = 0..L-3): [j][n]
-// followed by an f32 section: bias[L-1][128] (skip row = Lx.bias + Ly.bias), wlast[3][128],
-// blast[4].
-__host__ __device__ inline size_t packed_f32_offset(const Geo& g) {
-  return static_cast<size_t>(g.nblobs_train) * BLOB_BYTES;
-}
+// blob b (32 KB each):
+//   [0, nchunks)                 chunk c of [W0;Wy]: rows 0..127 = W0[:, 64c..], 128..255 = Wy  ([256][64])
+//   nchunks + (l-1), l=1..nhid   W_l (Lx for the skip layer; the bottleneck layer zero-padded to 128 rows):
+//                                [n][j] as two j-panels.  The forward GEMM reads it K-major (K = j), the dgrad
+//                                GEMM reads the SAME bytes MN-major (K = n), so no transposed copy exists.
+//   view: nchunks + nhid         Wd1[:, :bneck]  zero-padded to [128][128]
+//         nchunks + nhid + 1     Wd1[:, bneck:bneck+E] zero-padded to [128][64] (first 16 KB of the blob)
+// followed by an f32 section: bias[nb+1][128] (skip row = Lx.bias + Ly.bias; rows zero-padded),
+// wlast[3][128] (output weight, zero-padded beyond wout), blast[4].
+__host__ __device__ inline size_t packed_f32_offset(const Geo& g) { return static_cast<size_t>(g.nblobs) * BLOB_BYTES; }
+__host__ __device__ inline int packed_f32_count(const Geo& g) { return (g.nb + 1) * HID + OUT_DIM * HID + 4; }
 __host__ __device__ inline size_t packed_total_bytes(const Geo& g) {
-  return packed_f32_offset(g) + static_cast<size_t>((g.L - 1) * HID + OUT_DIM * HID + 4) * 4;
+  return packed_f32_offset(g) + static_cast<size_t>(packed_f32_count(g)) * 4;
 }
+__host__ __device__ inline int blob_hidden(const Geo& g, int l) { return g.nchunks + (l - 1); }  // l = 1..nhid
+__host__ __device__ inline int blob_wd1z(const Geo& g) { return g.nchunks + g.nhid; }
+__host__ __device__ inline int blob_wd1e(const Geo& g) { return g.nchunks + g.nhid + 1; }
+
 // Byte offset of element (row r, 16-bit column c) inside a [rows x 64] SWIZZLE_128B panel.
 __host__ __device__ inline uint32_t sw128_off(uint32_t r, uint32_t c) {
   return r * 128u + ((((c >> 3) ^ (r & 7u)) << 4) | ((c & 7u) << 1));
 }
 
 // ---- activation stash (forward/backward kernel -> wgrad kernel) --------------------------------
-// per tile `nslots` blobs: slot l = dz_l (l = 0..L-2), slot (L-1)+l = h_l (l = 0..L-3); each blob
-// is the smem image [128 rays][128 features] as two k-panels.
-__host__ __device__ inline int stash_slot_dz(const Geo& g, int l) { (void)g; return l; }
-__host__ __device__ inline int stash_slot_h(const Geo& g, int l) { return (g.L - 1) + l; }
+// per tile: `stash_blobs` blobs of 32 KB followed by nchunks x-panels of 16 KB, all smem images (fp16):
+//   blob l                 dz_l, l = 0..nb           [128 rays][128 features], two feature-panels
+//   blob (nb+1)+l          h_l,  l = 0..nb           (input of layer l+1; h_nb feeds the output layer)
+//   blob 2(nb+1)           misc: [0,16K) Fourier panel e [128 rays][64]; [16K,20K) dzl^T [16][128 rays]
+//   then x-panel c         x[:, 64c..64c+64)         [128 rays][64], the interpolated embedding in fp16
+__host__ __device__ inline size_t stash_tile_bytes(const Geo& g) {
+  return static_cast<size_t>(g.stash_blobs) * BLOB_BYTES + static_cast<size_t>(g.nchunks) * PANEL_BYTES;
+}
+__host__ __device__ inline size_t stash_off_dz(const Geo& g, int l) { (void)g; return static_cast<size_t>(l) * BLOB_BYTES; }
+__host__ __device__ inline size_t stash_off_h(const Geo& g, int l) { return static_cast<size_t>(g.nb + 1 + l) * BLOB_BYTES; }
+__host__ __device__ inline size_t stash_off_e(const Geo& g) { return static_cast<size_t>(2 * (g.nb + 1)) * BLOB_BYTES; }
+__host__ __device__ inline size_t stash_off_dzlt(const Geo& g) { return stash_off_e(g) + PANEL_BYTES; }
+__host__ __device__ inline size_t stash_off_x(const Geo& g, int c) {
+  return static_cast<size_t>(g.stash_blobs) * BLOB_BYTES + static_cast<size_t>(c) * PANEL_BYTES;
+}
 
 struct WorkspaceLayout {
   size_t stash_off, partw_off, part1_off, err_off, total;
@@ -82,13 +115,74 @@ __host__ inline WorkspaceLayout workspace_layout(const Geo& g, int64_t n_rays, b
   w.err_off = off; off += 256;
   if (training) {
     const int64_t ntiles = (n_rays + TILE_M - 1) / TILE_M;
-    w.stash_off = off; off += static_cast<size_t>(ntiles) * g.nslots * BLOB_BYTES;
+    w.stash_off = off; off += static_cast<size_t>(ntiles) * stash_tile_bytes(g);
     w.partw_off = off; off += static_cast<size_t>(MAX_CTAS) * WG_COLS * HID * 4;
     w.part1_off = off; off += static_cast<size_t>(MAX_CTAS) * K1_PART_FLOATS * 4;
   }
   w.total = off;
   return w;
 }
+
+// ---- wgrad work plan of the "hidden" slices -------------------------------------------------------
+// A unit accumulates, over the rays of a tile, products of one stashed A blob (read MN-major: TMEM lane =
+// feature of A) into TMEM columns of its slice:
+//   kind UNIT_W     D[n, col + j]      += sum_r A[r, n] * B[r, j],  B = stash blob/panel, j < ncols (MN-major)
+//   kind UNIT_LAST  D[j, col + c]      += sum_r A[r, j] * dzl^T[c, r]            (A = h_nb, B K-major, N = 16)
+//   bias_col >= 0   D[n, bias_col + *] += sum_r A[r, n] * 1                       (B = ones tile, N = 16)
+enum : int16_t { UNIT_W = 0, UNIT_LAST = 1, UNIT_BIAS_ONLY = 2 };
+struct WUnit {
+  int32_t a_off;      // byte offset of the A blob inside the tile's stash
+  int32_t b_off;      // byte offset of the B operand inside the tile's stash
+  int32_t b_bytes;    // bytes to load for B (0 for UNIT_BIAS_ONLY)
+  int16_t kind, ncols, col, bias_col, slice, layer;
+};
+struct WPlan {
+  WUnit u[MAX_UNITS];
+  int n;                        // units
+  int nslice;                   // hidden slices
+  int cols_used[MAX_HID_SLICES];
+  int bytes_per_tile[MAX_HID_SLICES];
+  int unit_w[MAX_MMA_LAYERS];   // unit accumulating the weight gradient of MMA layer l (1..nb)
+  int unit_e;                   // view: unit of dWd1[:, bneck:]
+  int unit_bias[MAX_MMA_LAYERS];// unit whose bias_col holds the bias gradient of layer l (0..nb)
+  int unit_last;                // output-layer weight gradient
+};
+__host__ inline WPlan make_wplan(const Geo& g) {
+  WPlan p{};
+  int slice = 0, col = 0;
+  auto place = [&](int need) {
+    if (col + need > WG_COLS) { ++slice; col = 0; }
+  };
+  auto add = [&](int kind, size_t a_off, size_t b_off, int b_bytes, int ncols, bool bias, int layer) -> int {
+    place(ncols + (bias ? 16 : 0));
+    WUnit w{};
+    w.a_off = static_cast<int32_t>(a_off); w.b_off = static_cast<int32_t>(b_off); w.b_bytes = b_bytes;
+    w.kind = static_cast<int16_t>(kind); w.ncols = static_cast<int16_t>(ncols); w.col = static_cast<int16_t>(col);
+    col += ncols;
+    w.bias_col = -1;
+    if (bias) { w.bias_col = static_cast<int16_t>(col); col += 16; }
+    w.slice = static_cast<int16_t>(slice); w.layer = static_cast<int16_t>(layer);
+    p.u[p.n] = w;
+    p.cols_used[slice] = col;
+    p.bytes_per_tile[slice] += BLOB_BYTES + b_bytes;
+    return p.n++;
+  };
+  p.unit_e = -1;
+  for (int l = 1; l <= g.nhid; ++l) {
+    p.unit_w[l] = add(UNIT_W, stash_off_dz(g, l), stash_off_h(g, l - 1), BLOB_BYTES, HID, true, l);
+    p.unit_bias[l] = p.unit_w[l];
+  }
+  if (g.view) {
+    p.unit_w[g.nb] = add(UNIT_W, stash_off_dz(g, g.nb), stash_off_h(g, g.nhid), BLOB_BYTES, HID, true, g.nb);
+    p.unit_bias[g.nb] = p.unit_w[g.nb];
+    p.unit_e = add(UNIT_W, stash_off_dz(g, g.nb), stash_off_e(g), PANEL_BYTES, KC, false, g.nb);
+  }
+  p.unit_bias[0] = add(UNIT_BIAS_ONLY, stash_off_dz(g, 0), 0, 0, 0, true, 0);
+  p.unit_last = add(UNIT_LAST, stash_off_h(g, g.nb), stash_off_dzlt(g), DZLT_BYTES, 16, false, g.nb);
+  p.nslice = slice + 1;
+  return p;
+}
+constexpr int BIG_BYTES_PER_TILE = 4 * BLOB_BYTES;  // dz_0 + dz_skip + 256 x-columns, per 128 rays
 
 // ---- kernel parameter blocks --------------------------------------------------------------------
 struct FieldParams {
@@ -98,6 +192,9 @@ struct FieldParams {
   const float* bary;
   const float* target;
   const float* grad_pred;
+  const float* dirs;          // (B,3) unit ray directions (view branch)
+  const void* face_idxs;      // (B,)  hit face ids (intrinsic view strategy)
+  const float* face_normals;  // (F,3)
   float* pred;
   const uint8_t* packed;
   uint8_t* stash;
@@ -109,26 +206,34 @@ struct FieldParams {
   int idx64;
   int dense;
   float ext_scale;  // multiplies grad_pred before it enters the fp16 backward chain
-  int prefetch;     // L2 prefetch distance of the gather (k-chunks / units ahead); 0 = off
-  int groups_big;   // wgrad: ray groups (CTAs) per big slice
-  int groups_hid;   // wgrad: ray groups (CTAs) per hidden slice
+  int groups_big;                   // wgrad: ray groups (CTAs) per big slice
+  int groups_hid[MAX_HID_SLICES];   // wgrad: ray groups (CTAs) per hidden slice
   Geo geo;
+  WPlan plan;
 };
 
 struct PackParams {
-  const float* w[INF_MAX_LAYERS];  // layer weight (Lx.weight for the skip layer)
-  const float* b[INF_MAX_LAYERS];  // layer bias   (Lx.bias   for the skip layer)
+  const float* w[MAX_MMA_LAYERS];  // weight of MMA layer l (Lx.weight for the skip layer; Wd1 for the view layer)
+  const float* b[MAX_MMA_LAYERS];  // bias of MMA layer l
   const float* wy;                 // Ly.weight (128 x k)
   const float* by;                 // Ly.bias
+  const float* wlast;              // output layer weight (3 x wout)
+  const float* blast;              // output layer bias (3)
   uint8_t* packed;
   Geo geo;
 };
 
+// One parameter tensor of the flat gradient vector.
+//   kind 0  W0 / Wy (a = 0/1): element (n, j) = big slice j/256, lane n, column (j%256) + 256a
+//   kind 1  weight from hidden unit(s): (n, j) = unit a column j for j < split, unit b column j-split beyond
+//   kind 2  bias: (n) = bias column of unit a, lane n
+//   kind 3  output weight: (c, j) = unit a, lane j, column c
+//   kind 4  output bias from the forward/backward kernel's per-CTA partials
 struct ReduceSeg {
   int64_t off;   // first element in the flat gradient vector
   int32_t rows, cols;
-  int32_t kind;  // 0 big W (a: 0=W0, 1=Wy)  1 hidden W (a: layer)  2 bias (a: layer)  3 last W  4 last b
-  int32_t a;
+  int32_t kind;
+  int32_t a, b, split;
 };
 struct ReduceParams {
   ReduceSeg seg[INF_MAX_PARAMS];
@@ -139,9 +244,12 @@ struct ReduceParams {
   float* flat;
   float* loss_sums;
   int ncta1;   // CTAs of the forward/backward kernel
-  int groups_big, groups_hid;  // ray groups per wgrad slice (big / hidden)
+  int groups_big;
+  int groups_hid[MAX_HID_SLICES];
+  int cta_base_hid[MAX_HID_SLICES];
   float scale;
   Geo geo;
+  WPlan plan;
 };
 
 }  // namespace inf

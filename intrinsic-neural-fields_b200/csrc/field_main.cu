@@ -1,17 +1,24 @@
 // Forward (+ loss + dgrad chain) kernel of the intrinsic-neural-field path, sm_100a.
 //
-// Per 128-ray tile (persistent CTAs, one per SM):
-//   producers (8 warps)  gather 3 table rows per ray with 16-byte loads, interpolate in fp32 with the
-//                        barycentric weights, round to fp16 and store the [128 x 64] A-panel of the
-//                        current k-chunk straight into the SWIZZLE_128B smem layout the tensor core
-//                        reads -- the interpolated embedding (mesh.py:313-324) never exists in HBM;
-//   loader (1 thread)    streams the weight operand images (32 KB blobs) with 1-D bulk copies (TMA);
-//   MMA (1 thread)       tcgen05.mma kind::f16: GEMM1 = x * [W0;Wy]^T (N=256, K=k_pad) into TMEM
-//                        columns [0,256), then the 128-wide hidden chain (model.py:98-112) and, when
-//                        training, the dgrad chain and the bias-gradient "ones" MMAs;
-//   epilogue (4 warps)   TMEM -> registers, bias + ReLU -> fp16 activation panel in smem (A operand of
-//                        the next layer), final 128->3 layer + sigmoid (+ L1 loss gradient) on CUDA
-//                        cores; when training, stashes h_l / dz_l tiles for the wgrad kernel.
+// Persistent CTAs (one per SM), 128-ray tiles, six warp roles connected by mbarrier rings:
+//   producers (8 warps)    gather 3 table rows per ray with 16-byte loads, interpolate in fp32 with the
+//                          barycentric weights, round to fp16 and store the [128 x 64] A-panel of the
+//                          current k-chunk straight into the SWIZZLE_128B smem layout the tensor core
+//                          reads -- the interpolated embedding (mesh.py:313-324) is never read back from HBM
+//                          by the forward pass;
+//   B1 loader (1 thread)   streams the [W0;Wy] operand chunks (32 KB blobs) with 1-D bulk copies (TMA);
+//   GEMM1 issuer (1 thr)   tcgen05.mma kind::f16: [z0|zy] = x * [W0;Wy]^T (N=256, K=k_pad) into one of TWO
+//                          256-column TMEM buffers, so the gather/GEMM1 of tile t+1 overlaps the layer chain of
+//                          tile t; when training it also bulk-stores each x panel to the stash (operand of
+//                          the first-layer weight gradient in field_wgrad.cu);
+//   B2 loader (1 thread)   streams the 128x128 hidden / view-branch weight images;
+//   chain issuer (1 thr)   the 128-wide hidden chain (model.py:98-112), the view-direction layer
+//                          (model.py:168-173) and, when training, the dgrad chain -- the dgrad GEMMs read the
+//                          SAME weight images MN-major, so no transposed weights exist;
+//   epilogue (4 warps)     TMEM -> registers, bias + ReLU -> fp16 activation panel in smem (A operand of
+//                          the next layer), Fourier features of the view direction (layers.py:21-25), final
+//                          -> 3 layer + sigmoid (+ L1 loss gradient) on CUDA cores; when training, stashes
+//                          h_l / dz_l tiles for the wgrad kernel.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -19,46 +26,70 @@ namespace inf {
 
 namespace {
 
-constexpr int NSTAGE_A = 4;
-constexpr int NSTAGE_B = 2;
+constexpr int NUM_THREADS_MAIN = 16 * 32;
+constexpr int EPI_WARPS = 4;      // warps 0..3: TMEM epilogue (warp w owns TMEM lanes 32w..32w+31)
+constexpr int PROD_WARPS = 8;     // warps 4..11: gather producers
+constexpr int W_G1 = 12;          // GEMM1 issuer + TMEM allocator
+constexpr int W_CH = 13;          // chain issuer
+constexpr int W_B1 = 14;          // [W0;Wy] chunk loader
+constexpr int W_B2 = 15;          // hidden-weight loader
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
 
-// shared memory carve-up (bytes, relative to a 1024-aligned base)
-constexpr uint32_t SM_A = 0;
-constexpr uint32_t SM_B = SM_A + NSTAGE_A * PANEL_BYTES;          //  65536
-constexpr uint32_t SM_H = SM_B + NSTAGE_B * BLOB_BYTES;           // 131072
-constexpr uint32_t SM_ONES = SM_H + 2 * BLOB_BYTES;               // 196608
-constexpr uint32_t SM_BIAS = SM_ONES + 2048;                      // f32 [L-1][128]
-constexpr uint32_t SM_WLAST = SM_BIAS + (INF_MAX_LAYERS - 1) * HID * 4;
-constexpr uint32_t SM_BLAST = SM_WLAST + OUT_DIM * HID * 4;
-constexpr uint32_t SM_VID = SM_BLAST + 16;                        // u32 [3][384]
-constexpr uint32_t SM_BARY = SM_VID + 3 * 384 * 4;                // f32 [3][384]
-constexpr uint32_t SM_DZL = SM_BARY + 3 * 384 * 4;                // f32 [128][4]
-constexpr uint32_t SM_RED = SM_DZL + TILE_M * 16;                 // f32 [8]
-constexpr uint32_t SM_MASK = SM_RED + 32;                         // u32x4 [L-1][128]
-constexpr uint32_t SM_BARS = SM_MASK + (INF_MAX_LAYERS - 1) * TILE_M * 16;
-constexpr uint32_t SM_TMEMPTR = SM_BARS + 16 * 8;
-constexpr uint32_t SM_TOTAL = SM_TMEMPTR + 16;
-constexpr uint32_t SM_ALLOC = SM_TOTAL + 1024;  // slack for manual 1024-byte alignment
+constexpr int NSTAGE_B1 = 2;
+constexpr int MAX_STAGE_A = 3;
+
+// shared memory carve-up (bytes from a 1024-aligned base); the A ring gives one stage to the Fourier panel
+// when the view branch is on
+struct Smem {
+  uint32_t a, b1, h, b2, e, dzlt, bias, wlast, vid, bary, red, bars, tmemptr, total;
+  int nstage_a;
+};
+__host__ __device__ constexpr Smem smem_layout(bool view) {
+  Smem s{};
+  s.nstage_a = view ? 2 : 3;
+  s.a = 0;
+  s.b1 = s.a + static_cast<uint32_t>(s.nstage_a) * PANEL_BYTES;
+  s.h = s.b1 + NSTAGE_B1 * BLOB_BYTES;
+  s.b2 = s.h + 2 * BLOB_BYTES;
+  s.e = s.b2 + BLOB_BYTES;
+  s.dzlt = 13 * PANEL_BYTES;                      // 212992 in both variants
+  s.bias = s.dzlt + DZLT_BYTES;                   // f32 [MAX_MMA_LAYERS][128]
+  s.wlast = s.bias + MAX_MMA_LAYERS * HID * 4;    // f32 [3][128] + blast[4]
+  s.vid = s.wlast + OUT_DIM * HID * 4 + 16;       // u32 [3][384]
+  s.bary = s.vid + 3 * 384 * 4;                   // f32 [3][384]
+  s.red = s.bary + 3 * 384 * 4;                   // f32 [20]
+  s.bars = s.red + 96;
+  s.tmemptr = s.bars + 32 * 8;
+  s.total = s.tmemptr + 16;
+  return s;
+}
+static_assert(smem_layout(false).e <= smem_layout(false).dzlt, "smem layout");
+static_assert(smem_layout(true).e + PANEL_BYTES <= smem_layout(true).dzlt, "smem layout (view)");
+static_assert(smem_layout(true).total <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 // barrier indices
-constexpr int BAR_A_FULL = 0;                 // [NSTAGE_A]
-constexpr int BAR_A_EMPTY = BAR_A_FULL + NSTAGE_A;
-constexpr int BAR_B_FULL = BAR_A_EMPTY + NSTAGE_A;
-constexpr int BAR_B_EMPTY = BAR_B_FULL + NSTAGE_B;
-constexpr int BAR_MMA_DONE = BAR_B_EMPTY + NSTAGE_B;
-constexpr int BAR_ACT_READY = BAR_MMA_DONE + 1;
-static_assert(BAR_ACT_READY < 16, "barrier table overflow");
+constexpr int BAR_A_FULL = 0;                          // [3]
+constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_STAGE_A;  // [3]
+constexpr int BAR_B1_FULL = BAR_A_EMPTY + MAX_STAGE_A; // [2]
+constexpr int BAR_B1_EMPTY = BAR_B1_FULL + NSTAGE_B1;  // [2]
+constexpr int BAR_B2_FULL = BAR_B1_EMPTY + NSTAGE_B1;
+constexpr int BAR_B2_EMPTY = BAR_B2_FULL + 1;
+constexpr int BAR_G_FULL = BAR_B2_EMPTY + 1;           // [2] GEMM1 accumulator buffer complete
+constexpr int BAR_G_EMPTY = BAR_G_FULL + 2;            // [2] chain of the tile that used the buffer is done
+constexpr int BAR_ACT_READY = BAR_G_EMPTY + 2;
+constexpr int BAR_MMA_DONE = BAR_ACT_READY + 1;
+static_assert(BAR_MMA_DONE < 32, "barrier table overflow");
 
-constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_Z0 = 0;      // z0 / hidden accumulators / dh
-constexpr uint32_t TM_ZY = 128;    // Ly(x) partial, then z_skip
-constexpr uint32_t TM_DB = 256;    // bias-gradient accumulators, 16 columns per layer
+constexpr uint32_t TMEM_COLS = 512;   // two GEMM1 buffers: [256 buf, +128) z0 / chain accumulators, [+128, +256) zy
 
 constexpr uint32_t IDESC_N256 = umma_idesc_f16(128, 256, 0, 0);
 constexpr uint32_t IDESC_N128 = umma_idesc_f16(128, 128, 0, 0);
-constexpr uint32_t IDESC_DB = umma_idesc_f16(128, 16, 1, 0);  // A = dz^T (MN-major), B = ones
+constexpr uint32_t IDESC_N128_BMN = umma_idesc_f16(128, 128, 0, 1);  // dgrad: B = weight image read MN-major
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+constexpr float PI_F = 3.14159274101257324f;  // float32(torch.pi), layers.py:14
+
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
 // 32 fp32 values (columns 32*cb .. 32*cb+31 of row r) -> fp16, into the 2-panel activation image.
 __device__ __forceinline__ void store_act_chunk(uint32_t hbuf, int r, int cb, const float (&h)[32]) {
@@ -134,55 +165,89 @@ struct RowLoader<__half> {
   }
 };
 
+// Element `idx` of FourierFeatEnc(x) (layers.py:21-25, use_logspace=True -> freq_j = 2^j * pi):
+// cat(cos(x*f) [input-major, freq-minor], sin(x*f), x); zero beyond the embedding.
+__device__ __forceinline__ float fourier_feature(int idx, float x0, float x1, float x2, int d, int emb, int include) {
+  const int nf = d * emb;
+  if (idx < 2 * nf) {
+    const int q = idx < nf ? idx : idx - nf;
+    const int dim = q / emb, j = q - dim * emb;
+    const float x = dim == 0 ? x0 : (dim == 1 ? x1 : x2);
+    const float arg = x * ldexpf(PI_F, j);
+    return idx < nf ? cosf(arg) : sinf(arg);
+  }
+  if (include && idx < 2 * nf + d) {
+    const int dim = idx - 2 * nf;
+    return dim == 0 ? x0 : (dim == 1 ? x1 : x2);
+  }
+  return 0.f;
+}
+
 }  // namespace
 
 template <bool kTrain, typename TableT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+__global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const FieldParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const Geo g = p.geo;
-  const int L = g.L;
+  const bool view = g.view != INF_VIEW_NONE;
+  const Smem sm = smem_layout(view);
+  const int nstage_a = sm.nstage_a;
+  const int nb = g.nb, nhid = g.nhid;
 
-  auto bar = [&](int i) -> uint32_t { return smem_base + SM_BARS + 8u * static_cast<uint32_t>(i); };
+  auto bar = [&](int i) -> uint32_t { return smem_base + sm.bars + 8u * static_cast<uint32_t>(i); };
+
+  if ((smem_base & 1023u) != 0) {  // SWIZZLE_128B operand images need a 1024-byte aligned base
+    if (tid == 0 && p.err) atomicExch(p.err, 0xBAD00001u);
+    return;
+  }
 
   // ---- one-time setup ---------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE_A; ++i) { mbar_init(bar(BAR_A_FULL + i), PROD_WARPS); mbar_init(bar(BAR_A_EMPTY + i), 1); }
-    for (int i = 0; i < NSTAGE_B; ++i) { mbar_init(bar(BAR_B_FULL + i), 1); mbar_init(bar(BAR_B_EMPTY + i), 1); }
-    mbar_init(bar(BAR_MMA_DONE), 1);
+    for (int i = 0; i < MAX_STAGE_A; ++i) {
+      mbar_init(bar(BAR_A_FULL + i), PROD_WARPS);
+      mbar_init(bar(BAR_A_EMPTY + i), kTrain ? 2 : 1);  // MMA commit (+ x-panel stash store finished reading)
+    }
+    for (int i = 0; i < NSTAGE_B1; ++i) { mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), 1); }
+    mbar_init(bar(BAR_B2_FULL), 1);
+    mbar_init(bar(BAR_B2_EMPTY), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_G_FULL + i), 1); mbar_init(bar(BAR_G_EMPTY + i), EPI_WARPS); }
     mbar_init(bar(BAR_ACT_READY), 1);
+    mbar_init(bar(BAR_MMA_DONE), 1);
     mbar_fence_init();
   }
-  if (warp == MMA_WARP) {
-    tmem_alloc(smem_base + SM_TMEMPTR, TMEM_COLS);
+  if (warp == W_G1) {
+    tmem_alloc(smem_base + sm.tmemptr, TMEM_COLS);
     tmem_relinquish();
   }
   {
-    // f32 section of the packed buffer -> smem; ones tile for the bias-gradient MMAs
+    // f32 section of the packed buffer -> smem (bias rows, then wlast + blast which are contiguous in both)
     const float* f32sec = reinterpret_cast<const float*>(p.packed + packed_f32_offset(g));
-    float* s_bias = reinterpret_cast<float*>(smem + SM_BIAS);
-    const int nf = (L - 1) * HID + OUT_DIM * HID + 4;
-    for (int i = tid; i < nf; i += NUM_THREADS) {
+    float* s_bias = reinterpret_cast<float*>(smem + sm.bias);
+    float* s_wl = reinterpret_cast<float*>(smem + sm.wlast);
+    const int nbias = (nb + 1) * HID;
+    const int nf = packed_f32_count(g);
+    for (int i = tid; i < nf; i += NUM_THREADS_MAIN) {
       const float v = f32sec[i];
-      if (i < (L - 1) * HID) s_bias[i] = v;
-      else reinterpret_cast<float*>(smem + SM_WLAST)[i - (L - 1) * HID] = v;  // wlast then blast (contiguous)
+      if (i < nbias) s_bias[i] = v;
+      else s_wl[i - nbias] = v;
     }
-    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + SM_ONES);
-    for (int i = tid; i < 512; i += NUM_THREADS) ones[i] = 0x3C003C00u;  // fp16 1.0 x2
+    uint32_t* dz = reinterpret_cast<uint32_t*>(smem + sm.dzlt);   // rows 3..15 of dzl^T stay zero
+    for (int i = tid; i < DZLT_BYTES / 4; i += NUM_THREADS_MAIN) dz[i] = 0u;
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + sm.tmemptr);
 
   const int ntiles = p.ntiles;
   const int nchunks = g.nchunks;
+  const size_t tile_stride = stash_tile_bytes(g);
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // =========================== gather producers ===========================================
@@ -190,8 +255,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
     const int pw = pt >> 5;
     const int s = lane & 7, gq = lane >> 3;
     const TableT* table = reinterpret_cast<const TableT*>(p.table);
-    uint32_t* s_vid = reinterpret_cast<uint32_t*>(smem + SM_VID);
-    float* s_bary = reinterpret_cast<float*>(smem + SM_BARY);
+    uint32_t* s_vid = reinterpret_cast<uint32_t*>(smem + sm.vid);
+    float* s_bary = reinterpret_cast<float*>(smem + sm.bary);
     int stage = 0;
     uint32_t phase = 0;
     // tile metadata ring (3 deep): entry i = (ray i/3, vertex i%3) -> vertex id, barycentric weight
@@ -254,7 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
       named_bar_sync(2, PROD_THREADS);
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(bar(BAR_A_EMPTY + stage), phase ^ 1u, p.err, 0x10);
-        const uint32_t panel = smem_base + SM_A + static_cast<uint32_t>(stage) * PANEL_BYTES;
+        const uint32_t panel = smem_base + sm.a + static_cast<uint32_t>(stage) * PANEL_BYTES;
         consume(slot, 0, ld0, panel); issue(L, ld0); advance(L);
         consume(slot, 1, ld1, panel); issue(L, ld1); advance(L);
         consume(slot, 2, ld0, panel); issue(L, ld0); advance(L);
@@ -262,144 +327,227 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_A_FULL + stage));
-        if (++stage == NSTAGE_A) { stage = 0; phase ^= 1u; }
+        if (++stage == nstage_a) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == LOAD_WARP) {
-    // =========================== weight loader ================================================
+  } else if (warp == W_B1) {
+    // =========================== [W0;Wy] chunk loader =========================================
     if (lane == 0) {
-      const int nblobs = kTrain ? g.nblobs_train : g.nblobs_fwd;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int b = 0; b < nblobs; ++b) {
-          mbar_wait(bar(BAR_B_EMPTY + stage), phase ^ 1u, p.err, 0x20);
-          mbar_arrive_expect_tx(bar(BAR_B_FULL + stage), BLOB_BYTES);
-          bulk_g2s(smem_base + SM_B + static_cast<uint32_t>(stage) * BLOB_BYTES,
-                   p.packed + static_cast<size_t>(b) * BLOB_BYTES, BLOB_BYTES, bar(BAR_B_FULL + stage));
-          if (++stage == NSTAGE_B) { stage = 0; phase ^= 1u; }
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(bar(BAR_B1_EMPTY + stage), phase ^ 1u, p.err, 0x20);
+          mbar_arrive_expect_tx(bar(BAR_B1_FULL + stage), BLOB_BYTES);
+          bulk_g2s(smem_base + sm.b1 + static_cast<uint32_t>(stage) * BLOB_BYTES,
+                   p.packed + static_cast<size_t>(c) * BLOB_BYTES, BLOB_BYTES, bar(BAR_B1_FULL + stage));
+          if (++stage == NSTAGE_B1) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == MMA_WARP) {
-    // =========================== MMA issuer ====================================================
+  } else if (warp == W_B2) {
+    // =========================== hidden-weight loader ========================================
+    if (lane == 0) {
+      uint32_t phase = 0;
+      auto load = [&](int blob, uint32_t bytes) {
+        mbar_wait(bar(BAR_B2_EMPTY), phase ^ 1u, p.err, 0x21);
+        mbar_arrive_expect_tx(bar(BAR_B2_FULL), bytes);
+        bulk_g2s(smem_base + sm.b2, p.packed + static_cast<size_t>(blob) * BLOB_BYTES, bytes, bar(BAR_B2_FULL));
+        phase ^= 1u;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 1; l <= nhid; ++l) load(blob_hidden(g, l), BLOB_BYTES);
+        if (view) { load(blob_wd1z(g), BLOB_BYTES); load(blob_wd1e(g), PANEL_BYTES); }
+        if (kTrain) {
+          if (view) load(blob_wd1z(g), BLOB_BYTES);
+          for (int l = nhid; l >= 1; --l) load(blob_hidden(g, l), BLOB_BYTES);
+        }
+      }
+    }
+  } else if (warp == W_G1) {
+    // =========================== GEMM1 issuer ================================================
     if (lane == 0) {
       int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0, pact = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t gph[2] = {0u, 0u};
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar(BAR_G_EMPTY + buf), gph[buf] ^ 1u, p.err, 0x33);  // chain of tile it-2 left this buffer
+        gph[buf] ^= 1u;
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + 256u * static_cast<uint32_t>(buf);
+        uint8_t* xdst = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride + stash_off_x(g, 0) : nullptr;
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(bar(BAR_A_FULL + sa), pa, p.err, 0x30);
+          mbar_wait(bar(BAR_B1_FULL + sb), pb, p.err, 0x32);
+          tc_fence_after();
+          const uint32_t abase = smem_base + sm.a + static_cast<uint32_t>(sa) * PANEL_BYTES;
+          const uint32_t bbase = smem_base + sm.b1 + static_cast<uint32_t>(sb) * BLOB_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_f16(dcol, umma_desc_sw128(abase + kk * 32u, 0, 1024), umma_desc_sw128(bbase + kk * 32u, 0, 1024),
+                     IDESC_N256, (c > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(bar(BAR_A_EMPTY + sa));
+          umma_commit(bar(BAR_B1_EMPTY + sb));
+          if (kTrain) {
+            // x panel -> stash (the B operand of dW0 / dWy in the wgrad kernel)
+            bulk_s2g(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES);
+            bulk_commit();
+            bulk_wait_read<0>();
+            mbar_arrive(bar(BAR_A_EMPTY + sa));
+          }
+          if (++sa == nstage_a) { sa = 0; pa ^= 1u; }
+          if (++sb == NSTAGE_B1) { sb = 0; pb ^= 1u; }
+        }
+        umma_commit(bar(BAR_G_FULL + buf));
+      }
+      if (kTrain) bulk_wait<0>();
+    }
+  } else if (warp == W_CH) {
+    // =========================== chain issuer ================================================
+    if (lane == 0) {
+      uint32_t pact = 0, pb2 = 0;
+      uint32_t wr = 0;  // running index of the activation-buffer write being consumed (buffer = wr & 1)
       int it = 0;
       auto wait_act = [&]() { mbar_wait(bar(BAR_ACT_READY), pact, p.err, 0x31); pact ^= 1u; tc_fence_after(); };
-      auto wait_b = [&]() -> uint32_t {
-        mbar_wait(bar(BAR_B_FULL + sb), pb, p.err, 0x32);
-        tc_fence_after();
-        return smem_base + SM_B + static_cast<uint32_t>(sb) * BLOB_BYTES;
-      };
-      auto release_b = [&]() { umma_commit(bar(BAR_B_EMPTY + sb)); if (++sb == NSTAGE_B) { sb = 0; pb ^= 1u; } };
-      // 128x128x128 product of two 2-panel K-major images
-      auto mma_128 = [&](uint32_t dcol, uint32_t abase, uint32_t bbase, bool acc_first) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+      auto wait_b2 = [&]() { mbar_wait(bar(BAR_B2_FULL), pb2, p.err, 0x34); pb2 ^= 1u; tc_fence_after(); };
+      const uint32_t bbase = smem_base + sm.b2;
+      auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (w & 1u) * BLOB_BYTES; };
+      // D[128 x 128] (+)= A[128 x 64*npanel] * B^T, both K-major two-panel images
+      auto mma_fwd = [&](uint32_t dcol, uint32_t abase, int npanel, bool acc_first) {
+        for (int kk = 0; kk < 4 * npanel; ++kk) {
           const uint32_t o = static_cast<uint32_t>(kk >> 2) * PANEL_BYTES + static_cast<uint32_t>(kk & 3) * 32u;
-          umma_f16(tmem_base + dcol, umma_desc_sw128(abase + o, 0, 1024), umma_desc_sw128(bbase + o, 0, 1024),
-                   IDESC_N128, (acc_first || kk > 0) ? 1u : 0u);
+          umma_f16(dcol, umma_desc_sw128(abase + o, 0, 1024), umma_desc_sw128(bbase + o, 0, 1024), IDESC_N128,
+                   (acc_first || kk > 0) ? 1u : 0u);
         }
       };
-      // bias gradient: D[n, 0..15] += sum_rays dz[ray, n] * 1
-      auto mma_db = [&](int l, uint32_t abase, bool acc_first) {
+      // dh[128 x 128] = dz[128 x 128] * W: A K-major, B = the forward weight image read MN-major (K = row n)
+      auto mma_dgrad = [&](uint32_t dcol, uint32_t abase) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          umma_f16(tmem_base + TM_DB + 16u * static_cast<uint32_t>(l),
-                   umma_desc_sw128(abase + static_cast<uint32_t>(kk) * 2048u, PANEL_BYTES, 1024),
-                   umma_desc_sw128(smem_base + SM_ONES, 0, 1024), IDESC_DB, (acc_first || kk > 0) ? 1u : 0u);
+          const uint32_t oa = static_cast<uint32_t>(kk >> 2) * PANEL_BYTES + static_cast<uint32_t>(kk & 3) * 32u;
+          umma_f16(dcol, umma_desc_sw128(abase + oa, 0, 1024),
+                   umma_desc_sw128(bbase + static_cast<uint32_t>(kk) * 2048u, PANEL_BYTES, 1024), IDESC_N128_BMN,
+                   kk > 0 ? 1u : 0u);
         }
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        // ---- GEMM1: [z0 | zy] = x * [W0;Wy]^T --------------------------------------------
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(bar(BAR_A_FULL + sa), pa, p.err, 0x30);
-          const uint32_t bbase = wait_b();
-          const uint32_t abase = smem_base + SM_A + static_cast<uint32_t>(sa) * PANEL_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_f16(tmem_base + TM_Z0, umma_desc_sw128(abase + kk * 32u, 0, 1024),
-                     umma_desc_sw128(bbase + kk * 32u, 0, 1024), IDESC_N256, (c > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(bar(BAR_A_EMPTY + sa));
-          if (++sa == NSTAGE_A) { sa = 0; pa ^= 1u; }
-          release_b();
-        }
-        umma_commit(bar(BAR_MMA_DONE));
-        // ---- hidden chain, layers 1..L-2 -----------------------------------------------------
-        int wr = 0;  // index of the activation-buffer write being consumed (buffer = wr & 1)
-        for (int l = 1; l <= L - 2; ++l, ++wr) {
+        const uint32_t base = tmem_base + 256u * static_cast<uint32_t>(it & 1);
+        for (int l = 1; l <= nhid; ++l, ++wr) {
           wait_act();
-          const uint32_t bbase = wait_b();
-          const uint32_t abase = smem_base + SM_H + static_cast<uint32_t>(wr & 1) * BLOB_BYTES;
+          wait_b2();
           const bool is_skip = (l == g.skip);
-          mma_128(is_skip ? TM_ZY : TM_Z0, abase, bbase, is_skip);
-          release_b();
+          mma_fwd(is_skip ? base + 128u : base, hbuf(wr), 2, is_skip);   // skip: Lx(h) on top of Ly(x)
+          umma_commit(bar(BAR_B2_EMPTY));
           umma_commit(bar(BAR_MMA_DONE));
         }
-        wait_act();  // epilogue of layer L-2 done (inference: tile finished; training: dz_{L-2} ready)
+        if (view) {
+          wait_act();
+          wait_b2();
+          mma_fwd(base, hbuf(wr), 2, false);                 // bottleneck part of directional_mlp.0
+          umma_commit(bar(BAR_B2_EMPTY));
+          wait_b2();
+          mma_fwd(base, smem_base + sm.e, 1, true);          // Fourier part
+          umma_commit(bar(BAR_B2_EMPTY));
+          umma_commit(bar(BAR_MMA_DONE));
+          ++wr;
+        }
         if (kTrain) {
-          wr = L - 1;  // write L-2 was h_{L-2} (CUDA-core consumer), write L-1 is dz_{L-2}
-          for (int l = L - 2; l >= 1; --l, ++wr) {
-            const uint32_t abase = smem_base + SM_H + static_cast<uint32_t>(wr & 1) * BLOB_BYTES;
-            mma_db(l, abase, it > 0);
-            const uint32_t bbase = wait_b();
-            mma_128(TM_Z0, abase, bbase, false);  // dh_{l-1} = dz_l * W_l
-            release_b();
+          wait_act();   // h_nb in buffer wr, dz_nb in buffer wr+1
+          ++wr;
+          for (int l = nb; l >= 1; --l, ++wr) {
+            wait_b2();
+            mma_dgrad(base, hbuf(wr));                       // dh_{l-1} = dz_l * W_l
+            umma_commit(bar(BAR_B2_EMPTY));
             umma_commit(bar(BAR_MMA_DONE));
-            wait_act();  // dz_{l-1} written
+            if (l > 1) wait_act();                           // dz_{l-1} written
           }
-          mma_db(0, smem_base + SM_H + static_cast<uint32_t>(wr & 1) * BLOB_BYTES, it > 0);
+          ++wr;                                              // dz_0: written by the epilogue, consumed by nobody here
         }
       }
-      if (kTrain) umma_commit(bar(BAR_MMA_DONE));  // bias-gradient accumulators final
     }
-  } else {
+  } else if (warp < EPI_WARPS) {
     // =========================== epilogue warps ================================================
     const int r = tid;  // tile row == TMEM lane
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const float* s_bias = reinterpret_cast<const float*>(smem + SM_BIAS);
-    const float* s_wlast = reinterpret_cast<const float*>(smem + SM_WLAST);
-    const float* s_blast = reinterpret_cast<const float*>(smem + SM_BLAST);
-    float* s_dzl = reinterpret_cast<float*>(smem + SM_DZL);
-    uint4* s_mask = reinterpret_cast<uint4*>(smem + SM_MASK);
+    const float* s_bias = reinterpret_cast<const float*>(smem + sm.bias);
+    const float* s_wlast = reinterpret_cast<const float*>(smem + sm.wlast);
+    const float* s_blast = s_wlast + OUT_DIM * HID;
     uint32_t pdone = 0;
+    uint32_t gph[2] = {0u, 0u};
+    uint32_t wr = 0;
     float loss_abs = 0.f, loss_sq = 0.f;
-    float gw[3] = {0.f, 0.f, 0.f}, gb[3] = {0.f, 0.f, 0.f};
+    float gb[3] = {0.f, 0.f, 0.f};
+    uint32_t mk[MAX_MMA_LAYERS][4];   // ReLU masks of this row (local memory; indexed by layer)
 
     auto wait_done = [&]() { mbar_wait(bar(BAR_MMA_DONE), pdone, p.err, 0x40); pdone ^= 1u; tc_fence_after(); };
-    // end of an epilogue step: publish smem writes to the async proxy, stash, release the MMA thread
-    auto finish_step = [&](uint32_t hbuf, uint8_t* stash_dst) {
+    auto sync_epi = [&]() {
       fence_proxy_async_smem();
       tc_fence_before();
       named_bar_sync(1, EPI_THREADS);
-      if (tid == 0) {
-        if (kTrain) {
-          if (stash_dst != nullptr) bulk_s2g(stash_dst, hbuf, BLOB_BYTES);
-          bulk_commit();
-          bulk_wait_read<1>();
-        }
-        mbar_arrive(bar(BAR_ACT_READY));
-      }
     };
+    auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (w & 1u) * BLOB_BYTES; };
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t tb = tlane + 256u * static_cast<uint32_t>(buf);
       const int64_t ray = static_cast<int64_t>(tile) * TILE_M + r;
       const bool valid = ray < p.n_rays;
-      uint8_t* stash_tile = kTrain ? p.stash + static_cast<size_t>(tile) * g.nslots * BLOB_BYTES : nullptr;
-      int wr = 0;
-      // ---- forward layers 0..L-3: h_l = relu(z_l + b_l) -> activation panel ------------------
-      for (int l = 0; l <= L - 3; ++l, ++wr) {
-        wait_done();
-        const uint32_t hbuf = smem_base + SM_H + static_cast<uint32_t>(wr & 1) * BLOB_BYTES;
-        const uint32_t col0 = (l == g.skip) ? TM_ZY : TM_Z0;
+      uint8_t* stash_tile = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride : nullptr;
+
+      // ---- view branch prologue: Fourier features of this ray -> E panel (model.py:175-186) --------
+      if (view) {
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (valid) {
+          const float dx = p.dirs[ray * 3 + 0], dy = p.dirs[ray * 3 + 1], dz = p.dirs[ray * 3 + 2];
+          if (g.view == INF_VIEW_INTRINSIC) {
+            const int64_t f = p.idx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.face_idxs)[ray])
+                                      : static_cast<int64_t>(reinterpret_cast<const int*>(p.face_idxs)[ray]);
+            const float nx = p.face_normals[f * 3 + 0], ny = p.face_normals[f * 3 + 1], nz = p.face_normals[f * 3 + 2];
+            // F.cosine_similarity(-dir, n): each vector divided by max(|v|, 1e-8), then the dot product
+            const float ia = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
+            const float ib = 1.f / fmaxf(sqrtf(nx * nx + ny * ny + nz * nz), 1e-8f);
+            float c = (-dx * ia) * (nx * ib) + (-dy * ia) * (ny * ib) + (-dz * ia) * (nz * ib);
+            c = fminf(fmaxf(c, -1.f), 1.f);   // the reference yields NaN when rounding pushes |c| above 1
+            x0 = acosf(c);
+          } else {
+            x0 = dx; x1 = dy; x2 = dz;
+          }
+        }
+        const uint32_t row = smem_base + sm.e + static_cast<uint32_t>(r) * 128u;
+        for (int ch = 0; ch < 8; ++ch) {
+          float f[8];
+          if (8 * ch < g.edim) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fourier_feature(8 * ch + i, x0, x1, x2, g.vdim, g.emb, g.include);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = 0.f;
+          }
+          st_shared_v4(row + ((static_cast<uint32_t>(ch) ^ (static_cast<uint32_t>(r) & 7u)) << 4), pack_half2(f[0], f[1]),
+                       pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+        }
+      }
+
+      // ---- forward layers 0..nb-1: h_l = relu(z_l + b_l) -> activation panel -------------------
+      for (int l = 0; l < nb; ++l, ++wr) {
+        if (l == 0) {
+          mbar_wait(bar(BAR_G_FULL + buf), gph[buf], p.err, 0x41);
+          gph[buf] ^= 1u;
+          tc_fence_after();
+        } else {
+          wait_done();
+        }
+        const uint32_t hb = hbuf(wr);
+        const uint32_t col0 = (l == g.skip) ? tb + 128u : tb;
         uint32_t mbits[4];
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
           uint32_t v[32];
-          tmem_ld32(tlane + col0 + 32u * cb, v);
+          tmem_ld32(col0 + 32u * cb, v);
           tmem_ld_wait();
           float h[32];
           uint32_t m = 0;
@@ -410,29 +558,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
             h[j] = fminf(fmaxf(z, 0.f), 60000.f);
           }
           mbits[cb] = m;
-          store_act_chunk(hbuf, r, cb, h);
+          store_act_chunk(hb, r, cb, h);
         }
-        if (kTrain) s_mask[l * TILE_M + r] = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-        finish_step(hbuf, kTrain ? stash_tile + static_cast<size_t>(stash_slot_h(g, l)) * BLOB_BYTES : nullptr);
+        if (kTrain) { mk[l][0] = mbits[0]; mk[l][1] = mbits[1]; mk[l][2] = mbits[2]; mk[l][3] = mbits[3]; }
+        sync_epi();
+        if (tid == 0) {
+          if (kTrain) {
+            bulk_s2g(stash_tile + stash_off_h(g, l), hb, BLOB_BYTES);
+            if (l == 0 && view) bulk_s2g(stash_tile + stash_off_e(g), smem_base + sm.e, PANEL_BYTES);
+            bulk_commit();
+            bulk_wait_read<1>();   // the buffer written next is free before the chain may continue
+          }
+          mbar_arrive(bar(BAR_ACT_READY));
+        }
       }
-      // ---- layer L-2 epilogue + output layer (128 -> 3, sigmoid) on CUDA cores -----------------
+
+      // ---- layer nb epilogue + output layer (-> 3, sigmoid) on CUDA cores -----------------------
       {
-        const int l = L - 2;
         wait_done();
-        const uint32_t hbuf = smem_base + SM_H + static_cast<uint32_t>(wr & 1) * BLOB_BYTES;
-        const uint32_t col0 = (l == g.skip) ? TM_ZY : TM_Z0;
+        const uint32_t ha = hbuf(wr);
+        const uint32_t col0 = (nb == g.skip) ? tb + 128u : tb;
         float y[3] = {s_blast[0], s_blast[1], s_blast[2]};
         uint32_t mbits[4];
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
           uint32_t v[32];
-          tmem_ld32(tlane + col0 + 32u * cb, v);
+          tmem_ld32(col0 + 32u * cb, v);
           tmem_ld_wait();
           float h[32];
           uint32_t m = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float z = __uint_as_float(v[j]) + s_bias[l * HID + 32 * cb + j];
+            const float z = __uint_as_float(v[j]) + s_bias[nb * HID + 32 * cb + j];
             m |= (z > 0.f ? 1u : 0u) << j;
             h[j] = fmaxf(z, 0.f);
             y[0] = fmaf(s_wlast[0 * HID + 32 * cb + j], h[j], y[0]);
@@ -441,7 +598,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
             h[j] = fminf(h[j], 60000.f);
           }
           mbits[cb] = m;
-          if (kTrain) store_act_chunk(hbuf, r, cb, h);
+          if (kTrain) store_act_chunk(ha, r, cb, h);
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) y[c] = sigmoidf_(y[c]);
@@ -451,9 +608,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
           p.pred[ray * 3 + 2] = y[2];
         }
         if (!kTrain) {
-          finish_step(hbuf, nullptr);
+          // all TMEM reads of this tile are complete: hand the accumulator buffer back to the GEMM1 issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_G_EMPTY + buf));
         } else {
-          ++wr;
           float dzl[3] = {0.f, 0.f, 0.f};
           if (valid) {
 #pragma unroll
@@ -468,26 +627,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
                 gy = p.grad_pred[ray * 3 + c] * p.ext_scale;
               }
               dzl[c] = gy * y[c] * (1.f - y[c]) * DZ_SCALE;
+              gb[c] += dzl[c];
             }
           }
-          reinterpret_cast<float4*>(s_dzl)[r] = make_float4(dzl[0], dzl[1], dzl[2], 0.f);
-          if (tid == 0) { bulk_commit(); bulk_wait_read<1>(); }  // keeps the 2-buffer store ring in step
-          named_bar_sync(1, EPI_THREADS);
-          // output-layer weight gradient: thread j reduces over the tile's rays
-          {
-            const int j = tid;
-            const uint8_t* hp = smem + SM_H + (hbuf - (smem_base + SM_H)) + static_cast<uint32_t>(j >> 6) * PANEL_BYTES;
-            const uint32_t cj = static_cast<uint32_t>(j & 63);
-#pragma unroll 4
-            for (int m = 0; m < TILE_M; ++m) {
-              const float hv = __half2float(*reinterpret_cast<const __half*>(hp + sw128_off(m, cj)));
-              const float4 d = reinterpret_cast<const float4*>(s_dzl)[m];
-              gw[0] = fmaf(d.x, hv, gw[0]); gw[1] = fmaf(d.y, hv, gw[1]); gw[2] = fmaf(d.z, hv, gw[2]);
-              gb[0] += d.x; gb[1] += d.y; gb[2] += d.z;
-            }
+          // dzl^T tile [16 x 128 rays] (rows 3..15 stay zero): B operand of the output-layer weight gradient
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            *reinterpret_cast<__half*>(smem + sm.dzlt + static_cast<uint32_t>(r >> 6) * 2048u + sw128_off(c, r & 63)) =
+                __float2half_rn(dzl[c]);
           }
-          // dz_{L-2} = (dz_last * W_last) masked by relu'
-          const uint32_t hbuf2 = smem_base + SM_H + static_cast<uint32_t>(wr & 1) * BLOB_BYTES;
+          if (tid == 0) bulk_wait_read<0>();   // the other activation buffer (h_{nb-1}) has left smem
+          sync_epi();
+          // dz_nb = (dz_last * W_last) masked by relu'
+          const uint32_t hb2 = hbuf(wr + 1);
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
             float h[32];
@@ -497,59 +649,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
               const float dh = dzl[0] * s_wlast[col] + dzl[1] * s_wlast[HID + col] + dzl[2] * s_wlast[2 * HID + col];
               h[j] = ((mbits[cb] >> j) & 1u) ? dh : 0.f;
             }
-            store_act_chunk(hbuf2, r, cb, h);
+            store_act_chunk(hb2, r, cb, h);
           }
-          finish_step(hbuf2, stash_tile + static_cast<size_t>(stash_slot_dz(g, l)) * BLOB_BYTES);
-          ++wr;
-          // ---- dgrad chain: dz_l = dh_l * relu'(z_l), l = L-3..0 --------------------------------
-          for (int lb = L - 3; lb >= 0; --lb, ++wr) {
+          sync_epi();
+          if (tid == 0) {
+            bulk_s2g(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES);
+            bulk_commit();
+            bulk_s2g(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES);
+            bulk_s2g(stash_tile + stash_off_dzlt(g), smem_base + sm.dzlt, DZLT_BYTES);
+            bulk_commit();
+            bulk_wait_read<1>();
+            mbar_arrive(bar(BAR_ACT_READY));
+          }
+          wr += 2;
+          // ---- dgrad chain: dz_l = dh_l * relu'(z_l), l = nb-1..0 --------------------------------
+          for (int lb = nb - 1; lb >= 0; --lb, ++wr) {
             wait_done();
-            const uint32_t hb = smem_base + SM_H + static_cast<uint32_t>(wr & 1) * BLOB_BYTES;
-            const uint4 mk = s_mask[lb * TILE_M + r];
-            const uint32_t mm[4] = {mk.x, mk.y, mk.z, mk.w};
+            const uint32_t hb = hbuf(wr);
+            const uint32_t mm[4] = {mk[lb][0], mk[lb][1], mk[lb][2], mk[lb][3]};
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
               uint32_t v[32];
-              tmem_ld32(tlane + TM_Z0 + 32u * cb, v);
+              tmem_ld32(tb + 32u * cb, v);
               tmem_ld_wait();
               float h[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) h[j] = ((mm[cb] >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
               store_act_chunk(hb, r, cb, h);
             }
-            finish_step(hb, stash_tile + static_cast<size_t>(stash_slot_dz(g, lb)) * BLOB_BYTES);
+            if (lb == 0) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(BAR_G_EMPTY + buf));   // last TMEM read of this tile
+              if (tid == 0) bulk_wait_read<0>();  // no MMA gates the next tile's first write: drain the store ring
+            }
+            sync_epi();
+            if (tid == 0) {
+              bulk_s2g(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES);
+              bulk_commit();
+              if (lb > 0) {
+                bulk_wait_read<1>();
+                mbar_arrive(bar(BAR_ACT_READY));
+              }
+            }
           }
         }
       }
     }
     if (kTrain) {
-      // ---- per-CTA partials: bias gradients (TMEM), output layer, loss sums ---------------------
-      wait_done();
-      float* part = p.part1 + static_cast<size_t>(blockIdx.x) * K1_PART_FLOATS;
-      for (int l = 0; l <= L - 2; ++l) {
-        uint32_t v;
-        tmem_ld1(tlane + TM_DB + 16u * static_cast<uint32_t>(l), v);
-        tmem_ld_wait();
-        part[l * HID + tid] = __uint_as_float(v);
-      }
-      float* plast = part + (INF_MAX_LAYERS - 1) * HID;
-      plast[0 * HID + tid] = gw[0];
-      plast[1 * HID + tid] = gw[1];
-      plast[2 * HID + tid] = gw[2];
+      // ---- per-CTA partials: output-layer bias gradient, loss sums ------------------------------
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, o);
         loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, o);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gb[c] += __shfl_xor_sync(0xffffffffu, gb[c], o);
       }
-      float* s_red = reinterpret_cast<float*>(smem + SM_RED);
-      if (lane == 0) { s_red[warp] = loss_abs; s_red[4 + warp] = loss_sq; }
+      float* s_red = reinterpret_cast<float*>(smem + sm.red);   // [5][4]: per-warp partial sums
+      if (lane == 0) {
+        s_red[warp] = loss_abs; s_red[4 + warp] = loss_sq;
+        s_red[8 + warp] = gb[0]; s_red[12 + warp] = gb[1]; s_red[16 + warp] = gb[2];
+      }
       named_bar_sync(1, EPI_THREADS);
       if (tid == 0) {
-        plast[3 * HID + 0] = gb[0];
-        plast[3 * HID + 1] = gb[1];
-        plast[3 * HID + 2] = gb[2];
-        plast[3 * HID + 4] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
-        plast[3 * HID + 5] = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+        float* part = p.part1 + static_cast<size_t>(blockIdx.x) * K1_PART_FLOATS;
+        part[0] = s_red[8] + s_red[9] + s_red[10] + s_red[11];
+        part[1] = s_red[12] + s_red[13] + s_red[14] + s_red[15];
+        part[2] = s_red[16] + s_red[17] + s_red[18] + s_red[19];
+        part[3] = 0.f;
+        part[4] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        part[5] = s_red[4] + s_red[5] + s_red[6] + s_red[7];
         bulk_wait<0>();  // stash stores fully written before the grid completes
       }
     }
@@ -557,21 +726,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) field_main_kernel(const FieldP
   }
 
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == W_G1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ---- host launcher (kernels stay private to this translation unit) -----------------------------
-size_t field_main_smem_bytes() { return SM_ALLOC; }
-
 template <bool kTrain, typename TableT>
 static cudaError_t launch_one(const FieldParams& p, int grid, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(SM_ALLOC));
+  const int smem = static_cast<int>(smem_layout(p.geo.view != INF_VIEW_NONE).total);
+  cudaError_t e = cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) return e;
-  field_main_kernel<kTrain, TableT><<<grid, NUM_THREADS, SM_ALLOC, stream>>>(p);
+  field_main_kernel<kTrain, TableT><<<grid, NUM_THREADS_MAIN, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

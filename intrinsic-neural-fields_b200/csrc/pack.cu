@@ -6,12 +6,19 @@
 namespace inf {
 
 
+// Rows of MMA layer l that really exist (the rest of the 128-row image is zero padding).
+__device__ __forceinline__ int layer_rows(const Geo& g, int l) {
+  if (g.view && l == g.nhid) return g.bneck;
+  if (g.view && l == g.nb) return g.dh;
+  return HID;
+}
+
 // One thread per 16-bit element of the blob section + one per f32 of the tail section.
 __global__ void pack_weights_kernel(const PackParams pp) {
   const Geo g = pp.geo;
-  const int L = g.L;
-  const int64_t nhalf = static_cast<int64_t>(g.nblobs_train) * (BLOB_BYTES / 2);
-  const int nf32 = (L - 1) * HID + OUT_DIM * HID + 4;
+  const int64_t nhalf = static_cast<int64_t>(g.nblobs) * (BLOB_BYTES / 2);
+  const int nbias = (g.nb + 1) * HID;
+  const int nf32 = packed_f32_count(g);
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < nhalf) {
     const int blob = static_cast<int>(i / (BLOB_BYTES / 2));
@@ -26,31 +33,35 @@ __global__ void pack_weights_kernel(const PackParams pp) {
                                       : pp.wy[static_cast<size_t>(row - HID) * g.k + kcol];
       off = sw128_off(row, c);
     } else {
-      // [128 rows][128 cols] as two 64-column panels
+      // [128 rows n][128 cols j] as two 64-column panels
       const int row = e >> 7, col = e & 127;
       const int hb = blob - g.nchunks;
-      if (hb < L - 2) {
-        const int l = hb + 1;                       // W_l[n=row][k=col]
-        v = pp.w[l][row * HID + col];
-      } else {
-        const int l = (L - 2) - (hb - (L - 2));     // W_l^T: [j=row][n=col] = W_l[col][row]
-        v = pp.w[l][col * HID + row];
+      if (hb < g.nhid) {
+        const int l = hb + 1;                                   // W_l[n=row][j=col]
+        if (row < layer_rows(g, l)) v = pp.w[l][row * HID + col];
+      } else if (hb == g.nhid) {                                 // Wd1[:, :bneck]
+        if (row < g.dh && col < g.bneck) v = pp.w[g.nb][static_cast<size_t>(row) * (g.bneck + g.edim) + col];
+      } else {                                                   // Wd1[:, bneck:bneck+E] in the first panel
+        if (row < g.dh && col < g.edim) v = pp.w[g.nb][static_cast<size_t>(row) * (g.bneck + g.edim) + g.bneck + col];
       }
       off = static_cast<uint32_t>(col >> 6) * PANEL_BYTES + sw128_off(row, col & 63);
     }
     *reinterpret_cast<__half*>(pp.packed + static_cast<size_t>(blob) * BLOB_BYTES + off) = __float2half_rn(v);
   } else if (i < nhalf + nf32) {
     const int e = static_cast<int>(i - nhalf);
-    float v;
-    if (e < (L - 1) * HID) {
+    float v = 0.f;
+    if (e < nbias) {
       const int l = e / HID, n = e % HID;
-      v = pp.b[l][n];
-      if (l == g.skip) v += pp.by[n];
-    } else if (e < (L - 1) * HID + OUT_DIM * HID) {
-      v = pp.w[L - 1][e - (L - 1) * HID];
+      if (n < layer_rows(g, l)) {
+        v = pp.b[l][n];
+        if (l == g.skip) v += pp.by[n];
+      }
+    } else if (e < nbias + OUT_DIM * HID) {
+      const int c = (e - nbias) / HID, j = (e - nbias) % HID;
+      if (j < g.wout) v = pp.wlast[c * g.wout + j];
     } else {
-      const int c = e - (L - 1) * HID - OUT_DIM * HID;
-      v = (c < OUT_DIM) ? pp.b[L - 1][c] : 0.f;
+      const int c = e - nbias - OUT_DIM * HID;
+      v = (c < OUT_DIM) ? pp.blast[c] : 0.f;
     }
     reinterpret_cast<float*>(pp.packed + packed_f32_offset(g))[e] = v;
   }
@@ -58,7 +69,7 @@ __global__ void pack_weights_kernel(const PackParams pp) {
 
 void launch_pack_weights(const PackParams& pp, cudaStream_t stream) {
   const Geo g = pp.geo;
-  const int64_t n = static_cast<int64_t>(g.nblobs_train) * (BLOB_BYTES / 2) + (g.L - 1) * HID + OUT_DIM * HID + 4;
+  const int64_t n = static_cast<int64_t>(g.nblobs) * (BLOB_BYTES / 2) + packed_f32_count(g);
   const int threads = 256;
   pack_weights_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0, stream>>>(pp);
 }
@@ -102,7 +113,7 @@ umma_probe_kernel(int mode, int n, int k, const float* __restrict__ a, const flo
   // layout: A image 32 KB | B image 64 KB | bar | tmem ptr
   const uint32_t SA = 0, SB = 32768, SBAR = 32768 + 65536, SPTR = SBAR + 8;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool a_mn = mode >= 1, b_mn = mode >= 2;
+  const bool a_mn = mode == 1 || mode == 2, b_mn = mode >= 2;   // 3: A K-major, B MN-major
   __half* sa = reinterpret_cast<__half*>(smem + SA);
   __half* sb = reinterpret_cast<__half*>(smem + SB);
   // K-major image: element (row m, col kk) -> panel kk/64 (stride rows*128 B), sw128(row, kk%64)

@@ -43,70 +43,44 @@ def _linear_block(in_dim: int, out_dim: int) -> nn.Sequential:
 
 
 class _FieldFunction(torch.autograd.Function):
-    """pred = field(table, vids, bary; params).  No gradient flows into table / vids / bary
-    (none requires grad in the reference either)."""
+    """pred = field(table, vids, bary[, dirs, face_idxs]; params).  No gradient flows into table / vids / bary /
+    dirs (none requires grad in the reference either)."""
 
     @staticmethod
-    def forward(ctx, module, table, vids, bary, dense, *params):
-        cfg = module.cfg
+    def forward(ctx, module, table, vids, bary, dense, dirs, face_idxs, face_normals, *params):
         packed = module._packed_weights()
         ctx.module, ctx.dense = module, dense
-        ctx.save_for_backward(table, vids, bary)
-        return torch.ops.inf_b200.field_forward(table, vids, bary, packed, cfg.k, cfg.num_layers, cfg.skip, dense)
+        ctx.save_for_backward(table, vids, bary, dirs, face_idxs, face_normals)
+        return torch.ops.inf_b200.field_forward(table, vids, bary, packed, dirs, face_idxs, face_normals,
+                                                module.cfg.key(), dense)
 
     @staticmethod
     def backward(ctx, grad_pred):
         module = ctx.module
-        cfg = module.cfg
-        table, vids, bary = ctx.saved_tensors
+        table, vids, bary, dirs, face_idxs, face_normals = ctx.saved_tensors
         _, flat, _ = torch.ops.inf_b200.field_forward_backward(
-            table, vids, bary, module._packed_weights(), None, grad_pred.contiguous().float(), cfg.k, cfg.num_layers,
-            cfg.skip, ctx.dense, 1.0)
+            table, vids, bary, module._packed_weights(), None, grad_pred.contiguous().float(), dirs, face_idxs,
+            face_normals, module.cfg.key(), ctx.dense, 1.0)
         grads = [flat[off:off + r * c].view(p.shape) for (off, r, c), p in zip(module._layout, module._ordered_params())]
-        return (None, None, None, None, None, *grads)
+        return (None,) * 8 + tuple(grads)
 
 
-class TextureField(nn.Module):
-    """6-layer/128-wide ReLU MLP with an input skip connection, RGB sigmoid head (model.py:12-112)."""
+class _FusedFieldBase(nn.Module):
+    """Shared host logic of the two drop-in modules: operand packing cache, batch decoding, forward through the
+    custom ops, and the fused L1 training step."""
 
-    def __init__(self, num_layers, in_dim, hidden_dim, skip_layer_idx, input_feature_embed=None, embed_dim=None,
-                 embed_include_input=True, embed_std=1., return_rgb=True, out_dim=RGB_COLOR_DIM, batchnorm=False,
-                 activation=nn.ReLU, table_dtype: str = "f32"):
-        super().__init__()
-        assert num_layers > 2 and 0 < skip_layer_idx and skip_layer_idx < num_layers - 1   # model.py:27
-        if input_feature_embed not in (None, "efuncs"):
-            raise NotImplementedError(f"feature_strategy={input_feature_embed!r}: only the intrinsic 'efuncs' path is "
-                                      "implemented by the B200 kernels (extrinsic ff/rff/xyz baselines are out of scope)")
-        if batchnorm:
-            raise NotImplementedError("batchnorm=True is not supported by the B200 kernels (no shipped config uses it)")
-        if activation is not nn.ReLU:
-            raise NotImplementedError("only activation='relu' is supported by the B200 kernels")
-        if not return_rgb or out_dim != RGB_COLOR_DIM:
-            raise NotImplementedError("spatial MLP with a bottleneck head (view-direction branch) is not built yet")
-        if hidden_dim != ops.HIDDEN:
-            raise NotImplementedError(f"mlp_hidden_dim={hidden_dim}: compiled set is {{{ops.HIDDEN}}}")
-        self.skip_layer_idx = skip_layer_idx
-        self.cfg = FieldConfig(k=in_dim, num_layers=num_layers, skip=skip_layer_idx, hidden=hidden_dim)
-        self.table_dtype = table_dtype
-        layers: List[nn.Module] = [_linear_block(in_dim, hidden_dim)]
-        for i in range(1, num_layers - 1):
-            layers.append(_SkipLinear(hidden_dim, in_dim, hidden_dim) if i == skip_layer_idx
-                          else _linear_block(hidden_dim, hidden_dim))
-        layers.append(_linear_block(hidden_dim, out_dim))
-        self.layers = nn.ModuleList(layers)
+    cfg: FieldConfig
+
+    def _init_cache(self):
         self._layout = None
         self._packed = None
         self._packed_key = None
 
-    # ---- parameters in the flat / state_dict order the C ABI expects -------------------------------
     def _ordered_params(self) -> List[torch.Tensor]:
-        out = []
-        for i, layer in enumerate(self.layers):
-            if i == self.skip_layer_idx:
-                out += [layer.Lx.weight, layer.Lx.bias, layer.Ly.weight, layer.Ly.bias]
-            else:
-                out += [layer[0].weight, layer[0].bias]
-        return out
+        raise NotImplementedError
+
+    def _view_inputs(self, batch):
+        return None, None, None
 
     def _packed_weights(self) -> torch.Tensor:
         """Operand images of the current parameter values (re-packed when any parameter changed)."""
@@ -149,12 +123,12 @@ class TextureField(nn.Module):
 
     def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         table, vids, bary, dense = self._inputs(batch)
+        dirs, face_idxs, normals = self._view_inputs(batch)
         params = self._ordered_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _FieldFunction.apply(self, table, vids, bary, dense, *params)
-        cfg = self.cfg
-        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(), cfg.k, cfg.num_layers,
-                                                cfg.skip, dense)
+            return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, *params)
+        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(), dirs, face_idxs, normals,
+                                                self.cfg.key(), dense)
 
     # ---- fused training pass -----------------------------------------------------------------------
     def l1_step(self, batch: Dict[str, torch.Tensor], global_rays: Optional[int] = None,
@@ -167,18 +141,136 @@ class TextureField(nn.Module):
         ``global_rays`` is the number of rays of the whole (all-rank) batch; it defaults to this call's B.
         """
         table, vids, bary, dense = self._inputs(batch)
+        dirs, face_idxs, normals = self._view_inputs(batch)
         target = batch["expected_rgbs"].contiguous()
         B = target.shape[0]
-        cfg = self.cfg
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
         pred, flat, sums = torch.ops.inf_b200.field_forward_backward(
-            table, vids, bary, self._packed_weights(), target, None, cfg.k, cfg.num_layers, cfg.skip, dense, scale)
+            table, vids, bary, self._packed_weights(), target, None, dirs, face_idxs, normals, self.cfg.key(), dense,
+            scale)
         if flat_grad is not None:
             flat_grad.copy_(flat)
             flat = flat_grad
         for (off, r, c), p in zip(self._layout, self._ordered_params()):
             p.grad = flat[off:off + r * c].view(p.shape)
         return sums, pred, flat
+
+
+def _check_common(hidden_dim, input_feature_embed, batchnorm, activation):
+    if input_feature_embed not in (None, "efuncs"):
+        raise NotImplementedError(f"feature_strategy={input_feature_embed!r}: only the intrinsic 'efuncs' path is "
+                                  "implemented by the B200 kernels (extrinsic ff/rff/xyz baselines are out of scope)")
+    if batchnorm:
+        raise NotImplementedError("batchnorm=True is not supported by the B200 kernels (no shipped config uses it)")
+    if activation is not nn.ReLU:
+        raise NotImplementedError("only activation='relu' is supported by the B200 kernels")
+    if hidden_dim != ops.HIDDEN:
+        raise NotImplementedError(f"mlp_hidden_dim={hidden_dim}: compiled set is {{{ops.HIDDEN}}}")
+
+
+def _spatial_layers(num_layers, in_dim, hidden_dim, skip_layer_idx, out_dim) -> nn.ModuleList:
+    layers: List[nn.Module] = [_linear_block(in_dim, hidden_dim)]
+    for i in range(1, num_layers - 1):
+        layers.append(_SkipLinear(hidden_dim, in_dim, hidden_dim) if i == skip_layer_idx
+                      else _linear_block(hidden_dim, hidden_dim))
+    layers.append(_linear_block(hidden_dim, out_dim))
+    return nn.ModuleList(layers)
+
+
+def _spatial_params(layers, skip_layer_idx) -> List[torch.Tensor]:
+    out = []
+    for i, layer in enumerate(layers):
+        if i == skip_layer_idx:
+            out += [layer.Lx.weight, layer.Lx.bias, layer.Ly.weight, layer.Ly.bias]
+        else:
+            out += [layer[0].weight, layer[0].bias]
+    return out
+
+
+class TextureField(_FusedFieldBase):
+    """6-layer/128-wide ReLU MLP with an input skip connection, RGB sigmoid head (model.py:12-112)."""
+
+    def __init__(self, num_layers, in_dim, hidden_dim, skip_layer_idx, input_feature_embed=None, embed_dim=None,
+                 embed_include_input=True, embed_std=1., return_rgb=True, out_dim=RGB_COLOR_DIM, batchnorm=False,
+                 activation=nn.ReLU, table_dtype: str = "f32"):
+        super().__init__()
+        assert num_layers > 2 and 0 < skip_layer_idx and skip_layer_idx < num_layers - 1   # model.py:27
+        _check_common(hidden_dim, input_feature_embed, batchnorm, activation)
+        if return_rgb and out_dim != RGB_COLOR_DIM:
+            raise NotImplementedError("an RGB head has 3 outputs (model.py:9)")
+        self.skip_layer_idx = skip_layer_idx
+        self.return_rgb = return_rgb
+        self.cfg = FieldConfig(k=in_dim, num_layers=num_layers, skip=skip_layer_idx, hidden=hidden_dim)
+        self.table_dtype = table_dtype
+        self.layers = _spatial_layers(num_layers, in_dim, hidden_dim, skip_layer_idx, out_dim)
+        self._init_cache()
+
+    # ---- parameters in the flat / state_dict order the C ABI expects -------------------------------
+    def _ordered_params(self) -> List[torch.Tensor]:
+        return _spatial_params(self.layers, self.skip_layer_idx)
+
+    def forward(self, batch):
+        if not self.return_rgb:
+            raise NotImplementedError("a spatial MLP with a bottleneck head only runs fused inside "
+                                      "TextureFieldWithViewDependency (model.py:156-157)")
+        return super().forward(batch)
+
+
+class _FourierBands(nn.Module):
+    """Holds the reference's non-persistent ``freq_bands`` buffer (layers.py:11-19) so module structure matches."""
+
+    def __init__(self, k, include_input=True):
+        super().__init__()
+        self.register_buffer("freq_bands", 2 ** torch.arange(0, k) * torch.pi, persistent=False)
+        self.include_input = include_input
+
+
+class TextureFieldWithViewDependency(_FusedFieldBase):
+    """Spatial MLP -> bottleneck, Fourier-embedded view direction, 2-layer directional MLP (model.py:123-191);
+    the whole thing runs inside the fused kernels."""
+
+    def __init__(self, num_layers, in_dim, hidden_dim, skip_layer_idx, bottleneck_vec_dim, in_dim_view_dir,
+                 include_view_dir, view_dir_embedding_size, directional_hidden_dim, input_feature_embed=None,
+                 embed_dim=None, embed_include_input=True, embed_std=1., face_normals=None,
+                 view_dir_strategy="intrinsic", batchnorm=False, activation=nn.ReLU, table_dtype: str = "f32"):
+        super().__init__()
+        assert num_layers > 2 and 0 < skip_layer_idx and skip_layer_idx < num_layers - 1   # model.py:27
+        _check_common(hidden_dim, input_feature_embed, batchnorm, activation)
+        if view_dir_strategy not in ("intrinsic", "extrinsic"):
+            raise RuntimeError("Unknown viewing direction strategy.")                        # model.py:186
+        if in_dim_view_dir != (1 if view_dir_strategy == "intrinsic" else 3):
+            raise ValueError(f"in_dim_view_dir={in_dim_view_dir} does not match the {view_dir_strategy} strategy "
+                             "(an angle has 1 dim, a direction 3)")
+        self.view_dir_strategy = view_dir_strategy
+        self.skip_layer_idx = skip_layer_idx
+        self.table_dtype = table_dtype
+        if face_normals is not None:
+            self.register_buffer("face_normals", face_normals.to(torch.float32).contiguous(), persistent=False)  # model.py:146
+        self.spatial_mlp = TextureField(num_layers, in_dim, hidden_dim, skip_layer_idx,
+                                        input_feature_embed=input_feature_embed, return_rgb=False,
+                                        out_dim=bottleneck_vec_dim, batchnorm=batchnorm, activation=activation)
+        self.embedding = _FourierBands(view_dir_embedding_size, include_input=include_view_dir)
+        embedding_size = in_dim_view_dir * view_dir_embedding_size * 2 + (in_dim_view_dir if include_view_dir else 0)
+        self.directional_mlp = nn.Sequential(nn.Linear(bottleneck_vec_dim + embedding_size, directional_hidden_dim),
+                                             activation(), nn.Linear(directional_hidden_dim, RGB_COLOR_DIM), nn.Sigmoid())
+        self.cfg = FieldConfig(k=in_dim, num_layers=num_layers, skip=skip_layer_idx, hidden=hidden_dim,
+                               view=view_dir_strategy, view_embed=view_dir_embedding_size,
+                               view_include=bool(include_view_dir), view_bneck=bottleneck_vec_dim,
+                               view_hidden=directional_hidden_dim)
+        self._init_cache()
+
+    def _ordered_params(self) -> List[torch.Tensor]:
+        return _spatial_params(self.spatial_mlp.layers, self.skip_layer_idx) + [
+            self.directional_mlp[0].weight, self.directional_mlp[0].bias,
+            self.directional_mlp[2].weight, self.directional_mlp[2].bias]
+
+    def _view_inputs(self, batch):
+        dirs = batch["unit_ray_dirs"].contiguous()
+        if self.view_dir_strategy == "extrinsic":
+            return dirs, None, None
+        if getattr(self, "face_normals", None) is None:
+            raise RuntimeError("the intrinsic view strategy needs face_normals (make_model(..., mesh=mesh))")
+        return dirs, batch["hit_face_idxs"].contiguous(), self.face_normals
 
 
 def init_weights(m):
@@ -199,11 +291,19 @@ def make_model(model_config: dict, mesh=None) -> nn.Module:
     act = model_config.get("activation", "relu")
     if act != "relu":
         raise NotImplementedError(f"Activation function {act} is not implemented by the B200 kernels.")
-    if view_cfg is not None:
-        raise NotImplementedError("view_dependence branch is not built yet")
-    model = TextureField(model_config["num_layers"], in_dim, model_config["mlp_hidden_dim"],
-                         model_config["skip_layer_idx"], input_feature_embed=feature_strategy,
-                         batchnorm=model_config.get("batchnorm", False),
-                         table_dtype=model_config.get("table_dtype", "f32"))
+    common = dict(input_feature_embed=feature_strategy, batchnorm=model_config.get("batchnorm", False),
+                  table_dtype=model_config.get("table_dtype", "f32"))
+    if view_cfg is None:
+        model = TextureField(model_config["num_layers"], in_dim, model_config["mlp_hidden_dim"],
+                             model_config["skip_layer_idx"], **common)
+    else:
+        assert mesh is not None                                          # model.py:237
+        import numpy as np
+        face_normals = torch.from_numpy(np.asarray(mesh.face_normals).copy()).to(dtype=torch.float32)
+        model = TextureFieldWithViewDependency(
+            model_config["num_layers"], in_dim, model_config["mlp_hidden_dim"], model_config["skip_layer_idx"],
+            view_cfg["bottleneck_vec_dim"], view_cfg["in_dim_view_dir"], view_cfg["include_view_dir"],
+            view_cfg["embed_size"], view_cfg["directional_hidden_dim"], face_normals=face_normals,
+            view_dir_strategy=view_cfg["strategy"], **common)
     model.apply(init_weights)                                           # model.py:257
     return model

@@ -25,19 +25,43 @@ def pad_k(k: int) -> int:
 
 @dataclass(frozen=True)
 class FieldConfig:
-    """Static shape of the spatial MLP (model.py:12-96 of the reference)."""
+    """Static shape of the model: spatial MLP (model.py:12-96 of the reference) and, when ``view`` is not
+    "none", the view-direction branch (model.py:123-173)."""
     k: int
     num_layers: int = 6
     skip: int = 3
     hidden: int = HIDDEN
+    view: str = "none"            # "none" | "intrinsic" | "extrinsic"  (view_dependence.strategy)
+    view_embed: int = 0           # view_dependence.embed_size
+    view_include: bool = True     # view_dependence.include_view_dir
+    view_bneck: int = 0           # view_dependence.bottleneck_vec_dim
+    view_hidden: int = 0          # view_dependence.directional_hidden_dim
 
     @property
     def k_pad(self) -> int:
         return pad_k(self.k)
 
+    @property
+    def has_view(self) -> bool:
+        return self.view != "none"
+
+    def key(self) -> List[int]:
+        """Flat integer encoding (the custom ops take plain ints)."""
+        return [self.k, self.num_layers, self.skip, self.hidden, _VIEW_CODES[self.view], self.view_embed,
+                int(self.view_include), self.view_bneck, self.view_hidden]
+
+    @staticmethod
+    def from_key(key: Sequence[int]) -> "FieldConfig":
+        k, L, skip, hid, view, emb, inc, bneck, dh = [int(v) for v in key]
+        return FieldConfig(k, L, skip, hid, _VIEW_NAMES[view], emb, bool(inc), bneck, dh)
+
+
+_VIEW_CODES = {"none": _lib.VIEW_NONE, "intrinsic": _lib.VIEW_INTRINSIC, "extrinsic": _lib.VIEW_EXTRINSIC}
+_VIEW_NAMES = {v: k for k, v in _VIEW_CODES.items()}
+
 
 def _desc(cfg: FieldConfig, n_rays: int, n_rows: int, *, idx64: bool = True, table_f16: bool = False,
-          dense: bool = False, grad_scale: float = 1.0) -> _lib.InfDesc:
+          dense: bool = False, grad_scale: float = 1.0, n_faces: int = 0) -> _lib.InfDesc:
     d = _lib.InfDesc()
     d.abi_version = _lib.ABI_VERSION
     d.idx_dtype = _lib.IDX_I64 if idx64 else _lib.IDX_I32
@@ -50,7 +74,14 @@ def _desc(cfg: FieldConfig, n_rays: int, n_rows: int, *, idx64: bool = True, tab
     d.skip = cfg.skip
     d.table_dtype = _lib.TABLE_F16 if table_f16 else _lib.TABLE_F32
     d.input_mode = _lib.INPUT_DENSE if dense else _lib.INPUT_GATHER
-    d.view_strategy = _lib.VIEW_NONE
+    if cfg.view not in _VIEW_CODES:
+        raise RuntimeError("Unknown viewing direction strategy.")          # model.py:186
+    d.view_strategy = _VIEW_CODES[cfg.view]
+    d.view_embed = cfg.view_embed
+    d.view_include = int(cfg.view_include)
+    d.view_bneck = cfg.view_bneck
+    d.view_hidden = cfg.view_hidden
+    d.n_faces = n_faces
     d.grad_scale = grad_scale
     return d
 
@@ -206,17 +237,44 @@ def _check_inputs(cfg, table, vids, bary, dense):
     return vids.shape[0]
 
 
-def _field_forward_impl(table, vids, bary, packed, k: int, num_layers: int, skip: int, dense: bool) -> torch.Tensor:
-    cfg = FieldConfig(k, num_layers, skip)
+def _check_view(cfg, B, idx64, dirs, face_idxs, face_normals):
+    """Validate / normalise the view-branch inputs (model.py:175-186); returns (dirs, face_idxs, normals, n_faces)."""
+    if not cfg.has_view:
+        return None, None, None, 0
+    if dirs is None:
+        raise KeyError("the view-direction branch needs batch['unit_ray_dirs']")
+    _require_cuda(dirs, "unit_ray_dirs")
+    if dirs.dtype != torch.float32 or tuple(dirs.shape) != (B, 3):
+        raise ValueError(f"unit_ray_dirs must be ({B},3) float32")
+    if cfg.view != "intrinsic":
+        return dirs, None, None, 0
+    if face_idxs is None or face_normals is None:
+        raise KeyError("the intrinsic view strategy needs batch['hit_face_idxs'] and the mesh face normals")
+    want = torch.int64 if idx64 else torch.int32
+    if face_idxs.dtype != want:
+        face_idxs = face_idxs.to(want)       # one index dtype per call (InfDesc.idx_dtype)
+    face_idxs = face_idxs.contiguous()
+    _require_cuda(face_idxs, "hit_face_idxs")
+    _require_cuda(face_normals, "face_normals")
+    if tuple(face_idxs.shape) != (B,) or face_normals.dtype != torch.float32 or face_normals.dim() != 2 \
+            or face_normals.shape[1] != 3:
+        raise ValueError("hit_face_idxs must be (B,) and face_normals (F,3) float32")
+    return dirs, face_idxs, face_normals, face_normals.shape[0]
+
+
+def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense: bool) -> torch.Tensor:
+    cfg = FieldConfig.from_key(cfg_key)
     B = _check_inputs(cfg, table, vids, bary, dense)
     device = table.device
     pred = torch.empty((B, 3), dtype=torch.float32, device=device)
     if B == 0:
         return pred
+    idx64 = vids is None or vids.dtype == torch.int64
+    dirs, face_idxs, face_normals, n_faces = _check_view(cfg, B, idx64, dirs, face_idxs, face_normals)
     ws = _workspace(device, workspace_bytes(cfg, B, False))
-    d = _desc(cfg, B, table.shape[0], idx64=(vids is None or vids.dtype == torch.int64),
-              table_f16=table.dtype == torch.float16, dense=dense)
-    t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), packed=packed.data_ptr(),
+    d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense, n_faces=n_faces)
+    t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), unit_ray_dirs=_ptr(dirs),
+                        face_idxs=_ptr(face_idxs), face_normals=_ptr(face_normals), packed=packed.data_ptr(),
                         pred=pred.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     with torch.cuda.device(device):
         rc = _lib.load().inf_forward(C.byref(d), C.byref(t), _stream(device))
@@ -224,9 +282,9 @@ def _field_forward_impl(table, vids, bary, packed, k: int, num_layers: int, skip
     return pred
 
 
-def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, k: int, num_layers: int, skip: int,
+def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key,
                                  dense: bool, grad_scale: float):
-    cfg = FieldConfig(k, num_layers, skip)
+    cfg = FieldConfig.from_key(cfg_key)
     B = _check_inputs(cfg, table, vids, bary, dense)
     device = table.device
     pred = torch.empty((B, 3), dtype=torch.float32, device=device)
@@ -237,11 +295,14 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, k
             _require_cuda(x, name)
             if x.dtype != torch.float32 or tuple(x.shape) != (B, 3):
                 raise ValueError(f"{name} must be ({B},3) float32")
+    idx64 = vids is None or vids.dtype == torch.int64
+    dirs, face_idxs, face_normals, n_faces = _check_view(cfg, B, idx64, dirs, face_idxs, face_normals)
     ws = _workspace(device, workspace_bytes(cfg, B, True))
-    d = _desc(cfg, B, table.shape[0], idx64=(vids is None or vids.dtype == torch.int64),
-              table_f16=table.dtype == torch.float16, dense=dense, grad_scale=grad_scale)
+    d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense,
+              grad_scale=grad_scale, n_faces=n_faces)
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), target=_ptr(target),
-                        grad_pred=_ptr(grad_pred), packed=packed.data_ptr(), pred=pred.data_ptr(),
+                        grad_pred=_ptr(grad_pred), unit_ray_dirs=_ptr(dirs), face_idxs=_ptr(face_idxs),
+                        face_normals=_ptr(face_normals), packed=packed.data_ptr(), pred=pred.data_ptr(),
                         workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     g = _lib.InfGrads(flat=flat.data_ptr(), loss_sums=sums.data_ptr())
     with torch.cuda.device(device):
@@ -255,12 +316,13 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, k
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("inf_b200::field_forward", mutates_args=())
 def field_forward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor],
-                  packed: torch.Tensor, k: int, num_layers: int, skip: int, dense: bool) -> torch.Tensor:
-    return _field_forward_impl(table, vids, bary, packed, k, num_layers, skip, dense)
+                  packed: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
+                  face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool) -> torch.Tensor:
+    return _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense)
 
 
 @field_forward.register_fake
-def _(table, vids, bary, packed, k, num_layers, skip, dense):
+def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense):
     B = table.shape[0] if dense else vids.shape[0]
     return table.new_empty((B, 3), dtype=torch.float32)
 
@@ -268,16 +330,17 @@ def _(table, vids, bary, packed, k, num_layers, skip, dense):
 @torch.library.custom_op("inf_b200::field_forward_backward", mutates_args=())
 def field_forward_backward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor],
                            packed: torch.Tensor, target: Optional[torch.Tensor], grad_pred: Optional[torch.Tensor],
-                           k: int, num_layers: int, skip: int, dense: bool,
+                           dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
+                           face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
                            grad_scale: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    return _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, k, num_layers, skip, dense,
-                                        grad_scale)
+    return _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals,
+                                        cfg_key, dense, grad_scale)
 
 
 @field_forward_backward.register_fake
-def _(table, vids, bary, packed, target, grad_pred, k, num_layers, skip, dense, grad_scale):
+def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale):
     B = table.shape[0] if dense else vids.shape[0]
-    n = num_params(FieldConfig(k, num_layers, skip))
+    n = num_params(FieldConfig.from_key(cfg_key))
     return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n,), dtype=torch.float32),
             table.new_empty((2,), dtype=torch.float32))
 
@@ -306,8 +369,8 @@ def debug_umma(mode: int, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Tensor-core self test: D(128,n) = A(128,k) B(n,k)^T with the operand-layout variant `mode`."""
     _require_cuda(a, "a")
     _require_cuda(b, "b")
-    k = a.shape[1] if mode == 0 else a.shape[0]
-    n = b.shape[1] if mode == 2 else b.shape[0]
+    k = a.shape[1] if mode in (0, 3) else a.shape[0]
+    n = b.shape[1] if mode >= 2 else b.shape[0]
     d = torch.empty((128, n), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         rc = _lib.load().inf_debug_umma(mode, n, k, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()),

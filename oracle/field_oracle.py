@@ -265,10 +265,12 @@ def _r16(a: np.ndarray) -> np.ndarray:
     return a.astype(np.float16).astype(np.float64)
 
 
-def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale=32.0, table_f16=False):
-    """The reference's forward/backward (model.py:98-112, trainer.py:76-81) restated in float64 with the
-    CUDA path's rounding points: table (optionally), interpolated embedding, weights, hidden activations
-    and backward signals are rounded to fp16 before each matrix product; accumulation is exact.
+def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale=32.0, table_f16=False,
+                        view: Optional[dict] = None, unit_ray_dirs=None, hit_face_idxs=None, face_normals=None):
+    """The reference's forward/backward (model.py:98-112,188-191, trainer.py:76-81) restated in float64 with the
+    CUDA path's rounding points: table (optionally), interpolated embedding, weights, hidden activations, the
+    Fourier view embedding and backward signals are rounded to fp16 before each matrix product; accumulation
+    is exact.
 
     Purpose: ReLU masks of a reduced-precision forward differ from the fp32 reference wherever |z| is
     below the rounding noise, which alone moves each gradient tensor by a few percent in Frobenius
@@ -288,46 +290,72 @@ def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale
     x = _r16(x32)
     t = target.double().numpy()
     L = num_layers
+    pre = "spatial_mlp." if view is not None else ""
 
-    def W(i):
-        return P[f"layers.{i}.Lx.weight" if i == skip else f"layers.{i}.0.weight"]
-
-    def bias(i):
+    # MMA layers 0..nb: (weight name, bias names); the last spatial layer is an MMA layer only with the view branch
+    def names(i):
         if i == skip:
-            return (P[f"layers.{i}.Lx.bias"].astype(np.float32) + P[f"layers.{i}.Ly.bias"].astype(np.float32)).astype(np.float64)
-        return P[f"layers.{i}.0.bias"]
+            return f"{pre}layers.{i}.Lx.weight", [f"{pre}layers.{i}.Lx.bias", f"{pre}layers.{i}.Ly.bias"]
+        return f"{pre}layers.{i}.0.weight", [f"{pre}layers.{i}.0.bias"]
+
+    n_spatial = L if view is not None else L - 1
+    def bias(i):
+        wn, bn = names(i)
+        acc = P[bn[0]].astype(np.float32)
+        for extra in bn[1:]:
+            acc = (acc + P[extra].astype(np.float32)).astype(np.float32)
+        return acc.astype(np.float64)
 
     hs, masks = [], []
     h16 = x
-    for i in range(L - 1):
-        z = h16 @ _r16(W(i)).T + bias(i)
+    for i in range(n_spatial):
+        wn, _ = names(i)
+        z = h16 @ _r16(P[wn]).T + bias(i)
         if i == skip:
-            z = z + x @ _r16(P[f"layers.{i}.Ly.weight"]).T
+            z = z + x @ _r16(P[f"{pre}layers.{i}.Ly.weight"]).T
         masks.append(z > 0)
         h = np.maximum(z, 0.0)
         hs.append(h)
         h16 = _r16(h)
-    z = hs[-1] @ W(L - 1).T + bias(L - 1)            # output layer runs in fp32 on CUDA cores
+    e16 = None
+    if view is not None:
+        e = view_embedding(unit_ray_dirs, hit_face_idxs, face_normals, view["strategy"], view["embed_size"],
+                           view["include_view_dir"]).double().numpy()
+        e16 = _r16(e)
+        bn = view["bottleneck_vec_dim"]
+        Wd1 = P["directional_mlp.0.weight"]
+        z = h16 @ _r16(Wd1[:, :bn]).T + e16 @ _r16(Wd1[:, bn:]).T + P["directional_mlp.0.bias"]
+        masks.append(z > 0)
+        hs.append(np.maximum(z, 0.0))
+        wl_n, bl_n = "directional_mlp.2.weight", "directional_mlp.2.bias"
+    else:
+        wl_n, bl_n = f"layers.{L-1}.0.weight", f"layers.{L-1}.0.bias"
+    z = hs[-1] @ P[wl_n].T + P[bl_n]                 # output layer runs in fp32 on CUDA cores
     y = 1.0 / (1.0 + np.exp(-z))
     B = y.shape[0]
     loss = np.abs(y - t).mean()
     dzl = np.sign(y - t) * y * (1.0 - y) * dz_scale
     g = {}
-    g[f"layers.{L-1}.0.weight"] = dzl.T @ _r16(hs[-1])
-    g[f"layers.{L-1}.0.bias"] = dzl.sum(0)
-    dz = _r16((dzl @ W(L - 1)) * masks[L - 2])
-    for i in range(L - 2, -1, -1):
+    g[wl_n] = _r16(dzl).T @ _r16(hs[-1])             # tensor-core product of the stashed fp16 tiles
+    g[bl_n] = dzl.sum(0)
+    nb = len(hs) - 1
+    dz = _r16((dzl @ P[wl_n]) * masks[nb])
+    if view is not None:
+        bn = view["bottleneck_vec_dim"]
+        Wd1 = P["directional_mlp.0.weight"]
+        g["directional_mlp.0.weight"] = np.concatenate([dz.T @ _r16(hs[nb - 1]), dz.T @ e16], axis=1)
+        g["directional_mlp.0.bias"] = dz.sum(0)
+        dz = _r16((dz @ _r16(Wd1[:, :bn])) * masks[nb - 1])
+    for i in range(n_spatial - 1, -1, -1):
         hin = x if i == 0 else _r16(hs[i - 1])
+        wn, bns = names(i)
+        g[wn] = dz.T @ hin
+        for bname in bns:
+            g[bname] = dz.sum(0)
         if i == skip:
-            g[f"layers.{i}.Lx.weight"] = dz.T @ hin
-            g[f"layers.{i}.Lx.bias"] = dz.sum(0)
-            g[f"layers.{i}.Ly.weight"] = dz.T @ x
-            g[f"layers.{i}.Ly.bias"] = dz.sum(0)
-        else:
-            g[f"layers.{i}.0.weight"] = dz.T @ hin
-            g[f"layers.{i}.0.bias"] = dz.sum(0)
+            g[f"{pre}layers.{i}.Ly.weight"] = dz.T @ x
         if i > 0:
-            dz = _r16((dz @ _r16(W(i))) * masks[i - 1])
+            dz = _r16((dz @ _r16(P[wn])) * masks[i - 1])
     s = 1.0 / (3.0 * B * dz_scale)
     return loss, y, {n: v * s for n, v in g.items()}
 

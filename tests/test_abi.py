@@ -28,10 +28,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.inf_version() == _lib.ABI_VERSION
 
 
-@pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1"])
+def _cfg_of(c):
+    v = c["view"]
+    if v is None:
+        return ops.FieldConfig(k=c["k"], num_layers=c["num_layers"], skip=c["skip"])
+    return ops.FieldConfig(k=c["k"], num_layers=c["num_layers"], skip=c["skip"], view=v["strategy"],
+                           view_embed=v["embed_size"], view_include=v["include_view_dir"],
+                           view_bneck=v["bottleneck_vec_dim"], view_hidden=v["directional_hidden_dim"])
+
+
+@pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1", "view_intrinsic", "view_extrinsic"])
 def test_param_layout_matches_reference_state_dict(name):
     c = load_golden(name)
-    cfg = ops.FieldConfig(k=c["k"], num_layers=c["num_layers"], skip=c["skip"])
+    cfg = _cfg_of(c)
     layout = ops.param_layout(cfg)
     assert len(layout) == len(c["param_names"])
     off = 0
@@ -48,7 +57,7 @@ def test_production_config_sizes():
     cfg = ops.FieldConfig(k=1023, num_layers=6, skip=3)
     assert cfg.k_pad == 1024
     assert ops.num_params(cfg) == 328579
-    assert ops.packed_bytes(cfg) == (16 + 8) * 32768 + (5 * 128 + 3 * 128 + 4) * 4
+    assert ops.packed_bytes(cfg) == (16 + 4) * 32768 + (5 * 128 + 3 * 128 + 4) * 4
     assert ops.workspace_bytes(cfg, 4096, False) == 256
     assert ops.workspace_bytes(cfg, 4096, True) > 32 * 9 * 32768
 
@@ -80,6 +89,23 @@ def test_model_state_dict_keys_match_reference():
     m.load_state_dict(c["params"])       # reference-trained weights load unchanged
     import copy
     copy.deepcopy(m)                      # trainer.py:67
+
+
+@pytest.mark.parametrize("name", ["view_intrinsic", "view_extrinsic"])
+def test_view_model_state_dict_keys_match_reference(name):
+    import copy
+    import types
+    c = load_golden(name)
+    m = inf_b200.make_model(dict(k=c["k"], num_layers=c["num_layers"], mlp_hidden_dim=128, skip_layer_idx=c["skip"],
+                                 view_dependence=c["view"]),
+                            mesh=types.SimpleNamespace(face_normals=c["face_normals"].numpy()))
+    sd = m.state_dict()
+    assert list(sd.keys()) == c["param_names"]          # face_normals / freq_bands are non-persistent (model.py:146)
+    assert [n for n, _ in m.named_parameters()] == c["param_names"]
+    for n in sd:
+        assert tuple(sd[n].shape) == tuple(c["params"][n].shape)
+    m.load_state_dict(c["params"])
+    copy.deepcopy(m)
 
 
 def test_unsupported_options_raise():

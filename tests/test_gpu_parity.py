@@ -21,21 +21,31 @@ RGB_MAX, RGB_MEAN = 2e-2, 1e-3      # BASELINE.json north_star tolerances
 GRAD_REL = 6e-2
 GRAD_COS = 0.997
 GRAD_REL_EMULATED = 1e-2
+GRAD_REL_VIEW, GRAD_COS_VIEW = 0.2, 0.98
 
 DEV = "cuda:0"
 
 
 def _model_from(case, table_dtype="f32"):
-    m = inf_b200.make_model(dict(k=case["k"], num_layers=case["num_layers"], mlp_hidden_dim=128,
-                                 skip_layer_idx=case["skip"]))
+    cfg = dict(k=case["k"], num_layers=case["num_layers"], mlp_hidden_dim=128, skip_layer_idx=case["skip"])
+    mesh = None
+    if case.get("view") is not None:
+        import types
+        cfg["view_dependence"] = case["view"]
+        mesh = types.SimpleNamespace(face_normals=case["face_normals"].numpy())
+    m = inf_b200.make_model(cfg, mesh=mesh)
     m.load_state_dict(case["params"])
     return m.to(DEV)
 
 
 def _batch(case, table_dtype="f32", idx_dtype=torch.int64):
     tab = inf_b200.EigenTable.from_dense(case["table"], device=DEV, dtype=table_dtype)
-    return {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": case["vids"].to(DEV).to(idx_dtype),
-            "barycentric_coords": case["bary"].to(DEV), "expected_rgbs": case["target"].to(DEV)}
+    b = {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": case["vids"].to(DEV).to(idx_dtype),
+         "barycentric_coords": case["bary"].to(DEV), "expected_rgbs": case["target"].to(DEV)}
+    if case.get("view") is not None:
+        b["unit_ray_dirs"] = case["unit_ray_dirs"].to(DEV)
+        b["hit_face_idxs"] = case["face_idxs"].to(DEV)
+    return b
 
 
 def _check_no_watchdog():
@@ -47,13 +57,13 @@ def _check_no_watchdog():
 # tensor-core operand layouts (localises descriptor bugs before the full kernels are judged)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode,n,k", [(0, 128, 128), (0, 256, 64), (0, 16, 64), (1, 16, 128), (1, 128, 64),
-                                      (2, 128, 128), (2, 256, 64), (2, 64, 128)])
+                                      (2, 128, 128), (2, 256, 64), (2, 64, 128), (3, 128, 128), (3, 64, 64)])
 def test_umma_operand_layouts(mode, n, k):
     g = torch.Generator().manual_seed(mode * 100 + n + k)
     A = (torch.randn(128, k, generator=g)).half().float()
     B = (torch.randn(n, k, generator=g)).half().float()
     ref = A.double() @ B.double().T
-    a_in = A if mode == 0 else A.T.contiguous()      # MN-major sources are (k,128) / (k,n)
+    a_in = A if mode in (0, 3) else A.T.contiguous()      # MN-major sources are (k,128) / (k,n)
     b_in = B if mode < 2 else B.T.contiguous()
     d = inf_b200.debug_umma(mode, a_in.to(DEV), b_in.to(DEV)).cpu().double()
     assert torch.allclose(d, ref, atol=1e-2, rtol=1e-3), float((d - ref).abs().max())
@@ -62,7 +72,7 @@ def test_umma_operand_layouts(mode, n, k):
 # ---------------------------------------------------------------------------------------------
 # forward
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1"])
+@pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1", "view_intrinsic", "view_extrinsic"])
 @pytest.mark.parametrize("table_dtype", ["f32", "f16"])
 def test_forward_matches_reference_golden(name, table_dtype):
     c = load_golden(name)
@@ -146,12 +156,16 @@ def _check_grads(m, ref_grads, tol=GRAD_REL, cos_min=GRAD_COS):
 
 
 def _check_grads_emulated(m, case, table_f16=False):
+    kw = {}
+    if case.get("view") is not None:
+        kw = dict(view=case["view"], unit_ray_dirs=case["unit_ray_dirs"], hit_face_idxs=case["face_idxs"],
+                  face_normals=case["face_normals"])
     _, _, g = O.emulated_fp16_grads(case["params"], case["table"], case["vids"], case["bary"], case["target"],
-                                    case["num_layers"], case["skip"], table_f16=table_f16)
+                                    case["num_layers"], case["skip"], table_f16=table_f16, **kw)
     return _check_grads(m, g, tol=GRAD_REL_EMULATED, cos_min=0.9999)
 
 
-@pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1"])
+@pytest.mark.parametrize("name", ["tf_k64", "tf_k1023", "tf_k100_l5s1", "view_intrinsic", "view_extrinsic"])
 @pytest.mark.parametrize("table_dtype", ["f32", "f16"])
 def test_fused_l1_step_matches_reference_golden(name, table_dtype):
     c = load_golden(name)
@@ -164,7 +178,9 @@ def test_fused_l1_step_matches_reference_golden(name, table_dtype):
     sse_ref = ((c["pred"] - c["target"]) ** 2).sum().item()
     assert abs(sums[1].item() - sse_ref) <= 2e-2 * max(1.0, sse_ref)
     assert (pred.cpu() - c["pred"]).abs().max().item() <= RGB_MAX
-    _check_grads(m, c["grads"])
+    # the deeper view-branch chain on 96-140 rays amplifies the ReLU-mask flips of a reduced-precision forward
+    _check_grads(m, c["grads"], tol=GRAD_REL if c["view"] is None else GRAD_REL_VIEW,
+                 cos_min=GRAD_COS if c["view"] is None else GRAD_COS_VIEW)
     _check_grads_emulated(m, c, table_f16=(table_dtype == "f16"))
 
 
@@ -185,6 +201,39 @@ def test_autograd_path_matches_fused_step_and_reference():
     ref = torch.nn.functional.mse_loss(O.field_forward(q, c["table"], c["vids"], c["bary"], num_layers=6, skip=3), c["target"])
     ref.backward()
     _check_grads(m2, {n: t.grad for n, t in q.items()})
+
+
+def test_view_branch_padded_widths_and_int32_faces():
+    # bottleneck / directional widths below 128 are zero-padded inside; face ids follow the index dtype of the call
+    torch.manual_seed(3)
+    view = dict(strategy="intrinsic", in_dim_view_dir=1, include_view_dir=False, embed_size=6,
+                bottleneck_vec_dim=96, directional_hidden_dim=48)
+    V, F_, B, k = 200, 300, 333, 80
+    E = torch.randn(V, k) / 4
+    normals = torch.nn.functional.normalize(torch.randn(F_, 3), dim=-1)
+    fid = torch.randint(0, F_, (B,))
+    dirs = torch.nn.functional.normalize(torch.randn(B, 3), dim=-1)
+    dirs = torch.where(((-dirs * normals[fid]).sum(-1) < 0)[:, None], -dirs, dirs)
+    vids = torch.randint(0, V, (B, 3))
+    u = torch.rand(B, 3); bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3)
+    params = O.make_params(k, num_layers=5, skip=2, view=view, seed=11)
+    import types
+    m = inf_b200.make_model(dict(k=k, num_layers=5, mlp_hidden_dim=128, skip_layer_idx=2, view_dependence=view),
+                            mesh=types.SimpleNamespace(face_normals=normals.numpy()))
+    m.load_state_dict(params)
+    m = m.to(DEV)
+    b = {"eigenfunction_table": inf_b200.EigenTable.from_dense(E, device=DEV), "vertex_idxs_of_hit_faces": vids.to(DEV).int(),
+         "barycentric_coords": bary.to(DEV), "expected_rgbs": target.to(DEV), "unit_ray_dirs": dirs.to(DEV),
+         "hit_face_idxs": fid.to(DEV)}
+    sums, pred, flat = m.l1_step(b)
+    _check_no_watchdog()
+    kw = dict(num_layers=5, skip=2, view=view, unit_ray_dirs=dirs, hit_face_idxs=fid, face_normals=normals)
+    loss, pref, grads = O.loss_and_grads(params, E, vids, bary, target, **kw)
+    err = (pred.cpu() - pref).abs()
+    assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN
+    assert abs(sums[0].item() / (3 * B) - loss) <= 1e-3
+    _check_grads(m, grads)
 
 
 def test_gradients_are_deterministic():
