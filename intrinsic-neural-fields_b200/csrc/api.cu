@@ -199,12 +199,17 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   p.idx64 = d->idx_dtype == INF_IDX_I64;
   p.dense = d->input_mode == INF_INPUT_DENSE;
   p.ext_scale = 1.f;
+  {
+    const char* e = getenv("INF_DEBUG");   // measurement only; bits 1|2|4 produce wrong gradients
+    p.debug = e ? atoi(e) : 0;
+  }
   p.geo = geo_of(d);
   p.plan = make_wplan(p.geo);
-  if (t->workspace != nullptr && t->workspace_bytes >= 256) {
+  if (t->workspace != nullptr && t->workspace_bytes >= ERR_AREA_BYTES) {
     const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training);
     uint8_t* ws = reinterpret_cast<uint8_t*>(t->workspace);
     p.err = reinterpret_cast<unsigned int*>(ws + w.err_off);
+    p.trace = (p.debug & 8) ? reinterpret_cast<unsigned long long*>(ws + w.err_off + 1024) : nullptr;
     if (training) {
       p.stash = ws + w.stash_off;
       p.partw = reinterpret_cast<float*>(ws + w.partw_off);

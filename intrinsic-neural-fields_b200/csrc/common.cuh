@@ -23,6 +23,8 @@ constexpr int K1_PART_FLOATS = 8;  // per-CTA partials of the forward/backward k
 constexpr int WG_COLS = 512;     // TMEM columns = accumulator columns of a wgrad CTA
 constexpr int MAX_UNITS = 16;    // wgrad work units of the hidden slices
 constexpr int MAX_HID_SLICES = 4;
+constexpr int ERR_AREA_BYTES = 65536;
+constexpr int TRACE_SLOTS = 4000;  // u64 clock stamps of CTA 0 (measurement only)
 
 // Model geometry.  MMA "layers" are numbered 0..nb:
 //   layer 0            x (k_pad) -> 128, fused with the skip branch Ly in GEMM1
@@ -112,7 +114,7 @@ struct WorkspaceLayout {
 __host__ inline WorkspaceLayout workspace_layout(const Geo& g, int64_t n_rays, bool training) {
   WorkspaceLayout w{};
   size_t off = 0;
-  w.err_off = off; off += 256;
+  w.err_off = off; off += ERR_AREA_BYTES;   // error word, then the optional timing trace (INF_DEBUG & 8)
   if (training) {
     const int64_t ntiles = (n_rays + TILE_M - 1) / TILE_M;
     w.stash_off = off; off += static_cast<size_t>(ntiles) * stash_tile_bytes(g);
@@ -206,6 +208,8 @@ struct FieldParams {
   int idx64;
   int dense;
   float ext_scale;  // multiplies grad_pred before it enters the fp16 backward chain
+  unsigned long long* trace;  // (INF_DEBUG & 8) clock64 stamps of CTA 0's chain: [0] = count, then (tag<<48 | clock)
+  int debug;        // measurement knobs (INF_DEBUG env): 1 no x stash, 2 no h/dz stash, 4 no dgrad chain -- wrong results
   int groups_big;                   // wgrad: ray groups (CTAs) per big slice
   int groups_hid[MAX_HID_SLICES];   // wgrad: ray groups (CTAs) per hidden slice
   Geo geo;

@@ -26,13 +26,17 @@ namespace inf {
 
 namespace {
 
-constexpr int NUM_THREADS_MAIN = 16 * 32;
+// Six warpgroups.  Registers are re-partitioned at kernel start (setmaxnreg): the epilogue warpgroup needs
+// ~150 (32-column TMEM slices in flight), a producer warp ~80 (two gather passes in flight), the four
+// single-thread roles almost none.
+constexpr int NUM_THREADS_MAIN = 24 * 32;
 constexpr int EPI_WARPS = 4;      // warps 0..3: TMEM epilogue (warp w owns TMEM lanes 32w..32w+31)
-constexpr int PROD_WARPS = 8;     // warps 4..11: gather producers
-constexpr int W_G1 = 12;          // GEMM1 issuer + TMEM allocator
-constexpr int W_CH = 13;          // chain issuer
-constexpr int W_B1 = 14;          // [W0;Wy] chunk loader
-constexpr int W_B2 = 15;          // hidden-weight loader
+constexpr int PROD_WARPS = 16;    // warps 4..19: gather producers (8 tile rows each)
+constexpr int W_G1 = 20;          // GEMM1 issuer + TMEM allocator
+constexpr int W_CH = 21;          // chain issuer
+constexpr int W_B1 = 22;          // [W0;Wy] chunk loader
+constexpr int W_B2 = 23;          // hidden-weight loader
+constexpr int REGS_EPI = 128, REGS_UTIL = 32;   // pool = 768 x 80 (launch value): 128*128 + 512*80 + 128*32
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 
@@ -87,30 +91,47 @@ constexpr uint32_t IDESC_N256 = umma_idesc_f16(128, 256, 0, 0);
 constexpr uint32_t IDESC_N128 = umma_idesc_f16(128, 128, 0, 0);
 constexpr uint32_t IDESC_N128_BMN = umma_idesc_f16(128, 128, 0, 1);  // dgrad: B = weight image read MN-major
 
+constexpr uint32_t DESC_HI = umma_desc_hi(1024);   // every operand image here: SWIZZLE_128B, 1024 B between 8-row groups
+
 constexpr float PI_F = 3.14159274101257324f;  // float32(torch.pi), layers.py:14
 
 __device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
-// 32 fp32 values (columns 32*cb .. 32*cb+31 of row r) -> fp16, into the 2-panel activation image.
-__device__ __forceinline__ void store_act_chunk(uint32_t hbuf, int r, int cb, const float (&h)[32]) {
+// 16 packed f16x2 words (columns 32*cb .. 32*cb+31 of row r) into the 2-panel activation image.
+__device__ __forceinline__ void store_act_words(uint32_t hbuf, int r, int cb, const uint32_t (&w)[16]) {
   const uint32_t panel = hbuf + static_cast<uint32_t>(cb >> 1) * PANEL_BYTES + static_cast<uint32_t>(r) * 128u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t chunk = static_cast<uint32_t>((cb & 1) * 4 + i);
     const uint32_t addr = panel + ((chunk ^ (static_cast<uint32_t>(r) & 7u)) << 4);
-    st_shared_v4(addr, pack_half2(h[8 * i + 0], h[8 * i + 1]), pack_half2(h[8 * i + 2], h[8 * i + 3]),
-                 pack_half2(h[8 * i + 4], h[8 * i + 5]), pack_half2(h[8 * i + 6], h[8 * i + 7]));
+    st_shared_v4(addr, w[4 * i + 0], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
   }
 }
+// ReLU mask of 16 packed non-negative f16x2 words: bit i = (low half of word i != 0), bit 16+i = (high half != 0).
+// (h + 0x7FFF sets bit 15 exactly when the non-negative half h is non-zero; halves cannot carry into each other.)
+__device__ __forceinline__ uint32_t relu_mask16(const uint32_t (&w)[16]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m |= ((w[i] + 0x7FFF7FFFu) >> (15 - i)) & (0x00010001u << i);
+  return m;
+}
+// keep / zero the halves of word i according to the mask layout of relu_mask16
+__device__ __forceinline__ uint32_t apply_mask(uint32_t w, uint32_t m, int i) {
+  return w & (((m >> i) & 0x00010001u) * 0xFFFFu);
+}
 
+// A producer warp owns 8 rows of every A panel: two "quads" of 4 rows; lanes 8g..8g+7 serve row
+// {0,4,1,5}[g] (+2 for the second quad) of the warp's 8-row swizzle atom, which makes the panel stores
+// bank-conflict free.  A pass is what one RowLoader holds in registers between issue and consume.
 template <typename TableT>
 struct RowLoader;
 
-// fp32 table: per k-chunk a ray needs 3 x 256 B; 8 lanes x 2 float4 per row.
+// fp32 table: a pass = one quad; per k-chunk a ray needs 3 x 256 B = 8 lanes x 2 float4 per row.
 template <>
 struct RowLoader<float> {
+  static constexpr int QUADS = 1;        // quads per pass
   float4 a[3], b[3];
-  __device__ __forceinline__ void load(const float* base, const int64_t (&roff)[3], int koff, int s) {
+  __device__ __forceinline__ void load(int, const float* base, const int64_t (&roff)[3], int koff, int s) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float* p = base + roff[j] + koff + 4 * s;
@@ -119,7 +140,7 @@ struct RowLoader<float> {
     }
   }
   // writes fp16 k-offsets [4s,4s+4) and [32+4s, 32+4s+4) of panel row r
-  __device__ __forceinline__ void store(uint32_t panel, int r, int s, const float (&w)[3]) const {
+  __device__ __forceinline__ void store(int, uint32_t panel, int r, int s, const float (&w)[3]) const {
     float x0 = w[0] * a[0].x, x1 = w[0] * a[0].y, x2 = w[0] * a[0].z, x3 = w[0] * a[0].w;
     float y0 = w[0] * b[0].x, y1 = w[0] * b[0].y, y2 = w[0] * b[0].z, y3 = w[0] * b[0].w;
 #pragma unroll
@@ -138,22 +159,24 @@ struct RowLoader<float> {
   }
 };
 
-// fp16 table: per k-chunk a ray needs 3 x 128 B; 8 lanes x one 16-byte load per row.
+// fp16 table: a pass = both quads (same bytes in flight as the fp32 pass); per k-chunk a ray needs
+// 3 x 128 B = 8 lanes x one 16-byte load per row.
 template <>
 struct RowLoader<__half> {
-  uint4 a[3];
-  __device__ __forceinline__ void load(const __half* base, const int64_t (&roff)[3], int koff, int s) {
+  static constexpr int QUADS = 2;
+  uint4 a[2][3];
+  __device__ __forceinline__ void load(int u, const __half* base, const int64_t (&roff)[3], int koff, int s) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) a[j] = ldg_nc_u4(base + roff[j] + koff + 8 * s);
+    for (int j = 0; j < 3; ++j) a[u][j] = ldg_nc_u4(base + roff[j] + koff + 8 * s);
   }
-  __device__ __forceinline__ void store(uint32_t panel, int r, int s, const float (&w)[3]) const {
+  __device__ __forceinline__ void store(int u, uint32_t panel, int r, int s, const float (&w)[3]) const {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const uint32_t u[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+      const uint32_t v[4] = {a[u][j].x, a[u][j].y, a[u][j].z, a[u][j].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[i]));
         if (j == 0) { acc[2 * i] = w[0] * f.x; acc[2 * i + 1] = w[0] * f.y; }
         else { acc[2 * i] = fmaf(w[j], f.x, acc[2 * i]); acc[2 * i + 1] = fmaf(w[j], f.y, acc[2 * i + 1]); }
       }
@@ -164,6 +187,11 @@ struct RowLoader<__half> {
                  pack_half2(acc[6], acc[7]));
   }
 };
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // Element `idx` of FourierFeatEnc(x) (layers.py:21-25, use_logspace=True -> freq_j = 2^j * pi):
 // cat(cos(x*f) [input-major, freq-minor], sin(x*f), x); zero beyond the embedding.
@@ -200,6 +228,10 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   const int nb = g.nb, nhid = g.nhid;
 
   auto bar = [&](int i) -> uint32_t { return smem_base + sm.bars + 8u * static_cast<uint32_t>(i); };
+  // measurement only (INF_DEBUG & 8): per-role cycle accounting of CTA 0, written once at the end of the kernel
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto now = [&]() -> long long { return tracing ? clock64() : 0ll; };
+  auto put = [&](int slot, long long v) { if (tracing) p.trace[slot] = static_cast<unsigned long long>(v); };
 
   if ((smem_base & 1023u) != 0) {  // SWIZZLE_128B operand images need a 1024-byte aligned base
     if (tid == 0 && p.err) atomicExch(p.err, 0xBAD00001u);
@@ -249,6 +281,8 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   const int nchunks = g.nchunks;
   const size_t tile_stride = stash_tile_bytes(g);
 
+  // Register re-partition: ONE setmaxnreg instance per warpgroup (all four warps of a warpgroup must execute the
+  // same instruction), placed so that it dominates the role's code -- ptxas budgets each region from it.
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // =========================== gather producers ===========================================
     const int pt = tid - EPI_THREADS;
@@ -278,30 +312,37 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         s_bary[slot * 384 + i] = w;
       }
     };
-    // Software-pipelined gather.  A "pass" = 4 rays per warp (8 lanes per ray) of one k-chunk.  Two passes
-    // are always in flight: the loads of pass n+2 are issued right after pass n has been consumed -- also
-    // across k-chunk and tile boundaries, because a load needs registers only, not a free ring slot.
+    // Software-pipelined gather: two passes are always in flight per warp.  The loads of pass n+2 are issued
+    // right after pass n has been consumed -- also across k-chunk and tile boundaries, because a load needs
+    // registers only, not a free ring slot.
+    constexpr int QUADS = RowLoader<TableT>::QUADS;
+    constexpr int PPC = 2 / QUADS;   // passes per k-chunk
     struct Cursor { int tile, slot, c, q; };
     auto advance = [&](Cursor& k) {
-      if (++k.q == 4) {
+      if (++k.q == PPC) {
         k.q = 0;
         if (++k.c == nchunks) { k.c = 0; k.tile += gridDim.x; k.slot = (k.slot + 1) % 3; }
       }
     };
-    // rows of a pass: lanes 8g..8g+7 take row base + {0,4,1,5}[g] so that 64-bit stores are bank-conflict free
-    auto pass_row = [&](int q) { return 16 * pw + 8 * (q >> 1) + 2 * (q & 1) + (gq >> 1) + 4 * (gq & 1); };
+    auto quad_row = [&](int j) { return 8 * pw + 2 * j + (gq >> 1) + 4 * (gq & 1); };
     auto issue = [&](const Cursor& k, RowLoader<TableT>& ld) {
       if (k.tile >= ntiles) return;
-      const int e = k.slot * 384 + 3 * pass_row(k.q);
-      int64_t roff[3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) roff[j] = static_cast<int64_t>(s_vid[e + j]) * p.row_stride;
-      ld.load(table, roff, k.c * KC, s);
+      for (int u = 0; u < QUADS; ++u) {
+        const int e = k.slot * 384 + 3 * quad_row(k.q * QUADS + u);
+        int64_t roff[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) roff[j] = static_cast<int64_t>(s_vid[e + j]) * p.row_stride;
+        ld.load(u, table, roff, k.c * KC, s);
+      }
     };
     auto consume = [&](int slot, int q, const RowLoader<TableT>& ld, uint32_t panel) {
-      const int r = pass_row(q);
-      const float w[3] = {s_bary[slot * 384 + 3 * r], s_bary[slot * 384 + 3 * r + 1], s_bary[slot * 384 + 3 * r + 2]};
-      ld.store(panel, r, s, w);
+#pragma unroll
+      for (int u = 0; u < QUADS; ++u) {
+        const int r = quad_row(q * QUADS + u);
+        const float w[3] = {s_bary[slot * 384 + 3 * r], s_bary[slot * 384 + 3 * r + 1], s_bary[slot * 384 + 3 * r + 2]};
+        ld.store(u, panel, r, s, w);
+      }
     };
     RowLoader<TableT> ld0, ld1;
     Cursor L{static_cast<int>(blockIdx.x), 0, 0, 0};
@@ -312,25 +353,35 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       issue(L, ld1); advance(L);
     }
     int it = 0;
+    uint32_t n = 0;   // running pass index: pass n lives in ld0 (even) / ld1 (odd)
+    long long t_prod_wait = 0;
+    const long long t_prod0 = now();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int slot = it % 3;
       const int next_tile = tile + gridDim.x;
       if (next_tile < ntiles) load_meta(next_tile, (it + 1) % 3);   // the load cursor enters it 2 passes early
       named_bar_sync(2, PROD_THREADS);
       for (int c = 0; c < nchunks; ++c) {
+        const long long tw0 = now();
         mbar_wait(bar(BAR_A_EMPTY + stage), phase ^ 1u, p.err, 0x10);
+        t_prod_wait += now() - tw0;
         const uint32_t panel = smem_base + sm.a + static_cast<uint32_t>(stage) * PANEL_BYTES;
-        consume(slot, 0, ld0, panel); issue(L, ld0); advance(L);
-        consume(slot, 1, ld1, panel); issue(L, ld1); advance(L);
-        consume(slot, 2, ld0, panel); issue(L, ld0); advance(L);
-        consume(slot, 3, ld1, panel); issue(L, ld1); advance(L);
+#pragma unroll
+        for (int q = 0; q < PPC; ++q, ++n) {
+          if (n & 1u) { consume(slot, q, ld1, panel); issue(L, ld1); }
+          else { consume(slot, q, ld0, panel); issue(L, ld0); }
+          advance(L);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_A_FULL + stage));
         if (++stage == nstage_a) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == W_B1) {
+    if (pt == 0) { put(0, now() - t_prod0); put(1, t_prod_wait); }
+  } else if (warp >= W_G1) {
+   setmaxnreg_dec<REGS_UTIL>();
+   if (warp == W_B1) {
     // =========================== [W0;Wy] chunk loader =========================================
     if (lane == 0) {
       int stage = 0;
@@ -359,6 +410,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         for (int l = 1; l <= nhid; ++l) load(blob_hidden(g, l), BLOB_BYTES);
         if (view) { load(blob_wd1z(g), BLOB_BYTES); load(blob_wd1e(g), PANEL_BYTES); }
         if (kTrain) {
+          if (p.debug & 4) continue;
           if (view) load(blob_wd1z(g), BLOB_BYTES);
           for (int l = nhid; l >= 1; --l) load(blob_hidden(g, l), BLOB_BYTES);
         }
@@ -371,31 +423,42 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       uint32_t pa = 0, pb = 0;
       uint32_t gph[2] = {0u, 0u};
       int it = 0;
+      long long t_g = 0, t_a = 0, t_b = 0, t_st = 0;
+      const long long t_g1_0 = now();
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
+        const long long tg0 = now();
         mbar_wait(bar(BAR_G_EMPTY + buf), gph[buf] ^ 1u, p.err, 0x33);  // chain of tile it-2 left this buffer
+        t_g += now() - tg0;
         gph[buf] ^= 1u;
         tc_fence_after();
         const uint32_t dcol = tmem_base + 256u * static_cast<uint32_t>(buf);
         uint8_t* xdst = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride + stash_off_x(g, 0) : nullptr;
         for (int c = 0; c < nchunks; ++c) {
+          const long long ta0 = now();
           mbar_wait(bar(BAR_A_FULL + sa), pa, p.err, 0x30);
+          const long long ta1 = now();
           mbar_wait(bar(BAR_B1_FULL + sb), pb, p.err, 0x32);
+          const long long ta2 = now();
+          t_a += ta1 - ta0; t_b += ta2 - ta1;
           tc_fence_after();
           const uint32_t abase = smem_base + sm.a + static_cast<uint32_t>(sa) * PANEL_BYTES;
           const uint32_t bbase = smem_base + sm.b1 + static_cast<uint32_t>(sb) * BLOB_BYTES;
+          const uint32_t alo = umma_desc_lo(abase, 0), blo = umma_desc_lo(bbase, 0);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            umma_f16(dcol, umma_desc_sw128(abase + kk * 32u, 0, 1024), umma_desc_sw128(bbase + kk * 32u, 0, 1024),
-                     IDESC_N256, (c > 0 || kk > 0) ? 1u : 0u);
+            umma_f16(dcol, umma_desc_join(alo + 2u * kk, DESC_HI), umma_desc_join(blo + 2u * kk, DESC_HI), IDESC_N256,
+                     (c > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(bar(BAR_A_EMPTY + sa));
           umma_commit(bar(BAR_B1_EMPTY + sb));
           if (kTrain) {
             // x panel -> stash (the B operand of dW0 / dWy in the wgrad kernel)
-            bulk_s2g(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES);
+            if (!(p.debug & 1)) bulk_s2g(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES);
             bulk_commit();
+            const long long ts0 = now();
             bulk_wait_read<0>();
+            t_st += now() - ts0;
             mbar_arrive(bar(BAR_A_EMPTY + sa));
           }
           if (++sa == nstage_a) { sa = 0; pa ^= 1u; }
@@ -403,6 +466,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         }
         umma_commit(bar(BAR_G_FULL + buf));
       }
+      put(4, now() - t_g1_0); put(5, t_g); put(6, t_a); put(7, t_b); put(8, t_st);
       if (kTrain) bulk_wait<0>();
     }
   } else if (warp == W_CH) {
@@ -411,26 +475,42 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       uint32_t pact = 0, pb2 = 0;
       uint32_t wr = 0;  // running index of the activation-buffer write being consumed (buffer = wr & 1)
       int it = 0;
-      auto wait_act = [&]() { mbar_wait(bar(BAR_ACT_READY), pact, p.err, 0x31); pact ^= 1u; tc_fence_after(); };
-      auto wait_b2 = [&]() { mbar_wait(bar(BAR_B2_FULL), pb2, p.err, 0x34); pb2 ^= 1u; tc_fence_after(); };
+      long long t_act = 0, t_b2 = 0;
+      const long long t_ch0 = now();
+      auto wait_act = [&]() {
+        const long long t0 = now();
+        mbar_wait(bar(BAR_ACT_READY), pact, p.err, 0x31); pact ^= 1u; tc_fence_after();
+        t_act += now() - t0;
+      };
+      auto wait_b2 = [&]() {
+        const long long t0 = now();
+        mbar_wait(bar(BAR_B2_FULL), pb2, p.err, 0x34); pb2 ^= 1u; tc_fence_after();
+        t_b2 += now() - t0;
+      };
       const uint32_t bbase = smem_base + sm.b2;
       auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (w & 1u) * BLOB_BYTES; };
-      // D[128 x 128] (+)= A[128 x 64*npanel] * B^T, both K-major two-panel images
+      const uint32_t blo_k = umma_desc_lo(bbase, 0);             // weight image read K-major (forward)
+      const uint32_t blo_mn = umma_desc_lo(bbase, PANEL_BYTES);   // the same image read MN-major (dgrad)
+      // D[128 x 128] (+)= A[128 x 64*npanel] * B^T, both K-major panel images
       auto mma_fwd = [&](uint32_t dcol, uint32_t abase, int npanel, bool acc_first) {
-        for (int kk = 0; kk < 4 * npanel; ++kk) {
-          const uint32_t o = static_cast<uint32_t>(kk >> 2) * PANEL_BYTES + static_cast<uint32_t>(kk & 3) * 32u;
-          umma_f16(dcol, umma_desc_sw128(abase + o, 0, 1024), umma_desc_sw128(bbase + o, 0, 1024), IDESC_N128,
-                   (acc_first || kk > 0) ? 1u : 0u);
+        const uint32_t alo = umma_desc_lo(abase, 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          if (kk < 4 * npanel) {
+            const uint32_t o = static_cast<uint32_t>(kk >> 2) * (PANEL_BYTES >> 4) + static_cast<uint32_t>(kk & 3) * 2u;
+            umma_f16(dcol, umma_desc_join(alo + o, DESC_HI), umma_desc_join(blo_k + o, DESC_HI), IDESC_N128,
+                     (acc_first || kk > 0) ? 1u : 0u);
+          }
         }
       };
       // dh[128 x 128] = dz[128 x 128] * W: A K-major, B = the forward weight image read MN-major (K = row n)
       auto mma_dgrad = [&](uint32_t dcol, uint32_t abase) {
+        const uint32_t alo = umma_desc_lo(abase, 0);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t oa = static_cast<uint32_t>(kk >> 2) * PANEL_BYTES + static_cast<uint32_t>(kk & 3) * 32u;
-          umma_f16(dcol, umma_desc_sw128(abase + oa, 0, 1024),
-                   umma_desc_sw128(bbase + static_cast<uint32_t>(kk) * 2048u, PANEL_BYTES, 1024), IDESC_N128_BMN,
-                   kk > 0 ? 1u : 0u);
+          const uint32_t oa = static_cast<uint32_t>(kk >> 2) * (PANEL_BYTES >> 4) + static_cast<uint32_t>(kk & 3) * 2u;
+          umma_f16(dcol, umma_desc_join(alo + oa, DESC_HI), umma_desc_join(blo_mn + static_cast<uint32_t>(kk) * 128u, DESC_HI),
+                   IDESC_N128_BMN, kk > 0 ? 1u : 0u);
         }
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -457,7 +537,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         if (kTrain) {
           wait_act();   // h_nb in buffer wr, dz_nb in buffer wr+1
           ++wr;
-          for (int l = nb; l >= 1; --l, ++wr) {
+          for (int l = (p.debug & 4) ? 0 : nb; l >= 1; --l, ++wr) {
             wait_b2();
             mma_dgrad(base, hbuf(wr));                       // dh_{l-1} = dz_l * W_l
             umma_commit(bar(BAR_B2_EMPTY));
@@ -467,9 +547,12 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           ++wr;                                              // dz_0: written by the epilogue, consumed by nobody here
         }
       }
+      put(10, now() - t_ch0); put(11, t_act); put(12, t_b2);
     }
-  } else if (warp < EPI_WARPS) {
+   }
+  } else {
     // =========================== epilogue warps ================================================
+    setmaxnreg_inc<REGS_EPI>();
     const int r = tid;  // tile row == TMEM lane
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const float* s_bias = reinterpret_cast<const float*>(smem + sm.bias);
@@ -482,11 +565,19 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     float gb[3] = {0.f, 0.f, 0.f};
     uint32_t mk[MAX_MMA_LAYERS][4];   // ReLU masks of this row (local memory; indexed by layer)
 
-    auto wait_done = [&]() { mbar_wait(bar(BAR_MMA_DONE), pdone, p.err, 0x40); pdone ^= 1u; tc_fence_after(); };
+    long long t_done = 0, t_gfull = 0, t_sync = 0, t_store = 0;
+    const long long t_epi0 = now();
+    auto wait_done = [&]() {
+      const long long t0 = now();
+      mbar_wait(bar(BAR_MMA_DONE), pdone, p.err, 0x40); pdone ^= 1u; tc_fence_after();
+      t_done += now() - t0;
+    };
     auto sync_epi = [&]() {
+      const long long t0 = now();
       fence_proxy_async_smem();
       tc_fence_before();
       named_bar_sync(1, EPI_THREADS);
+      t_sync += now() - t0;
     };
     auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (w & 1u) * BLOB_BYTES; };
 
@@ -535,9 +626,11 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       // ---- forward layers 0..nb-1: h_l = relu(z_l + b_l) -> activation panel -------------------
       for (int l = 0; l < nb; ++l, ++wr) {
         if (l == 0) {
+          const long long t0 = now();
           mbar_wait(bar(BAR_G_FULL + buf), gph[buf], p.err, 0x41);
           gph[buf] ^= 1u;
           tc_fence_after();
+          t_gfull += now() - t0;
         } else {
           wait_done();
         }
@@ -549,25 +642,27 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           uint32_t v[32];
           tmem_ld32(col0 + 32u * cb, v);
           tmem_ld_wait();
-          float h[32];
-          uint32_t m = 0;
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + l * HID + 32 * cb);
+          uint32_t w[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float z = __uint_as_float(v[j]) + s_bias[l * HID + 32 * cb + j];
-            m |= (z > 0.f ? 1u : 0u) << j;
-            h[j] = fminf(fmaxf(z, 0.f), 60000.f);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i];
+            w[2 * i] = pack_half2_relu_sat(__uint_as_float(v[4 * i]) + bb.x, __uint_as_float(v[4 * i + 1]) + bb.y);
+            w[2 * i + 1] = pack_half2_relu_sat(__uint_as_float(v[4 * i + 2]) + bb.z, __uint_as_float(v[4 * i + 3]) + bb.w);
           }
-          mbits[cb] = m;
-          store_act_chunk(hb, r, cb, h);
+          if (kTrain) mbits[cb] = relu_mask16(w);
+          store_act_words(hb, r, cb, w);
         }
         if (kTrain) { mk[l][0] = mbits[0]; mk[l][1] = mbits[1]; mk[l][2] = mbits[2]; mk[l][3] = mbits[3]; }
         sync_epi();
         if (tid == 0) {
           if (kTrain) {
-            bulk_s2g(stash_tile + stash_off_h(g, l), hb, BLOB_BYTES);
+            if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_h(g, l), hb, BLOB_BYTES);
             if (l == 0 && view) bulk_s2g(stash_tile + stash_off_e(g), smem_base + sm.e, PANEL_BYTES);
             bulk_commit();
+            const long long t0 = now();
             bulk_wait_read<1>();   // the buffer written next is free before the chain may continue
+            t_store += now() - t0;
           }
           mbar_arrive(bar(BAR_ACT_READY));
         }
@@ -585,20 +680,25 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           uint32_t v[32];
           tmem_ld32(col0 + 32u * cb, v);
           tmem_ld_wait();
-          float h[32];
-          uint32_t m = 0;
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + nb * HID + 32 * cb);
+          const float4* w0 = reinterpret_cast<const float4*>(s_wlast + 0 * HID + 32 * cb);
+          const float4* w1 = reinterpret_cast<const float4*>(s_wlast + 1 * HID + 32 * cb);
+          const float4* w2 = reinterpret_cast<const float4*>(s_wlast + 2 * HID + 32 * cb);
+          uint32_t w[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float z = __uint_as_float(v[j]) + s_bias[nb * HID + 32 * cb + j];
-            m |= (z > 0.f ? 1u : 0u) << j;
-            h[j] = fmaxf(z, 0.f);
-            y[0] = fmaf(s_wlast[0 * HID + 32 * cb + j], h[j], y[0]);
-            y[1] = fmaf(s_wlast[1 * HID + 32 * cb + j], h[j], y[1]);
-            y[2] = fmaf(s_wlast[2 * HID + 32 * cb + j], h[j], y[2]);
-            h[j] = fminf(h[j], 60000.f);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i], a0 = w0[i], a1 = w1[i], a2 = w2[i];
+            const float h0 = fmaxf(__uint_as_float(v[4 * i]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * i + 1]) + bb.y, 0.f);
+            const float h2 = fmaxf(__uint_as_float(v[4 * i + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * i + 3]) + bb.w, 0.f);
+            y[0] = fmaf(a0.w, h3, fmaf(a0.z, h2, fmaf(a0.y, h1, fmaf(a0.x, h0, y[0]))));
+            y[1] = fmaf(a1.w, h3, fmaf(a1.z, h2, fmaf(a1.y, h1, fmaf(a1.x, h0, y[1]))));
+            y[2] = fmaf(a2.w, h3, fmaf(a2.z, h2, fmaf(a2.y, h1, fmaf(a2.x, h0, y[2]))));
+            if (kTrain) { w[2 * i] = pack_half2_sat(h0, h1); w[2 * i + 1] = pack_half2_sat(h2, h3); }
           }
-          mbits[cb] = m;
-          if (kTrain) store_act_chunk(ha, r, cb, h);
+          if (kTrain) {
+            mbits[cb] = relu_mask16(w);
+            store_act_words(ha, r, cb, w);
+          }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) y[c] = sigmoidf_(y[c]);
@@ -642,28 +742,40 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           const uint32_t hb2 = hbuf(wr + 1);
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
-            float h[32];
+            const float4* w0 = reinterpret_cast<const float4*>(s_wlast + 0 * HID + 32 * cb);
+            const float4* w1 = reinterpret_cast<const float4*>(s_wlast + 1 * HID + 32 * cb);
+            const float4* w2 = reinterpret_cast<const float4*>(s_wlast + 2 * HID + 32 * cb);
+            uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = 32 * cb + j;
-              const float dh = dzl[0] * s_wlast[col] + dzl[1] * s_wlast[HID + col] + dzl[2] * s_wlast[2 * HID + col];
-              h[j] = ((mbits[cb] >> j) & 1u) ? dh : 0.f;
+            for (int i = 0; i < 8; ++i) {
+              const float4 a0 = w0[i], a1 = w1[i], a2 = w2[i];
+              const float d0 = fmaf(dzl[2], a2.x, fmaf(dzl[1], a1.x, dzl[0] * a0.x));
+              const float d1 = fmaf(dzl[2], a2.y, fmaf(dzl[1], a1.y, dzl[0] * a0.y));
+              const float d2 = fmaf(dzl[2], a2.z, fmaf(dzl[1], a1.z, dzl[0] * a0.z));
+              const float d3 = fmaf(dzl[2], a2.w, fmaf(dzl[1], a1.w, dzl[0] * a0.w));
+              w[2 * i] = apply_mask(pack_half2_sat(d0, d1), mbits[cb], 2 * i);
+              w[2 * i + 1] = apply_mask(pack_half2_sat(d2, d3), mbits[cb], 2 * i + 1);
             }
-            store_act_chunk(hb2, r, cb, h);
+            store_act_words(hb2, r, cb, w);
           }
           sync_epi();
           if (tid == 0) {
-            bulk_s2g(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES);
+            if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES);
             bulk_commit();
-            bulk_s2g(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES);
+            if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES);
             bulk_s2g(stash_tile + stash_off_dzlt(g), smem_base + sm.dzlt, DZLT_BYTES);
             bulk_commit();
             bulk_wait_read<1>();
             mbar_arrive(bar(BAR_ACT_READY));
           }
           wr += 2;
+          if (p.debug & 4) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_G_EMPTY + buf));
+          }
           // ---- dgrad chain: dz_l = dh_l * relu'(z_l), l = nb-1..0 --------------------------------
-          for (int lb = nb - 1; lb >= 0; --lb, ++wr) {
+          for (int lb = (p.debug & 4) ? -1 : nb - 1; lb >= 0; --lb, ++wr) {
             wait_done();
             const uint32_t hb = hbuf(wr);
             const uint32_t mm[4] = {mk[lb][0], mk[lb][1], mk[lb][2], mk[lb][3]};
@@ -672,10 +784,11 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
               uint32_t v[32];
               tmem_ld32(tb + 32u * cb, v);
               tmem_ld_wait();
-              float h[32];
+              uint32_t w[16];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) h[j] = ((mm[cb] >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
-              store_act_chunk(hb, r, cb, h);
+              for (int i = 0; i < 16; ++i)
+                w[i] = apply_mask(pack_half2_sat(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), mm[cb], i);
+              store_act_words(hb, r, cb, w);
             }
             if (lb == 0) {
               tc_fence_before();
@@ -685,7 +798,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             }
             sync_epi();
             if (tid == 0) {
-              bulk_s2g(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES);
+              if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES);
               bulk_commit();
               if (lb > 0) {
                 bulk_wait_read<1>();
@@ -696,6 +809,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         }
       }
     }
+    if (tid == 0) { put(16, now() - t_epi0); put(17, t_gfull); put(18, t_done); put(19, t_sync); put(20, t_store); }
     if (kTrain) {
       // ---- per-CTA partials: output-layer bias gradient, loss sums ------------------------------
 #pragma unroll

@@ -174,6 +174,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
+// The same descriptor split into its 32-bit halves: hi is a constant per (SBO, swizzle), lo advances with the
+// operand address (+ (bytes >> 4)); smem addresses stay below 2^18, so the 14-bit field never carries.
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // Instruction descriptor, kind::f16: F16 operands, F32 accumulator, M x N tile.
 //   [4,6) c_format=1 (F32)  [7,10) a_format=0 (F16)  [10,13) b_format=0 (F16)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
@@ -203,6 +216,17 @@ __device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// two floats -> packed f16x2 (lo, hi) with saturation to the finite range; the relu variant clamps negatives to +0
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_half2_relu_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {

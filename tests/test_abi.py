@@ -58,7 +58,7 @@ def test_production_config_sizes():
     assert cfg.k_pad == 1024
     assert ops.num_params(cfg) == 328579
     assert ops.packed_bytes(cfg) == (16 + 4) * 32768 + (5 * 128 + 3 * 128 + 4) * 4
-    assert ops.workspace_bytes(cfg, 4096, False) == 256
+    assert ops.workspace_bytes(cfg, 4096, False) == 65536
     assert ops.workspace_bytes(cfg, 4096, True) > 32 * 9 * 32768
 
 

@@ -273,3 +273,91 @@ def test_large_batch_linearity_of_gradients():
     ref = O.field_forward({n: p.detach().cpu() for n, p in m.state_dict().items()}, E, vids.cpu()[idx], bary.cpu()[idx])
     err = (p_all.cpu()[idx] - ref).abs()
     assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN
+
+
+# ---------------------------------------------------------------------------------------------
+# fixed-step training: PSNR parity with the reference fp32 path (BASELINE.json: within 0.1 dB)
+# ---------------------------------------------------------------------------------------------
+PSNR_TOL_DB = 0.1
+
+
+def _training_problem(view, seed=0, V=1500, F_=2500, k=64, N=8192):
+    g = torch.Generator().manual_seed(seed)
+    E = torch.randn(V, k, generator=g)
+    E = (E / (E.max(0, keepdim=True).values - E.min(0, keepdim=True).values)).float()
+    faces = torch.stack([torch.randperm(V, generator=g)[:3] for _ in range(F_)])
+    fid = torch.randint(0, F_, (N,), generator=g)
+    vids = faces[fid]
+    u = torch.rand(N, 3, generator=g)
+    bary = (u / u.sum(-1, keepdim=True)).float()
+    normals = torch.nn.functional.normalize(torch.randn(F_, 3, generator=g), dim=-1)
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1)
+    dirs = torch.where(((-dirs * normals[fid]).sum(-1) < 0)[:, None], -dirs, dirs).float()
+    # smooth procedural colour of the hit point (+ a view-dependent tint when the branch is on)
+    x = O.gather_interpolate(E, vids, bary)
+    mix = torch.randn(k, 3, generator=g) * 1.5
+    logits = x @ mix
+    if view is not None:
+        logits = logits + 0.5 * (-dirs * normals[fid]).sum(-1, keepdim=True)
+    target = torch.sigmoid(logits)
+    return E, vids, bary, target, dirs, fid, normals
+
+
+@pytest.mark.parametrize("view_name", [None, "view_intrinsic"])
+def test_fixed_step_training_psnr_parity(view_name):
+    import types
+    from conftest import VIEW_CFGS
+    from inf_b200 import trainer
+    view = VIEW_CFGS[view_name] if view_name else None
+    # lr = the shipped configs' 1e-4 (intrinsic_cat.yaml:33).  At 10x that lr the fp32 reference itself moves by 1-2 dB
+    # when its initial weights are perturbed by 1e-3 relative (measured), so no implementation could hold 0.1 dB there.
+    k, L, skip, B, steps, lr = 64, 6, 3, 512, 400, 1e-4
+    E, vids, bary, target, dirs, fid, normals = _training_problem(view)
+    ntrain = 4096
+    params = O.make_params(k, num_layers=L, skip=skip, view=view, seed=5)
+    gi = torch.Generator().manual_seed(9)
+    idx_lists = [torch.randperm(ntrain, generator=gi)[:B] for _ in range(steps)]   # identical batches on both sides
+    kw = dict(num_layers=L, skip=skip)
+    if view is not None:
+        kw.update(view=view, unit_ray_dirs=dirs, hit_face_idxs=fid, face_normals=normals)
+    ref_params, ref_losses = O.adam_train_steps(params, E, vids, bary, target, idx_lists, lr=lr, **kw)
+    hold = slice(ntrain, None)
+    kw_h = dict(kw)
+    if view is not None:
+        kw_h.update(unit_ray_dirs=dirs[hold], hit_face_idxs=fid[hold])
+    with torch.no_grad():
+        pr = O.field_forward(ref_params, E, vids[hold], bary[hold], **kw_h)
+    n_hold = pr.shape[0]
+    psnr_ref = O.epoch_psnr(float(((pr - target[hold]) ** 2).sum()), n_hold)
+
+    cfg = dict(k=k, num_layers=L, mlp_hidden_dim=128, skip_layer_idx=skip)
+    mesh = None
+    if view is not None:
+        cfg["view_dependence"] = view
+        mesh = types.SimpleNamespace(face_normals=normals.numpy())
+    m = inf_b200.make_model(cfg, mesh=mesh)
+    m.load_state_dict(params)
+    m = m.to(DEV)
+    opt = torch.optim.Adam(m.parameters(), lr=lr)
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV)
+    dv, db, dt, dd, df = (t.to(DEV) for t in (vids, bary, target, dirs, fid))
+
+    def batch(sel):
+        b = {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": dv[sel].contiguous(),
+             "barycentric_coords": db[sel].contiguous(), "expected_rgbs": dt[sel].contiguous()}
+        if view is not None:
+            b["unit_ray_dirs"] = dd[sel].contiguous()
+            b["hit_face_idxs"] = df[sel].contiguous()
+        return b
+
+    losses = []
+    for idx in idx_lists:
+        loss, _ = trainer.train_step(m, opt, batch(idx.to(DEV)))                 # trainer.py:71-84
+        losses.append(loss)
+    _check_no_watchdog()
+    with torch.no_grad():
+        pg = m(batch(hold)).cpu()
+    psnr_gpu = O.epoch_psnr(float(((pg - target[hold]) ** 2).sum()), n_hold)   # trainer.py:254,263
+    assert losses[-1] < 0.8 * losses[0]                                          # it trained
+    assert abs(losses[-1] - ref_losses[-1]) < 5e-3
+    assert abs(psnr_gpu - psnr_ref) <= PSNR_TOL_DB, (psnr_gpu, psnr_ref)
