@@ -82,3 +82,108 @@ class RayDataLoader:
             batch["unit_ray_dirs"] = self.unit_ray_dirs[batch_idxs]
             batch["hit_face_idxs"] = self.face_idxs[batch_idxs]
         return batch
+
+
+class HostRayLoader:
+    """Batch producer for splits that live in (pinned) HOST memory: the 36-68 B/ray gather inputs are copied to the
+    device one batch ahead of the consumer on a dedicated copy stream, so the H2D transfer of batch i+1 overlaps the
+    kernels of batch i.  Same batch dict as :class:`RayDataLoader`; same index-select semantics
+    (ray_dataloader.py:115-145) when ``shuffle`` is on (the permutation is drawn on the host).
+
+    ``vertex_idxs_of_hit_faces`` / ``face_idxs`` may be int32 exactly as the reference stores them on disk
+    (mesh.py:513-516) -- the kernels consume either width and the values pass through bit-exactly -- which halves the
+    index bytes on the wire compared with the reference's int64 upcast (dataset.py:16,31).
+    """
+
+    def __init__(self, table, vertex_idxs_of_hit_faces, barycentric_coords, expected_rgbs=None, unit_ray_dirs=None,
+                 face_idxs=None, batch_size=1 << 17, shuffle=False, drop_last=False, device="cuda", generator=None,
+                 depth: int = 2):
+        if not isinstance(table, EigenTable):
+            raise TypeError("table must be an inf_b200.EigenTable (device resident)")
+        self.table = table
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("HostRayLoader feeds the CUDA path: device must be a CUDA device")
+
+        self.rebind(vertex_idxs_of_hit_faces, barycentric_coords, expected_rgbs, unit_ray_dirs, face_idxs)
+        self.N = self.host["vertex_idxs_of_hit_faces"].shape[0]
+        self.B = batch_size
+        self.shuffle, self.drop_last, self.generator = shuffle, drop_last, generator
+        self.num_batches = self.N // self.B if drop_last else (self.N + self.B - 1) // self.B
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(self.device)
+        # device staging ring; each slot: tensors + "copy done" / "consumer done" events
+        self.slots = []
+        for _ in range(depth):
+            bufs = {k: torch.empty((self.B,) + tuple(v.shape[1:]), dtype=v.dtype, device=self.device) for k, v in self.host.items()}
+            self.slots.append({"bufs": bufs, "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "used": False})
+        self.perm = None
+        self.h2d_bytes_per_ray = sum(v[0].numel() * v.element_size() for v in self.host.values())
+        self._next_issue = self._next_take = 0
+
+    def rebind(self, vertex_idxs_of_hit_faces, barycentric_coords, expected_rgbs=None, unit_ray_dirs=None, face_idxs=None):
+        """Point the loader at other host arrays of the same layout (staging buffers, streams and events are kept)."""
+        def pin(t):
+            if t is None:
+                return None
+            t = t.contiguous()
+            return t if t.is_pinned() else t.pin_memory()
+
+        host = {"vertex_idxs_of_hit_faces": pin(vertex_idxs_of_hit_faces), "barycentric_coords": pin(barycentric_coords),
+                "expected_rgbs": pin(expected_rgbs), "unit_ray_dirs": pin(unit_ray_dirs), "hit_face_idxs": pin(face_idxs)}
+        host = {k: v for k, v in host.items() if v is not None}
+        assert host["barycentric_coords"].dtype == torch.float32
+        if getattr(self, "slots", None):
+            old = self.host
+            assert host.keys() == old.keys() and all(host[k].dtype == old[k].dtype and host[k].shape[1:] == old[k].shape[1:]
+                                                     for k in host), "rebind needs the same keys / dtypes"
+            self.N = host["vertex_idxs_of_hit_faces"].shape[0]
+            self.num_batches = self.N // self.B if self.drop_last else (self.N + self.B - 1) // self.B
+        self.host = host
+        return self
+
+    def __len__(self):
+        return self.num_batches
+
+    def __iter__(self):
+        self.perm = torch.randperm(self.N, generator=self.generator) if self.shuffle else None
+        self._next_issue = self._next_take = 0
+        for _ in range(min(self.depth, self.num_batches)):
+            self._issue()
+        return self
+
+    def _issue(self):
+        i = self._next_issue
+        if i >= self.num_batches:
+            return
+        lo, hi = i * self.B, min((i + 1) * self.B, self.N)
+        slot = self.slots[i % self.depth]
+        with torch.cuda.stream(self.copy_stream):
+            if slot["used"]:
+                self.copy_stream.wait_event(slot["free"])       # the kernels that read this slot have finished
+            for k, src in self.host.items():
+                h = src[lo:hi] if self.perm is None else src[self.perm[lo:hi]].pin_memory()
+                slot["bufs"][k][: hi - lo].copy_(h, non_blocking=True)
+            slot["ready"].record(self.copy_stream)
+        slot["n"] = hi - lo
+        self._next_issue = i + 1
+
+    def __next__(self):
+        i = self._next_take
+        if i >= self.num_batches:
+            raise StopIteration
+        slot = self.slots[i % self.depth]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(slot["ready"])
+        n = slot["n"]
+        batch = {k: (v if n == self.B else v[:n]) for k, v in slot["bufs"].items()}
+        batch["eigenfunction_table"] = self.table
+        self._next_take = i + 1
+        # the slot handed out `depth` batches ago is reused by the copy of the batch issued now; its consumer is
+        # whatever the caller enqueued on the current stream before this call
+        if i >= 1:
+            prev = self.slots[(i - 1) % self.depth]
+            prev["free"].record(cur)
+            prev["used"] = True
+            self._issue()
+        return batch

@@ -49,6 +49,47 @@ class FieldRenderer:
         return out
 
     @torch.no_grad()
+    def predict_hits_host(self, vertex_idxs_of_hit_faces: torch.Tensor, barycentric_coords: torch.Tensor,
+                          unit_ray_dirs: Optional[torch.Tensor] = None, face_idxs: Optional[torch.Tensor] = None,
+                          chunk: int = 1 << 17, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host -> host inference of renderer.py:113-119: gather inputs in (pinned) host memory, RGB back in pinned
+        host memory.  The reference uploads the 4 KB/ray embedding per 2^15-ray chunk and blocks on ``.cpu()``; here the
+        36-68 B/ray inputs of chunk i+1 are copied while chunk i computes and the RGB of chunk i-1 is copied back, on
+        dedicated copy streams.  Returns after the last D2H copy has completed."""
+        from .ray_dataloader import HostRayLoader
+        self.model.eval()
+        M = vertex_idxs_of_hit_faces.shape[0]
+        if out is None:
+            out = torch.empty((M, 3), dtype=torch.float32).pin_memory()
+        if M == 0:
+            return out
+        key = (min(chunk, M), vertex_idxs_of_hit_faces.dtype, unit_ray_dirs is not None, face_idxs is not None)
+        if getattr(self, "_hl_key", None) == key and self._hl.table is self.table:
+            loader = self._hl.rebind(vertex_idxs_of_hit_faces, barycentric_coords, None, unit_ray_dirs, face_idxs)
+        else:
+            loader = HostRayLoader(self.table, vertex_idxs_of_hit_faces, barycentric_coords, None, unit_ray_dirs, face_idxs,
+                                   batch_size=min(chunk, M), device=self.device, depth=3)
+            self._hl, self._hl_key = loader, key
+        if not hasattr(self, "_d2h"):
+            self._d2h = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
+        lo = 0
+        keep = []
+        for batch in loader:
+            pred = self.model(batch)
+            n = pred.shape[0]
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(ev)
+                out[lo:lo + n].copy_(pred, non_blocking=True)
+            pred.record_stream(self._d2h)
+            keep.append(pred)
+            lo += n
+        self._d2h.synchronize()
+        return out
+
+    @torch.no_grad()
     def render_hits(self, vertex_idxs_of_hit_faces, barycentric_coords, hit_ray_idxs, obj_mask_1d=None,
                     unit_ray_dirs=None, face_idxs=None, eval_render: bool = False):
         """Canvas assembly of renderer.py:119-146 on the device; returns (H,W,3) numpy (or torch + hit idxs)."""

@@ -361,3 +361,80 @@ def test_fixed_step_training_psnr_parity(view_name):
     assert losses[-1] < 0.8 * losses[0]                                          # it trained
     assert abs(losses[-1] - ref_losses[-1]) < 5e-3
     assert abs(psnr_gpu - psnr_ref) <= PSNR_TOL_DB, (psnr_gpu, psnr_ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# data path: bit-exact pass-through of the gather inputs, host loaders
+# ---------------------------------------------------------------------------------------------
+def test_ray_dataloader_passes_gather_inputs_through_bit_exactly():
+    from inf_b200.ray_dataloader import RayDataLoader, HostRayLoader
+    c = load_golden("tf_k64")
+    N = c["vids"].shape[0]
+    dl = RayDataLoader(c["table"], "efuncs", c["vids"], c["bary"], c["target"], None, None, batch_size=100, shuffle=False,
+                       drop_last=False, device=DEV)
+    seen = 0
+    for b in dl:
+        n = b["expected_rgbs"].shape[0]
+        assert torch.equal(b["vertex_idxs_of_hit_faces"].cpu(), c["vids"][seen:seen + n])       # int64 as dataset.py:16
+        assert torch.equal(b["barycentric_coords"].cpu(), c["bary"][seen:seen + n])             # f32 bits untouched
+        assert torch.equal(b["expected_rgbs"].cpu(), c["target"][seen:seen + n])
+        seen += n
+    assert seen == N and len(dl) == 3
+    # host-resident split, int32 ids as stored on disk (mesh.py:513-516), copied one batch ahead
+    tab = inf_b200.EigenTable.from_dense(c["table"], device=DEV)
+    hl = HostRayLoader(tab, c["vids"].to(torch.int32), c["bary"], c["target"], batch_size=100, device=DEV)
+    m = _model_from(c)
+    seen, preds = 0, []
+    for b in hl:
+        n = b["expected_rgbs"].shape[0]
+        assert b["vertex_idxs_of_hit_faces"].dtype == torch.int32
+        assert torch.equal(b["vertex_idxs_of_hit_faces"].cpu().long(), c["vids"][seen:seen + n])
+        assert torch.equal(b["barycentric_coords"].cpu(), c["bary"][seen:seen + n])
+        with torch.no_grad():
+            preds.append(m(b).cpu())
+        seen += n
+    assert seen == N
+    assert (torch.cat(preds) - c["pred"]).abs().max().item() <= RGB_MAX
+
+
+def test_renderer_host_pipeline_matches_device_path_and_canvas():
+    from inf_b200.renderer import FieldRenderer
+    c = load_golden("tf_k64")
+    m = _model_from(c)
+    M = c["vids"].shape[0]
+    H, W = 20, 20
+    r = FieldRenderer(m, c["table"], H=H, W=W, device=DEV)
+    a = r.predict_hits(c["vids"], c["bary"]).cpu()
+    b = r.predict_hits_host(c["vids"].to(torch.int32), c["bary"], chunk=64)
+    assert torch.equal(a, b)                                   # chunking / index width do not change a single bit
+    assert (a - c["pred"]).abs().max().item() <= RGB_MAX
+    # canvas assembly of renderer.py:119-130: hits scattered by ray index, background elsewhere
+    hit = torch.randperm(H * W)[:M]
+    img = r.render_hits(c["vids"], c["bary"], hit)
+    flat = torch.from_numpy(img).reshape(-1, 3)
+    assert torch.equal(flat[hit], a)
+    rest = torch.ones(H * W, dtype=torch.bool); rest[hit] = False
+    assert torch.all(flat[rest] == 1.0)
+
+
+def test_graphed_train_step_equals_eager_steps():
+    # the CUDA-graph replay of the whole step (pack, forward/backward, wgrad, reduce, Adam) must reproduce eager steps
+    from inf_b200 import trainer
+    c = load_golden("tf_k64")
+    b = _batch(c)
+    runs = []
+    for graphed in (False, True):
+        m = _model_from(c)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+        gs = trainer.GraphedTrainStep(m, opt)
+        losses = []
+        for _ in range(5):
+            loss, pred = gs.step(b) if graphed else trainer.train_step(m, opt, b)
+            losses.append(loss)
+        runs.append((losses, [p.detach().clone() for p in m.parameters()], pred.clone()))
+    _check_no_watchdog()
+    (l0, p0, y0), (l1, p1, y1) = runs
+    assert l0 == l1
+    assert torch.equal(y0, y1)
+    for a, bb in zip(p0, p1):
+        assert torch.equal(a, bb)
