@@ -181,6 +181,11 @@ def workload_config(args, batch_override=None):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _say(msg):
+    if os.environ.get("INF_BENCH_VERBOSE"):
+        print(f"[bench r{os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch.distributed as dist
     import inf_b200
@@ -267,8 +272,10 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    _say("setup done")
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+    _say("warmup done")
     lib = _lib.load()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -282,6 +289,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     assert inf_b200.kernel_error_word(dev) == 0, "kernel watchdog fired"
 
+    _say("resident timing done")
     run_e2e(6 if train else 2)       # per staging slot: one eager step, one graph capture, then replays
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,6 +301,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = t_e2e.item()
+    _say("e2e timing done")
 
     # shipped batch size (intrinsic_cat.yaml:32) for context, same model/table
     small = None

@@ -98,29 +98,48 @@ class GraphedTrainStep:
         return tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in sorted(batch.items()) if torch.is_tensor(v)) + \
             (id(batch.get("eigenfunction_table")),)
 
-    def _eager(self, batch):
+    # The step is split at the gradient allreduce: [pack, forward/backward, wgrad, reduce] | NCCL | [loss, Adam].
+    # Single-process runs capture both halves into one graph; multi-rank runs capture them separately and issue
+    # the collective eagerly between the two replays (no NCCL call inside a capture).
+    def _front(self, batch):
         world = parallel.world_size(self.group)
         B = batch["expected_rgbs"].shape[0]
         self.optim.zero_grad(set_to_none=True)
-        sums, pred, flat = self.model.l1_step(batch, global_rays=B * world)
+        return self.model.l1_step(batch, global_rays=B * world)          # sums, pred, flat
+
+    def _back(self, sums, n_global):
+        loss = sums[0] / (3.0 * n_global)
+        self.optim.step()
+        return loss
+
+    def _eager(self, batch):
+        world = parallel.world_size(self.group)
+        sums, pred, flat = self._front(batch)
         if world > 1:
             parallel.allreduce_flat(flat, sums, self.group)
-        loss = sums[0] / (3.0 * B * world)
-        self.optim.step()
-        return loss, pred
+        return self._back(sums, batch["expected_rgbs"].shape[0] * world), pred
 
     def _capture(self, batch):
+        world = parallel.world_size(self.group)
+        n_global = batch["expected_rgbs"].shape[0] * world
         self.model._packed_key = None                       # record the operand re-pack inside the graph
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            loss, pred = self._eager(batch)
-        return g, loss, pred
+        g1 = torch.cuda.CUDAGraph()
+        if world == 1:
+            with torch.cuda.graph(g1):
+                loss, pred = self._eager(batch)
+            return (g1, None, None, None, loss, pred)
+        with torch.cuda.graph(g1):
+            sums, pred, flat = self._front(batch)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            loss = self._back(sums, n_global)
+        return (g1, g2, flat, sums, loss, pred)
 
     def step_async(self, batch):
         """Exactly one optimisation step per call.  The first call with a given set of input buffers runs eagerly
         (it also sizes the workspace and creates the optimiser state, which must exist before a capture: state
         tensors allocated during capture would be re-zeroed by every replay); the second call captures, and from
-        then on the step is one graph launch."""
+        then on the step is one graph launch (two around the allreduce when multi-rank)."""
         key = self._key(batch)
         ent = self.graphs.get(key)
         if ent is None:
@@ -129,8 +148,11 @@ class GraphedTrainStep:
             return self._eager(batch)
         if ent == "warm":
             ent = self.graphs[key] = self._capture(batch)
-        g, loss, pred = ent
-        g.replay()
+        g1, g2, flat, sums, loss, pred = ent
+        g1.replay()
+        if g2 is not None:
+            parallel.allreduce_flat(flat, sums, self.group)
+            g2.replay()
         self.model._packed_key = None                       # eager calls after this re-pack from the live parameters
         return loss, pred
 
