@@ -202,6 +202,9 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   {
     const char* e = getenv("INF_DEBUG");   // measurement only; bits 1|2|4 produce wrong gradients
     p.debug = e ? atoi(e) : 0;
+    const char* f = getenv("INF_PREFETCH");   // tuning knob: L2 prefetch distance of the gather in k-chunks
+    p.prefetch = f ? atoi(f) : 2;
+    if (p.prefetch < 0 || p.prefetch > 8 || d->input_mode == INF_INPUT_DENSE) p.prefetch = 0;
   }
   p.geo = geo_of(d);
   p.plan = make_wplan(p.geo);

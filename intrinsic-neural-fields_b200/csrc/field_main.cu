@@ -325,6 +325,10 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       }
     };
     auto quad_row = [&](int j) { return 8 * pw + 2 * j + (gq >> 1) + 4 * (gq & 1); };
+    // DRAM -> L2 prefetch, `pf` k-chunks at a time and `pf` chunks ahead of the loads: every table row is pulled
+    // from HBM in (pf * 64 * sizeof(TableT))-byte pieces (one DRAM page visit instead of pf separate 128/256-byte
+    // ones), through the bulk-copy engine, which does not occupy the LSU's outstanding-load slots.
+    const int pf = p.prefetch;
     auto issue = [&](const Cursor& k, RowLoader<TableT>& ld) {
       if (k.tile >= ntiles) return;
 #pragma unroll
@@ -334,6 +338,21 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
 #pragma unroll
         for (int j = 0; j < 3; ++j) roff[j] = static_cast<int64_t>(s_vid[e + j]) * p.row_stride;
         ld.load(u, table, roff, k.c * KC, s);
+        if (pf > 0 && s == 0 && (k.c % pf) == 0) {
+          int c2 = k.c + pf;
+          if (c2 < nchunks) {
+            const uint32_t bytes = static_cast<uint32_t>(min(pf, nchunks - c2) * KC * sizeof(TableT));
+#pragma unroll
+            for (int j = 0; j < 3; ++j) bulk_prefetch_l2(table + roff[j] + c2 * KC, bytes);
+          } else if (k.tile + static_cast<int>(gridDim.x) < ntiles) {
+            // first piece of the next tile's rows (its metadata slot was filled when this tile started)
+            const int e2 = ((k.slot + 1) % 3) * 384 + 3 * quad_row(k.q * QUADS + u);
+            const uint32_t bytes = static_cast<uint32_t>(min(pf, nchunks) * KC * sizeof(TableT));
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              bulk_prefetch_l2(table + static_cast<int64_t>(s_vid[e2 + j]) * p.row_stride, bytes);
+          }
+        }
       }
     };
     auto consume = [&](int slot, int q, const RowLoader<TableT>& ld, uint32_t panel) {

@@ -17,7 +17,7 @@ if os.path.exists(lcsv):
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out, f"{tag}_launches.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-        f.write(f"# command: python bench.py --steps 2 --warmup 3 --no-cpu-baseline   total {tot/1e3:.1f} us over {sum(v[0] for v in agg.values())} launches\n")
+        f.write(f"# command: python bench.py --steps 2 --warmup 3 --skip-e2e   total {tot/1e3:.1f} us over {sum(v[0] for v in agg.values())} launches\n")
         f.write(f"{'total_us':>10} {'n':>5} {'avg_us':>9} {'max_us':>9} {'share':>6}  kernel\n")
         for k, (n, v, mx) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{v/1e3:10.1f} {n:5d} {v/n/1e3:9.1f} {mx/1e3:9.1f} {100*v/tot:5.1f}%  {k}\n")
