@@ -203,8 +203,11 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
     const char* e = getenv("INF_DEBUG");   // measurement only; bits 1|2|4 produce wrong gradients
     p.debug = e ? atoi(e) : 0;
     const char* f = getenv("INF_PREFETCH");   // tuning knob: L2 prefetch distance of the gather in k-chunks
-    p.prefetch = f ? atoi(f) : 2;
+    p.prefetch = f ? atoi(f) : (d->table_dtype == INF_TABLE_F16 ? 0 : 2);   // fp16 rows: the L2::256B load hint already covers it
     if (p.prefetch < 0 || p.prefetch > 8 || d->input_mode == INF_INPUT_DENSE) p.prefetch = 0;
+    const char* w = getenv("INF_PREFETCH_WGRAD");
+    p.prefetch_wgrad = w ? atoi(w) : 0;   // measured: prefetches through the bulk-copy engine compete with its loads
+    if (p.prefetch_wgrad < 0 || p.prefetch_wgrad > 32) p.prefetch_wgrad = 0;
   }
   p.geo = geo_of(d);
   p.plan = make_wplan(p.geo);

@@ -201,14 +201,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int a_mn_maj
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
   return v;

@@ -48,7 +48,7 @@ class _FieldFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, table, vids, bary, dense, dirs, face_idxs, face_normals, *params):
-        packed = module._packed_weights()
+        packed = module._packed_weights(force=True)
         ctx.module, ctx.dense = module, dense
         ctx.save_for_backward(table, vids, bary, dirs, face_idxs, face_normals)
         return torch.ops.inf_b200.field_forward(table, vids, bary, packed, dirs, face_idxs, face_normals,
@@ -82,17 +82,29 @@ class _FusedFieldBase(nn.Module):
     def _view_inputs(self, batch):
         return None, None, None
 
-    def _packed_weights(self) -> torch.Tensor:
-        """Operand images of the current parameter values (re-packed when any parameter changed)."""
+    def _packed_weights(self, force: bool = False) -> torch.Tensor:
+        """Operand images of the current parameter values.
+
+        Re-packed (one 5 us kernel) on every training-mode call: in-place optimiser kernels such as
+        ``torch.optim.Adam(fused=True)`` update the parameters WITHOUT bumping their version counters, so a
+        version-keyed cache would silently serve stale weights.  In eval mode the images are cached, keyed on the
+        parameters' storage and version; ``train()`` / ``eval()`` and :meth:`invalidate_packed` drop the cache."""
         params = self._ordered_params()
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is None or self._packed_key != key or self._packed.device != params[0].device:
+        if force or self._packed is None or self._packed_key != key or self._packed.device != params[0].device:
             with torch.no_grad():
                 self._packed = ops.pack_weights(self.cfg, [p.detach().contiguous() for p in params], None)
             self._packed_key = key
         if self._layout is None:
             self._layout = ops.param_layout(self.cfg)
         return self._packed
+
+    def invalidate_packed(self):
+        self._packed_key = None
+
+    def train(self, mode: bool = True):
+        self._packed_key = None
+        return super().train(mode)
 
     def __deepcopy__(self, memo):
         # trainer.py:67,274 deep-copies the model; cached device buffers are rebuilt lazily
@@ -127,8 +139,8 @@ class _FusedFieldBase(nn.Module):
         params = self._ordered_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, *params)
-        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(), dirs, face_idxs, normals,
-                                                self.cfg.key(), dense)
+        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(force=self.training), dirs,
+                                                face_idxs, normals, self.cfg.key(), dense)
 
     # ---- fused training pass -----------------------------------------------------------------------
     def l1_step(self, batch: Dict[str, torch.Tensor], global_rays: Optional[int] = None,
@@ -146,8 +158,8 @@ class _FusedFieldBase(nn.Module):
         B = target.shape[0]
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
         pred, flat, sums = torch.ops.inf_b200.field_forward_backward(
-            table, vids, bary, self._packed_weights(), target, None, dirs, face_idxs, normals, self.cfg.key(), dense,
-            scale)
+            table, vids, bary, self._packed_weights(force=True), target, None, dirs, face_idxs, normals, self.cfg.key(),
+            dense, scale)
         if flat_grad is not None:
             flat_grad.copy_(flat)
             flat = flat_grad

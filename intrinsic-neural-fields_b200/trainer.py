@@ -122,7 +122,6 @@ class GraphedTrainStep:
     def _capture(self, batch):
         world = parallel.world_size(self.group)
         n_global = batch["expected_rgbs"].shape[0] * world
-        self.model._packed_key = None                       # record the operand re-pack inside the graph
         g1 = torch.cuda.CUDAGraph()
         if world == 1:
             with torch.cuda.graph(g1):
@@ -144,7 +143,6 @@ class GraphedTrainStep:
         ent = self.graphs.get(key)
         if ent is None:
             self.graphs[key] = "warm"
-            self.model._packed_key = None
             return self._eager(batch)
         if ent == "warm":
             ent = self.graphs[key] = self._capture(batch)
@@ -153,7 +151,7 @@ class GraphedTrainStep:
         if g2 is not None:
             parallel.allreduce_flat(flat, sums, self.group)
             g2.replay()
-        self.model._packed_key = None                       # eager calls after this re-pack from the live parameters
+        self.model.invalidate_packed()                      # the replay changed the parameters behind torch's back
         return loss, pred
 
     def step(self, batch) -> Tuple[float, torch.Tensor]:

@@ -438,3 +438,23 @@ def test_graphed_train_step_equals_eager_steps():
     assert torch.equal(y0, y1)
     for a, bb in zip(p0, p1):
         assert torch.equal(a, bb)
+
+
+def test_fused_adam_without_version_bump_is_not_served_stale_weights():
+    # torch.optim.Adam(fused=True) updates parameters in place WITHOUT bumping ._version; the operand images must follow
+    from inf_b200 import trainer
+    c = load_golden("tf_k64")
+    b = _batch(c)
+    out = []
+    for fused in (False, True):
+        m = _model_from(c)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-2, fused=fused)
+        losses = [trainer.train_step(m, opt, b)[0] for _ in range(4)]
+        m.eval()
+        with torch.no_grad():
+            out.append((losses, m(b).cpu()))
+    (l0, y0), (l1, y1) = out
+    assert l0[0] == l1[0]
+    assert max(abs(a - bb) for a, bb in zip(l0, l1)) < 1e-4       # same trajectory (fused vs foreach arithmetic differs by ulps)
+    assert l0[-1] < l0[0] and l1[-1] < l1[0] and len(set(l1)) == 4   # stale operand images would freeze the loss
+    assert (y0 - y1).abs().max().item() < 1e-2                        # eval after train() -> eval() sees the last update
