@@ -17,6 +17,8 @@
  *                          renderer.py:113-118 per-chunk model(batch) of Renderer.render
  *   inf_forward_backward   trainer.py:71-84 Trainer._train_step (forward, loss, backward; Adam
  *                          stays torch.optim.Adam), config.py:117-118 (L1 = F.l1_loss, mean)
+ *   inf_train_step         the same plus config.py:108 torch.optim.Adam(model.parameters(), lr).step() and the refresh
+ *   inf_adam_pack_step     of the operand images, fused into the gradient-reduction kernel (trainer.py:78-82)
  *   inf_relayout_table     mesh.py:53-108   tail of load_first_k_eigenfunctions (dense (V,k) f32
  *                          table -> device-resident padded table the kernels gather from)
  *   inf_pack_weights       model.py:42-96   parameter tensors of TextureField (state_dict order)
@@ -44,7 +46,7 @@
 extern "C" {
 #endif
 
-#define INF_ABI_VERSION 2
+#define INF_ABI_VERSION 3
 
 /* error codes */
 #define INF_OK 0
@@ -116,6 +118,20 @@ typedef struct InfGrads {
   float* loss_sums;  /* 2 f32: sum|pred-target| and sum (pred-target)^2 over this call's rays */
 } InfGrads;
 
+/* Optimiser state of inf_train_step / inf_adam_pack_step: torch.optim.Adam defaults semantics (no weight decay, no
+ * amsgrad).  params / exp_avg / exp_avg_sq are flat f32 vectors of inf_num_params(desc) elements in state_dict order. */
+typedef struct InfAdam {
+  float* params;      /* master parameters, updated in place                                          */
+  float* exp_avg;     /* first moment                                                                  */
+  float* exp_avg_sq;  /* second moment                                                                 */
+  void* packed;       /* operand images (inf_pack_weights layout); the live entries are rewritten      */
+  const int32_t* step_dev; /* optional DEVICE counter holding t (read by the kernel; lets a CUDA graph replay   */
+                      /* the step with a changing t); when null, `step` below is used                  */
+  float lr, beta1, beta2, eps;
+  int32_t step;       /* 1-based step count t of THIS update (bias corrections 1 - beta^t)             */
+  int32_t reserved0;
+} InfAdam;
+
 /* version / errors */
 int inf_version(void);
 const char* inf_last_error(void);
@@ -142,6 +158,14 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream);
 
 /* fused training pass: pred, loss sums and all parameter gradients (scaled by grad_scale). */
 int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, void* stream);
+
+/* inf_forward_backward followed by an Adam step on the flat master parameters and the refresh of the operand images,
+ * all inside the gradient-reduction kernel (single-GPU training step in three launches).  g->flat still receives the
+ * gradient.  `t->packed` (read by this step's forward) and `adam->packed` (written at the end) may be the same buffer. */
+int inf_train_step(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, void* stream);
+
+/* Adam + operand refresh from an already reduced gradient (multi-GPU: call after the allreduce of g->flat). */
+int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* adam, void* stream);
 
 /* Materialising gather, mesh.py:313-324 get_k_eigenfunc_vec_vals as one kernel:
  * out (B,k) f32 = sum_j bary[:,j] * table[vids[:,j], :k].  For callers that need the dense embedding

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libinf_field.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 IDX_I32, IDX_I64 = 0, 1
 TABLE_F32, TABLE_F16 = 0, 1
 INPUT_GATHER, INPUT_DENSE = 0, 1
@@ -46,6 +46,12 @@ class InfGrads(C.Structure):
     _fields_ = [("flat", C.c_void_p), ("loss_sums", C.c_void_p)]
 
 
+class InfAdam(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("packed", C.c_void_p),
+                ("step_dev", C.c_void_p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("step", C.c_int32), ("reserved0", C.c_int32)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "inf_version": (C.c_int, []),
@@ -61,6 +67,8 @@ EXPORTS = {
     "inf_pack_weights": (C.c_int, [C.POINTER(InfDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "inf_forward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p]),
     "inf_forward_backward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.POINTER(InfGrads), C.c_void_p]),
+    "inf_train_step": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.POINTER(InfGrads), C.POINTER(InfAdam), C.c_void_p]),
+    "inf_adam_pack_step": (C.c_int, [C.POINTER(InfDesc), C.c_void_p, C.POINTER(InfAdam), C.c_void_p]),
     "inf_gather_interpolate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]),
     "inf_profile_enable": (C.c_int, [C.c_int]),

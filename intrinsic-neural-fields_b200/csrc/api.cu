@@ -2,6 +2,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -81,6 +82,8 @@ struct ParamInfo {
   int64_t off;
   int rows, cols;
   int kind, a, b, split;  // ReduceSeg fields
+  int layer;
+  int64_t pair_off;
 };
 
 // state_dict order (model.py:42-96, layers.py:50-58; with the view branch the spatial MLP comes first under
@@ -92,7 +95,10 @@ int build_param_table(const InfDesc* d, ParamInfo* out, int64_t* total) {
   int64_t off = 0;
   const int L = d->num_layers;
   auto add = [&](int rows, int cols, int kind, int a, int b = -1, int split = 1 << 30) {
-    out[n++] = ParamInfo{off, rows, cols, kind, a, b, split};
+    int layer = -1;
+    if (kind == 0) layer = (a == 0) ? 0 : d->skip;
+    else if (kind == 1 || kind == 2) layer = plan.u[a].layer;
+    out[n++] = ParamInfo{off, rows, cols, kind, a, b, split, layer, -1};
     off += static_cast<int64_t>(rows) * cols;
   };
   for (int i = 0; i < L; ++i) {
@@ -101,6 +107,8 @@ int build_param_table(const InfDesc* d, ParamInfo* out, int64_t* total) {
       add(HID, 1, 2, plan.unit_bias[i]);        // Lx.bias
       add(HID, d->k, 0, 1);                     // Ly.weight
       add(HID, 1, 2, plan.unit_bias[i]);        // Ly.bias (same gradient as Lx.bias)
+      out[n - 3].pair_off = out[n - 1].off;     // the optimiser tail updates both biases from the Lx.bias thread
+      out[n - 1].pair_off = -2;
     } else if (i == 0) {
       add(HID, d->k, 0, 0);
       add(HID, 1, 2, plan.unit_bias[0]);
@@ -339,7 +347,34 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream) {
   return INF_OK;
 }
 
-int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, void* stream) {
+static int check_adam(const InfAdam* a) {
+  if (a == nullptr) return INF_OK;
+  if (!a->params || !a->exp_avg || !a->exp_avg_sq || !a->packed)
+    return fail(INF_ERR_BAD_ARG, "adam: params / exp_avg / exp_avg_sq / packed must be non-null");
+  if ((a->step_dev == nullptr && a->step < 1) || !(a->lr >= 0.f) || !(a->beta1 >= 0.f && a->beta1 < 1.f) || !(a->beta2 >= 0.f && a->beta2 < 1.f) || !(a->eps >= 0.f))
+    return fail(INF_ERR_BAD_ARG, "adam: bad hyper-parameters (step=%d lr=%g betas=%g,%g eps=%g)", a->step, a->lr, a->beta1, a->beta2, a->eps);
+  return INF_OK;
+}
+
+static AdamParams adam_params(const InfAdam* a) {
+  AdamParams ap{};
+  if (a == nullptr) return ap;
+  ap.params = a->params; ap.exp_avg = a->exp_avg; ap.exp_avg_sq = a->exp_avg_sq;
+  ap.packed = reinterpret_cast<uint8_t*>(a->packed);
+  ap.step_dev = a->step_dev;
+  ap.lr = a->lr;
+  const int tstep = a->step < 1 ? 1 : a->step;
+  const double bc1 = 1.0 - pow(static_cast<double>(a->beta1), tstep);
+  const double bc2 = 1.0 - pow(static_cast<double>(a->beta2), tstep);
+  ap.step_size = static_cast<float>(static_cast<double>(a->lr) / bc1);
+  ap.bc2_sqrt = static_cast<float>(sqrt(bc2));
+  ap.beta1 = a->beta1; ap.beta2 = a->beta2; ap.eps = a->eps;
+  ap.omb1 = static_cast<float>(1.0 - static_cast<double>(a->beta1));
+  ap.omb2 = static_cast<float>(1.0 - static_cast<double>(a->beta2));
+  return ap;
+}
+
+static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, void* stream) {
   int rc = check_desc(desc);
   if (rc != INF_OK) return rc;
   rc = check_tensors(desc, t, true);
@@ -349,6 +384,7 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   ParamInfo pi[INF_MAX_PARAMS];
   int64_t total = 0;
   const int nparam = build_param_table(desc, pi, &total);
+  if (desc->n_rays == 0 && adam != nullptr) return fail(INF_ERR_BAD_ARG, "inf_train_step needs at least one ray");
   if (desc->n_rays == 0) {
     cudaError_t e = cudaMemsetAsync(g->flat, 0, static_cast<size_t>(total) * 4, st);
     if (e == cudaSuccess && g->loss_sums) e = cudaMemsetAsync(g->loss_sums, 0, 8, st);
@@ -398,7 +434,7 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
   ReduceParams rp{};
   rp.nseg = nparam;
   for (int i = 0; i < nparam; ++i)
-    rp.seg[i] = ReduceSeg{pi[i].off, pi[i].rows, pi[i].cols, pi[i].kind, pi[i].a, pi[i].b, pi[i].split};
+    rp.seg[i] = ReduceSeg{pi[i].off, pi[i].rows, pi[i].cols, pi[i].kind, pi[i].a, pi[i].b, pi[i].split, pi[i].layer, pi[i].pair_off};
   rp.total = total;
   rp.partw = p.partw;
   rp.part1 = p.part1;
@@ -413,12 +449,49 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
     base += gh[s];
   }
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
+  rp.do_reduce = 1;
+  rp.adam = adam_params(adam);
   rp.geo = geo;
   rp.plan = plan;
   e = launch_field_reduce(rp, st);
   prof_record(slot, 3, st);
   if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
   if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel launch");
+  return INF_OK;
+}
+
+int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, void* stream) {
+  return run_forward_backward(desc, t, g, nullptr, stream);
+}
+
+int inf_train_step(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, void* stream) {
+  if (adam == nullptr) return fail(INF_ERR_BAD_ARG, "adam is null");
+  int rc = check_adam(adam);
+  if (rc != INF_OK) return rc;
+  return run_forward_backward(desc, t, g, adam, stream);
+}
+
+int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* adam, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != INF_OK) return rc;
+  if (flat_grad == nullptr || adam == nullptr) return fail(INF_ERR_BAD_ARG, "flat_grad / adam must be non-null");
+  rc = check_adam(adam);
+  if (rc != INF_OK) return rc;
+  ParamInfo pi[INF_MAX_PARAMS];
+  int64_t total = 0;
+  const int nparam = build_param_table(desc, pi, &total);
+  ReduceParams rp{};
+  rp.nseg = nparam;
+  for (int i = 0; i < nparam; ++i)
+    rp.seg[i] = ReduceSeg{pi[i].off, pi[i].rows, pi[i].cols, pi[i].kind, pi[i].a, pi[i].b, pi[i].split, pi[i].layer, pi[i].pair_off};
+  rp.total = total;
+  rp.flat = flat_grad;
+  rp.do_reduce = 0;
+  rp.adam = adam_params(adam);
+  rp.geo = geo_of(desc);
+  rp.plan = make_wplan(rp.geo);
+  cudaError_t e = launch_field_reduce(rp, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel<adam> launch");
   return INF_OK;
 }
 

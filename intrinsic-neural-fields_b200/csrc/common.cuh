@@ -240,6 +240,22 @@ struct ReduceSeg {
   int32_t rows, cols;
   int32_t kind;
   int32_t a, b, split;
+  int32_t layer;      // MMA layer of the tensor (kinds 0..2); -1 otherwise
+  int64_t pair_off;   // kind 2, skip layer: offset of the partner bias (Lx.bias owns the update of both, its image entry
+                      // is their sum); -2 marks the partner itself (Ly.bias: nothing to do here); -1 otherwise
+};
+// Optional optimiser tail of the reduction kernel: Adam on the flat fp32 master parameters + refresh of the fp16
+// operand images, fused with the partial sums (config.py:108 torch.optim.Adam(lr), defaults).
+struct AdamParams {
+  float* params;      // flat master parameters, state_dict order (null = no optimiser step)
+  float* exp_avg;
+  float* exp_avg_sq;
+  uint8_t* packed;    // operand images to refresh
+  const int32_t* step_dev;  // optional device-resident step count t (CUDA-graph replays); else the host values below
+  float step_size;    // lr / (1 - beta1^t)
+  float bc2_sqrt;     // sqrt(1 - beta2^t)
+  float lr, beta1, beta2, eps;
+  float omb1, omb2;   // 1 - beta, rounded from double as torch does
 };
 struct ReduceParams {
   ReduceSeg seg[INF_MAX_PARAMS];
@@ -254,6 +270,8 @@ struct ReduceParams {
   int groups_hid[MAX_HID_SLICES];
   int cta_base_hid[MAX_HID_SLICES];
   float scale;
+  int do_reduce;   // 0: flat already holds the (all-reduced) gradient, only the optimiser tail runs
+  AdamParams adam;
   Geo geo;
   WPlan plan;
 };

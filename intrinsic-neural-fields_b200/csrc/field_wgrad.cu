@@ -250,11 +250,24 @@ cudaError_t launch_field_wgrad(const FieldParams& p, int grid, cudaStream_t stre
 }
 
 // ---------------------------------------------------------------------------------------------
-// Partial reduction: one thread per element of the flat gradient vector, fixed summation order.
+// Partial reduction (+ optional Adam step and operand refresh): one thread per element of the flat
+// gradient vector, fixed summation order.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_update(const AdamParams& a, float step_size, float bc2_sqrt, int64_t i, float g, float& p_new) {
+  // torch/optim/adam.py (single-tensor math, also the fused kernel's): lerp, mul+addcmul, bias-corrected addcdiv
+  float m = a.exp_avg[i], v = a.exp_avg_sq[i];
+  m = m + (g - m) * a.omb1;
+  v = v * a.beta2 + a.omb2 * g * g;
+  const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+  p_new = a.params[i] - step_size * (m / denom);
+  a.exp_avg[i] = m;
+  a.exp_avg_sq[i] = v;
+  a.params[i] = p_new;
+}
+
 __global__ void field_reduce_kernel(const ReduceParams rp) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i == 0 && rp.loss_sums != nullptr) {
+  if (i == 0 && rp.loss_sums != nullptr && rp.do_reduce) {
     float a = 0.f, b = 0.f;
     for (int c = 0; c < rp.ncta1; ++c) {
       const float* pl = rp.part1 + static_cast<size_t>(c) * K1_PART_FLOATS;
@@ -272,34 +285,81 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   const int64_t e = i - sg.off;
   const int row = static_cast<int>(e / sg.cols);
   const int col = static_cast<int>(e % sg.cols);
-  float acc = 0.f;
-  // (first CTA, #groups, lane, column) of the partials holding this element
-  int cta0 = 0, ng = 0, ln = row, c = 0;
-  auto from_unit = [&](int ui, int lane_, int col_) {
-    const WUnit w = rp.plan.u[ui];
-    cta0 = rp.cta_base_hid[w.slice];
-    ng = rp.groups_hid[w.slice];
-    ln = lane_;
-    c = col_;
-  };
-  if (sg.kind == 0) {  // W0 / Wy: row n, column j
-    cta0 = (col >> 8) * rp.groups_big;
-    ng = rp.groups_big;
-    c = (col & 255) + (sg.a ? 256 : 0);
-  } else if (sg.kind == 1) {  // hidden / view weight
-    if (col < sg.split) from_unit(sg.a, row, rp.plan.u[sg.a].col + col);
-    else from_unit(sg.b, row, rp.plan.u[sg.b].col + (col - sg.split));
-  } else if (sg.kind == 2) {  // bias (rows entries, cols == 1)
-    from_unit(sg.a, row, rp.plan.u[sg.a].bias_col);
-  } else if (sg.kind == 3) {  // output-layer weight [3][wout]: lane = input feature, column = channel
-    from_unit(sg.a, col, rp.plan.u[sg.a].col + row);
-  }
-  if (sg.kind == 4) {  // output-layer bias [3]
-    for (int k = 0; k < rp.ncta1; ++k) acc += rp.part1[static_cast<size_t>(k) * K1_PART_FLOATS + row];
+  float grad;
+  if (rp.do_reduce) {
+    float acc = 0.f;
+    // (first CTA, #groups, lane, column) of the partials holding this element
+    int cta0 = 0, ng = 0, ln = row, c = 0;
+    auto from_unit = [&](int ui, int lane_, int col_) {
+      const WUnit w = rp.plan.u[ui];
+      cta0 = rp.cta_base_hid[w.slice];
+      ng = rp.groups_hid[w.slice];
+      ln = lane_;
+      c = col_;
+    };
+    if (sg.kind == 0) {  // W0 / Wy: row n, column j
+      cta0 = (col >> 8) * rp.groups_big;
+      ng = rp.groups_big;
+      c = (col & 255) + (sg.a ? 256 : 0);
+    } else if (sg.kind == 1) {  // hidden / view weight
+      if (col < sg.split) from_unit(sg.a, row, rp.plan.u[sg.a].col + col);
+      else from_unit(sg.b, row, rp.plan.u[sg.b].col + (col - sg.split));
+    } else if (sg.kind == 2) {  // bias (rows entries, cols == 1)
+      from_unit(sg.a, row, rp.plan.u[sg.a].bias_col);
+    } else if (sg.kind == 3) {  // output-layer weight [3][wout]: lane = input feature, column = channel
+      from_unit(sg.a, col, rp.plan.u[sg.a].col + row);
+    }
+    if (sg.kind == 4) {  // output-layer bias [3]
+      for (int k = 0; k < rp.ncta1; ++k) acc += rp.part1[static_cast<size_t>(k) * K1_PART_FLOATS + row];
+    } else {
+      for (int gI = 0; gI < ng; ++gI) acc += rp.partw[(static_cast<size_t>(cta0 + gI) * HID + ln) * WG_COLS + c];
+    }
+    grad = acc * rp.scale;
+    rp.flat[i] = grad;
   } else {
-    for (int gI = 0; gI < ng; ++gI) acc += rp.partw[(static_cast<size_t>(cta0 + gI) * HID + ln) * WG_COLS + c];
+    grad = rp.flat[i];
   }
-  rp.flat[i] = acc * rp.scale;
+  const AdamParams& ad = rp.adam;
+  if (ad.params == nullptr) return;
+  // ---- Adam on the master parameter, then its entry of the fp16 / f32 operand images ----------------------------
+  if (sg.kind == 2 && sg.pair_off == -2) return;   // Ly.bias: handled by the thread of Lx.bias
+  float step_size = ad.step_size, bc2_sqrt = ad.bc2_sqrt;
+  if (ad.step_dev != nullptr) {
+    const double t = static_cast<double>(*ad.step_dev);
+    step_size = static_cast<float>(static_cast<double>(ad.lr) / (1.0 - pow(static_cast<double>(ad.beta1), t)));
+    bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(ad.beta2), t)));
+  }
+  float pn;
+  adam_update(ad, step_size, bc2_sqrt, i, grad, pn);
+  const Geo& g = rp.geo;
+  float* f32sec = reinterpret_cast<float*>(ad.packed + packed_f32_offset(g));
+  const int nbias = (g.nb + 1) * HID;
+  if (sg.kind == 0) {
+    const uint32_t off = sw128_off(static_cast<uint32_t>(row + (sg.a ? HID : 0)), static_cast<uint32_t>(col & 63));
+    *reinterpret_cast<__half*>(ad.packed + static_cast<size_t>(col >> 6) * BLOB_BYTES + off) = __float2half_rn(pn);
+  } else if (sg.kind == 1) {
+    int blob, jj = col;
+    if (g.view && sg.layer == g.nb) {
+      if (col < sg.split) blob = blob_wd1z(g);
+      else { blob = blob_wd1e(g); jj = col - sg.split; }
+    } else {
+      blob = blob_hidden(g, sg.layer);
+    }
+    const uint32_t off = static_cast<uint32_t>(jj >> 6) * PANEL_BYTES + sw128_off(static_cast<uint32_t>(row), static_cast<uint32_t>(jj & 63));
+    *reinterpret_cast<__half*>(ad.packed + static_cast<size_t>(blob) * BLOB_BYTES + off) = __float2half_rn(pn);
+  } else if (sg.kind == 2) {
+    float bsum = pn;
+    if (sg.pair_off >= 0) {   // skip layer: the image holds Lx.bias + Ly.bias; both share this gradient
+      float p2;
+      adam_update(ad, step_size, bc2_sqrt, sg.pair_off + row, grad, p2);
+      bsum += p2;
+    }
+    f32sec[sg.layer * HID + row] = bsum;
+  } else if (sg.kind == 3) {
+    f32sec[nbias + row * HID + col] = pn;
+  } else {
+    f32sec[nbias + OUT_DIM * HID + row] = pn;
+  }
 }
 
 cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream) {

@@ -282,8 +282,22 @@ def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals
     return pred
 
 
+def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev) -> "_lib.InfAdam":
+    n = params_flat.numel()
+    for name, x in (("params_flat", params_flat), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _require_cuda(x, name)
+        if x.dtype != torch.float32 or x.numel() != n or x.dim() != 1:
+            raise ValueError(f"{name} must be a flat float32 vector of {n} elements")
+    _require_cuda(step_dev, "step_dev")
+    if step_dev.dtype != torch.int32 or step_dev.numel() != 1:
+        raise ValueError("step_dev must be a 1-element int32 CUDA tensor holding the step count t of this update")
+    return _lib.InfAdam(params=params_flat.data_ptr(), exp_avg=exp_avg.data_ptr(), exp_avg_sq=exp_avg_sq.data_ptr(),
+                        packed=packed.data_ptr(), step_dev=step_dev.data_ptr(), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+                        step=0)
+
+
 def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key,
-                                 dense: bool, grad_scale: float):
+                                 dense: bool, grad_scale: float, adam=None):
     cfg = FieldConfig.from_key(cfg_key)
     B = _check_inputs(cfg, table, vids, bary, dense)
     device = table.device
@@ -306,8 +320,14 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
                         workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     g = _lib.InfGrads(flat=flat.data_ptr(), loss_sums=sums.data_ptr())
     with torch.cuda.device(device):
-        rc = _lib.load().inf_forward_backward(C.byref(d), C.byref(t), C.byref(g), _stream(device))
-    _lib.check(rc, "inf_forward_backward")
+        if adam is None:
+            rc = _lib.load().inf_forward_backward(C.byref(d), C.byref(t), C.byref(g), _stream(device))
+        else:
+            if adam.params_flat.numel() != flat.numel():
+                raise ValueError("flat parameter vector does not match the model configuration")
+            a = _adam_struct(*adam)
+            rc = _lib.load().inf_train_step(C.byref(d), C.byref(t), C.byref(g), C.byref(a), _stream(device))
+    _lib.check(rc, "inf_forward_backward" if adam is None else "inf_train_step")
     return pred, flat, sums
 
 
@@ -343,6 +363,47 @@ def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normal
     n = num_params(FieldConfig.from_key(cfg_key))
     return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n,), dtype=torch.float32),
             table.new_empty((2,), dtype=torch.float32))
+
+
+class _AdamArgs(tuple):
+    """(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)"""
+    params_flat = property(lambda self: self[0])
+
+
+@torch.library.custom_op("inf_b200::field_train_step", mutates_args=("packed", "params_flat", "exp_avg", "exp_avg_sq"))
+def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor], packed: torch.Tensor,
+                     target: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
+                     face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool, grad_scale: float,
+                     params_flat: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float,
+                     beta2: float, eps: float, step_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Forward + L1 loss + backward + Adam + operand refresh (trainer.py:75-82) in three kernel launches."""
+    return _field_forward_backward_impl(table, vids, bary, packed, target, None, dirs, face_idxs, face_normals, cfg_key,
+                                        dense, grad_scale,
+                                        adam=_AdamArgs((params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)))
+
+
+@field_train_step.register_fake
+def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, params_flat, exp_avg,
+      exp_avg_sq, lr, beta1, beta2, eps, step_dev):
+    B = table.shape[0] if dense else vids.shape[0]
+    return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty(params_flat.shape),
+            table.new_empty((2,), dtype=torch.float32))
+
+
+@torch.library.custom_op("inf_b200::field_adam_pack", mutates_args=("packed", "params_flat", "exp_avg", "exp_avg_sq"))
+def field_adam_pack(flat_grad: torch.Tensor, packed: torch.Tensor, cfg_key: List[int], params_flat: torch.Tensor,
+                    exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float,
+                    step_dev: torch.Tensor) -> None:
+    """Adam + operand refresh from an already (all-)reduced flat gradient."""
+    cfg = FieldConfig.from_key(cfg_key)
+    _require_cuda(flat_grad, "flat_grad")
+    if flat_grad.dtype != torch.float32 or flat_grad.numel() != num_params(cfg) or params_flat.numel() != flat_grad.numel():
+        raise ValueError("flat_grad / params_flat do not match the model configuration")
+    a = _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)
+    with torch.cuda.device(flat_grad.device):
+        rc = _lib.load().inf_adam_pack_step(C.byref(_desc(cfg, 0, 0)), C.c_void_p(flat_grad.data_ptr()), C.byref(a),
+                                            _stream(flat_grad.device))
+    _lib.check(rc, "inf_adam_pack_step")
 
 
 def gather_interpolate_dense(table: "EigenTable", vids: torch.Tensor, bary: torch.Tensor) -> torch.Tensor:

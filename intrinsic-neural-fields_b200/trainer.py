@@ -13,7 +13,7 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.nn.functional as F
 
-from . import parallel
+from . import ops, parallel
 
 
 def get_loss_fn(loss_type: str) -> Callable:
@@ -75,6 +75,120 @@ def epoch_psnr(x: float) -> float:
     return -10.0 * math.log10(x)
 
 
+class FusedFieldAdam:
+    """``torch.optim.Adam(model.parameters(), lr)`` (config.py:108; default betas/eps, no weight decay) whose update runs
+    INSIDE the gradient-reduction kernel of the fused training step, together with the refresh of the fp16 operand
+    images: a single-GPU optimisation step is three kernel launches (forward/backward, wgrad, reduce+Adam+pack).
+
+    The model's parameters are re-pointed to views of ONE flat fp32 buffer in state_dict order (so ``state_dict()``,
+    checkpoints and ``parameters()`` keep working); do not move the model to another device afterwards.
+    ``state_dict()`` / ``load_state_dict()`` use torch.optim.Adam's layout (per-parameter ``step``, ``exp_avg``,
+    ``exp_avg_sq``), so optimiser checkpoints are interchangeable (trainer.py:224-227,309-311)."""
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model = model
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        params = model._ordered_params()
+        layout = ops.param_layout(model.cfg)
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedFieldAdam needs the model on a CUDA device (no CPU fallback)")
+        self.flat = torch.empty(ops.num_params(model.cfg), dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for (off, r, c), p in zip(layout, params):
+                view = self.flat[off:off + r * c].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # t, on the device: a graph replay advances it
+        self.layout = layout
+        self.packed = ops.pack_weights(model.cfg, [p.detach() for p in params], None)     # zero padding written once
+
+    # ---- the two ways a step is taken ---------------------------------------------------------------------------
+    def fused_l1_step(self, batch, global_rays=None):
+        """Single rank: forward + L1 + backward + Adam + operand refresh; returns (loss_sums, pred, flat_grad)."""
+        m = self.model
+        table, vids, bary, dense = m._inputs(batch)
+        dirs, face_idxs, normals = m._view_inputs(batch)
+        target = batch["expected_rgbs"].contiguous()
+        B = target.shape[0]
+        scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
+        self.step_dev.add_(1)
+        pred, flat, sums = torch.ops.inf_b200.field_train_step(
+            table, vids, bary, self.packed, target, dirs, face_idxs, normals, m.cfg.key(), dense, scale, self.flat,
+            self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev)
+        m._packed, m._packed_key = self.packed, None
+        return sums, pred, flat
+
+    def backward_only(self, batch, global_rays):
+        """Multi rank, first half: gradients of this rank's rays into the flat buffer (no update)."""
+        m = self.model
+        table, vids, bary, dense = m._inputs(batch)
+        dirs, face_idxs, normals = m._view_inputs(batch)
+        target = batch["expected_rgbs"].contiguous()
+        scale = 1.0 / (3.0 * float(global_rays))
+        pred, flat, sums = torch.ops.inf_b200.field_forward_backward(
+            table, vids, bary, self.packed, target, None, dirs, face_idxs, normals, m.cfg.key(), dense, scale)
+        return sums, pred, flat
+
+    def apply(self, flat_grad):
+        """Multi rank, second half (after the allreduce of ``flat_grad``): Adam + operand refresh in one kernel."""
+        self.step_dev.add_(1)
+        torch.ops.inf_b200.field_adam_pack(flat_grad, self.packed, self.model.cfg.key(), self.flat, self.exp_avg,
+                                           self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev)
+        self.model._packed, self.model._packed_key = self.packed, None
+
+    # ---- torch.optim.Adam-compatible checkpoints -------------------------------------------------------------------
+    @property
+    def step_count(self) -> int:
+        return int(self.step_dev.item())
+
+    def state_dict(self):
+        state = {}
+        for i, (off, r, c) in enumerate(self.layout):
+            shape = self.model._ordered_params()[i].shape
+            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[off:off + r * c].view(shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + r * c].view(shape).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "params": list(range(len(self.layout)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(float(b) for b in g["betas"]), float(g["eps"])
+        for i, (off, r, c) in enumerate(self.layout):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            self.exp_avg[off:off + r * c].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + r * c].copy_(st["exp_avg_sq"].reshape(-1))
+            self.step_dev.fill_(int(float(st["step"])))
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.model.parameters():
+            p.grad = None
+
+
+def fused_train_step_async(model, fopt: "FusedFieldAdam", batch, group=None):
+    """One optimisation step with the fused optimiser; returns (loss device scalar, pred)."""
+    world = parallel.world_size(group)
+    B = batch["expected_rgbs"].shape[0]
+    if world == 1:
+        sums, pred, _ = fopt.fused_l1_step(batch)
+    else:
+        sums, pred, flat = fopt.backward_only(batch, B * world)
+        parallel.allreduce_flat(flat, sums, group)
+        fopt.apply(flat)
+    return sums[0] / (3.0 * B * world), pred
+
+
+def fused_train_step(model, fopt: "FusedFieldAdam", batch, group=None) -> Tuple[float, torch.Tensor]:
+    """trainer.py:71-84 with the fused optimiser: returns (loss.item(), pred_rgbs)."""
+    loss, pred = fused_train_step_async(model, fopt, batch, group)
+    return loss.item(), pred
+
+
 class GraphedTrainStep:
     """``Trainer._train_step`` (trainer.py:71-84) for ``loss_type: L1`` replayed from CUDA graphs.
 
@@ -104,12 +218,20 @@ class GraphedTrainStep:
     def _front(self, batch):
         world = parallel.world_size(self.group)
         B = batch["expected_rgbs"].shape[0]
+        if isinstance(self.optim, FusedFieldAdam):
+            if world == 1:
+                return self.optim.fused_l1_step(batch)                   # includes the update
+            return self.optim.backward_only(batch, B * world)
         self.optim.zero_grad(set_to_none=True)
         return self.model.l1_step(batch, global_rays=B * world)          # sums, pred, flat
 
-    def _back(self, sums, n_global):
+    def _back(self, sums, n_global, flat=None):
         loss = sums[0] / (3.0 * n_global)
-        self.optim.step()
+        if isinstance(self.optim, FusedFieldAdam):
+            if flat is not None:
+                self.optim.apply(flat)
+        else:
+            self.optim.step()
         return loss
 
     def _eager(self, batch):
@@ -117,7 +239,7 @@ class GraphedTrainStep:
         sums, pred, flat = self._front(batch)
         if world > 1:
             parallel.allreduce_flat(flat, sums, self.group)
-        return self._back(sums, batch["expected_rgbs"].shape[0] * world), pred
+        return self._back(sums, batch["expected_rgbs"].shape[0] * world, flat if world > 1 else None), pred
 
     def _capture(self, batch):
         world = parallel.world_size(self.group)
@@ -131,7 +253,7 @@ class GraphedTrainStep:
             sums, pred, flat = self._front(batch)
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2, pool=g1.pool()):
-            loss = self._back(sums, n_global)
+            loss = self._back(sums, n_global, flat)
         return (g1, g2, flat, sums, loss, pred)
 
     def step_async(self, batch):

@@ -458,3 +458,59 @@ def test_fused_adam_without_version_bump_is_not_served_stale_weights():
     assert max(abs(a - bb) for a, bb in zip(l0, l1)) < 1e-4       # same trajectory (fused vs foreach arithmetic differs by ulps)
     assert l0[-1] < l0[0] and l1[-1] < l1[0] and len(set(l1)) == 4   # stale operand images would freeze the loss
     assert (y0 - y1).abs().max().item() < 1e-2                        # eval after train() -> eval() sees the last update
+
+
+@pytest.mark.parametrize("name", ["tf_k64", "view_intrinsic"])
+def test_fused_adam_matches_torch_adam(name):
+    # Adam + operand refresh inside the reduction kernel == torch.optim.Adam + re-pack (config.py:108), step by step
+    from inf_b200 import trainer
+    c = load_golden(name)
+    b = _batch(c)
+    m0, m1 = _model_from(c), _model_from(c)
+    opt = torch.optim.Adam(m0.parameters(), lr=1e-4)
+    fopt = trainer.FusedFieldAdam(m1, lr=1e-4)
+    assert [n for n, _ in m1.named_parameters()] == c["param_names"]          # still the reference's state_dict
+    for step in range(6):
+        l0, p0 = trainer.train_step(m0, opt, b)
+        l1, p1 = trainer.fused_train_step(m1, fopt, b)
+        assert abs(l0 - l1) < 2e-5, (step, l0, l1)
+    _check_no_watchdog()
+    assert fopt.step_count == 6
+    for (n, a), (_, bb) in zip(m0.named_parameters(), m1.named_parameters()):
+        # a few ReLU-kink elements can flip with the 1-ulp differences of the update arithmetic; compare in bulk
+        rel = (a - bb).norm().item() / a.norm().item()
+        assert rel < 2e-4, (n, rel)
+    # optimiser checkpoints are interchangeable with torch.optim.Adam's
+    sd, ref_sd = fopt.state_dict(), opt.state_dict()
+    assert sd["state"].keys() == ref_sd["state"].keys()
+    for i in sd["state"]:
+        assert sd["state"][i]["exp_avg"].shape == ref_sd["state"][i]["exp_avg"].shape
+        assert float(sd["state"][i]["step"]) == float(ref_sd["state"][i]["step"])
+    m1.eval()
+    with torch.no_grad():
+        ya, yb = m0.eval()(b), m1(b)
+    assert (ya - yb).abs().max().item() < 2e-3
+    # the flat master buffer IS the parameters
+    assert all(p.data_ptr() >= fopt.flat.data_ptr() and p.data_ptr() < fopt.flat.data_ptr() + fopt.flat.numel() * 4
+               for p in m1.parameters())
+
+
+def test_graphed_fused_step_equals_eager_fused_steps():
+    from inf_b200 import trainer
+    c = load_golden("tf_k64")
+    b = _batch(c)
+    runs = []
+    for graphed in (False, True):
+        m = _model_from(c)
+        fopt = trainer.FusedFieldAdam(m, lr=1e-3)
+        gs = trainer.GraphedTrainStep(m, fopt)
+        losses = []
+        for _ in range(6):
+            loss, pred = gs.step(b) if graphed else trainer.fused_train_step(m, fopt, b)
+            losses.append(loss)
+        runs.append((losses, fopt.flat.clone(), fopt.step_count))
+    _check_no_watchdog()
+    (l0, f0, s0), (l1, f1, s1) = runs
+    assert s0 == s1 == 6                      # the device-resident step counter advances inside the replayed graph
+    assert l0 == l1
+    assert torch.equal(f0, f1)
