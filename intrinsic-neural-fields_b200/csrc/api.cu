@@ -213,6 +213,13 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
     const char* f = getenv("INF_PREFETCH");   // tuning knob: L2 prefetch distance of the gather in k-chunks
     p.prefetch = f ? atoi(f) : (d->table_dtype == INF_TABLE_F16 ? 0 : 2);   // fp16 rows: the L2::256B load hint already covers it
     if (p.prefetch < 0 || p.prefetch > 8 || d->input_mode == INF_INPUT_DENSE) p.prefetch = 0;
+    // L2 residency of the table: protect as many of its lines as fit beside the weight / stash streams (126 MB L2)
+    const char* k = getenv("INF_KEEP_MB");
+    const double keep_mb = k ? atof(k) : 80.0;
+    const double table_mb = static_cast<double>(d->input_mode == INF_INPUT_DENSE ? d->n_rays : d->n_rows) * d->k_pad *
+                            (d->table_dtype == INF_TABLE_F16 ? 2.0 : 4.0) / 1048576.0;
+    p.table_keep = static_cast<float>(table_mb <= keep_mb ? 1.0 : keep_mb / table_mb);
+    if (d->input_mode == INF_INPUT_DENSE) p.table_keep = 0.f;   // a dense embedding is read exactly once
     const char* w = getenv("INF_PREFETCH_WGRAD");
     p.prefetch_wgrad = w ? atoi(w) : 0;   // measured: prefetches through the bulk-copy engine compete with its loads
     if (p.prefetch_wgrad < 0 || p.prefetch_wgrad > 32) p.prefetch_wgrad = 0;

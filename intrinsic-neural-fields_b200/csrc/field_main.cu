@@ -131,12 +131,12 @@ template <>
 struct RowLoader<float> {
   static constexpr int QUADS = 1;        // quads per pass
   float4 a[3], b[3];
-  __device__ __forceinline__ void load(int, const float* base, const int64_t (&roff)[3], int koff, int s) {
+  __device__ __forceinline__ void load(int, const float* base, const int64_t (&roff)[3], int koff, int s, uint64_t pol) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float* p = base + roff[j] + koff + 4 * s;
-      a[j] = ldg_nc_f4(p);
-      b[j] = ldg_nc_f4(p + 32);
+      a[j] = ldg_nc_f4(p, pol);
+      b[j] = ldg_nc_f4(p + 32, pol);
     }
   }
   // writes fp16 k-offsets [4s,4s+4) and [32+4s, 32+4s+4) of panel row r
@@ -165,9 +165,9 @@ template <>
 struct RowLoader<__half> {
   static constexpr int QUADS = 2;
   uint4 a[2][3];
-  __device__ __forceinline__ void load(int u, const __half* base, const int64_t (&roff)[3], int koff, int s) {
+  __device__ __forceinline__ void load(int u, const __half* base, const int64_t (&roff)[3], int koff, int s, uint64_t pol) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) a[u][j] = ldg_nc_u4(base + roff[j] + koff + 8 * s);
+    for (int j = 0; j < 3; ++j) a[u][j] = ldg_nc_u4(base + roff[j] + koff + 8 * s, pol);
   }
   __device__ __forceinline__ void store(int u, uint32_t panel, int r, int s, const float (&w)[3]) const {
     float acc[8];
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   const int ntiles = p.ntiles;
   const int nchunks = g.nchunks;
   const size_t tile_stride = stash_tile_bytes(g);
+  const uint64_t stash_policy = l2_policy_evict_first();   // stash tiles are written once, read once by the next kernel
 
   // Register re-partition: ONE setmaxnreg instance per warpgroup (all four warps of a warpgroup must execute the
   // same instruction), placed so that it dominates the role's code -- ptxas budgets each region from it.
@@ -329,6 +330,8 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     // from HBM in (pf * 64 * sizeof(TableT))-byte pieces (one DRAM page visit instead of pf separate 128/256-byte
     // ones), through the bulk-copy engine, which does not occupy the LSU's outstanding-load slots.
     const int pf = p.prefetch;
+    // table rows are re-used by other rays (and by the next step): keep them in L2 ahead of the read-once streams
+    const uint64_t table_policy = l2_policy_evict_last(p.table_keep);
     auto issue = [&](const Cursor& k, RowLoader<TableT>& ld) {
       if (k.tile >= ntiles) return;
 #pragma unroll
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         int64_t roff[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) roff[j] = static_cast<int64_t>(s_vid[e + j]) * p.row_stride;
-        ld.load(u, table, roff, k.c * KC, s);
+        ld.load(u, table, roff, k.c * KC, s, table_policy);
         if (pf > 0 && s == 0 && (k.c % pf) == 0) {
           int c2 = k.c + pf;
           if (c2 < nchunks) {
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           umma_commit(bar(BAR_B1_EMPTY + sb));
           if (kTrain) {
             // x panel -> stash (the B operand of dW0 / dWy in the wgrad kernel)
-            if (!(p.debug & 1)) bulk_s2g(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES);
+            if (!(p.debug & 1)) bulk_s2g_hint(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES, stash_policy);
             bulk_commit();
             const long long ts0 = now();
             bulk_wait_read<0>();
@@ -676,8 +679,8 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         sync_epi();
         if (tid == 0) {
           if (kTrain) {
-            if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_h(g, l), hb, BLOB_BYTES);
-            if (l == 0 && view) bulk_s2g(stash_tile + stash_off_e(g), smem_base + sm.e, PANEL_BYTES);
+            if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_h(g, l), hb, BLOB_BYTES, stash_policy);
+            if (l == 0 && view) bulk_s2g_hint(stash_tile + stash_off_e(g), smem_base + sm.e, PANEL_BYTES, stash_policy);
             bulk_commit();
             const long long t0 = now();
             bulk_wait_read<1>();   // the buffer written next is free before the chain may continue
@@ -779,10 +782,10 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           }
           sync_epi();
           if (tid == 0) {
-            if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES);
+            if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES, stash_policy);
             bulk_commit();
-            if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES);
-            bulk_s2g(stash_tile + stash_off_dzlt(g), smem_base + sm.dzlt, DZLT_BYTES);
+            if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES, stash_policy);
+            bulk_s2g_hint(stash_tile + stash_off_dzlt(g), smem_base + sm.dzlt, DZLT_BYTES, stash_policy);
             bulk_commit();
             bulk_wait_read<1>();
             mbar_arrive(bar(BAR_ACT_READY));
@@ -817,7 +820,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             }
             sync_epi();
             if (tid == 0) {
-              if (!(p.debug & 2)) bulk_s2g(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES);
+              if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES, stash_policy);
               bulk_commit();
               if (lb > 0) {
                 bulk_wait_read<1>();

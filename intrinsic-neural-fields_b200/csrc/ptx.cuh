@@ -82,6 +82,26 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint
                "r"(src_smem), "r"(bytes)
                : "memory");
 }
+// L2 eviction policies for streams that are touched once (activation stash): keep them from displacing the
+// eigenfunction-table rows, which ARE re-used across rays.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
 // DRAM -> L2 prefetch through the bulk-copy engine (no destination: costs neither registers nor smem).
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
@@ -199,18 +219,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int a_mn_maj
 // ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+__device__ __forceinline__ uint64_t l2_policy_evict_last(float fraction) {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(p) : "f"(fraction));
+  return p;
+}
+// Gather loads: read-only path, no L1 allocation (each piece is used once per SM), 256-byte L2 fetch granularity (the
+// partner sector of a row piece arrives with the first touch), L2 policy supplied by the caller.
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p, uint64_t policy) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
+               : "l"(p), "l"(policy));
   return v;
 }
-__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p, uint64_t policy) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
+               : "l"(p), "l"(policy));
   return v;
 }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {

@@ -514,3 +514,51 @@ def test_graphed_fused_step_equals_eager_fused_steps():
     assert s0 == s1 == 6                      # the device-resident step counter advances inside the replayed graph
     assert l0 == l1
     assert torch.equal(f0, f1)
+
+
+# ---------------------------------------------------------------------------------------------
+# shape coverage of the compiled set: depth, skip position, wide k (many wgrad slices), view branch at max depth
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,L,skip,view_name", [(64, 3, 1, None), (200, 8, 6, None), (2047, 4, 2, None), (96, 7, 3, "view_extrinsic"),
+                                                (130, 3, 1, "view_intrinsic")])
+def test_shape_coverage_against_oracle(k, L, skip, view_name):
+    import types
+    from conftest import VIEW_CFGS
+    view = VIEW_CFGS[view_name] if view_name else None
+    g = torch.Generator().manual_seed(k + L)
+    V, F_, B = 400, 700, 517
+    E = torch.randn(V, k, generator=g) / 6
+    normals = torch.nn.functional.normalize(torch.randn(F_, 3, generator=g), dim=-1)
+    fid = torch.randint(0, F_, (B,), generator=g)
+    dirs = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    dirs = torch.where(((-dirs * normals[fid]).sum(-1) < 0)[:, None], -dirs, dirs)
+    vids = torch.randint(0, V, (B, 3), generator=g)
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    params = O.make_params(k, num_layers=L, skip=skip, view=view, seed=L)
+    cfg = dict(k=k, num_layers=L, mlp_hidden_dim=128, skip_layer_idx=skip)
+    mesh = None
+    kw = dict(num_layers=L, skip=skip)
+    if view is not None:
+        cfg["view_dependence"] = view
+        mesh = types.SimpleNamespace(face_normals=normals.numpy())
+        kw.update(view=view, unit_ray_dirs=dirs, hit_face_idxs=fid, face_normals=normals)
+    m = inf_b200.make_model(cfg, mesh=mesh)
+    m.load_state_dict(params)
+    m = m.to(DEV)
+    b = {"eigenfunction_table": inf_b200.EigenTable.from_dense(E, device=DEV), "vertex_idxs_of_hit_faces": vids.to(DEV),
+         "barycentric_coords": bary.to(DEV), "expected_rgbs": target.to(DEV)}
+    if view is not None:
+        b["unit_ray_dirs"] = dirs.to(DEV)
+        b["hit_face_idxs"] = fid.to(DEV)
+    sums, pred, flat = m.l1_step(b)
+    _check_no_watchdog()
+    loss, pref, grads = O.loss_and_grads(params, E, vids, bary, target, **kw)
+    err = (pred.cpu() - pref).abs()
+    assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN, (err.max().item(), err.mean().item())
+    assert abs(sums[0].item() / (3 * B) - loss) <= 1e-3
+    _check_grads(m, grads, tol=GRAD_REL_VIEW, cos_min=GRAD_COS_VIEW)
+    _, _, ge = O.emulated_fp16_grads(params, E, vids, bary, target, L, skip, **{k_: v for k_, v in kw.items()
+                                                                                  if k_ not in ("num_layers", "skip")})
+    _check_grads(m, ge, tol=GRAD_REL_EMULATED, cos_min=0.9999)
