@@ -58,9 +58,10 @@ class _FieldFunction(torch.autograd.Function):
     def backward(ctx, grad_pred):
         module = ctx.module
         table, vids, bary, dirs, face_idxs, face_normals = ctx.saved_tensors
-        _, flat, _ = torch.ops.inf_b200.field_forward_backward(
+        _, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, module._packed_weights(), None, grad_pred.contiguous().float(), dirs, face_idxs,
             face_normals, module.cfg.key(), ctx.dense, 1.0)
+        flat, _ = ops.split_flat(flat_full)
         grads = [flat[off:off + r * c].view(p.shape) for (off, r, c), p in zip(module._layout, module._ordered_params())]
         return (None,) * 8 + tuple(grads)
 
@@ -157,9 +158,10 @@ class _FusedFieldBase(nn.Module):
         target = batch["expected_rgbs"].contiguous()
         B = target.shape[0]
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
-        pred, flat, sums = torch.ops.inf_b200.field_forward_backward(
+        pred, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, self._packed_weights(force=True), target, None, dirs, face_idxs, normals, self.cfg.key(),
             dense, scale)
+        flat, sums = ops.split_flat(flat_full)
         if flat_grad is not None:
             flat_grad.copy_(flat)
             flat = flat_grad

@@ -302,8 +302,12 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
     B = _check_inputs(cfg, table, vids, bary, dense)
     device = table.device
     pred = torch.empty((B, 3), dtype=torch.float32, device=device)
-    flat = torch.empty(num_params(cfg), dtype=torch.float32, device=device)
-    sums = torch.zeros(2, dtype=torch.float32, device=device)
+    # flat gradient and the two loss sums share one allocation so that a multi-rank step needs a single allreduce
+    n_par = num_params(cfg)
+    flat_full = torch.empty(n_par + 2, dtype=torch.float32, device=device)
+    flat, sums = flat_full[:n_par], flat_full[n_par:]
+    if B == 0 or grad_pred is not None:
+        sums.zero_()
     for name, x in (("target", target), ("grad_pred", grad_pred)):
         if x is not None:
             _require_cuda(x, name)
@@ -323,12 +327,12 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
         if adam is None:
             rc = _lib.load().inf_forward_backward(C.byref(d), C.byref(t), C.byref(g), _stream(device))
         else:
-            if adam.params_flat.numel() != flat.numel():
+            if adam.params_flat.numel() != n_par:
                 raise ValueError("flat parameter vector does not match the model configuration")
             a = _adam_struct(*adam)
             rc = _lib.load().inf_train_step(C.byref(d), C.byref(t), C.byref(g), C.byref(a), _stream(device))
     _lib.check(rc, "inf_forward_backward" if adam is None else "inf_train_step")
-    return pred, flat, sums
+    return pred, flat_full
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,7 +356,9 @@ def field_forward_backward(table: torch.Tensor, vids: Optional[torch.Tensor], ba
                            packed: torch.Tensor, target: Optional[torch.Tensor], grad_pred: Optional[torch.Tensor],
                            dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                            face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
-                           grad_scale: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                           grad_scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (pred (B,3), flat (n_params + 2,)): the flat gradient followed by the two loss sums (one allocation,
+    one allreduce); use :func:`split_flat`."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals,
                                         cfg_key, dense, grad_scale)
 
@@ -361,8 +367,13 @@ def field_forward_backward(table: torch.Tensor, vids: Optional[torch.Tensor], ba
 def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale):
     B = table.shape[0] if dense else vids.shape[0]
     n = num_params(FieldConfig.from_key(cfg_key))
-    return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n,), dtype=torch.float32),
-            table.new_empty((2,), dtype=torch.float32))
+    return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n + 2,), dtype=torch.float32))
+
+
+def split_flat(flat_full: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(flat gradient, [sum|pred-target|, sum (pred-target)^2]) views of the fused step's single output buffer."""
+    n = flat_full.numel() - 2
+    return flat_full[:n], flat_full[n:]
 
 
 class _AdamArgs(tuple):
@@ -375,7 +386,7 @@ def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Op
                      target: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                      face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool, grad_scale: float,
                      params_flat: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float,
-                     beta2: float, eps: float, step_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                     beta2: float, eps: float, step_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Forward + L1 loss + backward + Adam + operand refresh (trainer.py:75-82) in three kernel launches."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, None, dirs, face_idxs, face_normals, cfg_key,
                                         dense, grad_scale,
@@ -386,8 +397,7 @@ def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Op
 def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, params_flat, exp_avg,
       exp_avg_sq, lr, beta1, beta2, eps, step_dev):
     B = table.shape[0] if dense else vids.shape[0]
-    return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty(params_flat.shape),
-            table.new_empty((2,), dtype=torch.float32))
+    return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty((params_flat.numel() + 2,)))
 
 
 @torch.library.custom_op("inf_b200::field_adam_pack", mutates_args=("packed", "params_flat", "exp_avg", "exp_avg_sq"))

@@ -25,7 +25,15 @@ def shard_range(n: int, group=None):
 
 
 def allreduce_flat(flat: torch.Tensor, sums: torch.Tensor, group=None):
-    """Sum the flat gradient vector (and the two loss sums) over ranks with a single collective each."""
+    """Sum the flat gradient vector and the two loss sums over ranks -- ONE collective when `sums` sits directly behind
+    `flat` in the same allocation (how the fused step returns them), else one each."""
+    adjacent = (flat.is_contiguous() and sums.is_contiguous() and flat.dtype == sums.dtype
+                and flat.untyped_storage().data_ptr() == sums.untyped_storage().data_ptr()
+                and sums.storage_offset() == flat.storage_offset() + flat.numel())
+    if adjacent:
+        both = torch.as_strided(flat, (flat.numel() + sums.numel(),), (1,))
+        dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
+        return
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
 

@@ -115,9 +115,10 @@ class FusedFieldAdam:
         B = target.shape[0]
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
         self.step_dev.add_(1)
-        pred, flat, sums = torch.ops.inf_b200.field_train_step(
+        pred, flat_full = torch.ops.inf_b200.field_train_step(
             table, vids, bary, self.packed, target, dirs, face_idxs, normals, m.cfg.key(), dense, scale, self.flat,
             self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev)
+        flat, sums = ops.split_flat(flat_full)
         m._packed, m._packed_key = self.packed, None
         return sums, pred, flat
 
@@ -128,8 +129,9 @@ class FusedFieldAdam:
         dirs, face_idxs, normals = m._view_inputs(batch)
         target = batch["expected_rgbs"].contiguous()
         scale = 1.0 / (3.0 * float(global_rays))
-        pred, flat, sums = torch.ops.inf_b200.field_forward_backward(
+        pred, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, self.packed, target, None, dirs, face_idxs, normals, m.cfg.key(), dense, scale)
+        flat, sums = ops.split_flat(flat_full)
         return sums, pred, flat
 
     def apply(self, flat_grad):

@@ -562,3 +562,29 @@ def test_shape_coverage_against_oracle(k, L, skip, view_name):
     _, _, ge = O.emulated_fp16_grads(params, E, vids, bary, target, L, skip, **{k_: v for k_, v in kw.items()
                                                                                   if k_ not in ("num_layers", "skip")})
     _check_grads(m, ge, tol=GRAD_REL_EMULATED, cos_min=0.9999)
+
+
+def test_evaluate_matches_reference_val_loop_and_host_loader_shuffle():
+    # Trainer.evaluate (trainer.py:164-187): mean L1 over rays-weighted batches + epoch PSNR = -10 log10(sum sq err / rays)
+    from inf_b200 import trainer
+    from inf_b200.ray_dataloader import RayDataLoader, HostRayLoader
+    c = load_golden("tf_k64")
+    m = _model_from(c)
+    dl = RayDataLoader(c["table"], "efuncs", c["vids"], c["bary"], c["target"], None, None, batch_size=100, shuffle=False,
+                       drop_last=False, device=DEV)
+    val_loss, psnr = trainer.evaluate(m, dl)
+    ref_pred = c["pred"]
+    assert abs(val_loss - (ref_pred - c["target"]).abs().mean().item()) < 1e-3
+    assert abs(psnr - O.epoch_psnr(float(((ref_pred - c["target"]) ** 2).sum()), ref_pred.shape[0])) < 0.05
+    # shuffled host loader: every ray exactly once per epoch, rows stay paired
+    tab = inf_b200.EigenTable.from_dense(c["table"], device=DEV)
+    hl = HostRayLoader(tab, c["vids"], c["bary"], c["target"], batch_size=64, shuffle=True, device=DEV,
+                       generator=torch.Generator().manual_seed(0))
+    got_v, got_t = [], []
+    for b in hl:
+        got_v.append(b["vertex_idxs_of_hit_faces"].cpu().clone())
+        got_t.append(b["expected_rgbs"].cpu().clone())
+    gv, gt = torch.cat(got_v), torch.cat(got_t)
+    assert gv.shape == c["vids"].shape
+    key = lambda v, t: sorted(map(tuple, torch.cat([v.double(), t.double()], 1).tolist()))
+    assert key(gv, gt) == key(c["vids"], c["target"])
