@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define INF_ABI_VERSION 3
+#define INF_ABI_VERSION 4
 
 /* error codes */
 #define INF_OK 0
@@ -92,6 +92,9 @@ typedef struct InfDesc {
   int32_t view_bneck;    /* bottleneck_vec_dim, 1..128 (zero-padded to 128 inside)            */
   int32_t view_hidden;   /* directional_hidden_dim, 1..128 (zero-padded to 128 inside)        */
   int64_t n_faces;       /* rows of face_normals (intrinsic view strategy)                    */
+  int64_t n_src_rays;    /* rows of the per-ray arrays when InfTensors.ray_idxs selects from them (else 0)  */
+  int32_t ray_idx_dtype; /* dtype of ray_idxs (INF_IDX_*)                                      */
+  int32_t reserved1;
   float grad_scale;      /* multiplies every summed gradient; 1/(3*B_global) for the L1 mean  */
   float reserved0;
 } InfDesc;
@@ -106,6 +109,10 @@ typedef struct InfTensors {
   const float* unit_ray_dirs; /* (B,3) f32, view branch                                             */
   const void* face_idxs;      /* (B,)  i32|i64, intrinsic view branch                               */
   const float* face_normals;  /* (F,3) f32, intrinsic view branch                                   */
+  const void* ray_idxs;       /* optional (B,) i32|i64 batch selection (ray_dataloader.py:103-145 folded into the   */
+                              /* kernels): ray r of this call reads row ray_idxs[r] of vids / bary / target /       */
+                              /* unit_ray_dirs / face_idxs, which are then the WHOLE split's arrays; pred, grad_pred */
+                              /* stay in batch order                                                                */
   const void* packed;         /* operand images written by inf_pack_weights                         */
   float* pred;                /* (B,3) f32 out                                                      */
   void* workspace;            /* >= inf_workspace_bytes(desc, training)                             */

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libinf_field.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 IDX_I32, IDX_I64 = 0, 1
 TABLE_F32, TABLE_F16 = 0, 1
 INPUT_GATHER, INPUT_DENSE = 0, 1
@@ -28,7 +28,7 @@ class InfDesc(C.Structure):
         ("skip", C.c_int32), ("table_dtype", C.c_int32), ("input_mode", C.c_int32),
         ("view_strategy", C.c_int32), ("view_embed", C.c_int32), ("view_include", C.c_int32),
         ("view_bneck", C.c_int32), ("view_hidden", C.c_int32),
-        ("n_faces", C.c_int64),
+        ("n_faces", C.c_int64), ("n_src_rays", C.c_int64), ("ray_idx_dtype", C.c_int32), ("reserved1", C.c_int32),
         ("grad_scale", C.c_float), ("reserved0", C.c_float),
     ]
 
@@ -37,7 +37,7 @@ class InfTensors(C.Structure):
     _fields_ = [
         ("table", C.c_void_p), ("vids", C.c_void_p), ("bary", C.c_void_p), ("target", C.c_void_p),
         ("grad_pred", C.c_void_p), ("unit_ray_dirs", C.c_void_p), ("face_idxs", C.c_void_p),
-        ("face_normals", C.c_void_p), ("packed", C.c_void_p), ("pred", C.c_void_p),
+        ("face_normals", C.c_void_p), ("ray_idxs", C.c_void_p), ("packed", C.c_void_p), ("pred", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 

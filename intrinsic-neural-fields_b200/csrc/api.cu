@@ -172,6 +172,11 @@ int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
   if ((reinterpret_cast<uintptr_t>(t->packed) & 127) != 0) return fail(INF_ERR_BAD_ARG, "packed must be 128-byte aligned");
   if (d->input_mode == INF_INPUT_GATHER && (t->vids == nullptr || t->bary == nullptr))
     return fail(INF_ERR_BAD_ARG, "vids / bary must be non-null in gather mode");
+  if (t->ray_idxs != nullptr) {
+    if (d->input_mode != INF_INPUT_GATHER) return fail(INF_ERR_BAD_ARG, "ray_idxs needs input_mode GATHER");
+    if (d->ray_idx_dtype != INF_IDX_I32 && d->ray_idx_dtype != INF_IDX_I64) return fail(INF_ERR_BAD_ARG, "bad ray_idx_dtype");
+    if (d->n_src_rays < 1) return fail(INF_ERR_BAD_ARG, "n_src_rays must be given with ray_idxs");
+  }
   if (d->view_strategy != INF_VIEW_NONE) {
     if (t->unit_ray_dirs == nullptr) return fail(INF_ERR_BAD_ARG, "unit_ray_dirs must be non-null with the view branch");
     if (d->view_strategy == INF_VIEW_INTRINSIC && (t->face_idxs == nullptr || t->face_normals == nullptr))
@@ -200,6 +205,8 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   p.dirs = t->unit_ray_dirs;
   p.face_idxs = t->face_idxs;
   p.face_normals = t->face_normals;
+  p.ridx = (d->input_mode == INF_INPUT_GATHER) ? t->ray_idxs : nullptr;
+  p.ridx64 = d->ray_idx_dtype == INF_IDX_I64;
   p.pred = t->pred;
   p.packed = reinterpret_cast<const uint8_t*>(t->packed);
   p.n_rays = d->n_rays;

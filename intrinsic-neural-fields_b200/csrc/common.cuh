@@ -197,6 +197,8 @@ struct FieldParams {
   const float* dirs;          // (B,3) unit ray directions (view branch)
   const void* face_idxs;      // (B,)  hit face ids (intrinsic view strategy)
   const float* face_normals;  // (F,3)
+  const void* ridx;           // optional (B,) batch selection into the per-ray arrays
+  int ridx64;
   float* pred;
   const uint8_t* packed;
   uint8_t* stash;

@@ -298,12 +298,18 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     auto load_meta = [&](int tile, int slot) {
       const int64_t ray0 = static_cast<int64_t>(tile) * TILE_M;
       for (int i = pt; i < 384; i += PROD_THREADS) {
-        const int64_t e = ray0 * 3 + i;
+        const int64_t ray = ray0 + i / 3;
         uint32_t v = 0;
         float w = 0.f;
-        if (e < p.n_rays * 3) {
-          if (p.dense) { v = static_cast<uint32_t>(ray0 + i / 3); w = (i % 3 == 0) ? 1.f : 0.f; }
+        if (ray < p.n_rays) {
+          if (p.dense) { v = static_cast<uint32_t>(ray); w = (i % 3 == 0) ? 1.f : 0.f; }
           else {
+            // batch selection folded in (ray_dataloader.py:122-126): row of the split's arrays this ray reads
+            int64_t src = ray;
+            if (p.ridx != nullptr)
+              src = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[ray])
+                             : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[ray]);
+            const int64_t e = src * 3 + i % 3;
             v = p.idx64 ? static_cast<uint32_t>(reinterpret_cast<const long long*>(p.vids)[e])
                         : static_cast<uint32_t>(reinterpret_cast<const int*>(p.vids)[e]);
             w = p.bary[e];
@@ -609,16 +615,20 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       const uint32_t tb = tlane + 256u * static_cast<uint32_t>(buf);
       const int64_t ray = static_cast<int64_t>(tile) * TILE_M + r;
       const bool valid = ray < p.n_rays;
+      int64_t src = ray;   // row of target / dirs / face_idxs this ray reads (batch selection folded in)
+      if (valid && p.ridx != nullptr)
+        src = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[ray])
+                       : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[ray]);
       uint8_t* stash_tile = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride : nullptr;
 
       // ---- view branch prologue: Fourier features of this ray -> E panel (model.py:175-186) --------
       if (view) {
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
         if (valid) {
-          const float dx = p.dirs[ray * 3 + 0], dy = p.dirs[ray * 3 + 1], dz = p.dirs[ray * 3 + 2];
+          const float dx = p.dirs[src * 3 + 0], dy = p.dirs[src * 3 + 1], dz = p.dirs[src * 3 + 2];
           if (g.view == INF_VIEW_INTRINSIC) {
-            const int64_t f = p.idx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.face_idxs)[ray])
-                                      : static_cast<int64_t>(reinterpret_cast<const int*>(p.face_idxs)[ray]);
+            const int64_t f = p.idx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.face_idxs)[src])
+                                      : static_cast<int64_t>(reinterpret_cast<const int*>(p.face_idxs)[src]);
             const float nx = p.face_normals[f * 3 + 0], ny = p.face_normals[f * 3 + 1], nz = p.face_normals[f * 3 + 2];
             // F.cosine_similarity(-dir, n): each vector divided by max(|v|, 1e-8), then the dot product
             const float ia = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
@@ -741,7 +751,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             for (int c = 0; c < 3; ++c) {
               float gy;
               if (p.target != nullptr) {
-                const float d = y[c] - p.target[ray * 3 + c];
+                const float d = y[c] - p.target[src * 3 + c];
                 loss_abs += fabsf(d);
                 loss_sq += d * d;
                 gy = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);  // d|d|/dd, sign(0) = 0 as F.l1_loss

@@ -47,23 +47,23 @@ class _FieldFunction(torch.autograd.Function):
     dirs (none requires grad in the reference either)."""
 
     @staticmethod
-    def forward(ctx, module, table, vids, bary, dense, dirs, face_idxs, face_normals, *params):
+    def forward(ctx, module, table, vids, bary, dense, dirs, face_idxs, face_normals, ray_idxs, *params):
         packed = module._packed_weights(force=True)
         ctx.module, ctx.dense = module, dense
-        ctx.save_for_backward(table, vids, bary, dirs, face_idxs, face_normals)
+        ctx.save_for_backward(table, vids, bary, dirs, face_idxs, face_normals, ray_idxs)
         return torch.ops.inf_b200.field_forward(table, vids, bary, packed, dirs, face_idxs, face_normals,
-                                                module.cfg.key(), dense)
+                                                module.cfg.key(), dense, ray_idxs)
 
     @staticmethod
     def backward(ctx, grad_pred):
         module = ctx.module
-        table, vids, bary, dirs, face_idxs, face_normals = ctx.saved_tensors
+        table, vids, bary, dirs, face_idxs, face_normals, ray_idxs = ctx.saved_tensors
         _, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, module._packed_weights(), None, grad_pred.contiguous().float(), dirs, face_idxs,
-            face_normals, module.cfg.key(), ctx.dense, 1.0)
+            face_normals, module.cfg.key(), ctx.dense, 1.0, ray_idxs)
         flat, _ = ops.split_flat(flat_full)
         grads = [flat[off:off + r * c].view(p.shape) for (off, r, c), p in zip(module._layout, module._ordered_params())]
-        return (None,) * 8 + tuple(grads)
+        return (None,) * 9 + tuple(grads)
 
 
 class _FusedFieldBase(nn.Module):
@@ -134,14 +134,22 @@ class _FusedFieldBase(nn.Module):
         raise KeyError("batch needs 'eigenfunction_table' + 'vertex_idxs_of_hit_faces' + 'barycentric_coords' "
                        "(fused path) or 'eigenfunctions' (dense path)")
 
+    @staticmethod
+    def _ray_idxs(batch):
+        """Optional batch selection folded into the kernels: the per-ray tensors of the batch are then the whole
+        split's arrays and ``batch['ray_idxs']`` (B,) picks this batch's rows (ray_dataloader.py:103-145)."""
+        r = batch.get("ray_idxs")
+        return None if r is None else r.contiguous()
+
     def forward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         table, vids, bary, dense = self._inputs(batch)
         dirs, face_idxs, normals = self._view_inputs(batch)
+        ridx = self._ray_idxs(batch)
         params = self._ordered_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, *params)
+            return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, ridx, *params)
         return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(force=self.training), dirs,
-                                                face_idxs, normals, self.cfg.key(), dense)
+                                                face_idxs, normals, self.cfg.key(), dense, ridx)
 
     # ---- fused training pass -----------------------------------------------------------------------
     def l1_step(self, batch: Dict[str, torch.Tensor], global_rays: Optional[int] = None,
@@ -156,11 +164,12 @@ class _FusedFieldBase(nn.Module):
         table, vids, bary, dense = self._inputs(batch)
         dirs, face_idxs, normals = self._view_inputs(batch)
         target = batch["expected_rgbs"].contiguous()
-        B = target.shape[0]
+        ridx = self._ray_idxs(batch)
+        B = target.shape[0] if ridx is None else ridx.shape[0]
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
         pred, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, self._packed_weights(force=True), target, None, dirs, face_idxs, normals, self.cfg.key(),
-            dense, scale)
+            dense, scale, ridx)
         flat, sums = ops.split_flat(flat_full)
         if flat_grad is not None:
             flat_grad.copy_(flat)

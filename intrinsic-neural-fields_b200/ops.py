@@ -61,7 +61,7 @@ _VIEW_NAMES = {v: k for k, v in _VIEW_CODES.items()}
 
 
 def _desc(cfg: FieldConfig, n_rays: int, n_rows: int, *, idx64: bool = True, table_f16: bool = False,
-          dense: bool = False, grad_scale: float = 1.0, n_faces: int = 0) -> _lib.InfDesc:
+          dense: bool = False, grad_scale: float = 1.0, n_faces: int = 0, ray_idxs=None, n_src_rays: int = 0) -> _lib.InfDesc:
     d = _lib.InfDesc()
     d.abi_version = _lib.ABI_VERSION
     d.idx_dtype = _lib.IDX_I64 if idx64 else _lib.IDX_I32
@@ -82,6 +82,9 @@ def _desc(cfg: FieldConfig, n_rays: int, n_rows: int, *, idx64: bool = True, tab
     d.view_bneck = cfg.view_bneck
     d.view_hidden = cfg.view_hidden
     d.n_faces = n_faces
+    if ray_idxs is not None:
+        d.n_src_rays = n_src_rays
+        d.ray_idx_dtype = _lib.IDX_I64 if ray_idxs.dtype == torch.int64 else _lib.IDX_I32
     d.grad_scale = grad_scale
     return d
 
@@ -222,22 +225,30 @@ def pack_weights(cfg: FieldConfig, params: Sequence[torch.Tensor], out: Optional
     return out
 
 
-def _check_inputs(cfg, table, vids, bary, dense):
+def _check_inputs(cfg, table, vids, bary, dense, ray_idxs=None):
+    """Returns (B, rows of the per-ray arrays)."""
     _require_cuda(table, "table")
     if table.dim() != 2 or table.shape[1] != cfg.k_pad or table.dtype not in (torch.float32, torch.float16):
         raise ValueError(f"table must be (V,{cfg.k_pad}) float32/float16 (use EigenTable.from_dense)")
     if dense:
-        return table.shape[0]
+        if ray_idxs is not None:
+            raise ValueError("ray_idxs cannot be combined with a dense 'eigenfunctions' batch")
+        return table.shape[0], table.shape[0]
     _require_cuda(vids, "vertex_idxs_of_hit_faces")
     _require_cuda(bary, "barycentric_coords")
     if vids.dtype not in (torch.int64, torch.int32) or vids.dim() != 2 or vids.shape[1] != 3:
         raise ValueError("vertex_idxs_of_hit_faces must be (B,3) int64/int32")
     if bary.dtype != torch.float32 or bary.shape != vids.shape:
         raise ValueError("barycentric_coords must be (B,3) float32")
-    return vids.shape[0]
+    if ray_idxs is None:
+        return vids.shape[0], vids.shape[0]
+    _require_cuda(ray_idxs, "ray_idxs")
+    if ray_idxs.dtype not in (torch.int64, torch.int32) or ray_idxs.dim() != 1:
+        raise ValueError("ray_idxs must be (B,) int64/int32")
+    return ray_idxs.shape[0], vids.shape[0]
 
 
-def _check_view(cfg, B, idx64, dirs, face_idxs, face_normals):
+def _check_view(cfg, B, idx64, dirs, face_idxs, face_normals):   # B = rows of the per-ray arrays
     """Validate / normalise the view-branch inputs (model.py:175-186); returns (dirs, face_idxs, normals, n_faces)."""
     if not cfg.has_view:
         return None, None, None, 0
@@ -262,19 +273,22 @@ def _check_view(cfg, B, idx64, dirs, face_idxs, face_normals):
     return dirs, face_idxs, face_normals, face_normals.shape[0]
 
 
-def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense: bool) -> torch.Tensor:
+def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense: bool,
+                        ray_idxs=None) -> torch.Tensor:
     cfg = FieldConfig.from_key(cfg_key)
-    B = _check_inputs(cfg, table, vids, bary, dense)
+    B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
     pred = torch.empty((B, 3), dtype=torch.float32, device=device)
     if B == 0:
         return pred
     idx64 = vids is None or vids.dtype == torch.int64
-    dirs, face_idxs, face_normals, n_faces = _check_view(cfg, B, idx64, dirs, face_idxs, face_normals)
+    dirs, face_idxs, face_normals, n_faces = _check_view(cfg, n_src, idx64, dirs, face_idxs, face_normals)
     ws = _workspace(device, workspace_bytes(cfg, B, False))
-    d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense, n_faces=n_faces)
+    d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense, n_faces=n_faces,
+              ray_idxs=ray_idxs, n_src_rays=n_src)
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), unit_ray_dirs=_ptr(dirs),
-                        face_idxs=_ptr(face_idxs), face_normals=_ptr(face_normals), packed=packed.data_ptr(),
+                        face_idxs=_ptr(face_idxs), face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs),
+                        packed=packed.data_ptr(),
                         pred=pred.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     with torch.cuda.device(device):
         rc = _lib.load().inf_forward(C.byref(d), C.byref(t), _stream(device))
@@ -297,9 +311,9 @@ def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps
 
 
 def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key,
-                                 dense: bool, grad_scale: float, adam=None):
+                                 dense: bool, grad_scale: float, adam=None, ray_idxs=None):
     cfg = FieldConfig.from_key(cfg_key)
-    B = _check_inputs(cfg, table, vids, bary, dense)
+    B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
     pred = torch.empty((B, 3), dtype=torch.float32, device=device)
     # flat gradient and the two loss sums share one allocation so that a multi-rank step needs a single allreduce
@@ -308,19 +322,20 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
     flat, sums = flat_full[:n_par], flat_full[n_par:]
     if B == 0 or grad_pred is not None:
         sums.zero_()
-    for name, x in (("target", target), ("grad_pred", grad_pred)):
+    for name, x, rows in (("target", target, n_src), ("grad_pred", grad_pred, B)):
         if x is not None:
             _require_cuda(x, name)
-            if x.dtype != torch.float32 or tuple(x.shape) != (B, 3):
-                raise ValueError(f"{name} must be ({B},3) float32")
+            if x.dtype != torch.float32 or tuple(x.shape) != (rows, 3):
+                raise ValueError(f"{name} must be ({rows},3) float32")
     idx64 = vids is None or vids.dtype == torch.int64
-    dirs, face_idxs, face_normals, n_faces = _check_view(cfg, B, idx64, dirs, face_idxs, face_normals)
+    dirs, face_idxs, face_normals, n_faces = _check_view(cfg, n_src, idx64, dirs, face_idxs, face_normals)
     ws = _workspace(device, workspace_bytes(cfg, B, True))
     d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense,
-              grad_scale=grad_scale, n_faces=n_faces)
+              grad_scale=grad_scale, n_faces=n_faces, ray_idxs=ray_idxs, n_src_rays=n_src)
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), target=_ptr(target),
                         grad_pred=_ptr(grad_pred), unit_ray_dirs=_ptr(dirs), face_idxs=_ptr(face_idxs),
-                        face_normals=_ptr(face_normals), packed=packed.data_ptr(), pred=pred.data_ptr(),
+                        face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs), packed=packed.data_ptr(),
+                        pred=pred.data_ptr(),
                         workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     g = _lib.InfGrads(flat=flat.data_ptr(), loss_sums=sums.data_ptr())
     with torch.cuda.device(device):
@@ -341,13 +356,18 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
 @torch.library.custom_op("inf_b200::field_forward", mutates_args=())
 def field_forward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor],
                   packed: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
-                  face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool) -> torch.Tensor:
-    return _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense)
+                  face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
+                  ray_idxs: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs)
+
+
+def _fake_rows(table, vids, dense, ray_idxs):
+    return table.shape[0] if dense else (ray_idxs.shape[0] if ray_idxs is not None else vids.shape[0])
 
 
 @field_forward.register_fake
-def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense):
-    B = table.shape[0] if dense else vids.shape[0]
+def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs=None):
+    B = _fake_rows(table, vids, dense, ray_idxs)
     return table.new_empty((B, 3), dtype=torch.float32)
 
 
@@ -356,16 +376,16 @@ def field_forward_backward(table: torch.Tensor, vids: Optional[torch.Tensor], ba
                            packed: torch.Tensor, target: Optional[torch.Tensor], grad_pred: Optional[torch.Tensor],
                            dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                            face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
-                           grad_scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+                           grad_scale: float, ray_idxs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (pred (B,3), flat (n_params + 2,)): the flat gradient followed by the two loss sums (one allocation,
     one allreduce); use :func:`split_flat`."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals,
-                                        cfg_key, dense, grad_scale)
+                                        cfg_key, dense, grad_scale, ray_idxs=ray_idxs)
 
 
 @field_forward_backward.register_fake
-def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale):
-    B = table.shape[0] if dense else vids.shape[0]
+def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, ray_idxs=None):
+    B = _fake_rows(table, vids, dense, ray_idxs)
     n = num_params(FieldConfig.from_key(cfg_key))
     return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n + 2,), dtype=torch.float32))
 
@@ -386,17 +406,19 @@ def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Op
                      target: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                      face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool, grad_scale: float,
                      params_flat: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float,
-                     beta2: float, eps: float, step_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+                     beta2: float, eps: float, step_dev: torch.Tensor,
+                     ray_idxs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Forward + L1 loss + backward + Adam + operand refresh (trainer.py:75-82) in three kernel launches."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, None, dirs, face_idxs, face_normals, cfg_key,
                                         dense, grad_scale,
-                                        adam=_AdamArgs((params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)))
+                                        adam=_AdamArgs((params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)),
+                                        ray_idxs=ray_idxs)
 
 
 @field_train_step.register_fake
 def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, params_flat, exp_avg,
-      exp_avg_sq, lr, beta1, beta2, eps, step_dev):
-    B = table.shape[0] if dense else vids.shape[0]
+      exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None):
+    B = _fake_rows(table, vids, dense, ray_idxs)
     return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty((params_flat.numel() + 2,)))
 
 

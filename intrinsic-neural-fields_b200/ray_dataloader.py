@@ -17,7 +17,7 @@ from .ops import EigenTable
 class RayDataLoader:
     def __init__(self, features, feature_strategy, vertex_idxs_of_hit_faces, barycentric_coords, expected_rgbs,
                  unit_ray_dirs, face_idxs, batch_size, shuffle, drop_last, device="cuda", table_dtype="f32",
-                 materialize=False, generator=None):
+                 materialize=False, generator=None, fused_select=False):
         if feature_strategy != "efuncs":
             raise ValueError(f"Unknown / unsupported input feature strategy for the B200 path: {feature_strategy}")
         self.device = torch.device(device)
@@ -36,6 +36,9 @@ class RayDataLoader:
         assert self.barycentric_coords.dtype == torch.float32
         self.shuffle, self.drop_last = shuffle, drop_last
         self.materialize = materialize
+        # fused_select: do not run the per-batch index selects (ray_dataloader.py:122-126,142-143) at all; hand the
+        # kernels the whole split plus this batch's ray indices
+        self.fused_select = fused_select
         self.generator = generator
         self.B = batch_size
         self.N = self.vertex_idxs_of_hit_faces.shape[0]
@@ -68,6 +71,14 @@ class RayDataLoader:
         if self.i >= self.num_batches:
             raise StopIteration
         batch_idxs = self._get_next_batch_idxs()
+        if self.fused_select:
+            batch = {"ray_idxs": batch_idxs, "expected_rgbs": self.expected_rgbs,
+                     "vertex_idxs_of_hit_faces": self.vertex_idxs_of_hit_faces, "barycentric_coords": self.barycentric_coords,
+                     "eigenfunction_table": self.table}
+            if self.unit_ray_dirs is not None:
+                batch["unit_ray_dirs"] = self.unit_ray_dirs
+                batch["hit_face_idxs"] = self.face_idxs
+            return batch
         batch = {
             "expected_rgbs": self.expected_rgbs[batch_idxs],
             "vertex_idxs_of_hit_faces": self.vertex_idxs_of_hit_faces[batch_idxs],

@@ -16,6 +16,12 @@ import torch.nn.functional as F
 from . import ops, parallel
 
 
+def batch_rays(batch) -> int:
+    """Rays in a batch: its ``ray_idxs`` when the selection is folded into the kernels, else its target rows."""
+    r = batch.get("ray_idxs")
+    return int(r.shape[0]) if r is not None else int(batch["expected_rgbs"].shape[0])
+
+
 def get_loss_fn(loss_type: str) -> Callable:
     """config.py:113-122."""
     if loss_type == "L2":
@@ -31,7 +37,7 @@ def get_loss_fn(loss_type: str) -> Callable:
 def train_step_async(model, optim, batch, loss_fn=F.l1_loss, group=None, flat_grad=None):
     """One optimisation step without a host sync; returns (loss tensor (0-dim, device), pred)."""
     world = parallel.world_size(group)
-    B = batch["expected_rgbs"].shape[0]
+    B = batch_rays(batch)
     if loss_fn is F.l1_loss:
         optim.zero_grad(set_to_none=True)
         sums, pred, flat = model.l1_step(batch, global_rays=B * world, flat_grad=flat_grad)
@@ -63,9 +69,10 @@ def evaluate(model, data_loader, loss_fn=F.l1_loss):
     total = 0
     for batch in data_loader:
         pred = model(batch)
-        n = batch["expected_rgbs"].size()[0]
-        acc_l2 += F.mse_loss(pred, batch["expected_rgbs"], reduction="sum").item()
-        acc_loss += loss_fn(pred, batch["expected_rgbs"]).item() * n
+        gt = batch["expected_rgbs"] if batch.get("ray_idxs") is None else batch["expected_rgbs"][batch["ray_idxs"].long()]
+        n = gt.size()[0]
+        acc_l2 += F.mse_loss(pred, gt, reduction="sum").item()
+        acc_loss += loss_fn(pred, gt).item() * n
         total += n
     return acc_loss / total, epoch_psnr(acc_l2 / total)
 
@@ -112,12 +119,13 @@ class FusedFieldAdam:
         table, vids, bary, dense = m._inputs(batch)
         dirs, face_idxs, normals = m._view_inputs(batch)
         target = batch["expected_rgbs"].contiguous()
-        B = target.shape[0]
+        ridx = m._ray_idxs(batch)
+        B = batch_rays(batch)
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
         self.step_dev.add_(1)
         pred, flat_full = torch.ops.inf_b200.field_train_step(
             table, vids, bary, self.packed, target, dirs, face_idxs, normals, m.cfg.key(), dense, scale, self.flat,
-            self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev)
+            self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, ridx)
         flat, sums = ops.split_flat(flat_full)
         m._packed, m._packed_key = self.packed, None
         return sums, pred, flat
@@ -130,7 +138,8 @@ class FusedFieldAdam:
         target = batch["expected_rgbs"].contiguous()
         scale = 1.0 / (3.0 * float(global_rays))
         pred, flat_full = torch.ops.inf_b200.field_forward_backward(
-            table, vids, bary, self.packed, target, None, dirs, face_idxs, normals, m.cfg.key(), dense, scale)
+            table, vids, bary, self.packed, target, None, dirs, face_idxs, normals, m.cfg.key(), dense, scale,
+            m._ray_idxs(batch))
         flat, sums = ops.split_flat(flat_full)
         return sums, pred, flat
 
@@ -175,7 +184,7 @@ class FusedFieldAdam:
 def fused_train_step_async(model, fopt: "FusedFieldAdam", batch, group=None):
     """One optimisation step with the fused optimiser; returns (loss device scalar, pred)."""
     world = parallel.world_size(group)
-    B = batch["expected_rgbs"].shape[0]
+    B = batch_rays(batch)
     if world == 1:
         sums, pred, _ = fopt.fused_l1_step(batch)
     else:
@@ -208,6 +217,7 @@ class GraphedTrainStep:
     def __init__(self, model, optim, group=None):
         self.model, self.optim, self.group = model, optim, group
         self.graphs = {}
+        self._idx_bufs = {}
 
     @staticmethod
     def _key(batch):
@@ -219,7 +229,7 @@ class GraphedTrainStep:
     # the collective eagerly between the two replays (no NCCL call inside a capture).
     def _front(self, batch):
         world = parallel.world_size(self.group)
-        B = batch["expected_rgbs"].shape[0]
+        B = batch_rays(batch)
         if isinstance(self.optim, FusedFieldAdam):
             if world == 1:
                 return self.optim.fused_l1_step(batch)                   # includes the update
@@ -241,11 +251,11 @@ class GraphedTrainStep:
         sums, pred, flat = self._front(batch)
         if world > 1:
             parallel.allreduce_flat(flat, sums, self.group)
-        return self._back(sums, batch["expected_rgbs"].shape[0] * world, flat if world > 1 else None), pred
+        return self._back(sums, batch_rays(batch) * world, flat if world > 1 else None), pred
 
     def _capture(self, batch):
         world = parallel.world_size(self.group)
-        n_global = batch["expected_rgbs"].shape[0] * world
+        n_global = batch_rays(batch) * world
         g1 = torch.cuda.CUDAGraph()
         if world == 1:
             with torch.cuda.graph(g1):
@@ -263,6 +273,15 @@ class GraphedTrainStep:
         (it also sizes the workspace and creates the optimiser state, which must exist before a capture: state
         tensors allocated during capture would be re-zeroed by every replay); the second call captures, and from
         then on the step is one graph launch (two around the allreduce when multi-rank)."""
+        ridx = batch.get("ray_idxs")
+        if ridx is not None:
+            # a fused-select batch differs from the previous one only in its ray indices: stage them in a static buffer
+            # so that every batch of this shape replays the same graph
+            buf = self._idx_bufs.get((ridx.shape[0], ridx.dtype))
+            if buf is None:
+                buf = self._idx_bufs[(ridx.shape[0], ridx.dtype)] = torch.empty_like(ridx)
+            buf.copy_(ridx)
+            batch = dict(batch, ray_idxs=buf)
         key = self._key(batch)
         ent = self.graphs.get(key)
         if ent is None:

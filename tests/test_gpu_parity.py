@@ -588,3 +588,37 @@ def test_evaluate_matches_reference_val_loop_and_host_loader_shuffle():
     assert gv.shape == c["vids"].shape
     key = lambda v, t: sorted(map(tuple, torch.cat([v.double(), t.double()], 1).tolist()))
     assert key(gv, gt) == key(c["vids"], c["target"])
+
+
+@pytest.mark.parametrize("name", ["tf_k64", "view_intrinsic"])
+def test_fused_batch_selection_equals_index_select_batches(name):
+    # ray_dataloader.py:103-145: batch_idxs -> index selects -> model.  With fused_select the kernels read the whole split
+    # through the batch's ray indices; results must be bit-identical to the materialised batches, in every mode.
+    from inf_b200 import trainer
+    from inf_b200.ray_dataloader import RayDataLoader
+    c = load_golden(name)
+    view = c["view"] is not None
+    dirs, fids = (c["unit_ray_dirs"], c["face_idxs"]) if view else (None, None)
+    outs = []
+    for fused in (False, True):
+        gen = torch.Generator(device=DEV).manual_seed(3)
+        dl = RayDataLoader(c["table"], "efuncs", c["vids"], c["bary"], c["target"], dirs, fids, batch_size=50, shuffle=True,
+                           drop_last=False, device=DEV, generator=gen, fused_select=fused)
+        m = _model_from(c)
+        fopt = trainer.FusedFieldAdam(m, lr=1e-3)
+        gs = trainer.GraphedTrainStep(m, fopt)
+        losses, preds = [], []
+        for i, b in enumerate(dl):
+            if i < 2:
+                with torch.no_grad():
+                    preds.append(m(b).clone())                 # inference through the selection
+            loss, pred = gs.step(b) if i >= 2 else trainer.fused_train_step(m, fopt, b)
+            losses.append(loss)
+            preds.append(pred.clone())
+        m.eval()
+        val = trainer.evaluate(m, dl)
+        outs.append((losses, torch.cat(preds), fopt.flat.clone(), val))
+    _check_no_watchdog()
+    (l0, p0, f0, v0), (l1, p1, f1, v1) = outs
+    assert l0 == l1 and torch.equal(p0, p1) and torch.equal(f0, f1)
+    assert abs(v0[0] - v1[0]) < 1e-6 and abs(v0[1] - v1[1]) < 1e-4
