@@ -226,6 +226,12 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   const Smem sm = smem_layout(view);
   const int nstage_a = sm.nstage_a;
   const int nb = g.nb, nhid = g.nhid;
+  // Cluster of `cs` CTAs (1 or 2): every [W0;Wy] chunk is fetched from L2 ONCE per cluster -- each CTA loads 1/cs of it
+  // and multicasts that slice to all of them.  The CTAs of a cluster therefore run the same number of tile iterations;
+  // a CTA whose tile index is past the end processes a null tile (all rays invalid, nothing stored).
+  const int cs = p.cluster;
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
 
   auto bar = [&](int i) -> uint32_t { return smem_base + sm.bars + 8u * static_cast<uint32_t>(i); };
   // measurement only (INF_DEBUG & 8): per-role cycle accounting of CTA 0, written once at the end of the kernel
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       mbar_init(bar(BAR_A_FULL + i), PROD_WARPS);
       mbar_init(bar(BAR_A_EMPTY + i), kTrain ? 2 : 1);  // MMA commit (+ x-panel stash store finished reading)
     }
-    for (int i = 0; i < NSTAGE_B1; ++i) { mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), 1); }
+    for (int i = 0; i < NSTAGE_B1; ++i) { mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), cs); }
     mbar_init(bar(BAR_B2_FULL), 1);
     mbar_init(bar(BAR_B2_EMPTY), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_G_FULL + i), 1); mbar_init(bar(BAR_G_EMPTY + i), EPI_WARPS); }
@@ -274,10 +280,18 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // every CTA's barriers are initialised before a peer multicasts into / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + sm.tmemptr);
 
   const int ntiles = p.ntiles;
+  // loop bound of this CTA: as many iterations as the first CTA of its cluster needs
+  int nt_loop = ntiles;
+  if (cs > 1) {
+    const int first = (static_cast<int>(blockIdx.x) / cs) * cs;
+    const int iters = first < ntiles ? (ntiles - first + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+    nt_loop = iters > 0 ? static_cast<int>(blockIdx.x) + (iters - 1) * static_cast<int>(gridDim.x) + 1 : 0;
+  }
   const int nchunks = g.nchunks;
   const size_t tile_stride = stash_tile_bytes(g);
   const uint64_t stash_policy = l2_policy_evict_first();   // stash tiles are written once, read once by the next kernel
@@ -339,7 +353,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     // table rows are re-used by other rays (and by the next step): keep them in L2 ahead of the read-once streams
     const uint64_t table_policy = l2_policy_evict_last(p.table_keep);
     auto issue = [&](const Cursor& k, RowLoader<TableT>& ld) {
-      if (k.tile >= ntiles) return;
+      if (k.tile >= nt_loop) return;
 #pragma unroll
       for (int u = 0; u < QUADS; ++u) {
         const int e = k.slot * 384 + 3 * quad_row(k.q * QUADS + u);
@@ -374,8 +388,13 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     };
     RowLoader<TableT> ld0, ld1;
     Cursor L{static_cast<int>(blockIdx.x), 0, 0, 0};
-    if (static_cast<int>(blockIdx.x) < ntiles) {
+    // The load cursor runs two passes ahead of the consumer: one tile ahead at most when a tile has >= 2 passes per
+    // warp, two tiles ahead when it has a single pass (fp16 table with k_pad = 64).  Metadata is loaded `ahead` tiles
+    // ahead accordingly (three ring slots: consuming, +1, +2).
+    const int ahead = (nchunks * PPC >= 2) ? 1 : 2;
+    if (static_cast<int>(blockIdx.x) < nt_loop) {
       load_meta(blockIdx.x, 0);
+      if (ahead == 2 && static_cast<int>(blockIdx.x + gridDim.x) < nt_loop) load_meta(blockIdx.x + gridDim.x, 1);
       named_bar_sync(2, PROD_THREADS);
       issue(L, ld0); advance(L);
       issue(L, ld1); advance(L);
@@ -384,10 +403,11 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     uint32_t n = 0;   // running pass index: pass n lives in ld0 (even) / ld1 (odd)
     long long t_prod_wait = 0;
     const long long t_prod0 = now();
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++it) {
       const int slot = it % 3;
-      const int next_tile = tile + gridDim.x;
-      if (next_tile < ntiles) load_meta(next_tile, (it + 1) % 3);   // the load cursor enters it 2 passes early
+      const int next_tile = tile + ahead * static_cast<int>(gridDim.x);
+      if (ahead == 2) named_bar_sync(2, PROD_THREADS);   // slot (it+2)%3 was the previous tile's: everyone has left it
+      if (next_tile < nt_loop) load_meta(next_tile, (it + ahead) % 3);   // the load cursor enters it 2 passes early
       named_bar_sync(2, PROD_THREADS);
       for (int c = 0; c < nchunks; ++c) {
         const long long tw0 = now();
@@ -414,12 +434,15 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t slice = BLOB_BYTES / static_cast<uint32_t>(cs);
+      for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(bar(BAR_B1_EMPTY + stage), phase ^ 1u, p.err, 0x20);
+          mbar_wait(bar(BAR_B1_EMPTY + stage), phase ^ 1u, p.err, 0x20);   // released by every CTA of the cluster
           mbar_arrive_expect_tx(bar(BAR_B1_FULL + stage), BLOB_BYTES);
-          bulk_g2s(smem_base + sm.b1 + static_cast<uint32_t>(stage) * BLOB_BYTES,
-                   p.packed + static_cast<size_t>(c) * BLOB_BYTES, BLOB_BYTES, bar(BAR_B1_FULL + stage));
+          const uint32_t dst = smem_base + sm.b1 + static_cast<uint32_t>(stage) * BLOB_BYTES;
+          const uint8_t* src = p.packed + static_cast<size_t>(c) * BLOB_BYTES;
+          if (cs == 1) bulk_g2s(dst, src, BLOB_BYTES, bar(BAR_B1_FULL + stage));
+          else bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice, bar(BAR_B1_FULL + stage), cmask);
           if (++stage == NSTAGE_B1) { stage = 0; phase ^= 1u; }
         }
       }
@@ -434,7 +457,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         bulk_g2s(smem_base + sm.b2, p.packed + static_cast<size_t>(blob) * BLOB_BYTES, bytes, bar(BAR_B2_FULL));
         phase ^= 1u;
       };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x) {
         for (int l = 1; l <= nhid; ++l) load(blob_hidden(g, l), BLOB_BYTES);
         if (view) { load(blob_wd1z(g), BLOB_BYTES); load(blob_wd1e(g), PANEL_BYTES); }
         if (kTrain) {
@@ -453,7 +476,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       int it = 0;
       long long t_g = 0, t_a = 0, t_b = 0, t_st = 0;
       const long long t_g1_0 = now();
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const long long tg0 = now();
         mbar_wait(bar(BAR_G_EMPTY + buf), gph[buf] ^ 1u, p.err, 0x33);  // chain of tile it-2 left this buffer
@@ -461,7 +484,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         gph[buf] ^= 1u;
         tc_fence_after();
         const uint32_t dcol = tmem_base + 256u * static_cast<uint32_t>(buf);
-        uint8_t* xdst = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride + stash_off_x(g, 0) : nullptr;
+        uint8_t* xdst = (kTrain && tile < ntiles) ? p.stash + static_cast<size_t>(tile) * tile_stride + stash_off_x(g, 0) : nullptr;
         for (int c = 0; c < nchunks; ++c) {
           const long long ta0 = now();
           mbar_wait(bar(BAR_A_FULL + sa), pa, p.err, 0x30);
@@ -479,10 +502,11 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
                      (c > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(bar(BAR_A_EMPTY + sa));
-          umma_commit(bar(BAR_B1_EMPTY + sb));
+          if (cs == 1) umma_commit(bar(BAR_B1_EMPTY + sb));
+          else umma_commit_multicast(bar(BAR_B1_EMPTY + sb), cmask);   // the stage is refilled by every CTA of the cluster
           if (kTrain) {
             // x panel -> stash (the B operand of dW0 / dWy in the wgrad kernel)
-            if (!(p.debug & 1)) bulk_s2g_hint(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES, stash_policy);
+            if (!(p.debug & 1) && xdst != nullptr) bulk_s2g_hint(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES, stash_policy);
             bulk_commit();
             const long long ts0 = now();
             bulk_wait_read<0>();
@@ -541,7 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
                    IDESC_N128_BMN, kk > 0 ? 1u : 0u);
         }
       };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++it) {
         const uint32_t base = tmem_base + 256u * static_cast<uint32_t>(it & 1);
         for (int l = 1; l <= nhid; ++l, ++wr) {
           wait_act();
@@ -610,11 +634,12 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (w & 1u) * BLOB_BYTES; };
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t tb = tlane + 256u * static_cast<uint32_t>(buf);
       const int64_t ray = static_cast<int64_t>(tile) * TILE_M + r;
       const bool valid = ray < p.n_rays;
+      const bool store_tile = tile < ntiles;   // a null tile (cluster padding) leaves no trace in the stash
       int64_t src = ray;   // row of target / dirs / face_idxs this ray reads (batch selection folded in)
       if (valid && p.ridx != nullptr)
         src = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[ray])
@@ -689,8 +714,8 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         sync_epi();
         if (tid == 0) {
           if (kTrain) {
-            if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_h(g, l), hb, BLOB_BYTES, stash_policy);
-            if (l == 0 && view) bulk_s2g_hint(stash_tile + stash_off_e(g), smem_base + sm.e, PANEL_BYTES, stash_policy);
+            if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_h(g, l), hb, BLOB_BYTES, stash_policy);
+            if (l == 0 && view && store_tile) bulk_s2g_hint(stash_tile + stash_off_e(g), smem_base + sm.e, PANEL_BYTES, stash_policy);
             bulk_commit();
             const long long t0 = now();
             bulk_wait_read<1>();   // the buffer written next is free before the chain may continue
@@ -792,10 +817,10 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           }
           sync_epi();
           if (tid == 0) {
-            if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES, stash_policy);
+            if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES, stash_policy);
             bulk_commit();
-            if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES, stash_policy);
-            bulk_s2g_hint(stash_tile + stash_off_dzlt(g), smem_base + sm.dzlt, DZLT_BYTES, stash_policy);
+            if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES, stash_policy);
+            if (store_tile) bulk_s2g_hint(stash_tile + stash_off_dzlt(g), smem_base + sm.dzlt, DZLT_BYTES, stash_policy);
             bulk_commit();
             bulk_wait_read<1>();
             mbar_arrive(bar(BAR_ACT_READY));
@@ -830,7 +855,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             }
             sync_epi();
             if (tid == 0) {
-              if (!(p.debug & 2)) bulk_s2g_hint(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES, stash_policy);
+              if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES, stash_policy);
               bulk_commit();
               if (lb > 0) {
                 bulk_wait_read<1>();
@@ -872,6 +897,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   }
 
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == W_G1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -884,8 +910,44 @@ static cudaError_t launch_one(const FieldParams& p, int grid, cudaStream_t strea
   const int smem = static_cast<int>(smem_layout(p.geo.view != INF_VIEW_NONE).total);
   cudaError_t e = cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) return e;
-  field_main_kernel<kTrain, TableT><<<grid, NUM_THREADS_MAIN, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(NUM_THREADS_MAIN);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, field_main_kernel<kTrain, TableT>, p);
+}
+
+// Largest grid (a multiple of `cluster`) whose clusters are all co-resident with this kernel's footprint, 0 on error.
+template <bool kTrain, typename TableT>
+static int max_grid_one(int cluster, bool view) {
+  cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(cluster));
+  cfg.blockDim = dim3(NUM_THREADS_MAIN);
+  cfg.dynamicSmemBytes = smem_layout(view).total;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, field_main_kernel<kTrain, TableT>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n * cluster;
+}
+
+int field_main_max_grid(bool train, bool table_f16, int cluster, bool view) {
+  if (train) return table_f16 ? max_grid_one<true, __half>(cluster, view) : max_grid_one<true, float>(cluster, view);
+  return table_f16 ? max_grid_one<false, __half>(cluster, view) : max_grid_one<false, float>(cluster, view);
 }
 
 cudaError_t launch_field_main(const FieldParams& p, bool train, bool table_f16, int grid, cudaStream_t stream) {

@@ -102,6 +102,35 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src
       "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters: rank, barrier, multicast bulk copy, multicast MMA-completion arrive
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// One bulk copy delivered to the same smem offset of every CTA in `mask`; each destination CTA's mbarrier (same
+// offset) receives the complete_tx for the bytes that landed in it.
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit whose arrival is delivered to the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // DRAM -> L2 prefetch through the bulk-copy engine (no destination: costs neither registers nor smem).
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");

@@ -622,3 +622,33 @@ def test_fused_batch_selection_equals_index_select_batches(name):
     (l0, p0, f0, v0), (l1, p1, f1, v1) = outs
     assert l0 == l1 and torch.equal(p0, p1) and torch.equal(f0, f1)
     assert abs(v0[0] - v1[0]) < 1e-6 and abs(v0[1] - v1[1]) < 1e-4
+
+
+@pytest.mark.parametrize("table_dtype", ["f16", "f32"])
+def test_single_chunk_tiles_many_tiles_per_cta(table_dtype):
+    # k_pad = 64: one k-chunk per tile, so the gather's load cursor runs two TILES ahead of the consumer (fp16 table);
+    # 40 000 rays = 313 tiles > 2 per CTA.  Regression test for the metadata look-ahead of that case.
+    torch.manual_seed(5)
+    V, k, B = 3000, 64, 40000
+    E = torch.randn(V, k) / 4
+    params = O.make_params(k, seed=6)
+    m = inf_b200.make_model(dict(k=k, num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3))
+    m.load_state_dict(params)
+    m = m.to(DEV)
+    vids = torch.randint(0, V, (B, 3))
+    u = torch.rand(B, 3)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3)
+    b = {"eigenfunction_table": inf_b200.EigenTable.from_dense(E, device=DEV, dtype=table_dtype),
+         "vertex_idxs_of_hit_faces": vids.to(DEV), "barycentric_coords": bary.to(DEV), "expected_rgbs": target.to(DEV)}
+    with torch.no_grad():
+        p_inf = m(b).cpu()
+    sums, pred, flat = m.l1_step(b)
+    _check_no_watchdog()
+    assert torch.equal(p_inf, pred.cpu())
+    idx = torch.arange(0, B, 37)
+    ref = O.field_forward(params, E, vids[idx], bary[idx])
+    err = (p_inf[idx] - ref).abs()
+    assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN
+    loss_ref = (O.field_forward(params, E, vids, bary) - target).abs().mean().item()
+    assert abs(sums[0].item() / (3 * B) - loss_ref) < 1e-3
