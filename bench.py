@@ -164,6 +164,39 @@ def cpu_reference_rate(train: bool, steps: int, warmup: int, batch: int, V: int 
     return batch * len(times) / total, total / len(times) * 1e3
 
 
+def torch_gpu_context_rate(train: bool, dev, batch: int = 131072, steps: int = 5):
+    """Context only: the reference's PyTorch fp32 path (oracle restatement: materialised gather,
+    cuBLAS SGEMMs with TF32 off, autograd, Adam) on the SAME B200, same workload.  Not the baseline, not the product."""
+    from oracle import field_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    faces = torus_faces(GRID, dev)
+    table = make_table(GRID * GRID, K_EIG, dev)
+    params = {n: t.to(dev).requires_grad_(train) for n, t in O.make_params(K_EIG, HID, LAYERS, SKIP, seed=0).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=LR) if train else None
+    vids, bary, target = make_rays(faces, batch, dev, seed=5)
+
+    def one():
+        if train:
+            pred = O.field_forward(params, table, vids, bary, num_layers=LAYERS, skip=SKIP)
+            loss = O.l1_loss(pred, target)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                O.field_forward(params, table, vids, bary, num_layers=LAYERS, skip=SKIP)
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    return batch * steps / (e0.elapsed_time(e1) / 1e3)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -376,6 +409,12 @@ def run_ours(args):
         cr, cms = cpu_reference_rate(train, steps=6, warmup=1, batch=16384)
         out["cpu_baseline"] = {"value": cr, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
                                "sample": "6 steps x 16384 rays of the same workload (oracle/ restatement, torch CPU, all threads)"}
+        try:
+            out["context_reference_torch_fp32_on_this_gpu"] = {
+                "value": torch_gpu_context_rate(train, dev), "unit": "rays/s",
+                "note": "oracle restatement of the reference PyTorch path on the same B200 (TF32 off); context, not the baseline"}
+        except Exception as exc:      # context only: never fail the bench line
+            out["context_reference_torch_fp32_on_this_gpu"] = {"value": None, "note": f"not measured: {type(exc).__name__}"}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

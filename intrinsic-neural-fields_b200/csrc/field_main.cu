@@ -41,23 +41,27 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 
 constexpr int NSTAGE_B1 = 2;
-constexpr int MAX_STAGE_A = 3;
+constexpr int MAX_STAGE_A = 5;
 
-// shared memory carve-up (bytes from a 1024-aligned base); the A ring gives one stage to the Fourier panel
-// when the view branch is on
+// shared memory carve-up (bytes from a 1024-aligned base), 13 panels of 16 KB + small tables:
+//   training   A ring 3 (2 with the view branch: one stage goes to the Fourier panel), B1 2x32 KB, H 2x32 KB, B2 32 KB
+//   inference  no stash stores read the activation buffer after the MMA, so ONE H buffer is enough and the A ring gets
+//              its 32 KB: 5 stages (4 with the view branch).  Every producer warp contributes to every A panel, so a
+//              deeper ring is what decouples the warps from each other's tail latencies.
 struct Smem {
   uint32_t a, b1, h, b2, e, dzlt, bias, wlast, vid, bary, red, bars, tmemptr, total;
-  int nstage_a;
+  int nstage_a, nh;
 };
-__host__ __device__ constexpr Smem smem_layout(bool view) {
+__host__ __device__ constexpr Smem smem_layout(bool view, bool train) {
   Smem s{};
-  s.nstage_a = view ? 2 : 3;
+  s.nh = train ? 2 : 1;
+  s.nstage_a = (train ? 3 : 5) - (view ? 1 : 0);
   s.a = 0;
   s.b1 = s.a + static_cast<uint32_t>(s.nstage_a) * PANEL_BYTES;
   s.h = s.b1 + NSTAGE_B1 * BLOB_BYTES;
-  s.b2 = s.h + 2 * BLOB_BYTES;
+  s.b2 = s.h + static_cast<uint32_t>(s.nh) * BLOB_BYTES;
   s.e = s.b2 + BLOB_BYTES;
-  s.dzlt = 13 * PANEL_BYTES;                      // 212992 in both variants
+  s.dzlt = 13 * PANEL_BYTES;                      // 212992 in all variants
   s.bias = s.dzlt + DZLT_BYTES;                   // f32 [MAX_MMA_LAYERS][128]
   s.wlast = s.bias + MAX_MMA_LAYERS * HID * 4;    // f32 [3][128] + blast[4]
   s.vid = s.wlast + OUT_DIM * HID * 4 + 16;       // u32 [3][384]
@@ -68,13 +72,15 @@ __host__ __device__ constexpr Smem smem_layout(bool view) {
   s.total = s.tmemptr + 16;
   return s;
 }
-static_assert(smem_layout(false).e <= smem_layout(false).dzlt, "smem layout");
-static_assert(smem_layout(true).e + PANEL_BYTES <= smem_layout(true).dzlt, "smem layout (view)");
-static_assert(smem_layout(true).total <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+static_assert(smem_layout(false, true).e <= smem_layout(false, true).dzlt, "smem layout");
+static_assert(smem_layout(true, true).e + PANEL_BYTES <= smem_layout(true, true).dzlt, "smem layout (view)");
+static_assert(smem_layout(false, false).e <= smem_layout(false, false).dzlt, "smem layout (inference)");
+static_assert(smem_layout(true, false).e + PANEL_BYTES <= smem_layout(true, false).dzlt, "smem layout (inference, view)");
+static_assert(smem_layout(true, true).total <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 // barrier indices
-constexpr int BAR_A_FULL = 0;                          // [3]
-constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_STAGE_A;  // [3]
+constexpr int BAR_A_FULL = 0;                          // [5]
+constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_STAGE_A;  // [5]
 constexpr int BAR_B1_FULL = BAR_A_EMPTY + MAX_STAGE_A; // [2]
 constexpr int BAR_B1_EMPTY = BAR_B1_FULL + NSTAGE_B1;  // [2]
 constexpr int BAR_B2_FULL = BAR_B1_EMPTY + NSTAGE_B1;
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   const int lane = tid & 31;
   const Geo g = p.geo;
   const bool view = g.view != INF_VIEW_NONE;
-  const Smem sm = smem_layout(view);
+  const Smem sm = smem_layout(view, kTrain);
   const int nstage_a = sm.nstage_a;
   const int nb = g.nb, nhid = g.nhid;
   // Cluster of `cs` CTAs (1 or 2): every [W0;Wy] chunk is fetched from L2 ONCE per cluster -- each CTA loads 1/cs of it
@@ -540,7 +546,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         t_b2 += now() - t0;
       };
       const uint32_t bbase = smem_base + sm.b2;
-      auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (w & 1u) * BLOB_BYTES; };
+      auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (kTrain ? (w & 1u) * BLOB_BYTES : 0u); };
       const uint32_t blo_k = umma_desc_lo(bbase, 0);             // weight image read K-major (forward)
       const uint32_t blo_mn = umma_desc_lo(bbase, PANEL_BYTES);   // the same image read MN-major (dgrad)
       // D[128 x 128] (+)= A[128 x 64*npanel] * B^T, both K-major panel images
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       named_bar_sync(1, EPI_THREADS);
       t_sync += now() - t0;
     };
-    auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (w & 1u) * BLOB_BYTES; };
+    auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (kTrain ? (w & 1u) * BLOB_BYTES : 0u); };
 
     int it = 0;
     for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++it) {
@@ -907,7 +913,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
 // ---- host launcher (kernels stay private to this translation unit) -----------------------------
 template <bool kTrain, typename TableT>
 static cudaError_t launch_one(const FieldParams& p, int grid, cudaStream_t stream) {
-  const int smem = static_cast<int>(smem_layout(p.geo.view != INF_VIEW_NONE).total);
+  const int smem = static_cast<int>(smem_layout(p.geo.view != INF_VIEW_NONE, kTrain).total);
   cudaError_t e = cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -932,7 +938,7 @@ static int max_grid_one(int cluster, bool view) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(cluster));
   cfg.blockDim = dim3(NUM_THREADS_MAIN);
-  cfg.dynamicSmemBytes = smem_layout(view).total;
+  cfg.dynamicSmemBytes = smem_layout(view, kTrain).total;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);

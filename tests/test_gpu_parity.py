@@ -652,3 +652,21 @@ def test_single_chunk_tiles_many_tiles_per_cta(table_dtype):
     assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN
     loss_ref = (O.field_forward(params, E, vids, bary) - target).abs().mean().item()
     assert abs(sums[0].item() / (3 * B) - loss_ref) < 1e-3
+
+
+@pytest.mark.parametrize("scale", [2.0, 3.0])
+def test_rgb_parity_at_trained_scale_weights(scale):
+    # all-bf16 operands pass at Xavier init but leave the RGB tolerance once training has grown the weights
+    # (|W0|_inf 0.07 -> 0.13+); the fp16-operand path must hold it there.  Weights scaled up instead of a long CPU training.
+    c = load_golden("tf_k1023")
+    params = {n: (t * scale if n.endswith("weight") else t) for n, t in c["params"].items()}
+    m = inf_b200.make_model(dict(k=c["k"], num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3))
+    m.load_state_dict(params)
+    m = m.to(DEV)
+    for dt in ("f32", "f16"):
+        with torch.no_grad():
+            pred = m(_batch(c, dt)).cpu()
+        ref = O.field_forward(params, c["table"], c["vids"], c["bary"])
+        err = (pred - ref).abs()
+        assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN, (scale, dt, err.max().item(), err.mean().item())
+    _check_no_watchdog()
