@@ -254,9 +254,6 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
                             (d->table_dtype == INF_TABLE_F16 ? 2.0 : 4.0) / 1048576.0;
     p.table_keep = static_cast<float>(table_mb <= keep_mb ? 1.0 : keep_mb / table_mb);
     if (d->input_mode == INF_INPUT_DENSE) p.table_keep = 0.f;   // a dense embedding is read exactly once
-    const char* w = getenv("INF_PREFETCH_WGRAD");
-    p.prefetch_wgrad = w ? atoi(w) : 0;   // measured: prefetches through the bulk-copy engine compete with its loads
-    if (p.prefetch_wgrad < 0 || p.prefetch_wgrad > 32) p.prefetch_wgrad = 0;
   }
   p.geo = geo_of(d);
   p.plan = make_wplan(p.geo);

@@ -213,7 +213,6 @@ struct FieldParams {
   unsigned long long* trace;  // (INF_DEBUG & 8) clock64 stamps of CTA 0's chain: [0] = count, then (tag<<48 | clock)
   float table_keep; // fraction of the table's lines given the L2 evict_last policy (what fits beside the streams)
   int prefetch;     // gather L2 prefetch distance in k-chunks (0 = off)
-  int prefetch_wgrad;  // wgrad: L2 prefetch distance in ring units (0 = off)
   int cluster;      // CTAs per cluster of the forward/backward kernel (1 or 2): [W0;Wy] chunks are multicast within it
   int debug;        // measurement knobs (INF_DEBUG env): 1 no x stash, 2 no h/dz stash, 4 no dgrad chain -- wrong results
   int groups_big;                   // wgrad: ray groups (CTAs) per big slice

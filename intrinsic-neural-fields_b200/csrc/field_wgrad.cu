@@ -114,13 +114,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
       int stage = 0;
       uint32_t phase = 0;
       const uint64_t stash_policy = l2_policy_evict_first();   // read-once stream
-      // Issue (or only L2-prefetch) the operands of unit u.  The stash is DRAM resident when this kernel starts; the
-      // bulk-copy engine keeps only a small window of bytes in flight per SM, so the DRAM latency is taken by
-      // fire-and-forget L2 prefetches `pfd` units ahead and the ring loads then hit L2.
-      auto unit_io = [&](int u, bool prefetch_only, uint32_t sbase, uint32_t fb) {
+      // (L2 prefetches of upcoming units through the same bulk-copy engine, and cp.async copy warps sharing the ring,
+      //  were both measured slower than this plain 3-stage stream -- see DESIGN.md section 4)
+      for (int u = 0; u < nunits; ++u) {
         // newest tiles first: the forward/backward kernel wrote them last, so part of their stash is still in L2
         const int tile = ntiles - 1 - (grp + (u / units_per_tile) * groups);
         const uint8_t* st = p.stash + static_cast<size_t>(tile) * tile_stride;
+        mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1u, p.err, 0x60);
+        const uint32_t sbase = smem_base + SM_STAGES + static_cast<uint32_t>(stage) * STAGE_BYTES;
+        const uint32_t fb = bar(BAR_FULL + stage);
         if (big) {
           // half tile hh (64 rays): dz_0 and dz_skip halves (two n-panels each), x halves of this slice's panels
           const int hh = u & 1;
@@ -128,12 +130,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
           const uint8_t* dz0 = st + stash_off_dz(g, 0) + hh * HALF_PANEL;
           const uint8_t* dzs = st + stash_off_dz(g, g.skip) + hh * HALF_PANEL;
           const uint8_t* xs = st + stash_off_x(g, 4 * slice) + hh * HALF_PANEL;
-          if (prefetch_only) {
-            bulk_prefetch_l2(dz0, HALF_PANEL); bulk_prefetch_l2(dz0 + PANEL_BYTES, HALF_PANEL);
-            bulk_prefetch_l2(dzs, HALF_PANEL); bulk_prefetch_l2(dzs + PANEL_BYTES, HALF_PANEL);
-            for (int pn = 0; pn < npanels; ++pn) bulk_prefetch_l2(xs + static_cast<size_t>(pn) * PANEL_BYTES, HALF_PANEL);
-            return;
-          }
           mbar_arrive_expect_tx(fb, static_cast<uint32_t>(4 + npanels) * HALF_PANEL);
           bulk_g2s_hint(sbase + 0 * HALF_PANEL, dz0, HALF_PANEL, fb, stash_policy);
           bulk_g2s_hint(sbase + 1 * HALF_PANEL, dz0 + PANEL_BYTES, HALF_PANEL, fb, stash_policy);
@@ -141,25 +137,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
           bulk_g2s_hint(sbase + 3 * HALF_PANEL, dzs + PANEL_BYTES, HALF_PANEL, fb, stash_policy);
           for (int pn = 0; pn < npanels; ++pn)
             bulk_g2s_hint(sbase + BLOB_BYTES + static_cast<uint32_t>(pn) * HALF_PANEL, xs + static_cast<size_t>(pn) * PANEL_BYTES,
-                     HALF_PANEL, fb, stash_policy);
+                          HALF_PANEL, fb, stash_policy);
         } else {
           const WUnit w = p.plan.u[u0 + (u % units_per_tile)];
-          if (prefetch_only) {
-            bulk_prefetch_l2(st + w.a_off, BLOB_BYTES);
-            if (w.b_bytes > 0) bulk_prefetch_l2(st + w.b_off, static_cast<uint32_t>(w.b_bytes));
-            return;
-          }
           mbar_arrive_expect_tx(fb, static_cast<uint32_t>(BLOB_BYTES + w.b_bytes));
           bulk_g2s_hint(sbase, st + w.a_off, BLOB_BYTES, fb, stash_policy);
           if (w.b_bytes > 0) bulk_g2s_hint(sbase + BLOB_BYTES, st + w.b_off, static_cast<uint32_t>(w.b_bytes), fb, stash_policy);
         }
-      };
-      const int pfd = p.prefetch_wgrad;
-      for (int u = 0; u < pfd && u < nunits; ++u) unit_io(u, true, 0, 0);
-      for (int u = 0; u < nunits; ++u) {
-        if (pfd > 0 && u + pfd < nunits) unit_io(u + pfd, true, 0, 0);
-        mbar_wait(bar(BAR_EMPTY + stage), phase ^ 1u, p.err, 0x60);
-        unit_io(u, false, smem_base + SM_STAGES + static_cast<uint32_t>(stage) * STAGE_BYTES, bar(BAR_FULL + stage));
         if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
       }
     }

@@ -181,12 +181,16 @@ class EigenTable:
 # workspace cache (one growing buffer per device; the first 256 bytes hold the kernel error word)
 # ------------------------------------------------------------------------------------------------
 _workspaces = {}
+_retired = []   # outgrown workspaces stay alive: CUDA graphs captured earlier still point into them
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
+    """One growing scratch buffer per device (stream-ordered use: one call in flight per device at a time)."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired.append(ws)
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
@@ -196,10 +200,9 @@ def kernel_error_word(device) -> int:
     """Non-zero if a kernel watchdog fired (pipeline stall); 0 otherwise.  Synchronises."""
     key = (torch.device(device).type, torch.device(device).index if torch.device(device).index is not None
            else torch.cuda.current_device())
-    ws = _workspaces.get(key)
-    if ws is None:
-        return 0
-    return int(ws[:4].view(torch.int32).item())
+    words = [int(w[:4].view(torch.int32).item()) for w in [_workspaces.get(key)] + _retired
+             if w is not None and w.device == torch.device(device)]
+    return next((w for w in words if w != 0), 0)
 
 
 # ------------------------------------------------------------------------------------------------

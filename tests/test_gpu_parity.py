@@ -670,3 +670,31 @@ def test_rgb_parity_at_trained_scale_weights(scale):
         err = (pred - ref).abs()
         assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN, (scale, dt, err.max().item(), err.mean().item())
     _check_no_watchdog()
+
+
+def test_captured_graph_survives_workspace_growth():
+    # a CUDA graph captured at a small batch keeps pointing into the scratch buffer of that time; a later, larger call
+    # outgrows the buffer -- the old one must stay alive or the replay would write through a dangling pointer
+    from inf_b200 import trainer
+    c = load_golden("tf_k64")
+    b = _batch(c)
+    m = _model_from(c)
+    fopt = trainer.FusedFieldAdam(m, lr=1e-3)
+    gs = trainer.GraphedTrainStep(m, fopt)
+    l = [gs.step(b)[0] for _ in range(3)]                       # eager, capture, replay
+    # force the workspace to grow: a training call 200x larger
+    torch.manual_seed(0)
+    V, B = c["table"].shape[0], 60000
+    big = {"eigenfunction_table": b["eigenfunction_table"], "vertex_idxs_of_hit_faces": torch.randint(0, V, (B, 3), device=DEV),
+           "barycentric_coords": torch.full((B, 3), 1.0 / 3.0, device=DEV), "expected_rgbs": torch.rand(B, 3, device=DEV)}
+    m2 = _model_from(c)
+    m2.l1_step(big)
+    filler = [torch.full((1 << 18,), float("nan"), device=DEV) for _ in range(64)]   # reuse freed blocks, if any, with poison
+    l += [gs.step(b)[0] for _ in range(3)]
+    _check_no_watchdog()
+    del filler
+    ref_m = _model_from(c)
+    ropt = trainer.FusedFieldAdam(ref_m, lr=1e-3)
+    lr_ = [trainer.fused_train_step(ref_m, ropt, b)[0] for _ in range(6)]
+    assert l == lr_
+    assert torch.equal(fopt.flat, ropt.flat)
