@@ -87,9 +87,15 @@ def make_table(V: int, k: int, device, seed: int = 0) -> torch.Tensor:
     return t / (t.max(0, keepdim=True).values - t.min(0, keepdim=True).values)   # 'standard' rescale, mesh.py:99-102
 
 
-def make_rays(faces: torch.Tensor, B: int, device, seed: int):
+def make_rays(faces: torch.Tensor, B: int, device, seed: int, coherent: bool = False):
+    """Random hit faces (worst-case locality; what a shuffled training batch looks like) or, with `coherent`, a scanline
+    pattern: consecutive rays walk over neighbouring faces, ~8 rays per face (render_video.py:122-134 style frames)."""
     g = torch.Generator(device=device).manual_seed(seed)
-    fid = torch.randint(0, faces.shape[0], (B,), device=device, generator=g)
+    if coherent:
+        start = int(torch.randint(0, faces.shape[0], (1,), device=device, generator=g))
+        fid = (start + torch.arange(B, device=device) // 8) % faces.shape[0]
+    else:
+        fid = torch.randint(0, faces.shape[0], (B,), device=device, generator=g)
     vids = faces[fid].to(torch.int64).contiguous()
     u = torch.rand(B, 3, device=device, generator=g)
     bary = (u / u.sum(-1, keepdim=True)).float().contiguous()
@@ -221,10 +227,13 @@ def run_reference(args):
 
 def workload_config(args, batch_override=None):
     b = batch_override if batch_override is not None else args.batch
-    return {"workload": f"cat_texture_recon_{args.mode}_step_torus{GRID}x{GRID}_V{GRID * GRID}_k{K_EIG}_L{LAYERS}x{HID}_skip{SKIP}",
-            "rays_per_gpu_per_step": b, "table": f"{args.table_dtype} (V x 1024 padded)", "optimizer": "Adam lr 1e-4 (fused into the reduction kernel)",
-            "loss": "L1", "parallelism": f"ray-sharded dp{args.gpus}", "timing": "inputs larger than L2 (205 MB table + "
-            "per-step stash); 4 rotating ray batches"}
+    cfg = {"workload": f"cat_texture_recon_{args.mode}_step_torus{GRID}x{GRID}_V{GRID * GRID}_k{K_EIG}_L{LAYERS}x{HID}_skip{SKIP}",
+           "rays_per_gpu_per_step": b, "table": f"{args.table_dtype} (V x 1024 padded)",
+           "parallelism": f"ray-sharded dp{args.gpus}",
+           "timing": "inputs larger than L2 (205 MB table + per-step stash); 4 rotating ray batches of random hit faces"}
+    if args.mode == "train":
+        cfg.update(optimizer="Adam lr 1e-4 (fused into the reduction kernel)", loss="L1")
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------
@@ -360,6 +369,20 @@ def run_ours(args):
     _say("e2e timing done")
     clocks = sampler.stop() if rank == 0 else None
 
+    # rendering-style coherent rays: neighbouring pixels hit the same / adjacent faces
+    coherent = None
+    if (not train) and rank == 0 and world == 1:
+        cb = []
+        for i in range(NB):
+            v, b_, _t = make_rays(faces, B, dev, seed=77 + i, coherent=True)
+            cb.append({"eigenfunction_table": table, "vertex_idxs_of_hit_faces": v, "barycentric_coords": b_})
+        with torch.no_grad():
+            for i in range(3):
+                model(cb[i % NB])
+            ms_c = timed(lambda i: model(cb[i % NB]), args.steps)
+        coherent = {"rays_per_sec": B * args.steps / (ms_c / 1e3), "ms_per_step": ms_c / args.steps,
+                    "pattern": "scanline over neighbouring faces, 8 rays per face"}
+
     # shipped batch size (intrinsic_cat.yaml:32) for context, same model/table
     small = None
     if train and rank == 0 and world == 1:
@@ -405,6 +428,8 @@ def run_ours(args):
     }
     if small is not None:
         out["config_batch_4096"] = small
+    if coherent is not None:
+        out["coherent_rays"] = coherent
     if not args.no_cpu_baseline and world == 1:
         cr, cms = cpu_reference_rate(train, steps=6, warmup=1, batch=16384)
         out["cpu_baseline"] = {"value": cr, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
