@@ -24,7 +24,6 @@ constexpr int WG_COLS = 512;     // TMEM columns = accumulator columns of a wgra
 constexpr int MAX_UNITS = 16;    // wgrad work units of the hidden slices
 constexpr int MAX_HID_SLICES = 4;
 constexpr int ERR_AREA_BYTES = 65536;
-constexpr int TRACE_SLOTS = 4000;  // u64 clock stamps of CTA 0 (measurement only)
 
 // Model geometry.  MMA "layers" are numbered 0..nb:
 //   layer 0            x (k_pad) -> 128, fused with the skip branch Ly in GEMM1
@@ -210,7 +209,7 @@ struct FieldParams {
   int idx64;
   int dense;
   float ext_scale;  // multiplies grad_pred before it enters the fp16 backward chain
-  unsigned long long* trace;  // (INF_DEBUG & 8) clock64 stamps of CTA 0's chain: [0] = count, then (tag<<48 | clock)
+  unsigned long long* trace;  // (INF_DEBUG & 8) per-role cycle counters of CTA 0, 32 slots (scripts/trace_chain.py)
   float table_keep; // fraction of the table's lines given the L2 evict_last policy (what fits beside the streams)
   int prefetch;     // gather L2 prefetch distance in k-chunks (0 = off)
   int cluster;      // CTAs per cluster of the forward/backward kernel (1 or 2): [W0;Wy] chunks are multicast within it

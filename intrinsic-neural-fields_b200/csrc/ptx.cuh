@@ -41,9 +41,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 
 // Watchdog: a pipeline bug must surface as a trapped kernel with an error word, never as a hung
 // GPU.  ~2^28 failed probes (each a HW-suspended try_wait) is seconds; legitimate waits are us.
-struct Watchdog {
-  unsigned int* flag;  // global error word (may be null)
-};
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_flag,
                                           uint32_t tag) {
   uint32_t spins = 0;
@@ -76,11 +73,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
           dst_smem),
       "l"(src_gmem), "r"(bytes), "r"(bar)
       : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-               "r"(src_smem), "r"(bytes)
-               : "memory");
 }
 // L2 eviction policies for streams that are touched once (activation stash): keep them from displacing the
 // eigenfunction-table rows, which ARE re-used across rays.
@@ -292,14 +284,4 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 }  // namespace inf
