@@ -159,6 +159,7 @@ class HostRayLoader:
     def __iter__(self):
         self.perm = torch.randperm(self.N, generator=self.generator) if self.shuffle else None
         self._next_issue = self._next_take = 0
+        self._pending = False
         for _ in range(min(self.depth, self.num_batches)):
             self._issue()
         return self
@@ -183,6 +184,7 @@ class HostRayLoader:
         i = self._next_take
         if i >= self.num_batches:
             raise StopIteration
+        self._run_pending()                              # the consumer of the previous batch never called the hook
         slot = self.slots[i % self.depth]
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(slot["ready"])
@@ -190,11 +192,19 @@ class HostRayLoader:
         batch = {k: (v if n == self.B else v[:n]) for k, v in slot["bufs"].items()}
         batch["eigenfunction_table"] = self.table
         self._next_take = i + 1
-        # the slot handed out `depth` batches ago is reused by the copy of the batch issued now; its consumer is
-        # whatever the caller enqueued on the current stream before this call
+        # The slot handed out before this one is reused by the next copy; its consumer is whatever the caller enqueued
+        # on the current stream before this call.  Issuing that copy costs ~50 us of host time, so it is deferred: the
+        # trainer steps call batch["on_launched"]() right after they have enqueued this batch's kernels (the host
+        # then works while the GPU does); if nobody calls it, the next __next__ does.
         if i >= 1:
             prev = self.slots[(i - 1) % self.depth]
             prev["free"].record(cur)
             prev["used"] = True
-            self._issue()
+            self._pending = True
+            batch["on_launched"] = self._run_pending
         return batch
+
+    def _run_pending(self):
+        if getattr(self, "_pending", False):
+            self._pending = False
+            self._issue()

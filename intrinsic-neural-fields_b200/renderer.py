@@ -77,6 +77,9 @@ class FieldRenderer:
         keep = []
         for batch in loader:
             pred = self.model(batch)
+            hook = batch.get("on_launched")
+            if hook is not None:
+                hook()                                   # kernels enqueued: let the loader issue its next H2D copies
             n = pred.shape[0]
             ev = torch.cuda.Event()
             ev.record(cur)

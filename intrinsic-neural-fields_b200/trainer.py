@@ -22,6 +22,13 @@ def batch_rays(batch) -> int:
     return int(r.shape[0]) if r is not None else int(batch["expected_rgbs"].shape[0])
 
 
+def _launched(batch):
+    """Tell a prefetching loader that this batch's kernels are enqueued (HostRayLoader issues its next copies now)."""
+    cb = batch.get("on_launched")
+    if cb is not None:
+        cb()
+
+
 def get_loss_fn(loss_type: str) -> Callable:
     """config.py:113-122."""
     if loss_type == "L2":
@@ -52,6 +59,7 @@ def train_step_async(model, optim, batch, loss_fn=F.l1_loss, group=None, flat_gr
         if world > 1:
             parallel.allreduce_module_grads(model, group)
     optim.step()
+    _launched(batch)
     return loss, pred
 
 
@@ -191,6 +199,7 @@ def fused_train_step_async(model, fopt: "FusedFieldAdam", batch, group=None):
         sums, pred, flat = fopt.backward_only(batch, B * world)
         parallel.allreduce_flat(flat, sums, group)
         fopt.apply(flat)
+    _launched(batch)
     return sums[0] / (3.0 * B * world), pred
 
 
@@ -286,7 +295,9 @@ class GraphedTrainStep:
         ent = self.graphs.get(key)
         if ent is None:
             self.graphs[key] = "warm"
-            return self._eager(batch)
+            out = self._eager(batch)
+            _launched(batch)
+            return out
         if ent == "warm":
             ent = self.graphs[key] = self._capture(batch)
         g1, g2, flat, sums, loss, pred = ent
@@ -294,6 +305,7 @@ class GraphedTrainStep:
         if g2 is not None:
             parallel.allreduce_flat(flat, sums, self.group)
             g2.replay()
+        _launched(batch)
         self.model.invalidate_packed()                      # the replay changed the parameters behind torch's back
         return loss, pred
 
