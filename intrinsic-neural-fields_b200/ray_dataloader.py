@@ -14,84 +14,76 @@ import torch
 from .ops import EigenTable
 
 
+_RAY_KEYS = ("vertex_idxs_of_hit_faces", "barycentric_coords", "expected_rgbs", "unit_ray_dirs", "hit_face_idxs")
+
+
 class RayDataLoader:
+    """Device-resident split, one batch of gather inputs per ``next()``.
+
+    Constructor arguments and iterator protocol are the reference's (ray_dataloader.py:57-69,100-118).  Per-ray arrays
+    live in ``self.arrays`` (key = batch-dict key); a batch is either the index-selected rows of each array (the
+    reference's behaviour, ray_dataloader.py:122-126,142-143) or, with ``fused_select``, the arrays themselves plus the
+    batch's ray indices, which the kernels apply while loading.
+    """
+
     def __init__(self, features, feature_strategy, vertex_idxs_of_hit_faces, barycentric_coords, expected_rgbs,
                  unit_ray_dirs, face_idxs, batch_size, shuffle, drop_last, device="cuda", table_dtype="f32",
                  materialize=False, generator=None, fused_select=False):
         if feature_strategy != "efuncs":
             raise ValueError(f"Unknown / unsupported input feature strategy for the B200 path: {feature_strategy}")
+        if (unit_ray_dirs is None) != (face_idxs is None):
+            raise ValueError("unit_ray_dirs and face_idxs come together (view-direction branch) or not at all")
         self.device = torch.device(device)
         self.feature_strategy = feature_strategy
         self.table = features if isinstance(features, EigenTable) else EigenTable.from_dense(
             features.to(torch.float32), device=self.device, dtype=table_dtype)
-        self.vertex_idxs_of_hit_faces = vertex_idxs_of_hit_faces.to(self.device)
-        self.barycentric_coords = barycentric_coords.to(self.device)
-        self.expected_rgbs = expected_rgbs.to(self.device)
-        self.unit_ray_dirs = unit_ray_dirs
-        self.face_idxs = face_idxs
-        if self.unit_ray_dirs is not None:
-            assert self.face_idxs is not None
-            self.unit_ray_dirs = self.unit_ray_dirs.to(self.device)
-            self.face_idxs = self.face_idxs.to(self.device)
-        assert self.barycentric_coords.dtype == torch.float32
-        self.shuffle, self.drop_last = shuffle, drop_last
-        self.materialize = materialize
-        # fused_select: do not run the per-batch index selects (ray_dataloader.py:122-126,142-143) at all; hand the
-        # kernels the whole split plus this batch's ray indices
-        self.fused_select = fused_select
-        self.generator = generator
-        self.B = batch_size
-        self.N = self.vertex_idxs_of_hit_faces.shape[0]
-        self.num_batches = self.N // self.B if drop_last else (self.N + self.B - 1) // self.B
-        self.i = 0
-        self.idxs = torch.arange(self.N, device=self.device)
+        given = dict(zip(_RAY_KEYS, (vertex_idxs_of_hit_faces, barycentric_coords, expected_rgbs, unit_ray_dirs, face_idxs)))
+        self.arrays = {k: v.to(self.device) for k, v in given.items() if v is not None}      # H2D once, as :73-77
+        if self.arrays["barycentric_coords"].dtype != torch.float32:
+            raise TypeError("barycentric_coords must be float32 (ray_dataloader.py:132)")
+        self.shuffle, self.drop_last = bool(shuffle), bool(drop_last)
+        self.materialize, self.fused_select, self.generator = materialize, fused_select, generator
+        self.B = int(batch_size)
+        self.N = int(self.arrays["vertex_idxs_of_hit_faces"].shape[0])
+        self.num_batches = self.N // self.B if self.drop_last else -(-self.N // self.B)
+        self.order = torch.arange(self.N, device=self.device)
+        self.cursor = 0
+
+    # the reference's attribute names, for code that reaches into the loader
+    vertex_idxs_of_hit_faces = property(lambda self: self.arrays["vertex_idxs_of_hit_faces"])
+    barycentric_coords = property(lambda self: self.arrays["barycentric_coords"])
+    expected_rgbs = property(lambda self: self.arrays["expected_rgbs"])
+    unit_ray_dirs = property(lambda self: self.arrays.get("unit_ray_dirs"))
+    face_idxs = property(lambda self: self.arrays.get("hit_face_idxs"))
 
     def __len__(self):
         return self.num_batches
 
     def __iter__(self):
-        if self.shuffle:
-            self.idxs = torch.randperm(self.N, device=self.device, generator=self.generator)
-        self.i = 0
+        if self.shuffle:                                       # a fresh permutation per epoch (ray_dataloader.py:105)
+            self.order = torch.randperm(self.N, device=self.device, generator=self.generator)
+        self.cursor = 0
         return self
 
     def set_epoch_order(self, idxs: torch.Tensor):
         """Use an explicit ray order for the next epoch (parity runs feed CPU and CUDA the same batches)."""
-        self.idxs = idxs.to(self.device)
-        self.i = 0
+        self.order, self.cursor = idxs.to(self.device), 0
         return self
 
-    def _get_next_batch_idxs(self):
-        low = self.i * self.B
-        high = min((self.i + 1) * self.B, self.N)
-        self.i += 1
-        return self.idxs[low:high]
-
     def __next__(self):
-        if self.i >= self.num_batches:
+        if self.cursor >= self.num_batches:
             raise StopIteration
-        batch_idxs = self._get_next_batch_idxs()
+        sel = self.order[self.cursor * self.B:min((self.cursor + 1) * self.B, self.N)]
+        self.cursor += 1
         if self.fused_select:
-            batch = {"ray_idxs": batch_idxs, "expected_rgbs": self.expected_rgbs,
-                     "vertex_idxs_of_hit_faces": self.vertex_idxs_of_hit_faces, "barycentric_coords": self.barycentric_coords,
-                     "eigenfunction_table": self.table}
-            if self.unit_ray_dirs is not None:
-                batch["unit_ray_dirs"] = self.unit_ray_dirs
-                batch["hit_face_idxs"] = self.face_idxs
-            return batch
-        batch = {
-            "expected_rgbs": self.expected_rgbs[batch_idxs],
-            "vertex_idxs_of_hit_faces": self.vertex_idxs_of_hit_faces[batch_idxs],
-            "barycentric_coords": self.barycentric_coords[batch_idxs],
-            "eigenfunction_table": self.table,
-        }
-        if self.materialize:
+            batch = dict(self.arrays, ray_idxs=sel)
+        else:
+            batch = {k: v[sel] for k, v in self.arrays.items()}
+        batch["eigenfunction_table"] = self.table
+        if self.materialize and not self.fused_select:
             from .ops import gather_interpolate_dense
             batch["eigenfunctions"] = gather_interpolate_dense(self.table, batch["vertex_idxs_of_hit_faces"],
                                                               batch["barycentric_coords"])
-        if self.unit_ray_dirs is not None:
-            batch["unit_ray_dirs"] = self.unit_ray_dirs[batch_idxs]
-            batch["hit_face_idxs"] = self.face_idxs[batch_idxs]
         return batch
 
 
