@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     float gb[3] = {0.f, 0.f, 0.f};
     uint32_t mk[MAX_MMA_LAYERS][4];   // ReLU masks of this row (local memory; indexed by layer)
 
-    long long t_done = 0, t_gfull = 0, t_sync = 0, t_store = 0;
+    long long t_done = 0, t_gfull = 0, t_sync = 0, t_store = 0, t_fwd = 0, t_final = 0, t_bwd = 0, t_pro = 0;
     const long long t_epi0 = now();
     auto wait_done = [&]() {
       const long long t0 = now();
@@ -653,6 +653,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       uint8_t* stash_tile = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride : nullptr;
 
       // ---- view branch prologue: Fourier features of this ray -> E panel (model.py:175-186) --------
+      const long long tp0 = now();
       if (view) {
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;
         if (valid) {
@@ -686,6 +687,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         }
       }
 
+      t_pro += now() - tp0;
       // ---- forward layers 0..nb-1: h_l = relu(z_l + b_l) -> activation panel -------------------
       for (int l = 0; l < nb; ++l, ++wr) {
         if (l == 0) {
@@ -697,6 +699,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         } else {
           wait_done();
         }
+        const long long tf0 = now();
         const uint32_t hb = hbuf(wr);
         const uint32_t col0 = (l == g.skip) ? tb + 128u : tb;
         uint32_t mbits[4];
@@ -729,11 +732,13 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           }
           mbar_arrive(bar(BAR_ACT_READY));
         }
+        t_fwd += now() - tf0;
       }
 
       // ---- layer nb epilogue + output layer (-> 3, sigmoid) on CUDA cores -----------------------
       {
         wait_done();
+        const long long tl0 = now();
         const uint32_t ha = hbuf(wr);
         const uint32_t col0 = (nb == g.skip) ? tb + 128u : tb;
         float y[3] = {s_blast[0], s_blast[1], s_blast[2]};
@@ -832,6 +837,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             mbar_arrive(bar(BAR_ACT_READY));
           }
           wr += 2;
+          t_final += now() - tl0;
           if (p.debug & 4) {
             tc_fence_before();
             __syncwarp();
@@ -840,6 +846,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           // ---- dgrad chain: dz_l = dh_l * relu'(z_l), l = nb-1..0 --------------------------------
           for (int lb = (p.debug & 4) ? -1 : nb - 1; lb >= 0; --lb, ++wr) {
             wait_done();
+            const long long tb0 = now();
             const uint32_t hb = hbuf(wr);
             const uint32_t mm[4] = {mk[lb][0], mk[lb][1], mk[lb][2], mk[lb][3]};
 #pragma unroll
@@ -868,11 +875,15 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
                 mbar_arrive(bar(BAR_ACT_READY));
               }
             }
+            t_bwd += now() - tb0;
           }
         }
       }
     }
-    if (tid == 0) { put(16, now() - t_epi0); put(17, t_gfull); put(18, t_done); put(19, t_sync); put(20, t_store); }
+    if (tid == 0) {
+      put(16, now() - t_epi0); put(17, t_gfull); put(18, t_done); put(19, t_sync); put(20, t_store);
+      put(21, t_fwd); put(22, t_final); put(23, t_bwd); put(24, t_pro);
+    }
     if (kTrain) {
       // ---- per-CTA partials: output-layer bias gradient, loss sums ------------------------------
 #pragma unroll

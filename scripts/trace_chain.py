@@ -35,6 +35,7 @@ us = lambda c: c / 1.9e3
 labels = {0: "producer total", 1: "producer wait A_EMPTY", 4: "gemm1 issuer total", 5: "gemm1 wait G_EMPTY", 6: "gemm1 wait A_FULL",
           7: "gemm1 wait B1_FULL", 8: "gemm1 wait x-store read", 10: "chain issuer total", 11: "chain wait ACT_READY",
           12: "chain wait B2_FULL", 16: "epilogue total", 17: "epilogue wait G_FULL", 18: "epilogue wait MMA_DONE",
-          19: "epilogue fence+barrier", 20: "epilogue wait store read"}
+          19: "epilogue fence+barrier", 20: "epilogue wait store read",
+          21: "epilogue fwd steps (incl. sync)", 22: "epilogue final step", 23: "epilogue bwd steps", 24: "epilogue view prologue"}
 for k, name in labels.items():
     print(f"{name:28s} {tr[k]:10d} cyc  {us(tr[k]):8.1f} us")
