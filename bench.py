@@ -292,7 +292,7 @@ def run_ours(args):
     # (training: loss.item() as trainer.py:84; inference: the (B,3) RGB as renderer.py:117).
     from inf_b200.ray_dataloader import HostRayLoader
     from inf_b200.renderer import FieldRenderer
-    n_e2e = args.steps + 6
+    n_e2e = min(args.steps + 6, 24)      # host batches kept in pinned memory; longer runs cycle through them
     hv = torch.cat([host_parts[i % NB][0] for i in range(n_e2e)]).pin_memory()
     hb = torch.cat([host_parts[i % NB][1] for i in range(n_e2e)]).pin_memory()
     ht = torch.cat([host_parts[i % NB][2] for i in range(n_e2e)]).pin_memory() if train else None
@@ -303,15 +303,21 @@ def run_ours(args):
         e2e_out = torch.empty((n_e2e * B, 3), dtype=torch.float32).pin_memory()
 
     def run_e2e(steps):
+        done = 0
         if train:
-            for i, b in enumerate(e2e_loader):
-                if i >= steps:
-                    break
-                graphed.step(b)                                  # one graph launch; loss.item(): D2H read every step
+            while done < steps:
+                for b in e2e_loader:                             # one pass over the pinned host split
+                    if done >= steps:
+                        break
+                    graphed.step(b)                              # one graph launch; loss.item(): D2H read every step
+                    done += 1
         else:
-            # a stream of `steps` frames of B rays each through ONE renderer call: the copies of frame i+1 (in) and
-            # i-1 (out) overlap the kernels of frame i; the call returns when the last RGB is in host memory
-            e2e_renderer.predict_hits_host(hv[:steps * B], hb[:steps * B], chunk=B, out=e2e_out[:steps * B])
+            # a stream of frames of B rays each through ONE renderer call per pass over the host split: the copies of
+            # frame i+1 (in) and i-1 (out) overlap the kernels of frame i; a call returns when the last RGB is in host memory
+            while done < steps:
+                n = min(steps - done, n_e2e)
+                e2e_renderer.predict_hits_host(hv[:n * B], hb[:n * B], chunk=B, out=e2e_out[:n * B])
+                done += n
 
     def barrier():
         if world > 1:
