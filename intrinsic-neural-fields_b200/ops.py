@@ -116,7 +116,11 @@ def param_layout(cfg: FieldConfig) -> List[Tuple[int, int, int]]:
     lib = _lib.load()
     d = _desc(cfg, 0, 0)
     out = []
-    for i in range(lib.inf_num_param_tensors(C.byref(d))):
+    n = lib.inf_num_param_tensors(C.byref(d))
+    if n < 0:                                         # the descriptor was rejected: raise the library's own reason
+        off, r, c = C.c_int64(), C.c_int32(), C.c_int32()
+        _lib.check(lib.inf_param_info(C.byref(d), 0, C.byref(off), C.byref(r), C.byref(c)), "inf_param_info")
+    for i in range(n):
         off, r, c = C.c_int64(), C.c_int32(), C.c_int32()
         _lib.check(lib.inf_param_info(C.byref(d), i, C.byref(off), C.byref(r), C.byref(c)), "inf_param_info")
         out.append((off.value, r.value, c.value))

@@ -71,6 +71,14 @@ def test_bad_descriptors_are_rejected():
         _raise_for(ops.FieldConfig(k=64, num_layers=12, skip=3))
 
 
+def test_param_layout_reports_the_rejection_reason():
+    with pytest.raises(NotImplementedError, match="embed_size=31"):
+        ops.param_layout(ops.FieldConfig(k=1, num_layers=7, skip=4, view="intrinsic", view_embed=31, view_include=True,
+                                         view_bneck=100, view_hidden=48))
+    with pytest.raises(RuntimeError, match="skip_layer_idx"):
+        ops.param_layout(ops.FieldConfig(k=64, num_layers=6, skip=5))
+
+
 def _raise_for(cfg):
     lib = _lib.load()
     d = ops._desc(cfg, 0, 0)
