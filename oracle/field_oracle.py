@@ -199,6 +199,22 @@ def field_forward(p, E, vids, bary, *, num_layers=6, skip=3, view: Optional[dict
                                   emb=view["embed_size"], include_view_dir=view["include_view_dir"])
 
 
+def bake_pred_rgbs(p, features: np.ndarray, faces_index_efs: np.ndarray, barycentric_coords: np.ndarray,
+                   num_layers: int = 6, skip: int = 3, chunk: int = 1 << 15) -> np.ndarray:
+    """Texel prediction of UV baking (bake_texture_field.py:296-319): numpy gather of the three rows, an einsum
+    with the barycentric weights at numpy's promoted width (float64 when the weights are float64), a cast of the
+    embedding to float32, the MLP per 2^15-texel chunk."""
+    out = []
+    n = faces_index_efs.shape[0]
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        rows = features[faces_index_efs[lo:hi].reshape(-1)].reshape(hi - lo, 3, -1)
+        x = np.einsum("bij,bi->bj", rows, barycentric_coords[lo:hi]).astype(np.float32)
+        with torch.no_grad():
+            out.append(texture_field_forward(p, torch.from_numpy(x), num_layers, skip).numpy())
+    return np.concatenate(out, axis=0) if out else np.zeros((0, 3), np.float32)
+
+
 def l1_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """mean |pred-target| over B*3 elements (config.py:117-118)."""
     return F.l1_loss(pred, target)

@@ -784,3 +784,61 @@ def test_randomized_configurations(seed):
     ref = torch.cat([torch.from_numpy(ge[n]).float().reshape(-1) for n, _ in m.named_parameters()])
     rel = (got - ref).norm().item() / (ref.norm().item() + 1e-20)
     assert rel <= 2e-2, (cs, rel)
+
+
+# ---------------------------------------------------------------------------------------------
+# section 8(f) row 4: UV-baking call site and the preprocessed-ray directory feeding the loaders
+# ---------------------------------------------------------------------------------------------
+def test_bake_pred_rgbs_matches_reference_texel_path():
+    from inf_b200 import bake
+    c = load_golden("tf_k100_l5s1")
+    m = _model_from(c)
+    g = np.random.default_rng(0)
+    V = c["table"].shape[0]
+    n = 70000                                                      # three 2^15 chunks in the reference, ragged tail
+    faces = g.integers(0, V, size=(n, 3))                          # int64 like trimesh faces
+    u = g.random((n, 3))
+    bary64 = u / u.sum(-1, keepdims=True)                          # float64 like trimesh barycentrics
+    feats = c["table"].numpy()
+    got = bake.pred_rgbs(m, feats, faces, bary64, device=DEV)
+    _check_no_watchdog()
+    assert got.dtype == np.float32 and got.shape == (n, 3)
+    params = {k_: v for k_, v in c["params"].items()}
+    ref = O.bake_pred_rgbs(params, feats, faces, bary64, num_layers=c["num_layers"], skip=c["skip"])
+    err = np.abs(got - ref)
+    assert err.max() <= RGB_MAX and err.mean() <= RGB_MEAN, (err.max(), err.mean())
+    # int32 ids, a different chunking and an empty request give the same texels
+    assert np.array_equal(bake.pred_rgbs(m, feats, faces.astype(np.int32), bary64, device=DEV, chunk=4096), got)
+    assert bake.pred_rgbs(m, feats, faces[:0], bary64[:0], device=DEV).shape == (0, 3)
+    cv = load_golden("view_intrinsic")
+    with pytest.raises(NotImplementedError):
+        bake.pred_rgbs(_model_from(cv), cv["table"].numpy(), faces[:4] % cv["table"].shape[0], bary64[:4], device=DEV)
+
+
+def test_ray_store_round_trip_feeds_training_bit_exactly(tmp_path):
+    # writer -> five .npy files -> pinned int32 arrays -> HostRayLoader -> fused steps == the same steps from memory
+    from inf_b200 import ray_store, trainer
+    from inf_b200.ray_dataloader import HostRayLoader
+    c = load_golden("view_intrinsic")
+    n = c["vids"].shape[0]
+    with ray_store.RayCacheWriter(str(tmp_path)) as w:
+        for lo in range(0, n, 37):                                  # "views" of 37 hits
+            hi = min(n, lo + 37)
+            w.append_hits(c["vids"][lo:hi], c["bary"][lo:hi], c["target"][lo:hi], c["unit_ray_dirs"][lo:hi], c["face_idxs"][lo:hi])
+    data = ray_store.load_preprocessed_rays(str(tmp_path), pin=True)
+    assert data["vertex_idxs_of_hit_faces"].dtype == torch.int32 and data["vertex_idxs_of_hit_faces"].is_pinned()
+    assert torch.equal(data["vertex_idxs_of_hit_faces"].long(), c["vids"]) and torch.equal(data["barycentric_coords"], c["bary"])
+    tab = inf_b200.EigenTable.from_dense(c["table"], device=DEV)
+
+    def run(loader):
+        m = _model_from(c)
+        opt = trainer.FusedFieldAdam(m, lr=1e-3)
+        losses = []
+        for b in loader:
+            losses.append(trainer.fused_train_step(m, opt, b)[0])
+        return losses, opt.flat.clone()
+    la, pa = run(HostRayLoader(tab, data["vertex_idxs_of_hit_faces"], data["barycentric_coords"], data["expected_rgbs"],
+                               data["unit_ray_dirs"], data["face_idxs"], batch_size=48, device=DEV))
+    lb, pb = run(HostRayLoader(tab, c["vids"], c["bary"], c["target"], c["unit_ray_dirs"], c["face_idxs"], batch_size=48, device=DEV))
+    _check_no_watchdog()
+    assert la == lb and torch.equal(pa, pb)
