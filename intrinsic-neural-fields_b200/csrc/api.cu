@@ -241,19 +241,12 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   {
     const char* e = getenv("INF_DEBUG");   // measurement only; bits 1|2|4 produce wrong gradients
     p.debug = e ? atoi(e) : 0;
-    const char* f = getenv("INF_PREFETCH");   // tuning knob: L2 prefetch distance of the gather in k-chunks
-    // default: only for fp32 tables that do not fit in L2 (fp16 rows: the L2::256B load hint already covers the next
-    // piece; an L2-resident table gains nothing and pays the extra requests -- measured 0.19 -> 0.26 ms at V = 10 k)
-    const double tbl_mb = static_cast<double>(d->n_rows) * d->k_pad * 4.0 / 1048576.0;
-    p.prefetch = f ? atoi(f) : ((d->table_dtype == INF_TABLE_F16 || tbl_mb < 100.0) ? 0 : 2);
+    // L2 prefetch of the next row pieces through the bulk-copy engine (distance in k-chunks).  Off by default: it paid
+    // while the gather was throttled by a 28 KB L1 (227 KB shared-memory carve-out); with the 164 KB carve-out the plain
+    // loads run at the memory system's rate and the extra requests cost 3-13 % at every table size.
+    const char* f = getenv("INF_PREFETCH");
+    p.prefetch = f ? atoi(f) : 0;
     if (p.prefetch < 0 || p.prefetch > 8 || d->input_mode == INF_INPUT_DENSE) p.prefetch = 0;
-    // L2 residency of the table: protect as many of its lines as fit beside the weight / stash streams (126 MB L2)
-    const char* k = getenv("INF_KEEP_MB");
-    const double keep_mb = k ? atof(k) : 80.0;
-    const double table_mb = static_cast<double>(d->input_mode == INF_INPUT_DENSE ? d->n_rays : d->n_rows) * d->k_pad *
-                            (d->table_dtype == INF_TABLE_F16 ? 2.0 : 4.0) / 1048576.0;
-    p.table_keep = static_cast<float>(table_mb <= keep_mb ? 1.0 : keep_mb / table_mb);
-    if (d->input_mode == INF_INPUT_DENSE) p.table_keep = 0.f;   // a dense embedding is read exactly once
   }
   p.geo = geo_of(d);
   p.plan = make_wplan(p.geo);

@@ -210,7 +210,6 @@ struct FieldParams {
   int dense;
   float ext_scale;  // multiplies grad_pred before it enters the fp16 backward chain
   unsigned long long* trace;  // (INF_DEBUG & 8) per-role cycle counters of CTA 0, 32 slots (scripts/trace_chain.py)
-  float table_keep; // fraction of the table's lines given the L2 evict_last policy (what fits beside the streams)
   int prefetch;     // gather L2 prefetch distance in k-chunks (0 = off)
   int cluster;      // CTAs per cluster of the forward/backward kernel (1 or 2): [W0;Wy] chunks are multicast within it
   int debug;        // measurement knobs (INF_DEBUG env): 1 no x stash, 2 no h/dz stash, 4 no dgrad chain -- wrong results

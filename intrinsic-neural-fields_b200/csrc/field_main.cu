@@ -19,6 +19,7 @@
 //                          the next layer), Fourier features of the view direction (layers.py:21-25), final
 //                          -> 3 layer + sigmoid (+ L1 loss gradient) on CUDA cores; when training, stashes
 //                          h_l / dz_l tiles for the wgrad kernel.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -40,7 +41,7 @@ constexpr int REGS_EPI = 128, REGS_UTIL = 32;   // pool = 768 x 80 (launch value
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 
-constexpr int NSTAGE_B1 = 2;
+constexpr int MAX_STAGE_B1 = 4;   // half-stages of the [W0;Wy] ring
 constexpr int MAX_STAGE_A = 5;
 
 // shared memory carve-up (bytes from a 1024-aligned base), 13 panels of 16 KB + small tables:
@@ -50,19 +51,26 @@ constexpr int MAX_STAGE_A = 5;
 //              deeper ring is what decouples the warps from each other's tail latencies.
 struct Smem {
   uint32_t a, b1, h, b2, e, dzlt, bias, wlast, vid, bary, red, bars, tmemptr, total;
-  int nstage_a, nh;
+  int nstage_a, nstage_b1, nh;
 };
 __host__ __device__ constexpr Smem smem_layout(bool view, bool train) {
   Smem s{};
-  s.nh = train ? 2 : 1;
-  s.nstage_a = (train ? 3 : 5) - (view ? 1 : 0);
+  s.nh = 1;
+  // Inference stays within the 164 KB shared-memory carve-out: the gather's register loads are bounded by what is left
+  // of the 256 KB array for L1 (measured with scripts/probes/gather_probe.cu: 7.3 TB/s of random 4 KB rows at <= 164 KB of
+  // shared memory, 5.1-5.6 TB/s at 196/228 KB), and in inference the gather is the whole kernel.
+  // Training takes the same diet: one activation buffer (every stash store's shared-memory read is waited for before
+  // the chain continues) and ONE whole [W0;Wy] stage (its refill, ~1 us, hides behind the >= 2 us the producers need
+  // per k-chunk), which keeps the single N = 256 instruction per k-step.
+  s.nstage_a = train ? (view ? 2 : 3) : 2;
+  s.nstage_b1 = train ? 2 : (view ? 2 : 3);       // 16 KB half-stages: [W0 chunk] and [Wy chunk] are released separately
   s.a = 0;
   s.b1 = s.a + static_cast<uint32_t>(s.nstage_a) * PANEL_BYTES;
-  s.h = s.b1 + NSTAGE_B1 * BLOB_BYTES;
+  s.h = s.b1 + static_cast<uint32_t>(s.nstage_b1) * PANEL_BYTES;
   s.b2 = s.h + static_cast<uint32_t>(s.nh) * BLOB_BYTES;
   s.e = s.b2 + BLOB_BYTES;
-  s.dzlt = 13 * PANEL_BYTES;                      // 212992 in all variants
-  s.bias = s.dzlt + DZLT_BYTES;                   // f32 [MAX_MMA_LAYERS][128]
+  s.dzlt = s.e + (view ? PANEL_BYTES : 0u);
+  s.bias = s.dzlt + (train ? DZLT_BYTES : 0u);    // f32 [MAX_MMA_LAYERS][128]
   s.wlast = s.bias + MAX_MMA_LAYERS * HID * 4;    // f32 [3][128] + blast[4]
   s.vid = s.wlast + OUT_DIM * HID * 4 + 16;       // u32 [3][384]
   s.bary = s.vid + 3 * 384 * 4;                   // f32 [3][384]
@@ -72,18 +80,16 @@ __host__ __device__ constexpr Smem smem_layout(bool view, bool train) {
   s.total = s.tmemptr + 16;
   return s;
 }
-static_assert(smem_layout(false, true).e <= smem_layout(false, true).dzlt, "smem layout");
-static_assert(smem_layout(true, true).e + PANEL_BYTES <= smem_layout(true, true).dzlt, "smem layout (view)");
-static_assert(smem_layout(false, false).e <= smem_layout(false, false).dzlt, "smem layout (inference)");
-static_assert(smem_layout(true, false).e + PANEL_BYTES <= smem_layout(true, false).dzlt, "smem layout (inference, view)");
-static_assert(smem_layout(true, true).total <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+static_assert(smem_layout(false, false).total <= 166912 && smem_layout(true, false).total <= 166912 &&
+              smem_layout(false, true).total <= 166912 && smem_layout(true, true).total <= 166912,
+              "every variant must fit the 164 KB carve-out (1 KB of it is reserved per CTA)");
 
 // barrier indices
 constexpr int BAR_A_FULL = 0;                          // [5]
 constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_STAGE_A;  // [5]
-constexpr int BAR_B1_FULL = BAR_A_EMPTY + MAX_STAGE_A; // [2]
-constexpr int BAR_B1_EMPTY = BAR_B1_FULL + NSTAGE_B1;  // [2]
-constexpr int BAR_B2_FULL = BAR_B1_EMPTY + NSTAGE_B1;
+constexpr int BAR_B1_FULL = BAR_A_EMPTY + MAX_STAGE_A; // [4]
+constexpr int BAR_B1_EMPTY = BAR_B1_FULL + MAX_STAGE_B1;  // [4]
+constexpr int BAR_B2_FULL = BAR_B1_EMPTY + MAX_STAGE_B1;
 constexpr int BAR_B2_EMPTY = BAR_B2_FULL + 1;
 constexpr int BAR_G_FULL = BAR_B2_EMPTY + 1;           // [2] GEMM1 accumulator buffer complete
 constexpr int BAR_G_EMPTY = BAR_G_FULL + 2;            // [2] chain of the tile that used the buffer is done
@@ -137,12 +143,12 @@ template <>
 struct RowLoader<float> {
   static constexpr int QUADS = 1;        // quads per pass
   float4 a[3], b[3];
-  __device__ __forceinline__ void load(int, const float* base, const int64_t (&roff)[3], int koff, int s, uint64_t pol) {
+  __device__ __forceinline__ void load(int, const float* base, const int64_t (&roff)[3], int koff, int s) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float* p = base + roff[j] + koff + 4 * s;
-      a[j] = ldg_nc_f4(p, pol);
-      b[j] = ldg_nc_f4(p + 32, pol);
+      a[j] = ldg_nc_f4(p);
+      b[j] = ldg_nc_f4(p + 32);
     }
   }
   // writes fp16 k-offsets [4s,4s+4) and [32+4s, 32+4s+4) of panel row r
@@ -171,9 +177,9 @@ template <>
 struct RowLoader<__half> {
   static constexpr int QUADS = 2;
   uint4 a[2][3];
-  __device__ __forceinline__ void load(int u, const __half* base, const int64_t (&roff)[3], int koff, int s, uint64_t pol) {
+  __device__ __forceinline__ void load(int u, const __half* base, const int64_t (&roff)[3], int koff, int s) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) a[u][j] = ldg_nc_u4(base + roff[j] + koff + 8 * s, pol);
+    for (int j = 0; j < 3; ++j) a[u][j] = ldg_nc_u4(base + roff[j] + koff + 8 * s);
   }
   __device__ __forceinline__ void store(int u, uint32_t panel, int r, int s, const float (&w)[3]) const {
     float acc[8];
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   const Geo g = p.geo;
   const bool view = g.view != INF_VIEW_NONE;
   const Smem sm = smem_layout(view, kTrain);
-  const int nstage_a = sm.nstage_a;
+  const int nstage_a = sm.nstage_a, nstage_b1 = sm.nstage_b1;
   const int nb = g.nb, nhid = g.nhid;
   // Cluster of `cs` CTAs (1 or 2): every [W0;Wy] chunk is fetched from L2 ONCE per cluster -- each CTA loads 1/cs of it
   // and multicasts that slice to all of them.  The CTAs of a cluster therefore run the same number of tile iterations;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       mbar_init(bar(BAR_A_FULL + i), PROD_WARPS);
       mbar_init(bar(BAR_A_EMPTY + i), kTrain ? 2 : 1);  // MMA commit (+ x-panel stash store finished reading)
     }
-    for (int i = 0; i < NSTAGE_B1; ++i) { mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), cs); }
+    for (int i = 0; i < MAX_STAGE_B1; ++i) { mbar_init(bar(BAR_B1_FULL + i), 1); mbar_init(bar(BAR_B1_EMPTY + i), cs); }
     mbar_init(bar(BAR_B2_FULL), 1);
     mbar_init(bar(BAR_B2_EMPTY), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_G_FULL + i), 1); mbar_init(bar(BAR_G_EMPTY + i), EPI_WARPS); }
@@ -280,8 +286,10 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       if (i < nbias) s_bias[i] = v;
       else s_wl[i - nbias] = v;
     }
-    uint32_t* dz = reinterpret_cast<uint32_t*>(smem + sm.dzlt);   // rows 3..15 of dzl^T stay zero
-    for (int i = tid; i < DZLT_BYTES / 4; i += NUM_THREADS_MAIN) dz[i] = 0u;
+    if (kTrain) {
+      uint32_t* dz = reinterpret_cast<uint32_t*>(smem + sm.dzlt);   // rows 3..15 of dzl^T stay zero
+      for (int i = tid; i < DZLT_BYTES / 4; i += NUM_THREADS_MAIN) dz[i] = 0u;
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -356,8 +364,6 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     // from HBM in (pf * 64 * sizeof(TableT))-byte pieces (one DRAM page visit instead of pf separate 128/256-byte
     // ones), through the bulk-copy engine, which does not occupy the LSU's outstanding-load slots.
     const int pf = p.prefetch;
-    // table rows are re-used by other rays (and by the next step): keep them in L2 ahead of the read-once streams
-    const uint64_t table_policy = l2_policy_evict_last(p.table_keep);
     auto issue = [&](const Cursor& k, RowLoader<TableT>& ld) {
       if (k.tile >= nt_loop) return;
 #pragma unroll
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         int64_t roff[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) roff[j] = static_cast<int64_t>(s_vid[e + j]) * p.row_stride;
-        ld.load(u, table, roff, k.c * KC, s, table_policy);
+        ld.load(u, table, roff, k.c * KC, s);
         if (pf > 0 && s == 0 && (k.c % pf) == 0) {
           int c2 = k.c + pf;
           if (c2 < nchunks) {
@@ -440,16 +446,17 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t slice = BLOB_BYTES / static_cast<uint32_t>(cs);
+      const uint32_t slice = PANEL_BYTES / static_cast<uint32_t>(cs);
+      const int nhalf = 2 * nchunks;   // a chunk blob = [W0 rows | Wy rows], one 16 KB half-stage each
       for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x) {
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = 0; c < nhalf; ++c) {
           mbar_wait(bar(BAR_B1_EMPTY + stage), phase ^ 1u, p.err, 0x20);   // released by every CTA of the cluster
-          mbar_arrive_expect_tx(bar(BAR_B1_FULL + stage), BLOB_BYTES);
-          const uint32_t dst = smem_base + sm.b1 + static_cast<uint32_t>(stage) * BLOB_BYTES;
-          const uint8_t* src = p.packed + static_cast<size_t>(c) * BLOB_BYTES;
-          if (cs == 1) bulk_g2s(dst, src, BLOB_BYTES, bar(BAR_B1_FULL + stage));
+          mbar_arrive_expect_tx(bar(BAR_B1_FULL + stage), PANEL_BYTES);
+          const uint32_t dst = smem_base + sm.b1 + static_cast<uint32_t>(stage) * PANEL_BYTES;
+          const uint8_t* src = p.packed + static_cast<size_t>(c) * PANEL_BYTES;
+          if (cs == 1) bulk_g2s(dst, src, PANEL_BYTES, bar(BAR_B1_FULL + stage));
           else bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice, bar(BAR_B1_FULL + stage), cmask);
-          if (++stage == NSTAGE_B1) { stage = 0; phase ^= 1u; }
+          if (++stage == nstage_b1) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -494,22 +501,48 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         for (int c = 0; c < nchunks; ++c) {
           const long long ta0 = now();
           mbar_wait(bar(BAR_A_FULL + sa), pa, p.err, 0x30);
-          const long long ta1 = now();
-          mbar_wait(bar(BAR_B1_FULL + sb), pb, p.err, 0x32);
-          const long long ta2 = now();
-          t_a += ta1 - ta0; t_b += ta2 - ta1;
-          tc_fence_after();
+          t_a += now() - ta0;
           const uint32_t abase = smem_base + sm.a + static_cast<uint32_t>(sa) * PANEL_BYTES;
-          const uint32_t bbase = smem_base + sm.b1 + static_cast<uint32_t>(sb) * BLOB_BYTES;
-          const uint32_t alo = umma_desc_lo(abase, 0), blo = umma_desc_lo(bbase, 0);
+          const uint32_t alo = umma_desc_lo(abase, 0);
+          if (kTrain) {
+            // four half-stages = two whole [W0;Wy] chunks, each contiguous: one N = 256 instruction per k-step
+            const long long tb0 = now();
+            mbar_wait(bar(BAR_B1_FULL + sb), pb, p.err, 0x32);
+            mbar_wait(bar(BAR_B1_FULL + sb + 1), pb, p.err, 0x35);
+            t_b += now() - tb0;
+            tc_fence_after();
+            const uint32_t blo = umma_desc_lo(smem_base + sm.b1 + static_cast<uint32_t>(sb) * PANEL_BYTES, 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_f16(dcol, umma_desc_join(alo + 2u * kk, DESC_HI), umma_desc_join(blo + 2u * kk, DESC_HI), IDESC_N256,
-                     (c > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16(dcol, umma_desc_join(alo + 2u * kk, DESC_HI), umma_desc_join(blo + 2u * kk, DESC_HI), IDESC_N256,
+                       (c > 0 || kk > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              if (cs == 1) umma_commit(bar(BAR_B1_EMPTY + sb + half));
+              else umma_commit_multicast(bar(BAR_B1_EMPTY + sb + half), cmask);
+            }
+            sb += 2;
+            if (sb == nstage_b1) { sb = 0; pb ^= 1u; }
+          } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {   // z0 += x W0^T into columns [0,128), zy += x Wy^T into [128,256)
+            const long long tb0 = now();
+            mbar_wait(bar(BAR_B1_FULL + sb), pb, p.err, 0x32);
+            t_b += now() - tb0;
+            tc_fence_after();
+            const uint32_t blo = umma_desc_lo(smem_base + sm.b1 + static_cast<uint32_t>(sb) * PANEL_BYTES, 0);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16(dcol + 128u * static_cast<uint32_t>(half), umma_desc_join(alo + 2u * kk, DESC_HI),
+                       umma_desc_join(blo + 2u * kk, DESC_HI), IDESC_N128, (c > 0 || kk > 0) ? 1u : 0u);
+            }
+            if (cs == 1) umma_commit(bar(BAR_B1_EMPTY + sb));
+            else umma_commit_multicast(bar(BAR_B1_EMPTY + sb), cmask);   // the stage is refilled by every CTA of the cluster
+            if (++sb == nstage_b1) { sb = 0; pb ^= 1u; }
+          }
           }
           umma_commit(bar(BAR_A_EMPTY + sa));
-          if (cs == 1) umma_commit(bar(BAR_B1_EMPTY + sb));
-          else umma_commit_multicast(bar(BAR_B1_EMPTY + sb), cmask);   // the stage is refilled by every CTA of the cluster
           if (kTrain) {
             // x panel -> stash (the B operand of dW0 / dWy in the wgrad kernel)
             if (!(p.debug & 1) && xdst != nullptr) bulk_s2g_hint(xdst + static_cast<size_t>(c) * PANEL_BYTES, abase, PANEL_BYTES, stash_policy);
@@ -520,7 +553,6 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             mbar_arrive(bar(BAR_A_EMPTY + sa));
           }
           if (++sa == nstage_a) { sa = 0; pa ^= 1u; }
-          if (++sb == NSTAGE_B1) { sb = 0; pb ^= 1u; }
         }
         umma_commit(bar(BAR_G_FULL + buf));
       }
@@ -546,7 +578,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
         t_b2 += now() - t0;
       };
       const uint32_t bbase = smem_base + sm.b2;
-      auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (kTrain ? (w & 1u) * BLOB_BYTES : 0u); };
+      auto hbuf = [&](uint32_t) { return smem_base + sm.h; };
       const uint32_t blo_k = umma_desc_lo(bbase, 0);             // weight image read K-major (forward)
       const uint32_t blo_mn = umma_desc_lo(bbase, PANEL_BYTES);   // the same image read MN-major (dgrad)
       // D[128 x 128] (+)= A[128 x 64*npanel] * B^T, both K-major panel images
@@ -637,7 +669,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
       named_bar_sync(1, EPI_THREADS);
       t_sync += now() - t0;
     };
-    auto hbuf = [&](uint32_t w) { return smem_base + sm.h + (kTrain ? (w & 1u) * BLOB_BYTES : 0u); };
+    auto hbuf = [&](uint32_t) { return smem_base + sm.h; };   // ONE activation buffer: see the bulk_wait_read<0> below
 
     int it = 0;
     for (int tile = blockIdx.x; tile < nt_loop; tile += gridDim.x, ++it) {
@@ -727,7 +759,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             if (l == 0 && view && store_tile) bulk_s2g_hint(stash_tile + stash_off_e(g), smem_base + sm.e, PANEL_BYTES, stash_policy);
             bulk_commit();
             const long long t0 = now();
-            bulk_wait_read<1>();   // the buffer written next is free before the chain may continue
+            bulk_wait_read<0>();   // the next step overwrites this buffer: its stash store has left shared memory
             t_store += now() - t0;
           }
           mbar_arrive(bar(BAR_ACT_READY));
@@ -804,7 +836,13 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
             *reinterpret_cast<__half*>(smem + sm.dzlt + static_cast<uint32_t>(r >> 6) * 2048u + sw128_off(c, r & 63)) =
                 __float2half_rn(dzl[c]);
           }
-          if (tid == 0) bulk_wait_read<0>();   // the other activation buffer (h_{nb-1}) has left smem
+          // h_nb goes to the stash, then dz_nb takes its place in the activation buffer
+          sync_epi();
+          if (tid == 0) {
+            if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES, stash_policy);
+            bulk_commit();
+            bulk_wait_read<0>();
+          }
           sync_epi();
           // dz_nb = (dz_last * W_last) masked by relu'
           const uint32_t hb2 = hbuf(wr + 1);
@@ -828,12 +866,10 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
           }
           sync_epi();
           if (tid == 0) {
-            if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_h(g, nb), ha, BLOB_BYTES, stash_policy);
-            bulk_commit();
             if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_dz(g, nb), hb2, BLOB_BYTES, stash_policy);
             if (store_tile) bulk_s2g_hint(stash_tile + stash_off_dzlt(g), smem_base + sm.dzlt, DZLT_BYTES, stash_policy);
             bulk_commit();
-            bulk_wait_read<1>();
+            bulk_wait_read<0>();
             mbar_arrive(bar(BAR_ACT_READY));
           }
           wr += 2;
@@ -864,17 +900,16 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(BAR_G_EMPTY + buf));   // last TMEM read of this tile
-              if (tid == 0) bulk_wait_read<0>();  // no MMA gates the next tile's first write: drain the store ring
             }
             sync_epi();
             if (tid == 0) {
               if (!(p.debug & 2) && store_tile) bulk_s2g_hint(stash_tile + stash_off_dz(g, lb), hb, BLOB_BYTES, stash_policy);
               bulk_commit();
-              if (lb > 0) {
-                bulk_wait_read<1>();
-                mbar_arrive(bar(BAR_ACT_READY));
-              }
+              bulk_wait_read<0>();
+              if (lb > 0) mbar_arrive(bar(BAR_ACT_READY));
             }
+            // no MMA gates the next tile's first write into the activation buffer: everyone waits for dz_0 to leave it
+            if (lb == 0) named_bar_sync(1, EPI_THREADS);
             t_bwd += now() - tb0;
           }
         }
@@ -925,8 +960,18 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
 template <bool kTrain, typename TableT>
 static cudaError_t launch_one(const FieldParams& p, int grid, cudaStream_t stream) {
   const int smem = static_cast<int>(smem_layout(p.geo.view != INF_VIEW_NONE, kTrain).total);
-  cudaError_t e = cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  // exactly this launch's footprint: the driver sizes the L1 / shared-memory split from it
+  cudaError_t e = cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
+  {
+    // ask for the smallest carve-out that holds one CTA (+1 KB the system reserves): what is left of the 256 KB array
+    // is the L1 the gather's loads are tracked in
+    static const int env_carve = getenv("INF_CARVEOUT") ? atoi(getenv("INF_CARVEOUT")) : -2;
+    if (env_carve != -2) {
+      e = cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributePreferredSharedMemoryCarveout, env_carve);
+      if (e != cudaSuccess) return e;
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(NUM_THREADS_MAIN);
@@ -945,7 +990,8 @@ static cudaError_t launch_one(const FieldParams& p, int grid, cudaStream_t strea
 // Largest grid (a multiple of `cluster`) whose clusters are all co-resident with this kernel's footprint, 0 on error.
 template <bool kTrain, typename TableT>
 static int max_grid_one(int cluster, bool view) {
-  cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaFuncSetAttribute(field_main_kernel<kTrain, TableT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(smem_layout(view, kTrain).total));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(cluster));
   cfg.blockDim = dim3(NUM_THREADS_MAIN);

@@ -1,4 +1,4 @@
-"""Measurement helper: INF_DEBUG=8 python scripts/trace_chain.py [train] -- prints CTA 0's chain timeline (cycles)."""
+"""Measurement helper: INF_DEBUG=8 python scripts/trace_chain.py [train] [f16] [grid=N] -- prints CTA 0's chain timeline (cycles)."""
 import os, sys
 os.environ["INF_DEBUG"] = os.environ.get("INF_DEBUG", "8")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,7 @@ import bench
 train = "train" in sys.argv
 f16 = "f16" in sys.argv
 dev = torch.device("cuda")
-G = 100
+G = next((int(a.split("=")[1]) for a in sys.argv if a.startswith("grid=")), 100)
 faces = bench.torus_faces(G, dev)
 table = inf_b200.EigenTable.from_dense(bench.make_table(G * G, 1023, dev), device=dev, dtype="f16" if f16 else "f32")
 torch.manual_seed(0)
