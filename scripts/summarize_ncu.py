@@ -1,9 +1,9 @@
 """Summarise gpurun_out/launches.csv (ncu --metrics gpu__time_duration.sum) and a full .ncu-rep into
-profiles/<tag>_launches.txt and profiles/<tag>_kernels.txt.   usage: summarize_ncu.py <tag> [rep]"""
+profiles/<tag>_launches.txt and profiles/<tag>_kernels.txt.   usage: summarize_ncu.py <tag> [rep ...]"""
 import collections, csv, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
-rep = sys.argv[2] if len(sys.argv) > 2 else None
+reps = sys.argv[2:]
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 lcsv = os.path.join(ROOT, "gpurun_out", "launches.csv")
@@ -21,7 +21,8 @@ if os.path.exists(lcsv):
         f.write(f"{'total_us':>10} {'n':>5} {'avg_us':>9} {'max_us':>9} {'share':>6}  kernel\n")
         for k, (n, v, mx) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{v/1e3:10.1f} {n:5d} {v/n/1e3:9.1f} {mx/1e3:9.1f} {100*v/tot:5.1f}%  {k}\n")
-if rep:
+first = True
+for rep in reps:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     hdr, units = r[0], r[1]
@@ -30,10 +31,10 @@ if rep:
             "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max",
+            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_config_size", "sm__cycles_elapsed.max",
             "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
             "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_membar_per_warp_active.pct"]
-    with open(os.path.join(out, f"{tag}_kernels.txt"), "w") as f:
+    with open(os.path.join(out, f"{tag}_kernels.txt"), "w" if first else "a") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on ; report {os.path.basename(rep)}\n")
         for row in r[2:]:
             f.write("---\n")
@@ -41,4 +42,5 @@ if rep:
                 ii = [i for i, h in enumerate(hdr) if h == w]
                 if ii:
                     f.write(f"{w:72s} {row[ii[0]][:70]} [{units[ii[0]]}]\n")
+    first = False
 print("written", os.listdir(out))
