@@ -16,6 +16,7 @@ namespace inf {
 cudaError_t launch_field_main(const FieldParams& p, bool train, bool table_f16, int grid, cudaStream_t stream);
 int field_main_max_grid(bool train, bool table_f16, int cluster, bool view);
 cudaError_t launch_field_wgrad(const FieldParams& p, int grid, cudaStream_t stream);
+int field_wgrad_max_grid(int cluster);
 cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream);
 
 void launch_pack_weights(const PackParams& pp, cudaStream_t stream);
@@ -433,18 +434,42 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   const int grid1 = pick_main_grid(desc, p.ntiles, nsm, true, &p.cluster);
   // wgrad CTAs: every slice gets ray groups in proportion to the bytes it moves per tile
   const WPlan& plan = p.plan;
-  double wsum = static_cast<double>(geo.nbig) * BIG_BYTES_PER_TILE;
+  // clusters of cw big-slice CTAs share the dz_0 / dz_skip half-panels (multicast): cw = 4, 2 or 1, dividing nbig
+  int cw = 4;
+  {
+    static const int env_cw = getenv("INF_WGRAD_CLUSTER") ? atoi(getenv("INF_WGRAD_CLUSTER")) : 4;
+    cw = env_cw >= 4 ? 4 : (env_cw >= 2 ? 2 : 1);
+    while (cw > 1 && geo.nbig % cw != 0) cw >>= 1;
+  }
+  int nsm_w = nsm;
+  if (cw > 1) {
+    static int cached[5] = {-1, -1, -1, -1, -1};
+    if (cached[cw] < 0) cached[cw] = field_wgrad_max_grid(cw);
+    if (cached[cw] < cw) cw = 1;
+    else if (cached[cw] < nsm_w) nsm_w = cached[cw];
+  }
+  // bytes a CTA ingests per tile: the x panels of its 256 columns + its share of dz_0 / dz_skip
+  const double big_bytes = 2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw;
+  double wsum = static_cast<double>(geo.nbig) * big_bytes;
   for (int s = 0; s < plan.nslice; ++s) wsum += plan.bytes_per_tile[s];
   int used = 0;
   int gh[MAX_HID_SLICES] = {0, 0, 0, 0};
+  int smax = 0;
   for (int s = 0; s < plan.nslice; ++s) {
-    int v = static_cast<int>(nsm * (plan.bytes_per_tile[s] / wsum));
+    int v = static_cast<int>(nsm_w * (plan.bytes_per_tile[s] / wsum));
     if (v < 1) v = 1;
     if (v > p.ntiles) v = p.ntiles;
     gh[s] = v;
     used += v;
+    if (plan.bytes_per_tile[s] > plan.bytes_per_tile[smax]) smax = s;
   }
-  int gb = (nsm - used) / geo.nbig;
+  if (cw > 1 && used % cw != 0) {   // whole clusters only: pad the heaviest hidden slice
+    const int add = cw - used % cw;
+    if (plan.nslice > 0 && gh[smax] + add <= p.ntiles) { gh[smax] += add; used += add; }
+    else cw = 1;
+  }
+  p.wg_cluster = cw;
+  int gb = (nsm_w - used) / geo.nbig;
   if (gb < 1) gb = 1;
   if (gb > p.ntiles) gb = p.ntiles;
   p.groups_big = gb;

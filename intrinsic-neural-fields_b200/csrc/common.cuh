@@ -212,6 +212,7 @@ struct FieldParams {
   unsigned long long* trace;  // (INF_DEBUG & 8) per-role cycle counters of CTA 0, 32 slots (scripts/trace_chain.py)
   int prefetch;     // gather L2 prefetch distance in k-chunks (0 = off)
   int cluster;      // CTAs per cluster of the forward/backward kernel (1 or 2): [W0;Wy] chunks are multicast within it
+  int wg_cluster;   // CTAs per cluster of the wgrad kernel (1, 2 or 4): dz_0 / dz_skip half-panels are multicast within it
   int debug;        // measurement knobs (INF_DEBUG env): 1 no x stash, 2 no h/dz stash, 4 no dgrad chain -- wrong results
   int groups_big;                   // wgrad: ray groups (CTAs) per big slice
   int groups_hid[MAX_HID_SLICES];   // wgrad: ray groups (CTAs) per hidden slice

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
   }
   const int nchunks = g.nchunks;
   const size_t tile_stride = stash_tile_bytes(g);
-  const uint64_t stash_policy = l2_policy_evict_first();   // stash tiles are written once, read once by the next kernel
+  // stash tiles are written once, read once by the next kernel (INF_DEBUG & 64: no hint, measurement)
+  const uint64_t stash_policy = (p.debug & 64) ? 0ull : l2_policy_evict_first();
 
   // Register re-partition: ONE setmaxnreg instance per warpgroup (all four warps of a warpgroup must execute the
   // same instruction), placed so that it dominates the role's code -- ptxas budgets each region from it.

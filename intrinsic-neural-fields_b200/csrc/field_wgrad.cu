@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
   const bool big = static_cast<int>(blockIdx.x) < nbig_ctas;
   int slice, grp, groups;
   if (big) {
+    // group-major: the CTAs of one ray group sit next to each other, so a cluster = `cw` slices of the SAME tiles
     groups = p.groups_big;
-    slice = blockIdx.x / groups;
-    grp = blockIdx.x % groups;
+    slice = blockIdx.x % g.nbig;
+    grp = blockIdx.x / g.nbig;
   } else {
     int rel = blockIdx.x - nbig_ctas;
     int hs = 0;
@@ -79,11 +80,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
   }
 
   auto bar = [&](int i) -> uint32_t { return smem_base + SM_BARS + 8u * static_cast<uint32_t>(i); };
+  // Clusters of `cw` CTAs: the big slices of a cluster walk the same ray tiles and need the same dz_0 / dz_skip
+  // half-panels, so each CTA fetches 1/cw of them and multicasts -- per-SM ingest (what bounds this kernel, ~42 GB/s
+  // through the bulk-copy engine) drops from 64 KB to (32 + 32/cw) KB per 64-ray unit.  Hidden-slice CTAs share nothing.
+  const int cw = p.wg_cluster;
+  const uint32_t crank = cw > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cw) - 1u);
+  const bool mcast = big && cw > 1;
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(bar(BAR_FULL + i), 1);
-      mbar_init(bar(BAR_EMPTY + i), 1);
+      mbar_init(bar(BAR_EMPTY + i), mcast ? cw : 1);   // a stage is refilled by every CTA of the cluster
     }
     mbar_init(bar(BAR_DONE), 1);
     mbar_fence_init();
@@ -99,6 +107,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (cw > 1) cluster_sync_all();   // peers' barriers exist before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
 
@@ -113,7 +122,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint64_t stash_policy = l2_policy_evict_first();   // read-once stream
+      const uint64_t stash_policy = (p.debug & 128) ? 0ull : l2_policy_evict_first();   // read-once stream (INF_DEBUG & 128: no hint)
       // (L2 prefetches of upcoming units through the same bulk-copy engine, and cp.async copy warps sharing the ring,
       //  were both measured slower than this plain 3-stage stream -- see DESIGN.md section 4)
       for (int u = 0; u < nunits; ++u) {
@@ -131,10 +140,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
           const uint8_t* dzs = st + stash_off_dz(g, g.skip) + hh * HALF_PANEL;
           const uint8_t* xs = st + stash_off_x(g, 4 * slice) + hh * HALF_PANEL;
           mbar_arrive_expect_tx(fb, static_cast<uint32_t>(4 + npanels) * HALF_PANEL);
-          bulk_g2s_hint(sbase + 0 * HALF_PANEL, dz0, HALF_PANEL, fb, stash_policy);
-          bulk_g2s_hint(sbase + 1 * HALF_PANEL, dz0 + PANEL_BYTES, HALF_PANEL, fb, stash_policy);
-          bulk_g2s_hint(sbase + 2 * HALF_PANEL, dzs, HALF_PANEL, fb, stash_policy);
-          bulk_g2s_hint(sbase + 3 * HALF_PANEL, dzs + PANEL_BYTES, HALF_PANEL, fb, stash_policy);
+          const uint8_t* dzsrc[4] = {dz0, dz0 + PANEL_BYTES, dzs, dzs + PANEL_BYTES};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!mcast) bulk_g2s_hint(sbase + static_cast<uint32_t>(j) * HALF_PANEL, dzsrc[j], HALF_PANEL, fb, stash_policy);
+            else if (static_cast<uint32_t>(j % cw) == crank)
+              bulk_g2s_multicast(sbase + static_cast<uint32_t>(j) * HALF_PANEL, dzsrc[j], HALF_PANEL, fb, cmask);
+          }
           for (int pn = 0; pn < npanels; ++pn)
             bulk_g2s_hint(sbase + BLOB_BYTES + static_cast<uint32_t>(pn) * HALF_PANEL, xs + static_cast<size_t>(pn) * PANEL_BYTES,
                           HALF_PANEL, fb, stash_policy);
@@ -190,7 +202,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
             if (w.bias_col >= 0) umma_f16(tmem_base + static_cast<uint32_t>(w.bias_col), ad, ones_desc, idesc_ones, acc);
           }
         }
-        umma_commit(bar(BAR_EMPTY + stage));
+        if (mcast) umma_commit_multicast(bar(BAR_EMPTY + stage), cmask);
+        else umma_commit(bar(BAR_EMPTY + stage));
         if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
       }
       umma_commit(bar(BAR_DONE));
@@ -220,18 +233,45 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
   }
 
   __syncthreads();
+  if (cw > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == WG_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, WG_COLS);
   }
 }
 
+static void wgrad_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cluster, cudaStream_t stream) {
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(WG_THREADS);
+  cfg.dynamicSmemBytes = SM_TOTAL;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+
 cudaError_t launch_field_wgrad(const FieldParams& p, int grid, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(SM_TOTAL));
   if (e != cudaSuccess) return e;
-  field_wgrad_kernel<<<grid, WG_THREADS, SM_TOTAL, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  wgrad_launch_config(cfg, attr, grid, p.wg_cluster, stream);
+  return cudaLaunchKernelEx(&cfg, field_wgrad_kernel, p);
+}
+
+// Largest number of CTAs (a multiple of `cluster`) that are co-resident with clusters of that size, 0 on error.
+int field_wgrad_max_grid(int cluster) {
+  cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SM_TOTAL));
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  wgrad_launch_config(cfg, attr, cluster, cluster, nullptr);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, field_wgrad_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n * cluster;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,9 +322,11 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
       ln = lane_;
       c = col_;
     };
-    if (sg.kind == 0) {  // W0 / Wy: row n, column j
-      cta0 = (col >> 8) * rp.groups_big;
+    int gmul = 1;   // CTAs between consecutive ray groups of the same slice
+    if (sg.kind == 0) {  // W0 / Wy: row n, column j; big CTAs are group-major (CTA = group * nbig + slice)
+      cta0 = col >> 8;
       ng = rp.groups_big;
+      gmul = rp.geo.nbig;
       c = (col & 255) + (sg.a ? 256 : 0);
     } else if (sg.kind == 1) {  // hidden / view weight
       if (col < sg.split) from_unit(sg.a, row, rp.plan.u[sg.a].col + col);
@@ -299,7 +341,7 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
     } else {
       // fixed summation order; loads issued eight at a time so that their latencies overlap
       const float* src = rp.partw + (static_cast<size_t>(cta0) * HID + ln) * WG_COLS + c;
-      constexpr size_t GSTRIDE = static_cast<size_t>(HID) * WG_COLS;
+      const size_t GSTRIDE = static_cast<size_t>(HID) * WG_COLS * static_cast<size_t>(gmul);
       int gI = 0;
       for (; gI + 8 <= ng; gI += 8) {
         float v[8];
