@@ -290,8 +290,19 @@ __device__ __forceinline__ void adam_update(const AdamParams& a, float step_size
   a.params[i] = p_new;
 }
 
+__device__ __forceinline__ void reduce_element(const ReduceParams& rp, int64_t i, float dev_step_size, float dev_bc2_sqrt);
+
 __global__ void field_reduce_kernel(const ReduceParams rp) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // Adam's bias corrections from the device-resident step counter: two double-precision pow() -- once per CTA, not per
+  // element (FP64 transcendental code in every thread was most of this kernel's 21 us)
+  __shared__ float s_bias_corr[2];
+  if (threadIdx.x == 0 && rp.adam.params != nullptr && rp.adam.step_dev != nullptr) {
+    const double t = static_cast<double>(*rp.adam.step_dev);
+    s_bias_corr[0] = static_cast<float>(static_cast<double>(rp.adam.lr) / (1.0 - pow(static_cast<double>(rp.adam.beta1), t)));
+    s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(rp.adam.beta2), t)));
+  }
+  __syncthreads();
   if (i == 0 && rp.loss_sums != nullptr && rp.do_reduce) {
     float a = 0.f, b = 0.f;
     for (int c = 0; c < rp.ncta1; ++c) {
@@ -302,7 +313,12 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
     rp.loss_sums[0] = a;
     rp.loss_sums[1] = b;
   }
-  if (i >= rp.total) return;
+  // one resident wave: a CTA past the first wave would cost a whole extra pass for a handful of elements
+  for (int64_t e = i; e < rp.total; e += static_cast<int64_t>(gridDim.x) * blockDim.x) reduce_element(rp, e, s_bias_corr[0], s_bias_corr[1]);
+}
+
+__device__ __forceinline__ void reduce_element(const ReduceParams& rp, const int64_t i, const float dev_step_size,
+                                               const float dev_bc2_sqrt) {
   int sidx = 0;
   for (int s = 1; s < rp.nseg; ++s)
     if (i >= rp.seg[s].off) sidx = s;
@@ -363,9 +379,8 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   if (sg.kind == 2 && sg.pair_off == -2) return;   // Ly.bias: handled by the thread of Lx.bias
   float step_size = ad.step_size, bc2_sqrt = ad.bc2_sqrt;
   if (ad.step_dev != nullptr) {
-    const double t = static_cast<double>(*ad.step_dev);
-    step_size = static_cast<float>(static_cast<double>(ad.lr) / (1.0 - pow(static_cast<double>(ad.beta1), t)));
-    bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(ad.beta2), t)));
+    step_size = dev_step_size;
+    bc2_sqrt = dev_bc2_sqrt;
   }
   float pn;
   adam_update(ad, step_size, bc2_sqrt, i, grad, pn);
@@ -402,7 +417,17 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
 
 cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream) {
   const int threads = 256;
-  field_reduce_kernel<<<static_cast<unsigned>((rp.total + threads - 1) / threads), threads, 0, stream>>>(rp);
+  static int resident = 0;   // CTAs of one wave
+  if (resident == 0) {
+    int dev = 0, nsm = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm < 1)
+      nsm = 132;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, field_reduce_kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    resident = nsm * per_sm;
+  }
+  int64_t blocks = (rp.total + threads - 1) / threads;
+  if (blocks > resident) blocks = resident;
+  field_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(rp);
   return cudaGetLastError();
 }
 
