@@ -192,3 +192,62 @@ def test_config5_1080p_frame_inference_chunk_invariance():
     ref = O.field_forward({n: p.detach().cpu() for n, p in m.state_dict().items()}, tab_cpu, vids[idx].long(), bary[idx])
     err = (a[idx] - ref).abs()
     assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN
+
+
+def test_config2_cat_training_steps_at_shipped_batch_match_oracle():
+    # configs[1] as the reference ships it (intrinsic_cat.yaml:25-34): V ~ 50 k vertices, k = 1023, batch_size 4096, L1, Adam 1e-4.
+    # 12 optimisation steps through the whole fast path (int32 ids, batch selection folded into the kernels, fused Adam,
+    # CUDA-graph replay) against the fp32 oracle on identical batches: loss trajectory and held-out PSNR.
+    from inf_b200 import trainer
+    from inf_b200.ray_dataloader import RayDataLoader
+    G, k, B, steps, lr = 224, 1023, 4096, 12, 1e-4
+    V = G * G
+    g = torch.Generator().manual_seed(11)
+    E = torch.randn(V, k, generator=g)
+    E = (E / (E.max(0, keepdim=True).values - E.min(0, keepdim=True).values)).float()     # 'standard' rescale, mesh.py:99-102
+    ii, jj = torch.meshgrid(torch.arange(G), torch.arange(G), indexing="ij")
+    v00, v01, v10 = (ii * G + jj).reshape(-1), (ii * G + (jj + 1) % G).reshape(-1), (((ii + 1) % G) * G + jj).reshape(-1)
+    v11 = (((ii + 1) % G) * G + (jj + 1) % G).reshape(-1)
+    faces = torch.cat([torch.stack([v00, v01, v10], 1), torch.stack([v01, v11, v10], 1)])  # 100 352 triangles of a grid torus
+    N = B * 6 + 2048
+    fid = torch.randint(0, faces.shape[0], (N,), generator=g)
+    vids = faces[fid]
+    u = torch.rand(N, 3, generator=g)
+    bary = (u / u.sum(-1, keepdim=True)).float()
+    # a smooth procedural colour of the hit position (PSNR runs)
+    uv = (torch.stack([(vids // G).float(), (vids % G).float()], -1) * bary[..., None]).sum(1) / G
+    target = torch.stack([0.5 + 0.4 * torch.sin(6.28 * uv[:, 0]), 0.5 + 0.4 * torch.cos(6.28 * uv[:, 1]),
+                          0.5 + 0.3 * torch.sin(6.28 * (uv[:, 0] + uv[:, 1]))], -1).float()
+    ntrain = B * 6
+    idx_lists = [torch.randperm(ntrain, generator=g)[:B] for _ in range(steps)]
+    params = O.make_params(k, seed=21)
+    ref_params, ref_losses = O.adam_train_steps(params, E, vids, bary, target, idx_lists, lr=lr)
+    hold = slice(ntrain, None)
+    with torch.no_grad():
+        pr = O.field_forward(ref_params, E, vids[hold], bary[hold])
+    psnr_ref = O.epoch_psnr(float(((pr - target[hold]) ** 2).sum()), pr.shape[0])
+
+    m = inf_b200.make_model(dict(k=list(range(k)), num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3))
+    m.load_state_dict(params)
+    m = m.to(DEV)
+    loader = RayDataLoader(E, "efuncs", vids[:ntrain].to(torch.int32), bary[:ntrain], target[:ntrain], None, None, B,
+                           shuffle=False, drop_last=True, device=DEV, fused_select=True)
+    fopt = trainer.FusedFieldAdam(m, lr=lr)
+    gs = trainer.GraphedTrainStep(m, fopt)
+    losses = []
+    loader.num_batches = steps                       # the explicit order below holds `steps` batches
+    loader.N = steps * B
+    it = iter(loader)
+    loader.set_epoch_order(torch.cat(idx_lists))
+    for batch in it:
+        loss, _ = gs.step(batch)
+        losses.append(loss)
+    _check_no_watchdog()
+    assert len(losses) == steps
+    m.eval()
+    with torch.no_grad():
+        pg = m({"eigenfunction_table": loader.table, "vertex_idxs_of_hit_faces": vids[hold].to(DEV),
+                "barycentric_coords": bary[hold].to(DEV)}).cpu()
+    psnr_gpu = O.epoch_psnr(float(((pg - target[hold]) ** 2).sum()), pg.shape[0])
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-3, (losses[-3:], ref_losses[-3:])
+    assert abs(psnr_gpu - psnr_ref) <= 0.1, (psnr_gpu, psnr_ref)                 # BASELINE.json tolerance
