@@ -1,12 +1,13 @@
 // Forward (+ loss + dgrad chain) kernel of the intrinsic-neural-field path, sm_100a.
 //
 // Persistent CTAs (one per SM), 128-ray tiles, six warp roles connected by mbarrier rings:
-//   producers (8 warps)    gather 3 table rows per ray with 16-byte loads, interpolate in fp32 with the
+//   producers (16 warps)   gather 3 table rows per ray with 16-byte loads, interpolate in fp32 with the
 //                          barycentric weights, round to fp16 and store the [128 x 64] A-panel of the
 //                          current k-chunk straight into the SWIZZLE_128B smem layout the tensor core
 //                          reads -- the interpolated embedding (mesh.py:313-324) is never read back from HBM
 //                          by the forward pass;
-//   B1 loader (1 thread)   streams the [W0;Wy] operand chunks (32 KB blobs) with 1-D bulk copies (TMA);
+//   B1 loader (1 thread)   streams the [W0;Wy] operand chunks as 16 KB half-stages (W0 rows, Wy rows) with 1-D bulk
+//                          copies (TMA), each fetched once per 2-CTA cluster and multicast;
 //   GEMM1 issuer (1 thr)   tcgen05.mma kind::f16: [z0|zy] = x * [W0;Wy]^T (N=256, K=k_pad) into one of TWO
 //                          256-column TMEM buffers, so the gather/GEMM1 of tile t+1 overlaps the layer chain of
 //                          tile t; when training it also bulk-stores each x panel to the stash (operand of
@@ -44,11 +45,10 @@ constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int MAX_STAGE_B1 = 4;   // half-stages of the [W0;Wy] ring
 constexpr int MAX_STAGE_A = 5;
 
-// shared memory carve-up (bytes from a 1024-aligned base), 13 panels of 16 KB + small tables:
-//   training   A ring 3 (2 with the view branch: one stage goes to the Fourier panel), B1 2x32 KB, H 2x32 KB, B2 32 KB
-//   inference  no stash stores read the activation buffer after the MMA, so ONE H buffer is enough and the A ring gets
-//              its 32 KB: 5 stages (4 with the view branch).  Every producer warp contributes to every A panel, so a
-//              deeper ring is what decouples the warps from each other's tail latencies.
+// shared memory carve-up (bytes from a 1024-aligned base), at most 9 panels of 16 KB + small tables = 163 KB:
+//   training   A ring 3 x 16 KB (2 with the view branch: one stage goes to the Fourier panel), B1 one whole chunk
+//              (2 half-stages), H 32 KB, B2 32 KB
+//   inference  A ring 2, B1 3 half-stages (2 with the view branch), H 32 KB, B2 32 KB
 struct Smem {
   uint32_t a, b1, h, b2, e, dzlt, bias, wlast, vid, bary, red, bars, tmemptr, total;
   int nstage_a, nstage_b1, nh;
