@@ -123,3 +123,27 @@ def test_writer_edge_cases(tmp_path):
     assert torch.equal(d["face_idxs"], torch.cat([p[4] for p in parts]))
     with pytest.raises(RuntimeError):
         w.cache_single_view(None, None, torch.ones(2, 2, dtype=torch.bool), torch.zeros(2, 2, 3))
+
+
+@pytest.mark.parametrize("stem", STEMS)
+def test_reserved_header_matches_numpy_for_every_realistic_row_count(stem):
+    # the appender patches a 128-byte header in place; np.save must emit exactly that length for the same shape / dtype
+    import io
+    dt, tail = ray_store.FILES[stem]
+    for n in (0, 1, 9, 10, 12345, 10**6, 10**9, 2**31 - 1, 10**12, 10**15):
+        hdr = ray_store._npy_header(dt, (n,) + tail)
+        assert len(hdr) == ray_store._HEADER_RESERVE, (stem, n, len(hdr))
+        buf = io.BytesIO()
+        np.lib.format.write_array_header_1_0(buf, {"descr": np.lib.format.dtype_to_descr(np.dtype(dt)), "fortran_order": False,
+                                                   "shape": (n,) + tail})
+        assert buf.getvalue() == hdr
+    # and a real file of a few thousand rows equals np.save byte for byte
+    import tempfile
+    rows = np.arange(3000 * max(1, int(np.prod(tail))), dtype=dt).reshape((3000,) + tail)
+    with tempfile.TemporaryDirectory() as d:
+        a = ray_store.NpyAppender(os.path.join(d, "a.npy"), dt, tail)
+        for lo in range(0, 3000, 701):
+            a.append(rows[lo:lo + 701])
+        a.close()
+        np.save(os.path.join(d, "b.npy"), rows, allow_pickle=False)
+        assert open(os.path.join(d, "a.npy"), "rb").read() == open(os.path.join(d, "b.npy"), "rb").read()
