@@ -5,7 +5,7 @@ training backward, behind the call surface of tum-vision/intrinsic-neural-fields
 the preprocessed-ray files).  Import as ``inf_b200``."""
 from . import _lib
 from .ops import EigenTable, FieldConfig, pack_weights, param_layout, num_params, debug_umma, kernel_error_word
-from .model import TextureField, TextureFieldWithViewDependency, make_model, init_weights
+from .model import TextureField, TextureFieldWithViewDependency, make_model, init_weights, load_trained_model
 
-__all__ = ["EigenTable", "FieldConfig", "TextureField", "TextureFieldWithViewDependency", "make_model", "init_weights", "pack_weights",
+__all__ = ["EigenTable", "FieldConfig", "TextureField", "TextureFieldWithViewDependency", "make_model", "init_weights", "load_trained_model", "pack_weights",
            "param_layout", "num_params", "debug_umma", "kernel_error_word"]

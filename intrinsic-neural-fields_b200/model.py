@@ -330,3 +330,12 @@ def make_model(model_config: dict, mesh=None) -> nn.Module:
             view_dir_strategy=view_cfg["strategy"], **common)
     model.apply(init_weights)                                           # model.py:257
     return model
+
+
+def load_trained_model(model_config, weights_path, device, mesh=None):
+    """utils.py:22-29: build the model of ``config["model"]`` and load a checkpoint written by the reference
+    (either the bare ``state_dict`` or the trainer's ``{"model_state_dict": ...}`` wrapper)."""
+    model = make_model(model_config, mesh=mesh)
+    data = torch.load(weights_path, map_location="cpu")
+    model.load_state_dict(data["model_state_dict"] if "model_state_dict" in data else data)
+    return model.to(device)

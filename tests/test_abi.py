@@ -5,6 +5,7 @@ import os
 import re
 
 import pytest
+import torch
 
 from conftest import ROOT, load_golden
 
@@ -128,3 +129,15 @@ def test_cpu_tensors_fail_loudly():
     m = inf_b200.make_model(dict(k=64, num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3))
     with pytest.raises(RuntimeError):
         m({"eigenfunctions": torch.zeros(4, 64)})
+
+
+def test_load_trained_model_reads_both_checkpoint_forms(tmp_path):
+    # utils.py:22-29: a bare state_dict (train.py's model.pt) or the trainer's {"model_state_dict": ...} wrapper
+    c = load_golden("tf_k64")
+    cfg = dict(k=c["k"], num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3)
+    torch.save(c["params"], tmp_path / "bare.pt")
+    torch.save({"model_state_dict": c["params"], "epoch": 3}, tmp_path / "wrapped.pt")
+    for name in ("bare.pt", "wrapped.pt"):
+        m = inf_b200.load_trained_model(cfg, str(tmp_path / name), "cpu")
+        for n, t in m.state_dict().items():
+            assert torch.equal(t, c["params"][n]), n
