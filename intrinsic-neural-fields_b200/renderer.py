@@ -111,3 +111,53 @@ class FieldRenderer:
         if eval_render:
             return img, hit_ray_idxs
         return img.numpy()
+
+
+class Renderer(FieldRenderer):
+    """The reference's ``Renderer`` call surface (renderer.py:36-146): same constructor arguments, ``set_height`` /
+    ``set_width`` / ``apply_mesh_transform`` and ``render(camCv2world, K, obj_mask_1d, eval_render, ...)``.
+
+    Ray casting is not part of this package: ``intersect(ray_origins, unit_ray_dirs)`` is the caller's
+    ``ray_mesh_intersect`` (mesh.py:208-245; trimesh + pyembree in the reference) returning ``(vids (M,3), bary (M,3),
+    hit_ray_idxs (M,), face_idxs (M,))``.  Everything around it -- pixel rays (mesh.py:171-205), the 36-68 B/ray upload
+    instead of the CPU gather + 4 KB/ray embedding (mesh.py:327-339, renderer.py:116), chunked inference, the canvas
+    scatter (renderer.py:119-146) -- runs here.
+    """
+
+    def __init__(self, model, mesh, eigenfunctions=None, feature_strategy="efuncs", background="white", device="cuda",
+                 *, H, W, intersect=None, table_dtype: str = "f32"):
+        if feature_strategy != "efuncs":
+            raise NotImplementedError(f"feature strategy {feature_strategy!r}: only the intrinsic 'efuncs' path is built")
+        if eigenfunctions is None:
+            raise ValueError("the 'efuncs' strategy needs the eigenfunction table")
+        super().__init__(model, eigenfunctions, H, W, background=background, device=device, table_dtype=table_dtype)
+        self.mesh, self.feature_strategy, self.intersect = mesh, feature_strategy, intersect
+
+    def set_height(self, height):
+        self.H = height
+
+    def set_width(self, width):
+        self.W = width
+
+    def apply_mesh_transform(self, transform):
+        self.mesh.apply_transform(transform)
+        if hasattr(self.intersect, "rebuild"):          # the reference rebuilds its intersector here (renderer.py:62)
+            self.intersect.rebuild(self.mesh)
+
+    @torch.no_grad()
+    def render(self, camCv2world, K, obj_mask_1d=None, eval_render=False, distortion_coeffs=None, distortion_type=None,
+               pixel_coords=None):
+        from .ray_store import pixel_rays
+        if self.intersect is None:
+            raise RuntimeError("Renderer.render needs an intersector callable (ray casting is outside this package)")
+        if distortion_type is not None and pixel_coords is None:
+            raise NotImplementedError("distorted views: undistort the masked pixels first and pass them as pixel_coords")
+        assert obj_mask_1d is None or obj_mask_1d.size()[0] == self.H * self.W
+        mask = torch.ones(self.H * self.W, dtype=torch.bool) if obj_mask_1d is None else obj_mask_1d
+        origins, dirs = pixel_rays(camCv2world, K, mask, H=self.H, W=self.W, pixel_coords=pixel_coords)
+        vids, bary, hit_ray_idxs, face_idxs = self.intersect(origins, dirs)
+        assert vids.shape[0] > 0                                                         # renderer.py:110
+        view = getattr(self.model, "cfg", None) is not None and self.model.cfg.has_view
+        return self.render_hits(vids, bary.to(torch.float32), hit_ray_idxs, obj_mask_1d,
+                                unit_ray_dirs=dirs[hit_ray_idxs] if view else None,
+                                face_idxs=face_idxs if view else None, eval_render=eval_render)

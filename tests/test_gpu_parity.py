@@ -842,3 +842,59 @@ def test_ray_store_round_trip_feeds_training_bit_exactly(tmp_path):
     lb, pb = run(HostRayLoader(tab, c["vids"], c["bary"], c["target"], c["unit_ray_dirs"], c["face_idxs"], batch_size=48, device=DEV))
     _check_no_watchdog()
     assert la == lb and torch.equal(pa, pb)
+
+
+@pytest.mark.parametrize("name", ["tf_k64", "view_intrinsic"])
+def test_renderer_render_matches_reference_canvas(name):
+    # Renderer.render (renderer.py:64-146) with a recorded intersector: pixel rays -> hits -> RGB -> canvas, masked and not
+    import types
+    from inf_b200.renderer import Renderer
+    from inf_b200.ray_store import pixel_rays
+    c = load_golden(name)
+    m = _model_from(c)
+    H, W = 20, 24
+    g = torch.Generator().manual_seed(3)
+    n = c["vids"].shape[0]
+    cam = torch.tensor([[1.0, 0, 0, 0.1], [0, 1, 0, -0.2], [0, 0, 1, -3.0]])
+    K = torch.tensor([[30.0, 0, W / 2 - 0.5], [0, 28.0, H / 2 - 0.5], [0, 0, 1]])
+    for masked in (False, True):
+        mask = (torch.rand(H * W, generator=g) < 0.7) if masked else None
+        L = int(mask.sum()) if masked else H * W
+        hits = torch.randperm(L, generator=g)[:min(L, n) - 7]              # rays that hit, in intersector order
+        sel = torch.randint(0, n, (hits.numel(),), generator=g)            # which golden hit each of them is
+        seen = {}
+
+        def intersect(origins, dirs):
+            assert origins.shape == dirs.shape == (L, 3)
+            seen["dirs"] = dirs
+            fid = c["face_idxs"][sel] if c.get("view") is not None else torch.zeros(sel.numel(), dtype=torch.int64)
+            return c["vids"][sel], c["bary"][sel], hits, fid
+        mesh = types.SimpleNamespace(face_normals=c["face_normals"].numpy()) if c.get("view") is not None else None
+        r = Renderer(m, mesh, eigenfunctions=c["table"], device=DEV, H=H, W=W, intersect=intersect)
+        img = r.render(cam, K, obj_mask_1d=mask)
+        _check_no_watchdog()
+        assert img.shape == (H, W, 3) and img.dtype == np.float32
+        # restatement of renderer.py:113-146 with the oracle as the model
+        kw = dict(num_layers=c["num_layers"], skip=c["skip"])
+        if c.get("view") is not None:
+            _, dirs = pixel_rays(cam, K, mask if masked else torch.ones(H * W, dtype=torch.bool), H=H, W=W)
+            assert torch.equal(dirs, seen["dirs"])
+            kw.update(view=c["view"], unit_ray_dirs=dirs[hits], hit_face_idxs=c["face_idxs"][sel], face_normals=c["face_normals"])
+        pred = O.field_forward(c["params"], c["table"], c["vids"][sel], c["bary"][sel], **kw)
+        canvas = torch.ones(L, 3)
+        canvas[hits] = pred
+        if masked:
+            full = torch.ones(H * W, 3)
+            full[mask] = canvas
+            canvas = full
+        ref = canvas.reshape(H, W, 3).numpy()
+        bg = np.ones((H * W, 3), bool)
+        idx = torch.nonzero(mask).reshape(-1)[hits] if masked else hits
+        bg[idx.numpy()] = False
+        assert np.array_equal(img.reshape(-1, 3)[bg[:, 0]], ref.reshape(-1, 3)[bg[:, 0]])       # background untouched: exactly 1.0
+        err = np.abs(img - ref)
+        assert err.max() <= RGB_MAX and err.mean() <= RGB_MEAN
+    r.set_height(10); r.set_width(12)
+    assert (r.H, r.W) == (10, 12)
+    with pytest.raises(NotImplementedError):
+        Renderer(m, None, eigenfunctions=c["table"], feature_strategy="xyz", device=DEV, H=4, W=4)
