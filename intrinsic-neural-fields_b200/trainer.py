@@ -3,7 +3,7 @@
 ``train_step`` keeps ``_train_step``'s contract -- ``(loss.item(), pred_rgbs)`` after forward, loss,
 zero_grad, backward and ``optim.step()`` -- and uses the fused forward+backward kernel when the loss is
 the config's L1 (config.py:117-118); any other loss callable goes through autograd into the same
-backward kernels.  Epoch loops, TensorBoard, checkpoints stay the reference's host code.
+backward kernels.  ``Trainer`` is the reference's class around it (epoch loop, best model, scheduler, checkpoints).
 """
 from __future__ import annotations
 
@@ -119,6 +119,14 @@ class FusedFieldAdam:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # t, on the device: a graph replay advances it
         self.layout = layout
         self.packed = ops.pack_weights(model.cfg, [p.detach() for p in params], None)     # zero padding written once
+        # the operand images are refreshed by the Adam kernel only: weights written from outside (a checkpoint restored
+        # after the optimiser was built, trainer.py:214-231) must be re-packed before the next forward
+        model.register_load_state_dict_post_hook(lambda module, incompatible_keys: self.repack())
+
+    def repack(self):
+        """Rebuild the fp16 operand images from the flat fp32 parameters (in place: captured graphs keep their pointer)."""
+        ops.pack_weights(self.model.cfg, [p.detach() for p in self.model._ordered_params()], self.packed)
+        self.model._packed, self.model._packed_key = self.packed, None
 
     # ---- the two ways a step is taken ---------------------------------------------------------------------------
     def fused_l1_step(self, batch, global_rays=None):
@@ -312,3 +320,186 @@ class GraphedTrainStep:
     def step(self, batch) -> Tuple[float, torch.Tensor]:
         loss, pred = self.step_async(batch)
         return loss.item(), pred
+
+
+class _ScalarLog:
+    """Stand-in for ``tensorboardX.SummaryWriter`` (not installed in this image): keeps the scalars in memory."""
+
+    def __init__(self):
+        self.scalars = {}
+
+    def add_scalar(self, tag, value, global_step=None):
+        self.scalars.setdefault(tag, []).append((global_step, float(value)))
+
+    def add_image(self, *a, **k):
+        pass
+
+
+class Trainer:
+    """The reference's ``Trainer`` (trainer.py:18-340) over the fused path: same constructor arguments, ``_train_step``,
+    ``_eval_step``, ``evaluate``, ``test``, ``train`` (epoch loop, best-model tracking into ``model.pt``, ReduceLROnPlateau,
+    ``checkpoint.pt`` save / restore with the RNG states, ``model_last_epoch.pt``).
+
+    What differs on purpose: the epoch loop does not read ``loss.item()`` after every step (trainer.py:84,240-242) -- the
+    per-batch loss and squared-error sums stay on the device and are read once per epoch; with the config's L1 loss the
+    step is the fused kernel sequence, replayed from a CUDA graph when the optimiser allows it (``FusedFieldAdam`` or a
+    capturable ``torch.optim`` optimiser).  Rendering validation views into TensorBoard (trainer.py:107-156) needs the
+    reference's file readers and ray caster and is left to an optional ``vis_fn(trainer, epoch)`` callback; scalars go to
+    ``tensorboardX`` when it is importable, else to an in-memory log (``trainer.writer.scalars``).
+    """
+
+    def __init__(self, model, optim, loss_fn, renderer, data, mesh, config, device, *, writer=None, vis_fn=None, group=None):
+        import copy
+        import os
+        self.model, self.optim, self.loss_fn, self.renderer, self.mesh, self.config = model, optim, loss_fn, renderer, mesh, config
+        tr = config["training"]
+        self.use_lr_scheduler = tr.get("use_lr_scheduler", False)
+        self.lr_scheduler = None
+        if self.use_lr_scheduler:
+            if isinstance(optim, FusedFieldAdam):
+                raise NotImplementedError("use_lr_scheduler needs a torch.optim optimiser (FusedFieldAdam has a fixed lr)")
+            self.lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optim, mode="min", factor=0.2)   # trainer.py:36
+        self.train_data_loader, self.val_data_loader = data["train"], data["val"]
+        self.test_data_loader = data.get("test", None)
+        self.out_dir = tr["out_dir"]
+        os.makedirs(os.path.join(self.out_dir, "logs"), exist_ok=True)
+        if writer is None:
+            try:
+                from tensorboardX import SummaryWriter
+                writer = SummaryWriter(os.path.join(self.out_dir, "logs"))
+            except ImportError:
+                writer = _ScalarLog()
+        self.writer, self.vis_fn, self.group = writer, vis_fn, group
+        self.render_every, self.print_every, self.epochs = tr.get("render_every", 1 << 30), tr.get("print_every", 1), tr["epochs"]
+        self.checkpoint_every = tr.get("checkpoint_every")
+        self.checkpoint_path = os.path.join(self.out_dir, "checkpoint.pt")
+        self.device = device
+        self.best_model_weights_path = os.path.join(self.out_dir, "model.pt")
+        self.best_model = copy.deepcopy(model)                                                           # trainer.py:67
+        self.model_last_epoch_path = os.path.join(self.out_dir, "model_last_epoch.pt")
+        self._graphed = None
+        if loss_fn is F.l1_loss and (isinstance(optim, FusedFieldAdam) or
+                                     any(g.get("capturable", False) for g in getattr(optim, "param_groups", []))):
+            self._graphed = GraphedTrainStep(model, optim, group)
+
+    # ---- steps ------------------------------------------------------------------------------------------------------
+    def _train_step_async(self, batch):
+        if self._graphed is not None:
+            return self._graphed.step_async(batch)
+        if isinstance(self.optim, FusedFieldAdam):
+            return fused_train_step_async(self.model, self.optim, batch, self.group)
+        return train_step_async(self.model, self.optim, batch, self.loss_fn, self.group)
+
+    def _train_step(self, batch):
+        """trainer.py:71-84: ``(loss.item(), pred_rgbs)``."""
+        loss, pred = self._train_step_async(batch)
+        return loss.item(), pred
+
+    @torch.no_grad()
+    def _eval_step(self, model, batch):
+        pred = model(batch)
+        return self.loss_fn(pred, _targets(batch)), pred
+
+    def _epoch_metrics(self, model, loader, step):
+        """Rays-weighted mean loss and sum of squared errors over a loader, accumulated on the device."""
+        acc = torch.zeros(2, dtype=torch.float64, device=self.device)
+        total = 0
+        for batch in loader:
+            loss, pred = step(model, batch)
+            gt = _targets(batch)
+            n = gt.size()[0]
+            acc[0] += loss.detach().double() * n
+            acc[1] += F.mse_loss(pred.detach(), gt, reduction="sum").double()
+            total += n
+        a = acc.tolist()                                     # the epoch's only host read
+        return a[0] / total, epoch_psnr(a[1] / total)
+
+    def evaluate(self, epoch=None):
+        """trainer.py:164-187."""
+        self.model.eval()
+        val_loss, val_psnr = self._epoch_metrics(self.model, self.val_data_loader, self._eval_step)
+        self.writer.add_scalar("Val_Loss", val_loss, epoch)
+        self.writer.add_scalar("Val Epoch-PSNR", val_psnr, epoch)
+        return val_loss, val_psnr
+
+    def test(self):
+        """trainer.py:189-212."""
+        if self.test_data_loader is None:
+            return None
+        self.best_model.eval()
+        test_loss, _ = self._epoch_metrics(self.best_model, self.test_data_loader, self._eval_step)
+        self.writer.add_scalar("Test Loss", test_loss)
+        print(f"Test Loss: {test_loss}")
+        return test_loss
+
+    # ---- checkpoints ------------------------------------------------------------------------------------------------
+    def _checkpoint(self, epoch):
+        import random
+        import numpy as np
+        return {"epoch": epoch, "model_state_dict": self.model.state_dict(), "optimizer_state_dict": self.optim.state_dict(),
+                "pytorch_random_state": torch.random.get_rng_state(), "python_random_state": random.getstate(),
+                "numpy_random_state": np.random.get_state()}
+
+    def _init_or_load_checkpoint(self):
+        """trainer.py:214-231."""
+        import os
+        import random
+        import numpy as np
+        if self.checkpoint_every is None or not os.path.exists(self.checkpoint_path):
+            return 0
+        print("Restoring from checkpoint...")
+        ck = torch.load(self.checkpoint_path, map_location="cpu", weights_only=False)
+        self.model.load_state_dict(ck["model_state_dict"])
+        self.optim.load_state_dict(ck["optimizer_state_dict"])
+        if hasattr(self.model, "invalidate_packed"):
+            self.model.invalidate_packed()
+        torch.random.set_rng_state(ck["pytorch_random_state"])
+        random.setstate(ck["python_random_state"])
+        np.random.set_state(ck["numpy_random_state"])
+        print("Done.")
+        return ck["epoch"] + 1
+
+    # ---- epoch loop -------------------------------------------------------------------------------------------------
+    def train(self):
+        """trainer.py:233-340."""
+        import copy
+        import os
+        import time
+        print("Starting training...")
+        first = self._init_or_load_checkpoint()
+        min_val_loss = 1.0
+        for epoch in range(first, self.epochs):
+            self.model.train()
+            t0 = time.time()
+            train_loss, train_psnr = self._epoch_metrics(self.model, self.train_data_loader,
+                                                         lambda m, b: self._train_step_async(b))
+            t1 = time.time()
+            self.writer.add_scalar("Train_Loss", train_loss, epoch)
+            self.writer.add_scalar("Train Epoch-PSNR", train_psnr, epoch)
+            val_loss, val_psnr = self.evaluate(epoch)
+            if val_loss < min_val_loss:
+                min_val_loss = val_loss
+                torch.save(self.model.state_dict(), self.best_model_weights_path)
+                self.best_model = copy.deepcopy(self.model)
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step(val_loss)
+            if epoch == 0 or (epoch + 1) % self.print_every == 0:
+                print(f"Epoch: {epoch + 1} / {self.epochs}, Train Loss: {train_loss}, Train PSNR: {train_psnr}, "
+                      f"Val Loss: {val_loss}, Val PSNR: {val_psnr} Epoch Time: {t1 - t0}s")
+            if self.vis_fn is not None and (epoch == 0 or (epoch + 1) % self.render_every == 0):
+                self.model.eval()
+                self.vis_fn(self, epoch)
+            if self.checkpoint_every is not None and epoch % self.checkpoint_every == 0:
+                torch.save(self._checkpoint(epoch), self.checkpoint_path)
+            if epoch > 0 and (epoch + 1) == 200:                                             # trainer.py:315-334
+                torch.save(self._checkpoint(epoch), os.path.join(self.out_dir, f"checkpoint_{epoch}.pt"))
+                torch.save(self.best_model.state_dict(), os.path.join(self.out_dir, f"best_model_checkpoint_{epoch}.pt"))
+        self.test()
+        print("Done.")
+        torch.save(self.model.state_dict(), self.model_last_epoch_path)
+
+
+def _targets(batch):
+    """The batch's target rows (the whole split's array when the batch selection is folded into the kernels)."""
+    r = batch.get("ray_idxs")
+    return batch["expected_rgbs"] if r is None else batch["expected_rgbs"][r.long()]

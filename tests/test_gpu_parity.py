@@ -898,3 +898,71 @@ def test_renderer_render_matches_reference_canvas(name):
     assert (r.H, r.W) == (10, 12)
     with pytest.raises(NotImplementedError):
         Renderer(m, None, eigenfunctions=c["table"], feature_strategy="xyz", device=DEV, H=4, W=4)
+
+
+def test_trainer_epoch_loop_matches_reference_loop_and_resumes(tmp_path):
+    # Trainer (trainer.py:18-340): epoch metrics against the same loop run with the fp32 oracle, best-model / last-epoch /
+    # checkpoint files, and a resumed run that ends bit-identical to an uninterrupted one
+    from inf_b200 import trainer
+    from inf_b200.ray_dataloader import RayDataLoader
+    c = load_golden("tf_k64")
+    n, ntr, B, lr = c["vids"].shape[0], 192, 64, 1e-3
+    tr_sl, va_sl = slice(0, ntr), slice(ntr, n)
+
+    # ---- the reference's loop with the oracle as the model (CPU, fp32) ----
+    q = {k_: v.detach().clone().requires_grad_(True) for k_, v in c["params"].items()}
+    opt = torch.optim.Adam(list(q.values()), lr=lr)
+    ref = []
+    for epoch in range(3):
+        acc_l = acc_sq = 0.0
+        for lo in range(0, ntr, B):
+            sl = slice(lo, lo + B)
+            pred = O.field_forward(q, c["table"], c["vids"][sl], c["bary"][sl])
+            loss = O.l1_loss(pred, c["target"][sl])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            acc_l += loss.item() * B
+            acc_sq += float(((pred.detach() - c["target"][sl]) ** 2).sum())
+        with torch.no_grad():
+            pv = O.field_forward(q, c["table"], c["vids"][va_sl], c["bary"][va_sl])
+        ref.append((acc_l / ntr, O.epoch_psnr(acc_sq, ntr), float(O.l1_loss(pv, c["target"][va_sl])),
+                    O.epoch_psnr(float(((pv - c["target"][va_sl]) ** 2).sum()), n - ntr)))
+
+    def make(out_dir, epochs, fused_select):
+        m = _model_from(c)
+        tab = inf_b200.EigenTable.from_dense(c["table"], device=DEV)
+        mk = lambda sl, fs: RayDataLoader(tab, "efuncs", c["vids"][sl], c["bary"][sl], c["target"][sl], None, None, B, shuffle=False,
+                                          drop_last=False, device=DEV, fused_select=fs)
+        cfg = {"training": {"out_dir": str(out_dir), "epochs": epochs, "print_every": 100, "render_every": 100,
+                            "checkpoint_every": 1, "lr": lr, "loss_type": "L1"},
+               "data": {"img_height": 8, "img_width": 8}, "model": {}}
+        fopt = trainer.FusedFieldAdam(m, lr=lr)
+        data = {"train": mk(tr_sl, fused_select), "val": mk(va_sl, False), "test": mk(va_sl, False)}
+        return trainer.Trainer(m, fopt, trainer.get_loss_fn("L1"), None, data, None, cfg, DEV, writer=trainer._ScalarLog())
+
+    t3 = make(tmp_path / "a", 3, True)
+    t3.train()
+    _check_no_watchdog()
+    sc = t3.writer.scalars
+    for e, (trl, trp, val, vap) in enumerate(ref):
+        assert abs(sc["Train_Loss"][e][1] - trl) < 2e-3 and abs(sc["Val_Loss"][e][1] - val) < 2e-3, (e, sc["Train_Loss"][e], trl)
+        assert abs(sc["Train Epoch-PSNR"][e][1] - trp) < 0.1 and abs(sc["Val Epoch-PSNR"][e][1] - vap) < 0.1
+    assert [s for s, _ in sc["Val_Loss"]] == [0, 1, 2] and len(sc["Test Loss"]) == 1
+    for f in ("model.pt", "model_last_epoch.pt", "checkpoint.pt"):
+        assert (tmp_path / "a" / f).exists(), f
+    best = torch.load(tmp_path / "a" / "model.pt")
+    assert list(best.keys()) == c["param_names"]
+    ck = torch.load(tmp_path / "a" / "checkpoint.pt", weights_only=False)
+    assert ck["epoch"] == 2 and set(ck) >= {"model_state_dict", "optimizer_state_dict", "pytorch_random_state"}
+
+    # ---- resume: 3 epochs + restart to 5 == 5 epochs straight ----
+    t5 = make(tmp_path / "b", 5, False)
+    t5.train()
+    t_res = make(tmp_path / "a", 5, False)                   # finds a/checkpoint.pt (epoch 2) and continues at epoch 3
+    t_res.train()
+    assert [s for s, _ in t_res.writer.scalars["Val_Loss"]] == [3, 4]
+    a, b = t5.model.state_dict(), t_res.model.state_dict()
+    for k_ in a:
+        assert torch.equal(a[k_], b[k_]), k_
+    assert t5.optim.step_count == t_res.optim.step_count == 15
