@@ -200,3 +200,46 @@ class HostRayLoader:
         if getattr(self, "_pending", False):
             self._pending = False
             self._issue()
+
+
+def create_ray_dataloader(preproc_data_path, eigenfunctions_path, k, feature_strategy, mesh, rescale_strategy,
+                          eigenvalues_path, embed_strategy, batch_size, shuffle, drop_last, device="cuda",
+                          table=None, fused_select=False):
+    """ray_dataloader.py:7-58: eigenfunction table + preprocessed-ray directory -> ``RayDataLoader``.  Positional
+    order as the reference declares it (``eigenvalues_path`` before ``embed_strategy``).  The indices stay int32 as
+    stored (the kernels read either width); ``table`` lets several splits share one device-resident table instead of
+    uploading it once per loader as the reference does (ray_dataloader.py:73)."""
+    from .ray_store import load_first_k_eigenfunctions, load_preprocessed_rays
+    if feature_strategy != "efuncs":
+        raise ValueError(f"Unknown / unsupported input feature strategy for the B200 path: {feature_strategy}")
+    if table is None:
+        table = load_first_k_eigenfunctions(eigenfunctions_path, k, rescale_strategy=rescale_strategy,
+                                            embed_strategy=embed_strategy, eigenvalues_path=eigenvalues_path)
+    d = load_preprocessed_rays(preproc_data_path)
+    return RayDataLoader(table, feature_strategy, d["vertex_idxs_of_hit_faces"], d["barycentric_coords"], d["expected_rgbs"],
+                         d.get("unit_ray_dirs"), d.get("face_idxs"), batch_size, shuffle, drop_last, device=device,
+                         fused_select=fused_select)
+
+
+def get_data(config, device="cuda", fused_select=True):
+    """config.py:58-103: the train / val (/ test) loaders of a config.  The table is built and uploaded once and shared
+    by the splits.  (The reference passes ``embed_strategy`` and ``eigenvalues_path`` to ``create_ray_dataloader`` in
+    swapped positions, config.py:66-67 vs ray_dataloader.py:13-14; they are passed by name here.)"""
+    from .ray_store import load_first_k_eigenfunctions
+    dc, mc = config["data"], config["model"]
+    strategy = mc.get("feature_strategy", "efuncs")
+    if strategy != "efuncs":
+        raise ValueError(f"Unknown / unsupported input feature strategy for the B200 path: {strategy}")
+    feats = load_first_k_eigenfunctions(dc["eigenfunctions_path"], mc.get("k"), rescale_strategy=dc.get("rescale_strategy", "standard"),
+                                        embed_strategy=dc.get("embed_strategy"), eigenvalues_path=dc.get("eigenvalues_path"))
+    table = EigenTable.from_dense(feats, device=torch.device(device))
+    B = config["training"]["batch_size"]
+
+    def mk(path, shuffle, drop_last, fs):
+        return create_ray_dataloader(path, None, None, strategy, None, None, None, None, B, shuffle, drop_last, device=device,
+                                     table=table, fused_select=fs)
+    data = {"train": mk(dc["preproc_data_path_train"], True, dc.get("train_drop_last", True), fused_select),
+            "val": mk(dc["preproc_data_path_eval"], False, False, False)}
+    if dc.get("preproc_data_path_test") is not None:
+        data["test"] = mk(dc["preproc_data_path_test"], False, False, False)
+    return data

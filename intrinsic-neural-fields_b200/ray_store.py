@@ -195,3 +195,48 @@ def load_preprocessed_rays(preproc_data_path: str, *, index_dtype: torch.dtype =
         data["unit_ray_dirs"] = read("unit_ray_dirs", torch.float32)
         data["face_idxs"] = read("face_idxs", index_dtype)
     return data
+
+
+def load_first_k_eigenfunctions(eigenfunctions_path, k, rescale_strategy="standard", embed_strategy=None, eigenvalues_path=None,
+                                ts=128) -> torch.Tensor:
+    """The table the hot path gathers from, as the reference derives it from the stored eigen-decomposition
+    (mesh.py:53-107): column selection (first ``k`` or an explicit list), optional GPS / HKS embedding with the
+    eigenvalues, then the rescale (``standard``: each column divided by its range; ``one-norm``: each row by its
+    Euclidean norm; ``unscaled``).  The arithmetic runs in the stored dtype (float64 from the eigensolver) and is cast
+    to float32 once at the end, like the reference -- the result is bit-identical (tests/test_ray_store.py)."""
+    all_efuncs = np.load(eigenfunctions_path)
+    if isinstance(k, list):
+        efuncs = all_efuncs[:, np.array(k)]
+    else:
+        if k > all_efuncs.shape[1]:
+            raise ValueError(f"k={k} exceeds the {all_efuncs.shape[1]} stored eigenfunctions")
+        efuncs = all_efuncs[:, :k]
+    evals = None
+    if eigenvalues_path is not None:
+        all_evals = np.load(eigenvalues_path)
+        evals = all_evals[..., np.array(k)] if isinstance(k, list) else all_evals[:k]   # mesh.py:69-75
+        if np.abs(evals[0]) < 1e-10 and evals[0] < 0:          # numerically-zero first eigenvalue with the wrong sign
+            evals[0] *= -1
+        if not np.all(evals > 0):
+            raise ValueError(f"eigenvalues must be positive, min value: {evals.min()}")
+    if embed_strategy is not None:
+        if evals is None:
+            raise ValueError(f"embed_strategy={embed_strategy!r} needs eigenvalues_path")
+        if embed_strategy == "gps":                            # Global Point Signature
+            w = np.sqrt(evals)
+            w /= w[0]
+            # mesh.py:91 returns here, before any rescale -- as a float64 numpy array, which the reference's loaders cannot
+            # move to a device; same values, as the float32 tensor every other branch returns
+            return torch.from_numpy(efuncs / w).to(dtype=torch.float32)
+        if embed_strategy == "hks":                            # Heat Kernel Signature
+            t = np.logspace(-2, 0, num=ts)
+            efuncs = (efuncs * efuncs) @ np.exp(-evals[..., None] @ t[None, ...])
+        else:
+            raise ValueError(f"Unknown embedding strategy {embed_strategy}")
+    if rescale_strategy == "standard":
+        efuncs = efuncs / (np.max(efuncs, axis=0, keepdims=True) - np.min(efuncs, axis=0, keepdims=True))
+    elif rescale_strategy == "one-norm":
+        efuncs = efuncs / np.linalg.norm(efuncs, ord=2, axis=-1, keepdims=True)
+    elif rescale_strategy != "unscaled":
+        raise RuntimeError(f"Unknown rescaling strategy: {rescale_strategy}")
+    return torch.from_numpy(efuncs).to(dtype=torch.float32)

@@ -966,3 +966,36 @@ def test_trainer_epoch_loop_matches_reference_loop_and_resumes(tmp_path):
     for k_ in a:
         assert torch.equal(a[k_], b[k_]), k_
     assert t5.optim.step_count == t_res.optim.step_count == 15
+
+
+def test_get_data_builds_the_loaders_of_a_config(tmp_path):
+    # config.py:58-103 + ray_dataloader.py:7-58: stored eigen-decomposition + preprocessed-ray directories -> loaders
+    from inf_b200 import ray_store
+    from inf_b200.ray_dataloader import get_data
+    c = load_golden("view_intrinsic")
+    n, k = c["vids"].shape[0], c["table"].shape[1]
+    g = np.random.default_rng(0)
+    stored = g.standard_normal((c["table"].shape[0], k + 5))                      # float64, more columns than the model uses
+    np.save(tmp_path / "efuncs.npy", stored)
+    for split, sl in (("train", slice(0, 100)), ("eval", slice(100, n))):
+        with ray_store.RayCacheWriter(str(tmp_path / split)) as w:
+            w.append_hits(c["vids"][sl], c["bary"][sl], c["target"][sl], c["unit_ray_dirs"][sl], c["face_idxs"][sl])
+    cfg = {"data": {"eigenfunctions_path": str(tmp_path / "efuncs.npy"), "preproc_data_path_train": str(tmp_path / "train"),
+                    "preproc_data_path_eval": str(tmp_path / "eval")},
+           "model": {"k": k}, "training": {"batch_size": 32}}
+    data = get_data(cfg, DEV)
+    assert set(data) == {"train", "val"} and data["train"].table is data["val"].table
+    want = stored[:, :k] / (stored[:, :k].max(0, keepdims=True) - stored[:, :k].min(0, keepdims=True))
+    assert torch.equal(data["train"].table.data[:, :k].cpu(), torch.from_numpy(want).float())        # 'standard' rescale, bit-exact
+    assert len(data["train"]) == 3 and len(data["val"]) == (n - 100 + 31) // 32                      # drop_last True / False
+    seen = 0
+    for b in data["val"]:                                                      # unshuffled: rows in stored order, values untouched
+        m = b["expected_rgbs"].shape[0]
+        sl = slice(100 + seen, 100 + seen + m)
+        assert b["vertex_idxs_of_hit_faces"].dtype == torch.int32
+        assert torch.equal(b["vertex_idxs_of_hit_faces"].cpu().long(), c["vids"][sl]) and torch.equal(b["barycentric_coords"].cpu(), c["bary"][sl])
+        assert torch.equal(b["unit_ray_dirs"].cpu(), c["unit_ray_dirs"][sl]) and torch.equal(b["hit_face_idxs"].cpu().long(), c["face_idxs"][sl])
+        seen += m
+    assert seen == n - 100
+    b = next(iter(data["train"]))                                              # shuffled, selection folded into the kernels
+    assert b["ray_idxs"].shape == (32,) and b["vertex_idxs_of_hit_faces"].shape == (100, 3)

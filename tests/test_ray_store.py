@@ -147,3 +147,30 @@ def test_reserved_header_matches_numpy_for_every_realistic_row_count(stem):
         a.close()
         np.save(os.path.join(d, "b.npy"), rows, allow_pickle=False)
         assert open(os.path.join(d, "a.npy"), "rb").read() == open(os.path.join(d, "b.npy"), "rb").read()
+
+
+def test_load_first_k_eigenfunctions_matches_reference_bit_for_bit(tmp_path):
+    # golden tables from the live reference (tests/golden/make_efuncs_golden.py): selection, GPS / HKS embedding, rescales
+    z = np.load(os.path.join(GOLDEN_DIR, "efuncs.npz"))
+    ep, vp = str(tmp_path / "efuncs.npy"), str(tmp_path / "evals.npy")
+    np.save(ep, z["efuncs"])
+    np.save(vp, z["evals"])
+    cases = {
+        "first_k_standard": dict(k=24, rescale_strategy="standard"),
+        "list_k_standard": dict(k=[0, 1, 2, 7, 8, 30, 39], rescale_strategy="standard"),
+        "first_k_unscaled": dict(k=40, rescale_strategy="unscaled"),
+        "first_k_one_norm": dict(k=16, rescale_strategy="one-norm"),
+        "gps": dict(k=20, rescale_strategy="standard", embed_strategy="gps", eigenvalues_path=vp),
+        "hks_standard": dict(k=20, rescale_strategy="standard", embed_strategy="hks", eigenvalues_path=vp),
+    }
+    for name, kw in cases.items():
+        k = kw.pop("k")
+        got = ray_store.load_first_k_eigenfunctions(ep, k, **kw)
+        want = torch.from_numpy(z["out_" + name]).to(torch.float32)          # the GPS branch of the reference returns float64
+        assert got.dtype == torch.float32 and torch.equal(got, want), name
+    with pytest.raises(RuntimeError):
+        ray_store.load_first_k_eigenfunctions(ep, 4, rescale_strategy="bogus")
+    with pytest.raises(ValueError):
+        ray_store.load_first_k_eigenfunctions(ep, 4, embed_strategy="hks")        # no eigenvalues
+    with pytest.raises(ValueError):
+        ray_store.load_first_k_eigenfunctions(ep, 41)
