@@ -204,7 +204,7 @@ class HostRayLoader:
 
 def create_ray_dataloader(preproc_data_path, eigenfunctions_path, k, feature_strategy, mesh, rescale_strategy,
                           eigenvalues_path, embed_strategy, batch_size, shuffle, drop_last, device="cuda",
-                          table=None, fused_select=False):
+                          table=None, fused_select=False, group=None):
     """ray_dataloader.py:7-58: eigenfunction table + preprocessed-ray directory -> ``RayDataLoader``.  Positional
     order as the reference declares it (``eigenvalues_path`` before ``embed_strategy``).  The indices stay int32 as
     stored (the kernels read either width); ``table`` lets several splits share one device-resident table instead of
@@ -216,12 +216,19 @@ def create_ray_dataloader(preproc_data_path, eigenfunctions_path, k, feature_str
         table = load_first_k_eigenfunctions(eigenfunctions_path, k, rescale_strategy=rescale_strategy,
                                             embed_strategy=embed_strategy, eigenvalues_path=eigenvalues_path)
     d = load_preprocessed_rays(preproc_data_path)
+    from . import parallel
+    world = parallel.world_size(group)
+    if world > 1:      # this rank's contiguous 1/W of the split and of every batch
+        each = d["expected_rgbs"].shape[0] // world        # equal shards: every rank runs the same number of steps
+        lo = parallel.rank(group) * each
+        d = {k_: v[lo:lo + each] for k_, v in d.items()}
+        batch_size = max(1, batch_size // world)
     return RayDataLoader(table, feature_strategy, d["vertex_idxs_of_hit_faces"], d["barycentric_coords"], d["expected_rgbs"],
                          d.get("unit_ray_dirs"), d.get("face_idxs"), batch_size, shuffle, drop_last, device=device,
                          fused_select=fused_select)
 
 
-def get_data(config, device="cuda", fused_select=True):
+def get_data(config, device="cuda", fused_select=True, group=None):
     """config.py:58-103: the train / val (/ test) loaders of a config.  The table is built and uploaded once and shared
     by the splits.  (The reference passes ``embed_strategy`` and ``eigenvalues_path`` to ``create_ray_dataloader`` in
     swapped positions, config.py:66-67 vs ray_dataloader.py:13-14; they are passed by name here.)"""
@@ -237,7 +244,7 @@ def get_data(config, device="cuda", fused_select=True):
 
     def mk(path, shuffle, drop_last, fs):
         return create_ray_dataloader(path, None, None, strategy, None, None, None, None, B, shuffle, drop_last, device=device,
-                                     table=table, fused_select=fs)
+                                     table=table, fused_select=fs, group=group)
     data = {"train": mk(dc["preproc_data_path_train"], True, dc.get("train_drop_last", True), fused_select),
             "val": mk(dc["preproc_data_path_eval"], False, False, False)}
     if dc.get("preproc_data_path_test") is not None:

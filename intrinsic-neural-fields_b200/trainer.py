@@ -377,6 +377,7 @@ class Trainer:
         self.best_model_weights_path = os.path.join(self.out_dir, "model.pt")
         self.best_model = copy.deepcopy(model)                                                           # trainer.py:67
         self.model_last_epoch_path = os.path.join(self.out_dir, "model_last_epoch.pt")
+        self._writes_files = parallel.rank(group) == 0       # weights are identical on every rank: rank 0 keeps the files
         self._graphed = None
         if loss_fn is F.l1_loss and (isinstance(optim, FusedFieldAdam) or
                                      any(g.get("capturable", False) for g in getattr(optim, "param_groups", []))):
@@ -411,6 +412,13 @@ class Trainer:
             acc[0] += loss.detach().double() * n
             acc[1] += F.mse_loss(pred.detach(), gt, reduction="sum").double()
             total += n
+        world = parallel.world_size(self.group)
+        if world > 1:                                        # every rank saw its 1/W of the rays: one collective per epoch
+            import torch.distributed as dist
+            cnt = torch.tensor([float(total)], dtype=torch.float64, device=self.device)
+            both = torch.cat([acc, cnt])
+            dist.all_reduce(both, op=dist.ReduceOp.SUM, group=self.group)
+            acc, total = both[:2], int(both[2].item())
         a = acc.tolist()                                     # the epoch's only host read
         return a[0] / total, epoch_psnr(a[1] / total)
 
@@ -479,7 +487,8 @@ class Trainer:
             val_loss, val_psnr = self.evaluate(epoch)
             if val_loss < min_val_loss:
                 min_val_loss = val_loss
-                torch.save(self.model.state_dict(), self.best_model_weights_path)
+                if self._writes_files:
+                    torch.save(self.model.state_dict(), self.best_model_weights_path)
                 self.best_model = copy.deepcopy(self.model)
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step(val_loss)
@@ -489,14 +498,15 @@ class Trainer:
             if self.vis_fn is not None and (epoch == 0 or (epoch + 1) % self.render_every == 0):
                 self.model.eval()
                 self.vis_fn(self, epoch)
-            if self.checkpoint_every is not None and epoch % self.checkpoint_every == 0:
+            if self._writes_files and self.checkpoint_every is not None and epoch % self.checkpoint_every == 0:
                 torch.save(self._checkpoint(epoch), self.checkpoint_path)
-            if epoch > 0 and (epoch + 1) == 200:                                             # trainer.py:315-334
+            if self._writes_files and epoch > 0 and (epoch + 1) == 200:                      # trainer.py:315-334
                 torch.save(self._checkpoint(epoch), os.path.join(self.out_dir, f"checkpoint_{epoch}.pt"))
                 torch.save(self.best_model.state_dict(), os.path.join(self.out_dir, f"best_model_checkpoint_{epoch}.pt"))
         self.test()
         print("Done.")
-        torch.save(self.model.state_dict(), self.model_last_epoch_path)
+        if self._writes_files:
+            torch.save(self.model.state_dict(), self.model_last_epoch_path)
 
 
 def _targets(batch):
