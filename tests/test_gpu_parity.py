@@ -999,3 +999,39 @@ def test_get_data_builds_the_loaders_of_a_config(tmp_path):
     assert seen == n - 100
     b = next(iter(data["train"]))                                              # shuffled, selection folded into the kernels
     assert b["ray_idxs"].shape == (32,) and b["vertex_idxs_of_hit_faces"].shape == (100, 3)
+
+
+def test_trainer_with_torch_adam_and_l2_loss_uses_the_autograd_path(tmp_path):
+    # loss_type L2 (config.py:115) + torch.optim.Adam + ReduceLROnPlateau: the generic branch of Trainer._train_step
+    from inf_b200 import trainer
+    from inf_b200.ray_dataloader import RayDataLoader
+    c = load_golden("tf_k64")
+    n, ntr, B, lr = c["vids"].shape[0], 192, 64, 1e-3
+    q = {k_: v.detach().clone().requires_grad_(True) for k_, v in c["params"].items()}
+    opt = torch.optim.Adam(list(q.values()), lr=lr)
+    acc = 0.0
+    for lo in range(0, ntr, B):
+        sl = slice(lo, lo + B)
+        loss = torch.nn.functional.mse_loss(O.field_forward(q, c["table"], c["vids"][sl], c["bary"][sl]), c["target"][sl])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        acc += loss.item() * B
+    m = _model_from(c)
+    tab = inf_b200.EigenTable.from_dense(c["table"], device=DEV)
+    mk = lambda sl: RayDataLoader(tab, "efuncs", c["vids"][sl], c["bary"][sl], c["target"][sl], None, None, B, shuffle=False,
+                                  drop_last=False, device=DEV)
+    cfg = {"training": {"out_dir": str(tmp_path), "epochs": 1, "use_lr_scheduler": True}, "data": {}, "model": {}}
+    t = trainer.Trainer(m, torch.optim.Adam(m.parameters(), lr=lr), trainer.get_loss_fn("L2"), None,
+                        {"train": mk(slice(0, ntr)), "val": mk(slice(ntr, n))}, None, cfg, DEV, writer=trainer._ScalarLog())
+    assert t._graphed is None and t.lr_scheduler is not None
+    loss, pred = t._train_step(next(iter(mk(slice(0, B)))))            # trainer.py:71-84 contract
+    assert isinstance(loss, float) and pred.shape == (B, 3)
+    m.load_state_dict(c["params"])                                      # undo that step
+    t.optim = torch.optim.Adam(m.parameters(), lr=lr)
+    t.lr_scheduler = None
+    t.train()
+    _check_no_watchdog()
+    assert abs(t.writer.scalars["Train_Loss"][0][1] - acc / ntr) < 1e-3
+    with pytest.raises(NotImplementedError):
+        trainer.Trainer(m, trainer.FusedFieldAdam(m), trainer.get_loss_fn("L1"), None, {"train": [], "val": []}, None, cfg, DEV)
