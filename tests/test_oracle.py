@@ -104,3 +104,20 @@ def test_emulated_precision_restatement_tracks_reference():
             ref = ref.double().numpy().reshape(g[n].shape)
             rel = np.linalg.norm(g[n] - ref) / (np.linalg.norm(ref) + 1e-12)
             assert rel < 6e-2, (name, n, rel)
+
+
+def test_bake_oracle_agrees_with_the_ray_path_oracle():
+    # bake_texture_field.py:296-319 (numpy gather, einsum at float64 when the weights are float64) vs mesh.py:313-324 (fp32 bmm):
+    # same texels up to the fp32 rounding of the embedding
+    c = load_golden("tf_k100_l5s1")
+    g = np.random.default_rng(1)
+    V = c["table"].shape[0]
+    faces = g.integers(0, V, size=(500, 3))
+    u = g.random((500, 3))
+    bary64 = u / u.sum(-1, keepdims=True)
+    a = O.bake_pred_rgbs(c["params"], c["table"].numpy(), faces, bary64, num_layers=c["num_layers"], skip=c["skip"], chunk=128)
+    b = O.field_forward(c["params"], c["table"], torch.from_numpy(faces), torch.from_numpy(bary64).float(),
+                        num_layers=c["num_layers"], skip=c["skip"]).numpy()
+    assert a.shape == b.shape == (500, 3) and a.dtype == np.float32
+    assert np.abs(a - b).max() < 1e-5
+    assert O.bake_pred_rgbs(c["params"], c["table"].numpy(), faces[:0], bary64[:0]).shape == (0, 3)
