@@ -449,7 +449,9 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     else if (cached[cw] < nsm_w) nsm_w = cached[cw];
   }
   // bytes a CTA ingests per tile: the x panels of its 256 columns + its share of dz_0 / dz_skip
-  const double big_bytes = 2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw;
+  // (INF_WGRAD_BIGW scales the big slices' share: they also carry 2.5x the tensor work per ingested byte)
+  const char* bw_env = getenv("INF_WGRAD_BIGW");
+  const double big_bytes = (2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw) * (bw_env ? atof(bw_env) : 1.0);
   double wsum = static_cast<double>(geo.nbig) * big_bytes;
   for (int s = 0; s < plan.nslice; ++s) wsum += plan.bytes_per_tile[s];
   int used = 0;
