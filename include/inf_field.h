@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define INF_ABI_VERSION 4
+#define INF_ABI_VERSION 5
 
 /* error codes */
 #define INF_OK 0
@@ -68,6 +68,12 @@ extern "C" {
 #define INF_VIEW_NONE 0
 #define INF_VIEW_INTRINSIC 1 /* model.py:176-182 */
 #define INF_VIEW_EXTRINSIC 2 /* model.py:183-184 */
+
+/* InfDesc.path: how layer 0 + the skip branch Ly (the two K = k contractions) are evaluated */
+#define INF_PATH_AUTO 0   /* vertex path when a table image is given and n_rows <= 2 * n_rays, else per-ray        */
+#define INF_PATH_RAY 1    /* per ray: gather 3 table rows, interpolate, GEMM over the interpolated embedding       */
+#define INF_PATH_VERTEX 2 /* per vertex: P = E [W0;Wy]^T once per call (needs InfTensors.table_image), rays gather */
+                          /* 3 rows of P; backward: G = scatter of bary * dz by vertex, [dW0;dWy] = G^T E          */
 
 #define INF_MAX_LAYERS 8
 #define INF_MAX_PARAMS 20
@@ -94,7 +100,7 @@ typedef struct InfDesc {
   int64_t n_faces;       /* rows of face_normals (intrinsic view strategy)                    */
   int64_t n_src_rays;    /* rows of the per-ray arrays when InfTensors.ray_idxs selects from them (else 0)  */
   int32_t ray_idx_dtype; /* dtype of ray_idxs (INF_IDX_*)                                      */
-  int32_t reserved1;
+  int32_t path;          /* INF_PATH_*                                                         */
   float grad_scale;      /* multiplies every summed gradient; 1/(3*B_global) for the L1 mean  */
   float reserved0;
 } InfDesc;
@@ -113,6 +119,8 @@ typedef struct InfTensors {
                               /* kernels): ray r of this call reads row ray_idxs[r] of vids / bary / target /       */
                               /* unit_ray_dirs / face_idxs, which are then the WHOLE split's arrays; pred, grad_pred */
                               /* stay in batch order                                                                */
+  const void* table_image;    /* optional fp16 operand image of the table (inf_build_table_image); enables the      */
+                              /* vertex path; the workspace must then be sized with desc.n_rows set                 */
   const void* packed;         /* operand images written by inf_pack_weights                         */
   float* pred;                /* (B,3) f32 out                                                      */
   void* workspace;            /* >= inf_workspace_bytes(desc, training)                             */
@@ -157,6 +165,12 @@ size_t inf_workspace_bytes(const InfDesc* desc, int training);
 int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride,
                        void* dst, int32_t k_pad, int32_t dst_dtype, void* stream);
 
+/* Table operand image for the vertex path: (V,k_pad) f32|f16 row-major table -> fp16 [ceil(V/128)][k_pad/64] panels of
+ * [128 rows][64 columns] in the tensor core's SWIZZLE_128B layout (values rounded to fp16 once).  Built once where the
+ * reference moves the table to the device (ray_dataloader.py:73, renderer.py:43). */
+size_t inf_table_image_bytes(int64_t n_rows, int32_t k_pad);
+int inf_build_table_image(const void* table, int32_t table_dtype, int64_t n_rows, int32_t k_pad, void* image, void* stream);
+
 /* fp32 master parameters -> operand images.  `params[i]` = device pointer of tensor i. */
 int inf_pack_weights(const InfDesc* desc, const float* const* params, void* packed, void* stream);
 
@@ -187,6 +201,12 @@ int inf_gather_interpolate(const void* table, int32_t table_dtype, int32_t k, in
  * forward/backward kernel, the wgrad kernel and the reduction.  Single-threaded use only. */
 int inf_profile_enable(int on);
 int inf_profile_read(float* main_ms, float* wgrad_ms, float* reduce_ms, int* calls);
+/* The same per stage: stage_ms[0..5] = incidence lists (CSR), vertex projection, per-ray forward/backward kernel,
+ * vertex-gradient gather, weight-gradient kernel, reduction (+Adam); stages a call did not run read 0. */
+#define INF_PROFILE_STAGES 6
+int inf_profile_read_stages(float* stage_ms, int* calls);
+/* 1 if the call described by (desc, tensors) takes the vertex path, 0 for the per-ray path (host only). */
+int inf_uses_vertex_path(const InfDesc* desc, const InfTensors* t);
 
 /* Self-test hook used by tests/: D(128,n) = A(128,k) * B(n,k)^T on the tensor cores with the
  * operand-layout variant `mode` (0: A,B K-major; 1: A MN-major; 2: A,B MN-major; 3: B MN-major).  A and

@@ -11,11 +11,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libinf_field.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 IDX_I32, IDX_I64 = 0, 1
 TABLE_F32, TABLE_F16 = 0, 1
 INPUT_GATHER, INPUT_DENSE = 0, 1
 VIEW_NONE, VIEW_INTRINSIC, VIEW_EXTRINSIC = 0, 1, 2
+PATH_AUTO, PATH_RAY, PATH_VERTEX = 0, 1, 2
+PROFILE_STAGES = 6
 MAX_PARAMS = 20
 ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = -1, -2, -3, -4
 
@@ -28,7 +30,7 @@ class InfDesc(C.Structure):
         ("skip", C.c_int32), ("table_dtype", C.c_int32), ("input_mode", C.c_int32),
         ("view_strategy", C.c_int32), ("view_embed", C.c_int32), ("view_include", C.c_int32),
         ("view_bneck", C.c_int32), ("view_hidden", C.c_int32),
-        ("n_faces", C.c_int64), ("n_src_rays", C.c_int64), ("ray_idx_dtype", C.c_int32), ("reserved1", C.c_int32),
+        ("n_faces", C.c_int64), ("n_src_rays", C.c_int64), ("ray_idx_dtype", C.c_int32), ("path", C.c_int32),
         ("grad_scale", C.c_float), ("reserved0", C.c_float),
     ]
 
@@ -37,7 +39,8 @@ class InfTensors(C.Structure):
     _fields_ = [
         ("table", C.c_void_p), ("vids", C.c_void_p), ("bary", C.c_void_p), ("target", C.c_void_p),
         ("grad_pred", C.c_void_p), ("unit_ray_dirs", C.c_void_p), ("face_idxs", C.c_void_p),
-        ("face_normals", C.c_void_p), ("ray_idxs", C.c_void_p), ("packed", C.c_void_p), ("pred", C.c_void_p),
+        ("face_normals", C.c_void_p), ("ray_idxs", C.c_void_p), ("table_image", C.c_void_p), ("packed", C.c_void_p),
+        ("pred", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -64,6 +67,9 @@ EXPORTS = {
     "inf_workspace_bytes": (C.c_size_t, [C.POINTER(InfDesc), C.c_int]),
     "inf_relayout_table": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p]),
+    "inf_table_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "inf_build_table_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "inf_uses_vertex_path": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors)]),
     "inf_pack_weights": (C.c_int, [C.POINTER(InfDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "inf_forward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p]),
     "inf_forward_backward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.POINTER(InfGrads), C.c_void_p]),
@@ -74,6 +80,7 @@ EXPORTS = {
     "inf_profile_enable": (C.c_int, [C.c_int]),
     "inf_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.POINTER(C.c_int)]),
+    "inf_profile_read_stages": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "inf_debug_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

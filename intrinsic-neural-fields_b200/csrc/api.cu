@@ -19,6 +19,14 @@ cudaError_t launch_field_wgrad(const FieldParams& p, int grid, cudaStream_t stre
 int field_wgrad_max_grid(int cluster);
 cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream);
 
+cudaError_t launch_vertex_project(const FieldParams& p, int grid, int cluster, cudaStream_t stream);
+int vertex_project_max_grid(int cluster);
+void launch_table_image(const void* table, int table_f16, int64_t n_rows, int k_pad, void* image, cudaStream_t stream);
+cudaError_t launch_field_rays(const FieldParams& p, bool train, int grid, cudaStream_t stream);
+int field_rays_slots();
+cudaError_t launch_csr_build(const FieldParams& p, cudaStream_t stream);
+cudaError_t launch_vertex_gather(const FieldParams& p, int nsm, cudaStream_t stream);
+
 void launch_pack_weights(const PackParams& pp, cudaStream_t stream);
 void launch_relayout(const float* src, int64_t n_rows, int k, int64_t src_stride, void* dst, int k_pad, int dst_dtype,
                      cudaStream_t stream);
@@ -29,6 +37,28 @@ void launch_umma_probe(int mode, int n, int k, const float* a, const float* b, f
 namespace {
 
 thread_local char g_err[512] = "";
+
+// Environment knobs are read ONCE per process (not on every launch).  INF_DEBUG bits 1|2|4 are measurement switches
+// that skip work and produce WRONG gradients: bench.py refuses to run with them and records the value.
+struct Env {
+  int debug, prefetch, cluster, verbose, wg_cluster, force_path;
+  double wgrad_bigw;
+  Env() {
+    auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+    debug = geti("INF_DEBUG", 0);
+    prefetch = geti("INF_PREFETCH", 0);
+    cluster = geti("INF_CLUSTER", 2);
+    verbose = geti("INF_VERBOSE", 0);
+    wg_cluster = geti("INF_WGRAD_CLUSTER", 4);
+    force_path = geti("INF_PATH", 0);   // 1 = per-ray, 2 = vertex (when a table image is given): overrides InfDesc.path AUTO
+    const char* b = getenv("INF_WGRAD_BIGW");
+    wgrad_bigw = b ? atof(b) : 1.0;
+  }
+};
+const Env& env() {
+  static const Env e;
+  return e;
+}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -72,7 +102,20 @@ int check_desc(const InfDesc* d) {
   }
   if (d->input_mode == INF_INPUT_GATHER && d->n_rows > (int64_t(1) << 32) - 1)
     return fail(INF_ERR_BAD_ARG, "n_rows exceeds 2^32-1");
+  if (d->path != INF_PATH_AUTO && d->path != INF_PATH_RAY && d->path != INF_PATH_VERTEX) return fail(INF_ERR_BAD_ARG, "bad path %d", d->path);
   return INF_OK;
+}
+
+// Which evaluation of the two K = k contractions a call takes (include/inf_field.h, INF_PATH_*).  The vertex path costs
+// ~2 V k 256 MACs + one streaming pass over the table image per contraction (forward P, backward G^T E), the per-ray
+// path ~B k 256 MACs + 12 KB of gathered rows per ray per contraction: the vertex path wins while V <= ~2 B.
+bool vertex_path(const InfDesc* d, const InfTensors* t) {
+  if (d->input_mode != INF_INPUT_GATHER || t == nullptr || t->table_image == nullptr || d->n_rows < 1 || d->n_rays < 1) return false;
+  int path = d->path;
+  if (path == INF_PATH_AUTO && env().force_path != 0) path = env().force_path;
+  if (path == INF_PATH_RAY) return false;
+  if (path == INF_PATH_VERTEX) return true;
+  return d->n_rows <= 2 * d->n_rays;
 }
 
 Geo geo_of(const InfDesc* d) {
@@ -139,10 +182,13 @@ int build_param_table(const InfDesc* d, ParamInfo* out, int64_t* total) {
 
 // ---- optional per-kernel timing (inf_profile_*): library-owned CUDA events around the launches ----
 constexpr int PROF_SLOTS = 256;
+constexpr int PROF_EVENTS = INF_PROFILE_STAGES + 1;
 struct Profile {
   bool on = false;
   int n = 0;                       // recorded calls since inf_profile_enable(1)
-  cudaEvent_t ev[PROF_SLOTS][4];   // before main, after main, after wgrad, after reduce
+  // start, after incidence lists, after vertex projection, after the per-ray kernel, after the vertex gather,
+  // after wgrad, after reduce (stages a call does not run record a zero-length interval)
+  cudaEvent_t ev[PROF_SLOTS][PROF_EVENTS];
   bool created = false;
 } g_prof;
 
@@ -166,6 +212,8 @@ int sm_count(int* out) {
 }
 
 int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
+  const bool vp = vertex_path(d, t);
+  if (vp && (reinterpret_cast<uintptr_t>(t->table_image) & 127) != 0) return fail(INF_ERR_BAD_ARG, "table_image must be 128-byte aligned");
   if (t == nullptr) return fail(INF_ERR_BAD_ARG, "tensors is null");
   if (d->n_rays == 0) return INF_OK;
   if (t->table == nullptr || t->packed == nullptr || t->pred == nullptr)
@@ -187,7 +235,9 @@ int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
   if (training) {
     if ((t->target == nullptr) == (t->grad_pred == nullptr))
       return fail(INF_ERR_BAD_ARG, "exactly one of target / grad_pred must be given");
-    const WorkspaceLayout w = workspace_layout(geo_of(d), d->n_rays, true);
+  }
+  if (training || vp) {
+    const WorkspaceLayout w = workspace_layout(geo_of(d), d->n_rays, training, vp ? d->n_rows : 0);
     if (t->workspace == nullptr || t->workspace_bytes < w.total)
       return fail(INF_ERR_WORKSPACE, "workspace %zu B < required %zu B", t->workspace_bytes, w.total);
     if ((reinterpret_cast<uintptr_t>(t->workspace) & 255) != 0)
@@ -200,8 +250,7 @@ int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
 // least two tiles and the device can co-schedule them; INF_CLUSTER=1 forces single CTAs.
 int pick_main_grid(const InfDesc* d, int ntiles, int nsm, bool training, int* cluster) {
   static int cached[2][2][2] = {{{-1, -1}, {-1, -1}}, {{-1, -1}, {-1, -1}}};   // [train][f16][view] -> max grid at cluster 2
-  const char* e = getenv("INF_CLUSTER");
-  int cs = e ? atoi(e) : 2;
+  int cs = env().cluster;
   if (cs != 2 || ntiles < 2) cs = 1;
   int grid = ntiles < nsm ? ntiles : nsm;
   if (cs == 2) {
@@ -215,7 +264,7 @@ int pick_main_grid(const InfDesc* d, int ntiles, int nsm, bool training, int* cl
     }
   }
   *cluster = cs;
-  if (getenv("INF_VERBOSE")) fprintf(stderr, "[inf] field_main grid %d cluster %d (ntiles %d)\n", grid, cs, ntiles);
+  if (env().verbose) fprintf(stderr, "[inf] field_main grid %d cluster %d (ntiles %d)\n", grid, cs, ntiles);
   return grid;
 }
 
@@ -240,19 +289,20 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   p.dense = d->input_mode == INF_INPUT_DENSE;
   p.ext_scale = 1.f;
   {
-    const char* e = getenv("INF_DEBUG");   // measurement only; bits 1|2|4 produce wrong gradients
-    p.debug = e ? atoi(e) : 0;
+    p.debug = env().debug;   // measurement only; bits 1|2|4 produce wrong gradients
     // L2 prefetch of the next row pieces through the bulk-copy engine (distance in k-chunks).  Off by default: it paid
     // while the gather was throttled by a 28 KB L1 (227 KB shared-memory carve-out); with the 164 KB carve-out the plain
     // loads run at the memory system's rate and the extra requests cost 3-13 % at every table size.
-    const char* f = getenv("INF_PREFETCH");
-    p.prefetch = f ? atoi(f) : 0;
+    p.prefetch = env().prefetch;
     if (p.prefetch < 0 || p.prefetch > 8 || d->input_mode == INF_INPUT_DENSE) p.prefetch = 0;
   }
   p.geo = geo_of(d);
   p.plan = make_wplan(p.geo);
+  const bool vp = vertex_path(d, t);
+  p.stash_stride = vp ? stash_tile_bytes_vp(p.geo) : stash_tile_bytes(p.geo);
+  p.n_rows = d->n_rows;
   if (t->workspace != nullptr && t->workspace_bytes >= ERR_AREA_BYTES) {
-    const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training);
+    const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training, vp ? d->n_rows : 0);
     uint8_t* ws = reinterpret_cast<uint8_t*>(t->workspace);
     p.err = reinterpret_cast<unsigned int*>(ws + w.err_off);
     p.trace = (p.debug & 8) ? reinterpret_cast<unsigned long long*>(ws + w.err_off + 1024) : nullptr;
@@ -261,8 +311,41 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
       p.partw = reinterpret_cast<float*>(ws + w.partw_off);
       p.part1 = reinterpret_cast<float*>(ws + w.part1_off);
     }
+    if (vp) {
+      p.e_image = reinterpret_cast<const uint8_t*>(t->table_image);
+      p.ntiles_v = static_cast<int>((d->n_rows + TILE_M - 1) / TILE_M);
+      p.proj = ws + w.proj_off;
+      if (training) {
+        p.g_image = ws + w.gimg_off;
+        p.vstart = reinterpret_cast<int32_t*>(ws + w.vstart_off);
+        p.vcursor = reinterpret_cast<int32_t*>(ws + w.vcursor_off);
+        p.pairs = reinterpret_cast<int32_t*>(ws + w.pairs_off);
+        p.scan_tmp = reinterpret_cast<int32_t*>(ws + w.scan_off);
+      }
+    }
   }
   return p;
+}
+
+// Vertex projection P = E [W0;Wy]^T: persistent CTAs in clusters of 2 (the weight stream is multicast).
+int launch_projection(const FieldParams& p, int nsm, cudaStream_t st) {
+  static int max2 = -1;
+  if (max2 < 0) max2 = vertex_project_max_grid(2);
+  int cs = (env().cluster == 2 && max2 >= 2 && p.ntiles_v >= 2) ? 2 : 1;
+  int grid = p.ntiles_v < nsm ? p.ntiles_v : nsm;
+  if (cs == 2) {
+    if (grid > max2) grid = max2;
+    grid &= ~1;
+  }
+  cudaError_t e = launch_vertex_project(p, grid, cs, st);
+  if (e != cudaSuccess) return cuda_fail(e, "vertex_project_kernel launch");
+  return INF_OK;
+}
+
+// CTAs of the per-ray kernel: one per SM, each walking pairs of 128-ray tiles
+int rays_grid(const FieldParams& p, int nsm) {
+  const int npairs = (p.ntiles + field_rays_slots() - 1) / field_rays_slots();
+  return npairs < nsm ? npairs : nsm;
 }
 
 }  // namespace
@@ -309,7 +392,31 @@ size_t inf_packed_bytes(const InfDesc* desc) {
 
 size_t inf_workspace_bytes(const InfDesc* desc, int training) {
   if (check_desc(desc) != INF_OK) return 0;
-  return workspace_layout(geo_of(desc), desc->n_rays, training != 0).total;
+  // n_rows > 0 (and a path that may use it): sized for either path, so the caller need not know which one a call takes
+  const bool may_vp = desc->input_mode == INF_INPUT_GATHER && desc->path != INF_PATH_RAY && desc->n_rows > 0;
+  return workspace_layout(geo_of(desc), desc->n_rays, training != 0, may_vp ? desc->n_rows : 0).total;
+}
+
+size_t inf_table_image_bytes(int64_t n_rows, int32_t k_pad) {
+  if (n_rows < 0 || k_pad < KC || k_pad % KC != 0) return 0;
+  return static_cast<size_t>((n_rows + TILE_M - 1) / TILE_M) * static_cast<size_t>(k_pad / KC) * PANEL_BYTES;
+}
+
+int inf_build_table_image(const void* table, int32_t table_dtype, int64_t n_rows, int32_t k_pad, void* image, void* stream) {
+  if (table == nullptr || image == nullptr) return fail(INF_ERR_BAD_ARG, "table / image must be non-null");
+  if (n_rows < 0 || k_pad < KC || k_pad % KC != 0) return fail(INF_ERR_BAD_ARG, "bad table shape: rows=%lld k_pad=%d", static_cast<long long>(n_rows), k_pad);
+  if (table_dtype != INF_TABLE_F32 && table_dtype != INF_TABLE_F16) return fail(INF_ERR_BAD_ARG, "bad table_dtype");
+  if ((reinterpret_cast<uintptr_t>(table) & 15) != 0 || (reinterpret_cast<uintptr_t>(image) & 127) != 0)
+    return fail(INF_ERR_BAD_ARG, "table must be 16-byte and image 128-byte aligned");
+  launch_table_image(table, table_dtype == INF_TABLE_F16, n_rows, k_pad, image, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "table_image launch");
+  return INF_OK;
+}
+
+int inf_uses_vertex_path(const InfDesc* desc, const InfTensors* t) {
+  if (check_desc(desc) != INF_OK) return 0;
+  return vertex_path(desc, t) ? 1 : 0;
 }
 
 int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, void* dst, int32_t k_pad,
@@ -369,12 +476,23 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream) {
   rc = sm_count(&nsm);
   if (rc != INF_OK) return rc;
   FieldParams p = make_params(desc, t, false);
-  const int grid = pick_main_grid(desc, p.ntiles, nsm, false, &p.cluster);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int slot = g_prof.n;
-  prof_record(slot, 0, static_cast<cudaStream_t>(stream));
-  cudaError_t e = launch_field_main(p, false, desc->table_dtype == INF_TABLE_F16, grid, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<inference> launch");
-  for (int i = 1; i < 4; ++i) prof_record(slot, i, static_cast<cudaStream_t>(stream));
+  prof_record(slot, 0, st);
+  prof_record(slot, 1, st);
+  if (p.e_image != nullptr) {
+    rc = launch_projection(p, nsm, st);
+    if (rc != INF_OK) return rc;
+    prof_record(slot, 2, st);
+    cudaError_t e = launch_field_rays(p, false, rays_grid(p, nsm), st);
+    if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<inference> launch");
+  } else {
+    prof_record(slot, 2, st);
+    const int grid = pick_main_grid(desc, p.ntiles, nsm, false, &p.cluster);
+    cudaError_t e = launch_field_main(p, false, desc->table_dtype == INF_TABLE_F16, grid, st);
+    if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<inference> launch");
+  }
+  for (int i = 3; i < PROF_EVENTS; ++i) prof_record(slot, i, st);
   if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
   return INF_OK;
 }
@@ -427,17 +545,18 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   rc = sm_count(&nsm);
   if (rc != INF_OK) return rc;
   FieldParams p = make_params(desc, t, true);
+  const bool vp = p.e_image != nullptr;
   // External upstream gradients are typically O(1/(3B)); bring them to O(1) for the fp16 chain.
   const float ext = (t->grad_pred != nullptr) ? 3.f * static_cast<float>(desc->n_rays) : 1.f;
   p.ext_scale = ext;
   const Geo geo = p.geo;
-  const int grid1 = pick_main_grid(desc, p.ntiles, nsm, true, &p.cluster);
-  // wgrad CTAs: every slice gets ray groups in proportion to the bytes it moves per tile
+  const int grid1 = vp ? rays_grid(p, nsm) : pick_main_grid(desc, p.ntiles, nsm, true, &p.cluster);
+  // wgrad CTAs: every slice gets ray groups in proportion to the bytes it moves over the whole launch
   const WPlan& plan = p.plan;
   // clusters of cw big-slice CTAs share the dz_0 / dz_skip half-panels (multicast): cw = 4, 2 or 1, dividing nbig
   int cw = 4;
   {
-    static const int env_cw = getenv("INF_WGRAD_CLUSTER") ? atoi(getenv("INF_WGRAD_CLUSTER")) : 4;
+    const int env_cw = env().wg_cluster;
     cw = env_cw >= 4 ? 4 : (env_cw >= 2 ? 2 : 1);
     while (cw > 1 && geo.nbig % cw != 0) cw >>= 1;
   }
@@ -448,17 +567,18 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     if (cached[cw] < cw) cw = 1;
     else if (cached[cw] < nsm_w) nsm_w = cached[cw];
   }
+  // tiles a big slice walks: ray tiles, or vertex tiles on the vertex path ([dW0;dWy] = G^T E)
+  const int tiles_big = vp ? p.ntiles_v : p.ntiles;
   // bytes a CTA ingests per tile: the x panels of its 256 columns + its share of dz_0 / dz_skip
   // (INF_WGRAD_BIGW scales the big slices' share: they also carry 2.5x the tensor work per ingested byte)
-  const char* bw_env = getenv("INF_WGRAD_BIGW");
-  const double big_bytes = (2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw) * (bw_env ? atof(bw_env) : 1.0);
+  const double big_bytes = (2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw) * env().wgrad_bigw * tiles_big;
   double wsum = static_cast<double>(geo.nbig) * big_bytes;
-  for (int s = 0; s < plan.nslice; ++s) wsum += plan.bytes_per_tile[s];
+  for (int s = 0; s < plan.nslice; ++s) wsum += static_cast<double>(plan.bytes_per_tile[s]) * p.ntiles;
   int used = 0;
   int gh[MAX_HID_SLICES] = {0, 0, 0, 0};
   int smax = 0;
   for (int s = 0; s < plan.nslice; ++s) {
-    int v = static_cast<int>(nsm_w * (plan.bytes_per_tile[s] / wsum));
+    int v = static_cast<int>(nsm_w * (static_cast<double>(plan.bytes_per_tile[s]) * p.ntiles / wsum));
     if (v < 1) v = 1;
     if (v > p.ntiles) v = p.ntiles;
     gh[s] = v;
@@ -473,7 +593,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   p.wg_cluster = cw;
   int gb = (nsm_w - used) / geo.nbig;
   if (gb < 1) gb = 1;
-  if (gb > p.ntiles) gb = p.ntiles;
+  if (gb > tiles_big) gb = tiles_big;
   p.groups_big = gb;
   for (int s = 0; s < MAX_HID_SLICES; ++s) p.groups_hid[s] = gh[s];
   const int grid2 = geo.nbig * gb + used;
@@ -481,12 +601,31 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
 
   const bool f16 = desc->table_dtype == INF_TABLE_F16;
   const int slot = g_prof.n;
+  cudaError_t e;
   prof_record(slot, 0, st);
-  cudaError_t e = launch_field_main(p, true, f16, grid1, st);
-  if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<train> launch");
-  prof_record(slot, 1, st);
+  if (vp) {
+    e = launch_csr_build(p, st);
+    if (e != cudaSuccess) return cuda_fail(e, "incidence-list (CSR) kernels launch");
+    prof_record(slot, 1, st);
+    rc = launch_projection(p, nsm, st);
+    if (rc != INF_OK) return rc;
+    prof_record(slot, 2, st);
+    e = launch_field_rays(p, true, grid1, st);
+    if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<train> launch");
+    prof_record(slot, 3, st);
+    e = launch_vertex_gather(p, nsm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "vertex_gather_kernel launch");
+    prof_record(slot, 4, st);
+  } else {
+    prof_record(slot, 1, st);
+    prof_record(slot, 2, st);
+    e = launch_field_main(p, true, f16, grid1, st);
+    if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<train> launch");
+    prof_record(slot, 3, st);
+    prof_record(slot, 4, st);
+  }
   e = launch_field_wgrad(p, grid2, st);
-  prof_record(slot, 2, st);
+  prof_record(slot, 5, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_wgrad_kernel launch");
 
   ReduceParams rp{};
@@ -498,7 +637,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   rp.part1 = p.part1;
   rp.flat = g->flat;
   rp.loss_sums = (t->target != nullptr) ? g->loss_sums : nullptr;
-  rp.ncta1 = grid1;
+  rp.ncta1 = vp ? grid1 * field_rays_slots() : grid1;   // rows of the forward/backward kernel's partials
   rp.groups_big = gb;
   int base = geo.nbig * gb;
   for (int s = 0; s < MAX_HID_SLICES; ++s) {
@@ -512,7 +651,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   rp.geo = geo;
   rp.plan = plan;
   e = launch_field_reduce(rp, st);
-  prof_record(slot, 3, st);
+  prof_record(slot, 6, st);
   if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
   if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel launch");
   return INF_OK;
@@ -567,7 +706,7 @@ int inf_gather_interpolate(const void* table, int32_t table_dtype, int32_t k, in
 int inf_profile_enable(int on) {
   if (on && !g_prof.created) {
     for (int s = 0; s < PROF_SLOTS; ++s)
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < PROF_EVENTS; ++i) {
         cudaError_t e = cudaEventCreate(&g_prof.ev[s][i]);
         if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
       }
@@ -578,22 +717,31 @@ int inf_profile_enable(int on) {
   return INF_OK;
 }
 
-int inf_profile_read(float* main_ms, float* wgrad_ms, float* reduce_ms, int* calls) {
+int inf_profile_read_stages(float* stage_ms, int* calls) {
   const int n = g_prof.n < PROF_SLOTS ? g_prof.n : PROF_SLOTS;
-  double a = 0, b = 0, c = 0;
+  double acc[INF_PROFILE_STAGES] = {0, 0, 0, 0, 0, 0};
   for (int s = 0; s < n; ++s) {
-    cudaError_t e = cudaEventSynchronize(g_prof.ev[s][3]);
+    cudaError_t e = cudaEventSynchronize(g_prof.ev[s][PROF_EVENTS - 1]);
     if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
-    float t0 = 0, t1 = 0, t2 = 0;
-    cudaEventElapsedTime(&t0, g_prof.ev[s][0], g_prof.ev[s][1]);
-    cudaEventElapsedTime(&t1, g_prof.ev[s][1], g_prof.ev[s][2]);
-    cudaEventElapsedTime(&t2, g_prof.ev[s][2], g_prof.ev[s][3]);
-    a += t0; b += t1; c += t2;
+    for (int i = 0; i < INF_PROFILE_STAGES; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_prof.ev[s][i], g_prof.ev[s][i + 1]);
+      acc[i] += ms;
+    }
   }
-  if (main_ms) *main_ms = n ? static_cast<float>(a / n) : 0.f;
-  if (wgrad_ms) *wgrad_ms = n ? static_cast<float>(b / n) : 0.f;
-  if (reduce_ms) *reduce_ms = n ? static_cast<float>(c / n) : 0.f;
+  if (stage_ms)
+    for (int i = 0; i < INF_PROFILE_STAGES; ++i) stage_ms[i] = n ? static_cast<float>(acc[i] / n) : 0.f;
   if (calls) *calls = n;
+  return INF_OK;
+}
+
+int inf_profile_read(float* main_ms, float* wgrad_ms, float* reduce_ms, int* calls) {
+  float st[INF_PROFILE_STAGES];
+  int rc = inf_profile_read_stages(st, calls);
+  if (rc != INF_OK) return rc;
+  if (main_ms) *main_ms = st[2];
+  if (wgrad_ms) *wgrad_ms = st[4];
+  if (reduce_ms) *reduce_ms = st[5];
   return INF_OK;
 }
 

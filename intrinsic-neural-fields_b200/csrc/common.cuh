@@ -25,6 +25,24 @@ constexpr int MAX_UNITS = 16;    // wgrad work units of the hidden slices
 constexpr int MAX_HID_SLICES = 4;
 constexpr int ERR_AREA_BYTES = 65536;
 
+// ---- vertex-projected path ------------------------------------------------------------------------
+// Layer 0 and the skip branch Ly are linear in the table rows, so  x W^T = sum_j bary_j (E[v_j] W^T):
+// the K = k_pad contraction runs ONCE per vertex per step (a streaming GEMM over the table's fp16 operand image),
+// and a ray gathers three 512-byte rows of the projected table P = E [W0;Wy]^T instead of three 4 KB table rows.
+// The backward mirrors it: G[v] = sum over incident (ray, corner) of bary * [dz_0 | dz_skip][ray], then
+// [dW0;dWy] = G^T E, again a streaming GEMM with K = vertices.
+constexpr int PROJ_COLS = 2 * HID;                        // [z0 | zy] columns of a projected row
+constexpr int PROJ_ROW_BYTES = PROJ_COLS * 2;             // fp16
+constexpr int PROJ_TILE_BYTES = TILE_M * PROJ_ROW_BYTES;  // 64 KB per 128 vertices
+// 16-byte chunk q (8 columns, q = 0..31) of projected row v is stored at chunk q ^ (v & 7) of the row: the
+// projection kernel's epilogue stages whole rows in shared memory (thread = row) without bank conflicts and
+// ships a tile with one linear bulk store.
+__host__ __device__ inline uint32_t proj_chunk_off(uint32_t v, uint32_t q) { return (q ^ (v & 7u)) << 4; }
+// Vertex-gradient image G, per 128 vertices: [dz_0 part: two 64-feature panels][dz_skip part: two panels], every
+// panel [128 vertices][64 features] SWIZZLE_128B -- the layout of two stashed dz blobs, so the wgrad kernel reads it
+// exactly as it reads a ray tile's dz_0 / dz_skip.
+constexpr int GIMG_TILE_BYTES = 2 * BLOB_BYTES;
+
 // Model geometry.  MMA "layers" are numbered 0..nb:
 //   layer 0            x (k_pad) -> 128, fused with the skip branch Ly in GEMM1
 //   layers 1..nhid     128 -> 128 ReLU layers.  nhid = L-2, or L-1 with the view branch: its spatial MLP ends
@@ -107,18 +125,37 @@ __host__ __device__ inline size_t stash_off_x(const Geo& g, int c) {
   return static_cast<size_t>(g.stash_blobs) * BLOB_BYTES + static_cast<size_t>(c) * PANEL_BYTES;
 }
 
+// stash of the vertex-projected path: no x panels (the first-layer weight gradient is G^T E)
+__host__ __device__ inline size_t stash_tile_bytes_vp(const Geo& g) { return static_cast<size_t>(g.stash_blobs) * BLOB_BYTES; }
+
+constexpr int SCAN_BLOCK = 1024;   // elements per block of the CSR offset scan
 struct WorkspaceLayout {
   size_t stash_off, partw_off, part1_off, err_off, total;
+  size_t proj_off, gimg_off, vstart_off, vcursor_off, pairs_off, scan_off;   // vertex-projected path (n_rows > 0)
 };
-__host__ inline WorkspaceLayout workspace_layout(const Geo& g, int64_t n_rays, bool training) {
+// n_rows > 0 sizes the workspace for BOTH paths (the larger stash of the per-ray path plus the vertex buffers), so the
+// path can be chosen per call; n_rows == 0: per-ray gather path only.
+__host__ inline WorkspaceLayout workspace_layout(const Geo& g, int64_t n_rays, bool training, int64_t n_rows = 0) {
   WorkspaceLayout w{};
   size_t off = 0;
-  w.err_off = off; off += ERR_AREA_BYTES;   // error word, then the optional timing trace (INF_DEBUG & 8)
+  auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 1023) & ~static_cast<size_t>(1023); return at; };
+  w.err_off = take(ERR_AREA_BYTES);   // error word, then the optional timing trace (INF_DEBUG & 8)
+  const int64_t ntiles = (n_rays + TILE_M - 1) / TILE_M;
   if (training) {
-    const int64_t ntiles = (n_rays + TILE_M - 1) / TILE_M;
-    w.stash_off = off; off += static_cast<size_t>(ntiles) * stash_tile_bytes(g);
-    w.partw_off = off; off += static_cast<size_t>(MAX_CTAS) * WG_COLS * HID * 4;
-    w.part1_off = off; off += static_cast<size_t>(MAX_CTAS) * K1_PART_FLOATS * 4;
+    w.stash_off = take(static_cast<size_t>(ntiles) * stash_tile_bytes(g));
+    w.partw_off = take(static_cast<size_t>(MAX_CTAS) * WG_COLS * HID * 4);
+    w.part1_off = take(static_cast<size_t>(2 * MAX_CTAS) * K1_PART_FLOATS * 4);
+  }
+  if (n_rows > 0) {
+    const int64_t ntv = (n_rows + TILE_M - 1) / TILE_M;
+    w.proj_off = take(static_cast<size_t>(ntv) * PROJ_TILE_BYTES);
+    if (training) {
+      w.gimg_off = take(static_cast<size_t>(ntv) * GIMG_TILE_BYTES);
+      w.vstart_off = take(static_cast<size_t>(n_rows + 1) * 4);
+      w.vcursor_off = take(static_cast<size_t>(n_rows + 1) * 4);
+      w.pairs_off = take(static_cast<size_t>(ntiles) * TILE_M * 3 * 8);   // (ray, bary) per incident pair
+      w.scan_off = take(static_cast<size_t>((n_rows + SCAN_BLOCK) / SCAN_BLOCK + 1) * 4);
+    }
   }
   w.total = off;
   return w;
@@ -214,6 +251,17 @@ struct FieldParams {
   int cluster;      // CTAs per cluster of the forward/backward kernel (1 or 2): [W0;Wy] chunks are multicast within it
   int wg_cluster;   // CTAs per cluster of the wgrad kernel (1, 2 or 4): dz_0 / dz_skip half-panels are multicast within it
   int debug;        // measurement knobs (INF_DEBUG env): 1 no x stash, 2 no h/dz stash, 4 no dgrad chain -- wrong results
+  // vertex-projected path (e_image == nullptr: per-ray gather of table rows)
+  const uint8_t* e_image;           // fp16 operand image of the table: [ntiles_v][nchunks] panels [128 rows][64] SWIZZLE_128B
+  uint8_t* proj;                    // P [ntiles_v * 128][256] fp16 (chunks permuted, proj_chunk_off)
+  uint8_t* g_image;                 // G [ntiles_v][GIMG_TILE_BYTES]
+  int32_t* vstart;                  // [n_rows + 1] CSR offsets: incident (ray, corner) pairs of every vertex
+  int32_t* vcursor;                 // [n_rows + 1] counts, then fill cursors
+  int32_t* pairs;                   // [3 * n_rays] int2 (ray, bits of the barycentric weight), grouped by vertex
+  int32_t* scan_tmp;                // block sums of the offset scan
+  int64_t n_rows;                   // V
+  int ntiles_v;                     // ceil(V / 128)
+  size_t stash_stride;              // bytes per ray tile of the activation stash
   int groups_big;                   // wgrad: ray groups (CTAs) per big slice
   int groups_hid[MAX_HID_SLICES];   // wgrad: ray groups (CTAs) per hidden slice
   Geo geo;

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     nt_loop = iters > 0 ? static_cast<int>(blockIdx.x) + (iters - 1) * static_cast<int>(gridDim.x) + 1 : 0;
   }
   const int nchunks = g.nchunks;
-  const size_t tile_stride = stash_tile_bytes(g);
+  const size_t tile_stride = p.stash_stride;
   // stash tiles are written once, read once by the next kernel (INF_DEBUG & 64: no hint, measurement)
   const uint64_t stash_policy = (p.debug & 64) ? 0ull : l2_policy_evict_first();
 

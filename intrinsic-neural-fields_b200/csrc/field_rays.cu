@@ -1,0 +1,629 @@
+// Per-ray kernel of the vertex-projected path, sm_100a: gather -> interpolate -> hidden chain -> RGB
+// (+ L1 loss + dgrad chain when training).
+//
+// vertex_project.cu has already contracted the table with [W0;Wy] per vertex, so a ray's layer-0 pre-activation and
+// its skip-branch term are   [z0 | zy] = sum_j bary_j P[v_j]   (mesh.py:313-324 + model.py:98-104 + layers.py:60-62 by
+// linearity): three coalesced 512-byte row reads from a table that lives in L2, interpolated in fp32.  What is left
+// per ray is the 128-wide chain (model.py:105-112 / 168-173), which is latency-bound per tile (MMA 0.3 us, epilogue
+// ~1 us per layer), so a CTA runs TWO 128-ray tiles in lockstep: one hidden-weight image streamed from L2 feeds both
+// tiles' MMAs, and the two epilogue warpgroups overlap each other and the other tile's MMA.
+//
+//   warps 0..3 / 4..7   slot 0 / slot 1: gather + interpolation of the tile's rays (lane = 16-byte chunk of a P row),
+//                       layer-0 bias + ReLU -> fp16 activation panel, zy -> fp16 panel (added in the skip layer's
+//                       epilogue); then per layer TMEM -> registers -> bias/ReLU -> next A operand; output layer,
+//                       sigmoid, L1 gradient and the dgrad epilogues as in field_main.cu; when training every h_l / dz_l
+//                       tile is bulk-stored to the stash (hidden weight gradients: field_wgrad.cu; dz_0 / dz_skip also
+//                       feed the vertex gradient G, vertex_grad.cu)
+//   warp 8              chain issuer (+ TMEM allocator): per layer step, the MMAs of both slots from one weight stage
+//   warp 9              weight loader: 32 KB hidden / view-branch operand images through a 2-stage ring
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace inf {
+
+namespace {
+
+constexpr int RY_SLOTS = 2;
+constexpr int RY_EPI_WARPS = 4 * RY_SLOTS;
+constexpr int RY_W_CH = RY_EPI_WARPS;
+constexpr int RY_W_LD = RY_EPI_WARPS + 1;
+constexpr int RY_THREADS = (RY_EPI_WARPS + 2) * 32;
+constexpr int RY_WG_THREADS = 128;
+constexpr int RY_NSTAGE_W = 2;
+
+struct RySmem {
+  uint32_t h, zy, w, dzlt, bias, wlast, red, bars, tmemptr, total;
+};
+__host__ __device__ constexpr RySmem ry_smem(bool train) {
+  RySmem s{};
+  s.h = 0;                                                   // [2] activation images (32 KB each)
+  s.zy = s.h + RY_SLOTS * BLOB_BYTES;                        // [2] skip-branch term zy as fp16 image; view: Fourier panel after the skip layer
+  s.w = s.zy + RY_SLOTS * BLOB_BYTES;                        // weight ring
+  s.dzlt = s.w + RY_NSTAGE_W * BLOB_BYTES;                   // [2] dzl^T tiles (training)
+  s.bias = s.dzlt + (train ? RY_SLOTS * DZLT_BYTES : 0u);    // f32 [MAX_MMA_LAYERS][128]
+  s.wlast = s.bias + MAX_MMA_LAYERS * HID * 4;               // f32 [3][128] + blast[4]
+  s.red = s.wlast + OUT_DIM * HID * 4 + 16;                  // f32 [2][24]
+  s.bars = s.red + RY_SLOTS * 96;
+  s.tmemptr = s.bars + 32 * 8;
+  s.total = s.tmemptr + 16;
+  return s;
+}
+static_assert(ry_smem(true).total <= 232448, "shared memory budget");
+
+constexpr int RB_ACT_READY = 0;                    // [2] activation image of the slot written (A operand of the next step)
+constexpr int RB_MMA_DONE = RB_ACT_READY + RY_SLOTS;   // [2] the slot's accumulator is complete
+constexpr int RB_H_FREE = RB_MMA_DONE + RY_SLOTS;      // [2] training: the stash store has finished reading the activation image
+constexpr int RB_W_FULL = RB_H_FREE + RY_SLOTS;        // [stages]
+constexpr int RB_W_EMPTY = RB_W_FULL + RY_NSTAGE_W;
+static_assert(RB_W_EMPTY + RY_NSTAGE_W <= 32, "barrier table overflow");
+
+constexpr uint32_t RY_TMEM_COLS = 256;   // one 128-column accumulator per slot
+constexpr uint32_t RY_IDESC_N128 = umma_idesc_f16(128, 128, 0, 0);
+constexpr uint32_t RY_IDESC_N128_BMN = umma_idesc_f16(128, 128, 0, 1);
+constexpr uint32_t RY_DESC_HI = umma_desc_hi(1024);
+constexpr float RY_PI_F = 3.14159274101257324f;   // float32(torch.pi), layers.py:14
+
+__device__ __forceinline__ float ry_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+
+// 16 packed f16x2 words (columns 32*cb .. 32*cb+31 of row r) of a 2-panel [128 x 128] image
+__device__ __forceinline__ uint32_t act_chunk_addr(uint32_t img, int r, int cb, int i) {
+  const uint32_t panel = img + static_cast<uint32_t>(cb >> 1) * PANEL_BYTES + static_cast<uint32_t>(r) * 128u;
+  const uint32_t chunk = static_cast<uint32_t>((cb & 1) * 4 + i);
+  return panel + ((chunk ^ (static_cast<uint32_t>(r) & 7u)) << 4);
+}
+__device__ __forceinline__ void ry_store_words(uint32_t img, int r, int cb, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st_shared_v4(act_chunk_addr(img, r, cb, i), w[4 * i + 0], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+__device__ __forceinline__ void ry_load_words(uint32_t img, int r, int cb, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[4 * i + 0]), "=r"(w[4 * i + 1]), "=r"(w[4 * i + 2]), "=r"(w[4 * i + 3])
+                 : "r"(act_chunk_addr(img, r, cb, i)));
+}
+// bit i = (low half of word i != 0), bit 16+i = (high half != 0), for non-negative halves (see field_main.cu)
+__device__ __forceinline__ uint32_t ry_relu_mask16(const uint32_t (&w)[16]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m |= ((w[i] + 0x7FFF7FFFu) >> (15 - i)) & (0x00010001u << i);
+  return m;
+}
+__device__ __forceinline__ uint32_t ry_apply_mask(uint32_t w, uint32_t m, int i) {
+  return w & (((m >> i) & 0x00010001u) * 0xFFFFu);
+}
+__device__ __forceinline__ float2 ry_unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+
+// layers.py:21-25 (use_logspace=True): cat(cos(x f) [input-major, freq-minor], sin(x f), x), zero beyond the embedding
+__device__ __forceinline__ float ry_fourier(int idx, float x0, float x1, float x2, int d, int emb, int include) {
+  const int nf = d * emb;
+  if (idx < 2 * nf) {
+    const int q = idx < nf ? idx : idx - nf;
+    const int dim = q / emb, j = q - dim * emb;
+    const float x = dim == 0 ? x0 : (dim == 1 ? x1 : x2);
+    const float arg = x * ldexpf(RY_PI_F, j);
+    return idx < nf ? cosf(arg) : sinf(arg);
+  }
+  if (include && idx < 2 * nf + d) {
+    const int dim = idx - 2 * nf;
+    return dim == 0 ? x0 : (dim == 1 ? x1 : x2);
+  }
+  return 0.f;
+}
+
+}  // namespace
+
+template <bool kTrain>
+__global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Geo g = p.geo;
+  const bool view = g.view != INF_VIEW_NONE;
+  const RySmem sm = ry_smem(kTrain);
+  const int nb = g.nb, nhid = g.nhid;
+  auto bar = [&](int i) -> uint32_t { return smem_base + sm.bars + 8u * static_cast<uint32_t>(i); };
+
+  if ((smem_base & 1023u) != 0) {
+    if (tid == 0 && p.err) atomicExch(p.err, 0xBAD00004u);
+    return;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < RY_SLOTS; ++s) {
+      mbar_init(bar(RB_ACT_READY + s), 1);
+      mbar_init(bar(RB_MMA_DONE + s), 1);
+      mbar_init(bar(RB_H_FREE + s), 1);
+    }
+    for (int i = 0; i < RY_NSTAGE_W; ++i) { mbar_init(bar(RB_W_FULL + i), 1); mbar_init(bar(RB_W_EMPTY + i), 1); }
+    mbar_fence_init();
+  }
+  if (warp == RY_W_CH) {
+    tmem_alloc(smem_base + sm.tmemptr, RY_TMEM_COLS);
+    tmem_relinquish();
+  }
+  {
+    const float* f32sec = reinterpret_cast<const float*>(p.packed + packed_f32_offset(g));
+    float* s_bias = reinterpret_cast<float*>(smem + sm.bias);
+    float* s_wl = reinterpret_cast<float*>(smem + sm.wlast);
+    const int nbias = (nb + 1) * HID;
+    const int nf = packed_f32_count(g);
+    for (int i = tid; i < nf; i += RY_THREADS) {
+      const float v = f32sec[i];
+      if (i < nbias) s_bias[i] = v;
+      else s_wl[i - nbias] = v;
+    }
+    if (kTrain) {
+      uint32_t* dz = reinterpret_cast<uint32_t*>(smem + sm.dzlt);   // rows 3..15 of both dzl^T tiles stay zero
+      for (int i = tid; i < RY_SLOTS * DZLT_BYTES / 4; i += RY_THREADS) dz[i] = 0u;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + sm.tmemptr);
+
+  const int ntiles = p.ntiles;
+  const int npairs = (ntiles + RY_SLOTS - 1) / RY_SLOTS;
+  const size_t tile_stride = p.stash_stride;
+  const uint64_t stash_policy = 0ull;   // the stash is re-read by the wgrad / vertex-gradient kernels right after this launch
+
+  // weight images of one tile pair, in consumption order: hidden 1..nhid, [view: Wd1z, Wd1e], then the dgrad chain
+  // [view: Wd1z], hidden nhid..1
+  const int steps_fwd = nhid + (view ? 2 : 0);
+  const int steps_all = steps_fwd + (kTrain ? nb : 0);
+  auto step_blob = [&](int st, uint32_t& bytes) -> int {
+    bytes = BLOB_BYTES;
+    if (st < nhid) return blob_hidden(g, st + 1);
+    if (st < steps_fwd) {
+      if (st == nhid) return blob_wd1z(g);
+      bytes = PANEL_BYTES;
+      return blob_wd1e(g);
+    }
+    const int l = nb - (st - steps_fwd);   // dgrad of MMA layer l = nb..1
+    if (view && l == nb) return blob_wd1z(g);
+    return blob_hidden(g, l);
+  };
+
+  if (warp == RY_W_LD) {
+    // =========================== weight loader ==============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        for (int st = 0; st < steps_all; ++st) {
+          uint32_t bytes;
+          const int blob = step_blob(st, bytes);
+          mbar_wait(bar(RB_W_EMPTY + stage), phase ^ 1u, p.err, 0xB0);
+          mbar_arrive_expect_tx(bar(RB_W_FULL + stage), bytes);
+          bulk_g2s(smem_base + sm.w + static_cast<uint32_t>(stage) * BLOB_BYTES, p.packed + static_cast<size_t>(blob) * BLOB_BYTES, bytes,
+                   bar(RB_W_FULL + stage));
+          if (++stage == RY_NSTAGE_W) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == RY_W_CH) {
+    // =========================== chain issuer ===============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t wph = 0;
+      uint32_t aph[RY_SLOTS] = {0u, 0u};
+      // D[128 x 128] (+)= A[128 x 64*npanel] * B^T, both K-major panel images
+      auto mma_fwd = [&](uint32_t dcol, uint32_t abase, uint32_t bbase, int npanel, bool acc_first) {
+        const uint32_t alo = umma_desc_lo(abase, 0), blo = umma_desc_lo(bbase, 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          if (kk < 4 * npanel) {
+            const uint32_t o = static_cast<uint32_t>(kk >> 2) * (PANEL_BYTES >> 4) + static_cast<uint32_t>(kk & 3) * 2u;
+            umma_f16(dcol, umma_desc_join(alo + o, RY_DESC_HI), umma_desc_join(blo + o, RY_DESC_HI), RY_IDESC_N128,
+                     (acc_first || kk > 0) ? 1u : 0u);
+          }
+        }
+      };
+      // dh[128 x 128] = dz[128 x 128] * W: A K-major, B = the forward weight image read MN-major (K = row n)
+      auto mma_dgrad = [&](uint32_t dcol, uint32_t abase, uint32_t bbase) {
+        const uint32_t alo = umma_desc_lo(abase, 0), blo_mn = umma_desc_lo(bbase, PANEL_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t oa = static_cast<uint32_t>(kk >> 2) * (PANEL_BYTES >> 4) + static_cast<uint32_t>(kk & 3) * 2u;
+          umma_f16(dcol, umma_desc_join(alo + oa, RY_DESC_HI), umma_desc_join(blo_mn + static_cast<uint32_t>(kk) * 128u, RY_DESC_HI),
+                   RY_IDESC_N128_BMN, kk > 0 ? 1u : 0u);
+        }
+      };
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int nslot = (pair * RY_SLOTS + 1 < ntiles) ? 2 : 1;
+        for (int st = 0; st < steps_all; ++st) {
+          mbar_wait(bar(RB_W_FULL + stage), wph, p.err, 0xB1);
+          tc_fence_after();
+          const uint32_t bbase = smem_base + sm.w + static_cast<uint32_t>(stage) * BLOB_BYTES;
+          const bool fourier = view && st == nhid + 1;   // second half of the view layer: no new activation, same accumulator
+          const bool view_z = view && st == nhid;        // first half: the accumulator is completed by the Fourier part
+          for (int s = 0; s < nslot; ++s) {
+            const uint32_t dcol = tmem_base + 128u * static_cast<uint32_t>(s);
+            const uint32_t hbase = smem_base + sm.h + static_cast<uint32_t>(s) * BLOB_BYTES;
+            if (!fourier) {
+              mbar_wait(bar(RB_ACT_READY + s), aph[s], p.err, 0xB2);
+              aph[s] ^= 1u;
+              tc_fence_after();
+            }
+            if (st < steps_fwd) {
+              if (fourier) mma_fwd(dcol, smem_base + sm.zy + static_cast<uint32_t>(s) * BLOB_BYTES, bbase, 1, true);
+              else mma_fwd(dcol, hbase, bbase, 2, false);
+            } else {
+              mma_dgrad(dcol, hbase, bbase);
+            }
+            if (!view_z) umma_commit(bar(RB_MMA_DONE + s));
+          }
+          umma_commit(bar(RB_W_EMPTY + stage));
+          if (++stage == RY_NSTAGE_W) { stage = 0; wph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // =========================== gather + epilogue warpgroups ==================================
+    const int slot = warp >> 2;                 // warpgroup = tile slot
+    const int wq = warp & 3;                    // TMEM lane quarter of this warp
+    const int r = tid - slot * RY_WG_THREADS;   // tile row == TMEM lane
+    const uint32_t tb = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + 128u * static_cast<uint32_t>(slot);
+    const uint32_t himg = smem_base + sm.h + static_cast<uint32_t>(slot) * BLOB_BYTES;
+    const uint32_t zyimg = smem_base + sm.zy + static_cast<uint32_t>(slot) * BLOB_BYTES;
+    const uint32_t dzlt = sm.dzlt + static_cast<uint32_t>(slot) * DZLT_BYTES;
+    const float* s_bias = reinterpret_cast<const float*>(smem + sm.bias);
+    const float* s_wlast = reinterpret_cast<const float*>(smem + sm.wlast);
+    const float* s_blast = s_wlast + OUT_DIM * HID;
+    const uint32_t bar_id = 1u + static_cast<uint32_t>(slot);
+    uint32_t pdone = 0, pfree = 0;
+    float loss_abs = 0.f, loss_sq = 0.f;
+    float gb[3] = {0.f, 0.f, 0.f};
+    uint32_t mk[MAX_MMA_LAYERS][4];   // ReLU masks of this row (local memory; indexed by layer)
+
+    auto wait_done = [&]() {
+      mbar_wait(bar(RB_MMA_DONE + slot), pdone, p.err, 0xC0); pdone ^= 1u; tc_fence_after();
+      if (kTrain) { mbar_wait(bar(RB_H_FREE + slot), pfree, p.err, 0xC1); pfree ^= 1u; }
+    };
+    auto sync_epi = [&]() {
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(bar_id, RY_WG_THREADS);
+    };
+    // thread 0 of the warpgroup: publish the activation image (stash store when training), release the MMA
+    auto publish = [&](uint8_t* dst0, uint32_t src0, uint32_t bytes0, uint8_t* dst1, uint32_t src1, uint32_t bytes1, bool arrive_act) {
+      if (kTrain) {
+        if (dst0 != nullptr) bulk_s2g_hint(dst0, src0, bytes0, stash_policy);
+        if (dst1 != nullptr) bulk_s2g_hint(dst1, src1, bytes1, stash_policy);
+        bulk_commit();
+      }
+      if (arrive_act) mbar_arrive(bar(RB_ACT_READY + slot));
+      if (kTrain) {
+        bulk_wait_read<0>();   // overlaps the MMA that reads the same image
+        mbar_arrive(bar(RB_H_FREE + slot));
+      }
+    };
+
+    bool first_tile = true;
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int tile = pair * RY_SLOTS + slot;
+      if (tile >= ntiles) break;   // odd tile count: slot 1 sits out the last pair
+      const int64_t ray = static_cast<int64_t>(tile) * TILE_M + r;
+      const bool valid = ray < p.n_rays;
+      int64_t src = ray;   // row of the per-ray arrays this ray reads (batch selection folded in, ray_dataloader.py:122-126)
+      if (valid && p.ridx != nullptr)
+        src = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[ray])
+                       : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[ray]);
+      uint8_t* stash_tile = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride : nullptr;
+
+      // ---- gather + interpolate: [z0 | zy] = sum_j bary_j P[v_j] ------------------------------------
+      // Every lane keeps the metadata of ray 32*wq + lane; the warp then walks its 32 rays, lane = 16-byte chunk of the
+      // 512-byte P rows (fully coalesced), RU rays in flight.
+      uint32_t myv[3] = {0u, 0u, 0u};
+      float myb[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int64_t e = src * 3 + j;
+          myv[j] = p.idx64 ? static_cast<uint32_t>(reinterpret_cast<const long long*>(p.vids)[e])
+                           : static_cast<uint32_t>(reinterpret_cast<const int*>(p.vids)[e]);
+          myb[j] = p.bary[e];
+        }
+      }
+      if (kTrain && !first_tile) { mbar_wait(bar(RB_H_FREE + slot), pfree, p.err, 0xC2); pfree ^= 1u; }   // dz_0 has left the image
+      first_tile = false;
+      {
+        constexpr int RU = 4;
+        const bool z0_lane = lane < 16;
+        // bias of layer 0 for this lane's 8 columns (z0 lanes only)
+        float b0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b0[i] = z0_lane ? s_bias[8 * lane + i] : 0.f;
+        const uint32_t dst_img = z0_lane ? himg : zyimg;
+        const uint32_t cchunk = static_cast<uint32_t>(lane & 15);   // 16-byte chunk of the 128-column half
+        for (int rr0 = 0; rr0 < 32; rr0 += RU) {
+          uint4 q[RU][3];
+          float w[RU][3];
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const uint32_t v = __shfl_sync(0xffffffffu, myv[j], rr0 + u);
+              w[u][j] = __shfl_sync(0xffffffffu, myb[j], rr0 + u);
+              q[u][j] = ldg_nc_u4(p.proj + static_cast<size_t>(v) * PROJ_ROW_BYTES + proj_chunk_off(v, static_cast<uint32_t>(lane)));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < RU; ++u) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const uint32_t vv[4] = {q[u][j].x, q[u][j].y, q[u][j].z, q[u][j].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = ry_unpack(vv[i]);
+                if (j == 0) { acc[2 * i] = w[u][0] * f.x; acc[2 * i + 1] = w[u][0] * f.y; }
+                else { acc[2 * i] = fmaf(w[u][j], f.x, acc[2 * i]); acc[2 * i + 1] = fmaf(w[u][j], f.y, acc[2 * i + 1]); }
+              }
+            }
+            uint32_t o[4];
+            if (z0_lane) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = pack_half2_relu_sat(acc[2 * i] + b0[2 * i], acc[2 * i + 1] + b0[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = pack_half2_sat(acc[2 * i], acc[2 * i + 1]);
+            }
+            const int row = 32 * wq + rr0 + u;
+            const uint32_t addr = dst_img + (cchunk >> 3) * PANEL_BYTES + static_cast<uint32_t>(row) * 128u +
+                                  (((cchunk & 7u) ^ (static_cast<uint32_t>(row) & 7u)) << 4);
+            st_shared_v4(addr, o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      sync_epi();
+      if (kTrain) {
+        // ReLU mask of layer 0 for this thread's row, read back from the image the warp just wrote
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          uint32_t w[16];
+          ry_load_words(himg, r, cb, w);
+          mk[0][cb] = ry_relu_mask16(w);
+        }
+      }
+      if (r == 0) publish(kTrain ? stash_tile + stash_off_h(g, 0) : nullptr, himg, BLOB_BYTES, nullptr, 0u, 0u, true);
+
+      // ---- forward layers 1..nb-1: h_l = relu(z_l + b_l) -> activation image --------------------------
+      for (int l = 1; l < nb; ++l) {
+        wait_done();
+        const bool is_skip = (l == g.skip);
+        uint32_t mbits[4];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tb + 32u * cb, v);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + l * HID + 32 * cb);
+          uint32_t zw[16];
+          if (is_skip) ry_load_words(zyimg, r, cb, zw);   // Lx(h) + Ly(x): the interpolated zy of this row
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i];
+            float a0 = __uint_as_float(v[4 * i]) + bb.x, a1 = __uint_as_float(v[4 * i + 1]) + bb.y;
+            float a2 = __uint_as_float(v[4 * i + 2]) + bb.z, a3 = __uint_as_float(v[4 * i + 3]) + bb.w;
+            if (is_skip) {
+              const float2 z01 = ry_unpack(zw[2 * i]), z23 = ry_unpack(zw[2 * i + 1]);
+              a0 += z01.x; a1 += z01.y; a2 += z23.x; a3 += z23.y;
+            }
+            w[2 * i] = pack_half2_relu_sat(a0, a1);
+            w[2 * i + 1] = pack_half2_relu_sat(a2, a3);
+          }
+          if (kTrain) mbits[cb] = ry_relu_mask16(w);
+          ry_store_words(himg, r, cb, w);
+        }
+        if (kTrain) { mk[l][0] = mbits[0]; mk[l][1] = mbits[1]; mk[l][2] = mbits[2]; mk[l][3] = mbits[3]; }
+        if (view && l == nb - 1) {
+          // Fourier features of this ray's view direction (model.py:175-186) -> [128 x 64] panel in the zy buffer, whose
+          // last reader was the skip layer's epilogue (an earlier iteration of this loop, or the tail below when the
+          // skip layer IS layer nb-1: then every thread has read its own zy row above, and writes only its own E row)
+          float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+          if (valid) {
+            const float dx = p.dirs[src * 3 + 0], dy = p.dirs[src * 3 + 1], dz = p.dirs[src * 3 + 2];
+            if (g.view == INF_VIEW_INTRINSIC) {
+              const int64_t f = p.idx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.face_idxs)[src])
+                                        : static_cast<int64_t>(reinterpret_cast<const int*>(p.face_idxs)[src]);
+              const float nx = p.face_normals[f * 3 + 0], ny = p.face_normals[f * 3 + 1], nz = p.face_normals[f * 3 + 2];
+              // F.cosine_similarity(-dir, n): each vector divided by max(|v|, 1e-8), then the dot product
+              const float ia = 1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-8f);
+              const float ib = 1.f / fmaxf(sqrtf(nx * nx + ny * ny + nz * nz), 1e-8f);
+              float c = (-dx * ia) * (nx * ib) + (-dy * ia) * (ny * ib) + (-dz * ia) * (nz * ib);
+              c = fminf(fmaxf(c, -1.f), 1.f);   // the reference yields NaN when rounding pushes |c| above 1
+              x0 = acosf(c);
+            } else {
+              x0 = dx; x1 = dy; x2 = dz;
+            }
+          }
+          const uint32_t row = zyimg + static_cast<uint32_t>(r) * 128u;
+          for (int ch = 0; ch < 8; ++ch) {
+            float f[8];
+            if (8 * ch < g.edim) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = ry_fourier(8 * ch + i, x0, x1, x2, g.vdim, g.emb, g.include);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = 0.f;
+            }
+            st_shared_v4(row + ((static_cast<uint32_t>(ch) ^ (static_cast<uint32_t>(r) & 7u)) << 4), pack_half2(f[0], f[1]),
+                         pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+          }
+        }
+        sync_epi();
+        if (r == 0)
+          publish(kTrain ? stash_tile + stash_off_h(g, l) : nullptr, himg, BLOB_BYTES,
+                  (kTrain && view && l == nb - 1) ? stash_tile + stash_off_e(g) : nullptr, zyimg, PANEL_BYTES, true);
+      }
+
+      // ---- layer nb epilogue + output layer (-> 3, sigmoid) on CUDA cores --------------------------------
+      {
+        wait_done();
+        const bool is_skip = (nb == g.skip);
+        float y[3] = {s_blast[0], s_blast[1], s_blast[2]};
+        uint32_t mbits[4];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          uint32_t v[32];
+          tmem_ld32(tb + 32u * cb, v);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + nb * HID + 32 * cb);
+          const float4* w0 = reinterpret_cast<const float4*>(s_wlast + 0 * HID + 32 * cb);
+          const float4* w1 = reinterpret_cast<const float4*>(s_wlast + 1 * HID + 32 * cb);
+          const float4* w2 = reinterpret_cast<const float4*>(s_wlast + 2 * HID + 32 * cb);
+          uint32_t zw[16];
+          if (is_skip) ry_load_words(zyimg, r, cb, zw);
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i], a0 = w0[i], a1 = w1[i], a2 = w2[i];
+            float h0 = __uint_as_float(v[4 * i]) + bb.x, h1 = __uint_as_float(v[4 * i + 1]) + bb.y;
+            float h2 = __uint_as_float(v[4 * i + 2]) + bb.z, h3 = __uint_as_float(v[4 * i + 3]) + bb.w;
+            if (is_skip) {
+              const float2 z01 = ry_unpack(zw[2 * i]), z23 = ry_unpack(zw[2 * i + 1]);
+              h0 += z01.x; h1 += z01.y; h2 += z23.x; h3 += z23.y;
+            }
+            h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f);
+            y[0] = fmaf(a0.w, h3, fmaf(a0.z, h2, fmaf(a0.y, h1, fmaf(a0.x, h0, y[0]))));
+            y[1] = fmaf(a1.w, h3, fmaf(a1.z, h2, fmaf(a1.y, h1, fmaf(a1.x, h0, y[1]))));
+            y[2] = fmaf(a2.w, h3, fmaf(a2.z, h2, fmaf(a2.y, h1, fmaf(a2.x, h0, y[2]))));
+            if (kTrain) { w[2 * i] = pack_half2_sat(h0, h1); w[2 * i + 1] = pack_half2_sat(h2, h3); }
+          }
+          if (kTrain) {
+            mbits[cb] = ry_relu_mask16(w);
+            ry_store_words(himg, r, cb, w);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) y[c] = ry_sigmoid(y[c]);
+        if (valid) {
+          p.pred[ray * 3 + 0] = y[0];
+          p.pred[ray * 3 + 1] = y[1];
+          p.pred[ray * 3 + 2] = y[2];
+        }
+        if (kTrain) {
+          float dzl[3] = {0.f, 0.f, 0.f};
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float gy;
+              if (p.target != nullptr) {
+                const float d = y[c] - p.target[src * 3 + c];
+                loss_abs += fabsf(d);
+                loss_sq += d * d;
+                gy = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);  // d|d|/dd, sign(0) = 0 as F.l1_loss
+              } else {
+                gy = p.grad_pred[ray * 3 + c] * p.ext_scale;
+              }
+              dzl[c] = gy * y[c] * (1.f - y[c]) * DZ_SCALE;
+              gb[c] += dzl[c];
+            }
+          }
+          // dzl^T tile [16 x 128 rays] (rows 3..15 stay zero): B operand of the output-layer weight gradient
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<__half*>(smem + dzlt + static_cast<uint32_t>(r >> 6) * 2048u + sw128_off(c, r & 63)) = __float2half_rn(dzl[c]);
+          // h_nb goes to the stash, then dz_nb takes its place in the activation image
+          sync_epi();
+          if (r == 0) {
+            bulk_s2g_hint(stash_tile + stash_off_h(g, nb), himg, BLOB_BYTES, stash_policy);
+            bulk_commit();
+            bulk_wait_read<0>();
+          }
+          named_bar_sync(bar_id, RY_WG_THREADS);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            const float4* w0 = reinterpret_cast<const float4*>(s_wlast + 0 * HID + 32 * cb);
+            const float4* w1 = reinterpret_cast<const float4*>(s_wlast + 1 * HID + 32 * cb);
+            const float4* w2 = reinterpret_cast<const float4*>(s_wlast + 2 * HID + 32 * cb);
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a0 = w0[i], a1 = w1[i], a2 = w2[i];
+              const float d0 = fmaf(dzl[2], a2.x, fmaf(dzl[1], a1.x, dzl[0] * a0.x));
+              const float d1 = fmaf(dzl[2], a2.y, fmaf(dzl[1], a1.y, dzl[0] * a0.y));
+              const float d2 = fmaf(dzl[2], a2.z, fmaf(dzl[1], a1.z, dzl[0] * a0.z));
+              const float d3 = fmaf(dzl[2], a2.w, fmaf(dzl[1], a1.w, dzl[0] * a0.w));
+              w[2 * i] = ry_apply_mask(pack_half2_sat(d0, d1), mbits[cb], 2 * i);
+              w[2 * i + 1] = ry_apply_mask(pack_half2_sat(d2, d3), mbits[cb], 2 * i + 1);
+            }
+            ry_store_words(himg, r, cb, w);
+          }
+          sync_epi();
+          if (r == 0)
+            publish(stash_tile + stash_off_dz(g, nb), himg, BLOB_BYTES, stash_tile + stash_off_dzlt(g), smem_base + dzlt, DZLT_BYTES, true);
+
+          // ---- dgrad chain: dz_l = dh_l * relu'(z_l), l = nb-1..0 ----------------------------------------
+          for (int lb = nb - 1; lb >= 0; --lb) {
+            wait_done();
+            const uint32_t mm[4] = {mk[lb][0], mk[lb][1], mk[lb][2], mk[lb][3]};
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+              uint32_t v[32];
+              tmem_ld32(tb + 32u * cb, v);
+              tmem_ld_wait();
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                w[i] = ry_apply_mask(pack_half2_sat(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), mm[cb], i);
+              ry_store_words(himg, r, cb, w);
+            }
+            sync_epi();
+            if (r == 0) publish(stash_tile + stash_off_dz(g, lb), himg, BLOB_BYTES, nullptr, 0u, 0u, lb > 0);
+          }
+        }
+      }
+    }
+    if (kTrain) {
+      // ---- per-warpgroup partials: output-layer bias gradient, loss sums ------------------------------
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        loss_abs += __shfl_xor_sync(0xffffffffu, loss_abs, o);
+        loss_sq += __shfl_xor_sync(0xffffffffu, loss_sq, o);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gb[c] += __shfl_xor_sync(0xffffffffu, gb[c], o);
+      }
+      float* s_red = reinterpret_cast<float*>(smem + sm.red) + slot * 24;   // [5][4]: per-warp partial sums
+      if (lane == 0) {
+        s_red[wq] = loss_abs; s_red[4 + wq] = loss_sq;
+        s_red[8 + wq] = gb[0]; s_red[12 + wq] = gb[1]; s_red[16 + wq] = gb[2];
+      }
+      named_bar_sync(bar_id, RY_WG_THREADS);
+      if (r == 0) {
+        float* part = p.part1 + static_cast<size_t>(blockIdx.x * RY_SLOTS + slot) * K1_PART_FLOATS;
+        part[0] = s_red[8] + s_red[9] + s_red[10] + s_red[11];
+        part[1] = s_red[12] + s_red[13] + s_red[14] + s_red[15];
+        part[2] = s_red[16] + s_red[17] + s_red[18] + s_red[19];
+        part[3] = 0.f;
+        part[4] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        part[5] = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+        bulk_wait<0>();  // stash stores fully written before the grid completes
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == RY_W_CH) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, RY_TMEM_COLS);
+  }
+}
+
+cudaError_t launch_field_rays(const FieldParams& p, bool train, int grid, cudaStream_t stream) {
+  const int smem = static_cast<int>(ry_smem(train).total);
+  cudaError_t e = train ? cudaFuncSetAttribute(field_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                        : cudaFuncSetAttribute(field_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  if (train) field_rays_kernel<true><<<static_cast<unsigned>(grid), RY_THREADS, static_cast<size_t>(smem), stream>>>(p);
+  else field_rays_kernel<false><<<static_cast<unsigned>(grid), RY_THREADS, static_cast<size_t>(smem), stream>>>(p);
+  return cudaGetLastError();
+}
+
+int field_rays_slots() { return RY_SLOTS; }
+
+}  // namespace inf

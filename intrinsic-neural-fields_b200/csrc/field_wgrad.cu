@@ -111,11 +111,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
 
-  const int ntiles = p.ntiles;
+  // Vertex-projected path: the big slices contract over VERTEX tiles -- A = the vertex-gradient image G (laid out as a
+  // tile's dz_0 / dz_skip blobs), B = the table's operand image (laid out as a tile's x panels); [dW0;dWy] = G^T E.
+  const bool vp = p.e_image != nullptr;
+  const int ntiles = (big && vp) ? p.ntiles_v : p.ntiles;
   const int my_tiles = (ntiles > grp) ? (ntiles - grp + groups - 1) / groups : 0;
   const int units_per_tile = big ? 2 : (u1 - u0);
   const int nunits = my_tiles * units_per_tile;
-  const size_t tile_stride = stash_tile_bytes(g);
+  const size_t tile_stride = p.stash_stride;
 
   if (warp == WG_LOAD_WARP) {
     // ======================= stash loader ======================================================
@@ -139,6 +142,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
           const uint8_t* dz0 = st + stash_off_dz(g, 0) + hh * HALF_PANEL;
           const uint8_t* dzs = st + stash_off_dz(g, g.skip) + hh * HALF_PANEL;
           const uint8_t* xs = st + stash_off_x(g, 4 * slice) + hh * HALF_PANEL;
+          if (vp) {
+            dz0 = p.g_image + static_cast<size_t>(tile) * GIMG_TILE_BYTES + hh * HALF_PANEL;
+            dzs = dz0 + BLOB_BYTES;
+            xs = p.e_image + (static_cast<size_t>(tile) * g.nchunks + 4 * slice) * PANEL_BYTES + hh * HALF_PANEL;
+          }
           mbar_arrive_expect_tx(fb, static_cast<uint32_t>(4 + npanels) * HALF_PANEL);
           const uint8_t* dzsrc[4] = {dz0, dz0 + PANEL_BYTES, dzs, dzs + PANEL_BYTES};
 #pragma unroll

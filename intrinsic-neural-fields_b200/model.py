@@ -47,12 +47,12 @@ class _FieldFunction(torch.autograd.Function):
     dirs (none requires grad in the reference either)."""
 
     @staticmethod
-    def forward(ctx, module, table, vids, bary, dense, dirs, face_idxs, face_normals, ray_idxs, *params):
+    def forward(ctx, module, table, vids, bary, dense, dirs, face_idxs, face_normals, ray_idxs, extras, *params):
         packed = module._packed_weights(force=True)
-        ctx.module, ctx.dense = module, dense
+        ctx.module, ctx.dense, ctx.extras = module, dense, extras
         ctx.save_for_backward(table, vids, bary, dirs, face_idxs, face_normals, ray_idxs)
         return torch.ops.inf_b200.field_forward(table, vids, bary, packed, dirs, face_idxs, face_normals,
-                                                module.cfg.key(), dense, ray_idxs)
+                                                module.cfg.key(), dense, ray_idxs, extras[0], extras[1])
 
     @staticmethod
     def backward(ctx, grad_pred):
@@ -60,10 +60,10 @@ class _FieldFunction(torch.autograd.Function):
         table, vids, bary, dirs, face_idxs, face_normals, ray_idxs = ctx.saved_tensors
         _, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, module._packed_weights(), None, grad_pred.contiguous().float(), dirs, face_idxs,
-            face_normals, module.cfg.key(), ctx.dense, 1.0, ray_idxs)
+            face_normals, module.cfg.key(), ctx.dense, 1.0, ray_idxs, ctx.extras[0], ctx.extras[1])
         flat, _ = ops.split_flat(flat_full)
         grads = [flat[off:off + r * c].view(p.shape) for (off, r, c), p in zip(module._layout, module._ordered_params())]
-        return (None,) * 9 + tuple(grads)
+        return (None,) * 10 + tuple(grads)
 
 
 class _FusedFieldBase(nn.Module):
@@ -130,9 +130,17 @@ class _FusedFieldBase(nn.Module):
             x = batch["eigenfunctions"]
             if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.cfg.k:
                 raise ValueError(f"batch['eigenfunctions'] must be (B,{self.cfg.k}) float32")
-            return EigenTable.from_dense(x, device=x.device, dtype="f32").data, None, None, True
+            return EigenTable.from_dense(x, device=x.device, dtype="f32", image=False).data, None, None, True
         raise KeyError("batch needs 'eigenfunction_table' + 'vertex_idxs_of_hit_faces' + 'barycentric_coords' "
                        "(fused path) or 'eigenfunctions' (dense path)")
+
+    @staticmethod
+    def _table_extras(batch):
+        """(fp16 operand image of the table or None, InfDesc.path code): what selects / enables the vertex path."""
+        table = batch.get("eigenfunction_table")
+        if isinstance(table, EigenTable) and "vertex_idxs_of_hit_faces" in batch:
+            return table.image, ops.PATHS[table.path]
+        return None, 0
 
     @staticmethod
     def _ray_idxs(batch):
@@ -145,11 +153,12 @@ class _FusedFieldBase(nn.Module):
         table, vids, bary, dense = self._inputs(batch)
         dirs, face_idxs, normals = self._view_inputs(batch)
         ridx = self._ray_idxs(batch)
+        extras = self._table_extras(batch)
         params = self._ordered_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, ridx, *params)
+            return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, ridx, extras, *params)
         return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(force=self.training), dirs,
-                                                face_idxs, normals, self.cfg.key(), dense, ridx)
+                                                face_idxs, normals, self.cfg.key(), dense, ridx, extras[0], extras[1])
 
     # ---- fused training pass -----------------------------------------------------------------------
     def l1_step(self, batch: Dict[str, torch.Tensor], global_rays: Optional[int] = None,
@@ -169,7 +178,7 @@ class _FusedFieldBase(nn.Module):
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
         pred, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, self._packed_weights(force=True), target, None, dirs, face_idxs, normals, self.cfg.key(),
-            dense, scale, ridx)
+            dense, scale, ridx, *self._table_extras(batch))
         flat, sums = ops.split_flat(flat_full)
         if flat_grad is not None:
             flat_grad.copy_(flat)

@@ -60,8 +60,13 @@ _VIEW_CODES = {"none": _lib.VIEW_NONE, "intrinsic": _lib.VIEW_INTRINSIC, "extrin
 _VIEW_NAMES = {v: k for k, v in _VIEW_CODES.items()}
 
 
+PATHS = {"auto": _lib.PATH_AUTO, "ray": _lib.PATH_RAY, "vertex": _lib.PATH_VERTEX}
+DEFAULT_PATH = "auto"   # path of tables built without an explicit one (tests pin it to run every case on both paths)
+
+
 def _desc(cfg: FieldConfig, n_rays: int, n_rows: int, *, idx64: bool = True, table_f16: bool = False,
-          dense: bool = False, grad_scale: float = 1.0, n_faces: int = 0, ray_idxs=None, n_src_rays: int = 0) -> _lib.InfDesc:
+          dense: bool = False, grad_scale: float = 1.0, n_faces: int = 0, ray_idxs=None, n_src_rays: int = 0,
+          path: int = 0) -> _lib.InfDesc:
     d = _lib.InfDesc()
     d.abi_version = _lib.ABI_VERSION
     d.idx_dtype = _lib.IDX_I64 if idx64 else _lib.IDX_I32
@@ -86,6 +91,7 @@ def _desc(cfg: FieldConfig, n_rays: int, n_rows: int, *, idx64: bool = True, tab
         d.n_src_rays = n_src_rays
         d.ray_idx_dtype = _lib.IDX_I64 if ray_idxs.dtype == torch.int64 else _lib.IDX_I32
     d.grad_scale = grad_scale
+    d.path = path
     return d
 
 
@@ -131,8 +137,9 @@ def packed_bytes(cfg: FieldConfig) -> int:
     return int(_lib.load().inf_packed_bytes(C.byref(_desc(cfg, 0, 0))))
 
 
-def workspace_bytes(cfg: FieldConfig, n_rays: int, training: bool) -> int:
-    return int(_lib.load().inf_workspace_bytes(C.byref(_desc(cfg, n_rays, 0)), 1 if training else 0))
+def workspace_bytes(cfg: FieldConfig, n_rays: int, training: bool, n_rows: int = 0, path: int = 0) -> int:
+    """Scratch bytes of one call; ``n_rows`` > 0 (a table image is passed) sizes it for either evaluation path."""
+    return int(_lib.load().inf_workspace_bytes(C.byref(_desc(cfg, n_rays, n_rows, path=path)), 1 if training else 0))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -146,8 +153,36 @@ class EigenTable:
     gather traffic (values are rounded once, before interpolation).
     """
 
-    def __init__(self, data: torch.Tensor, k: int, dtype: str):
+    def __init__(self, data: torch.Tensor, k: int, dtype: str, image: Optional[torch.Tensor] = None, path: Optional[str] = None):
+        path = DEFAULT_PATH if path is None else path
+        if path not in PATHS:
+            raise ValueError(f"path must be one of {sorted(PATHS)}")
         self.data, self.k, self.dtype = data, k, dtype
+        self.image = image      # fp16 operand image of the table (vertex path), or None
+        self.path = path        # "auto" | "ray" | "vertex": InfDesc.path of every call on this table
+
+    def with_path(self, path: str) -> "EigenTable":
+        """The same device buffers with another evaluation path (no copy)."""
+        if path not in PATHS:
+            raise ValueError(f"path must be one of {sorted(PATHS)}")
+        if path == "vertex" and self.image is None:
+            self.build_image()
+        return EigenTable(self.data, self.k, self.dtype, self.image, path)
+
+    def build_image(self) -> torch.Tensor:
+        """fp16 tensor-core operand image of the table ([V/128][k_pad/64] panels, values rounded once): the A operand
+        of the per-vertex projection P = E [W0;Wy]^T and the B operand of [dW0;dWy] = G^T E."""
+        if self.image is None:
+            lib = _lib.load()
+            V, kp = self.data.shape
+            img = torch.empty(int(lib.inf_table_image_bytes(V, kp)), dtype=torch.uint8, device=self.data.device)
+            with torch.cuda.device(self.data.device):
+                rc = lib.inf_build_table_image(C.c_void_p(self.data.data_ptr()),
+                                               _lib.TABLE_F16 if self.data.dtype == torch.float16 else _lib.TABLE_F32, V, kp,
+                                               C.c_void_p(img.data_ptr()), _stream(self.data.device))
+            _lib.check(rc, "inf_build_table_image")
+            self.image = img
+        return self.image
 
     @property
     def n_rows(self) -> int:
@@ -162,7 +197,7 @@ class EigenTable:
         return self.data.device
 
     @staticmethod
-    def from_dense(E: torch.Tensor, device=None, dtype: str = "f32") -> "EigenTable":
+    def from_dense(E: torch.Tensor, device=None, dtype: str = "f32", image: bool = True, path: Optional[str] = None) -> "EigenTable":
         if E.dim() != 2 or E.dtype != torch.float32:
             raise ValueError("eigenfunction table must be a 2-D float32 tensor (mesh.py:105-108)")
         device = torch.device(device if device is not None else E.device)
@@ -178,7 +213,10 @@ class EigenTable:
             rc = _lib.load().inf_relayout_table(C.c_void_p(src.data_ptr()), V, k, src.stride(0), C.c_void_p(out.data_ptr()),
                                                 kp, _lib.TABLE_F16 if dtype == "f16" else _lib.TABLE_F32, _stream(device))
         _lib.check(rc, "inf_relayout_table")
-        return EigenTable(out, k, dtype)
+        t = EigenTable(out, k, dtype, None, path)
+        if image and V > 0:
+            t.build_image()
+        return t
 
 
 # ------------------------------------------------------------------------------------------------
@@ -281,7 +319,7 @@ def _check_view(cfg, B, idx64, dirs, face_idxs, face_normals):   # B = rows of t
 
 
 def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense: bool,
-                        ray_idxs=None) -> torch.Tensor:
+                        ray_idxs=None, table_image=None, path: int = 0) -> torch.Tensor:
     cfg = FieldConfig.from_key(cfg_key)
     B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
@@ -290,12 +328,14 @@ def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals
         return pred
     idx64 = vids is None or vids.dtype == torch.int64
     dirs, face_idxs, face_normals, n_faces = _check_view(cfg, n_src, idx64, dirs, face_idxs, face_normals)
-    ws = _workspace(device, workspace_bytes(cfg, B, False))
+    if dense:
+        table_image = None
+    ws = _workspace(device, workspace_bytes(cfg, B, False, table.shape[0] if table_image is not None else 0, path))
     d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense, n_faces=n_faces,
-              ray_idxs=ray_idxs, n_src_rays=n_src)
+              ray_idxs=ray_idxs, n_src_rays=n_src, path=path)
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), unit_ray_dirs=_ptr(dirs),
                         face_idxs=_ptr(face_idxs), face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs),
-                        packed=packed.data_ptr(),
+                        table_image=_ptr(table_image), packed=packed.data_ptr(),
                         pred=pred.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     with torch.cuda.device(device):
         rc = _lib.load().inf_forward(C.byref(d), C.byref(t), _stream(device))
@@ -318,7 +358,7 @@ def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps
 
 
 def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key,
-                                 dense: bool, grad_scale: float, adam=None, ray_idxs=None):
+                                 dense: bool, grad_scale: float, adam=None, ray_idxs=None, table_image=None, path: int = 0):
     cfg = FieldConfig.from_key(cfg_key)
     B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
@@ -336,12 +376,15 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
                 raise ValueError(f"{name} must be ({rows},3) float32")
     idx64 = vids is None or vids.dtype == torch.int64
     dirs, face_idxs, face_normals, n_faces = _check_view(cfg, n_src, idx64, dirs, face_idxs, face_normals)
-    ws = _workspace(device, workspace_bytes(cfg, B, True))
+    if dense:
+        table_image = None
+    ws = _workspace(device, workspace_bytes(cfg, B, True, table.shape[0] if table_image is not None else 0, path))
     d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense,
-              grad_scale=grad_scale, n_faces=n_faces, ray_idxs=ray_idxs, n_src_rays=n_src)
+              grad_scale=grad_scale, n_faces=n_faces, ray_idxs=ray_idxs, n_src_rays=n_src, path=path)
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), target=_ptr(target),
                         grad_pred=_ptr(grad_pred), unit_ray_dirs=_ptr(dirs), face_idxs=_ptr(face_idxs),
-                        face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs), packed=packed.data_ptr(),
+                        face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs), table_image=_ptr(table_image),
+                        packed=packed.data_ptr(),
                         pred=pred.data_ptr(),
                         workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     g = _lib.InfGrads(flat=flat.data_ptr(), loss_sums=sums.data_ptr())
@@ -364,8 +407,10 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
 def field_forward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor],
                   packed: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                   face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
-                  ray_idxs: Optional[torch.Tensor] = None) -> torch.Tensor:
-    return _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs)
+                  ray_idxs: Optional[torch.Tensor] = None, table_image: Optional[torch.Tensor] = None,
+                  path: int = 0) -> torch.Tensor:
+    return _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs,
+                               table_image, path)
 
 
 def _fake_rows(table, vids, dense, ray_idxs):
@@ -373,7 +418,7 @@ def _fake_rows(table, vids, dense, ray_idxs):
 
 
 @field_forward.register_fake
-def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs=None):
+def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs=None, table_image=None, path=0):
     B = _fake_rows(table, vids, dense, ray_idxs)
     return table.new_empty((B, 3), dtype=torch.float32)
 
@@ -383,15 +428,17 @@ def field_forward_backward(table: torch.Tensor, vids: Optional[torch.Tensor], ba
                            packed: torch.Tensor, target: Optional[torch.Tensor], grad_pred: Optional[torch.Tensor],
                            dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                            face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
-                           grad_scale: float, ray_idxs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                           grad_scale: float, ray_idxs: Optional[torch.Tensor] = None,
+                           table_image: Optional[torch.Tensor] = None, path: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (pred (B,3), flat (n_params + 2,)): the flat gradient followed by the two loss sums (one allocation,
     one allreduce); use :func:`split_flat`."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals,
-                                        cfg_key, dense, grad_scale, ray_idxs=ray_idxs)
+                                        cfg_key, dense, grad_scale, ray_idxs=ray_idxs, table_image=table_image, path=path)
 
 
 @field_forward_backward.register_fake
-def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, ray_idxs=None):
+def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, ray_idxs=None,
+      table_image=None, path=0):
     B = _fake_rows(table, vids, dense, ray_idxs)
     n = num_params(FieldConfig.from_key(cfg_key))
     return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n + 2,), dtype=torch.float32))
@@ -414,17 +461,19 @@ def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Op
                      face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool, grad_scale: float,
                      params_flat: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float,
                      beta2: float, eps: float, step_dev: torch.Tensor,
-                     ray_idxs: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Forward + L1 loss + backward + Adam + operand refresh (trainer.py:75-82) in three kernel launches."""
+                     ray_idxs: Optional[torch.Tensor] = None, table_image: Optional[torch.Tensor] = None,
+                     path: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Forward + L1 loss + backward + Adam + operand refresh (trainer.py:75-82); the optimiser runs inside the
+    gradient-reduction kernel."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, None, dirs, face_idxs, face_normals, cfg_key,
                                         dense, grad_scale,
                                         adam=_AdamArgs((params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)),
-                                        ray_idxs=ray_idxs)
+                                        ray_idxs=ray_idxs, table_image=table_image, path=path)
 
 
 @field_train_step.register_fake
 def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, params_flat, exp_avg,
-      exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None):
+      exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None, table_image=None, path=0):
     B = _fake_rows(table, vids, dense, ray_idxs)
     return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty((params_flat.numel() + 2,)))
 

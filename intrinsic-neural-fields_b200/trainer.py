@@ -141,7 +141,8 @@ class FusedFieldAdam:
         self.step_dev.add_(1)
         pred, flat_full = torch.ops.inf_b200.field_train_step(
             table, vids, bary, self.packed, target, dirs, face_idxs, normals, m.cfg.key(), dense, scale, self.flat,
-            self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, ridx)
+            self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, ridx,
+            *m._table_extras(batch))
         flat, sums = ops.split_flat(flat_full)
         m._packed, m._packed_key = self.packed, None
         return sums, pred, flat
@@ -155,7 +156,7 @@ class FusedFieldAdam:
         scale = 1.0 / (3.0 * float(global_rays))
         pred, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, self.packed, target, None, dirs, face_idxs, normals, m.cfg.key(), dense, scale,
-            m._ray_idxs(batch))
+            m._ray_idxs(batch), *m._table_extras(batch))
         flat, sums = ops.split_flat(flat_full)
         return sums, pred, flat
 

@@ -282,7 +282,8 @@ def _r16(a: np.ndarray) -> np.ndarray:
 
 
 def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale=32.0, table_f16=False,
-                        view: Optional[dict] = None, unit_ray_dirs=None, hit_face_idxs=None, face_normals=None):
+                        view: Optional[dict] = None, unit_ray_dirs=None, hit_face_idxs=None, face_normals=None,
+                        vertex_path: bool = False):
     """The reference's forward/backward (model.py:98-112,188-191, trainer.py:76-81) restated in float64 with the
     CUDA path's rounding points: table (optionally), interpolated embedding, weights, hidden activations, the
     Fourier view embedding and backward signals are rounded to fp16 before each matrix product; accumulation
@@ -292,10 +293,15 @@ def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale
     below the rounding noise, which alone moves each gradient tensor by a few percent in Frobenius
     norm.  Against THIS restatement the masks agree, so the kernels' arithmetic can be checked tightly.
     Returns (loss, pred, grads) with grads of the mean L1 loss.
+
+    ``vertex_path`` selects the rounding points of the per-vertex evaluation of the two K = k contractions
+    (csrc/vertex_project.cu, field_rays.cu, vertex_grad.cu): table rounded to fp16 once (the operand image),
+    P = fp16(E16 [W0;Wy]16^T) per vertex, [z0|zy] interpolated from P in fp32, zy rounded to fp16 before it is added in
+    the skip layer; backward G[v] = fp16(sum bary * dz) and [dW0;dWy] = G^T E16.
     """
     P = {n: t.double().numpy() for n, t in p.items()}
     Ed = E.double().numpy()
-    if table_f16:
+    if table_f16 or vertex_path:
         Ed = _r16(Ed)
     b = bary.numpy().astype(np.float32)
     rows = Ed[vids.numpy().reshape(-1)].reshape(vids.shape[0], 3, -1)
@@ -322,13 +328,29 @@ def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale
             acc = (acc + P[extra].astype(np.float32)).astype(np.float32)
         return acc.astype(np.float64)
 
+    vid_np = vids.numpy()
+    if vertex_path:
+        W0n, _ = names(0)
+        Pz0 = _r16(Ed @ _r16(P[W0n]).T)                                   # (V,128) fp16 projected rows
+        Pzy = _r16(Ed @ _r16(P[f"{pre}layers.{skip}.Ly.weight"]).T)
+
+        def interp(T):   # fp32: w0*t0, then two fma
+            a = (b[:, 0:1] * T[vid_np[:, 0]].astype(np.float32)).astype(np.float32)
+            a = (b[:, 1:2].astype(np.float64) * T[vid_np[:, 1]] + a).astype(np.float32)
+            return (b[:, 2:3].astype(np.float64) * T[vid_np[:, 2]] + a).astype(np.float32)
+        z0_vp = interp(Pz0).astype(np.float64)
+        zy_vp = _r16(interp(Pzy))
+
     hs, masks = [], []
     h16 = x
     for i in range(n_spatial):
         wn, _ = names(i)
-        z = h16 @ _r16(P[wn]).T + bias(i)
+        if vertex_path and i == 0:
+            z = (z0_vp.astype(np.float32) + bias(0).astype(np.float32)).astype(np.float64)
+        else:
+            z = h16 @ _r16(P[wn]).T + bias(i)
         if i == skip:
-            z = z + x @ _r16(P[f"{pre}layers.{i}.Ly.weight"]).T
+            z = z + (zy_vp if vertex_path else x @ _r16(P[f"{pre}layers.{i}.Ly.weight"]).T)
         masks.append(z > 0)
         h = np.maximum(z, 0.0)
         hs.append(h)
@@ -362,14 +384,21 @@ def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale
         g["directional_mlp.0.weight"] = np.concatenate([dz.T @ _r16(hs[nb - 1]), dz.T @ e16], axis=1)
         g["directional_mlp.0.bias"] = dz.sum(0)
         dz = _r16((dz @ _r16(Wd1[:, :bn])) * masks[nb - 1])
+    def vertex_grad(dzr):
+        # G[v] = fp16(sum over incident (ray, corner) of bary * dz[ray]); dW = G^T E16
+        G = np.zeros((Ed.shape[0], dzr.shape[1]))
+        for j in range(3):
+            np.add.at(G, vid_np[:, j], b[:, j:j + 1].astype(np.float64) * dzr)
+        return _r16(G).T @ Ed
+
     for i in range(n_spatial - 1, -1, -1):
         hin = x if i == 0 else _r16(hs[i - 1])
         wn, bns = names(i)
-        g[wn] = dz.T @ hin
+        g[wn] = vertex_grad(dz) if (vertex_path and i == 0) else dz.T @ hin
         for bname in bns:
             g[bname] = dz.sum(0)
         if i == skip:
-            g[f"{pre}layers.{i}.Ly.weight"] = dz.T @ x
+            g[f"{pre}layers.{i}.Ly.weight"] = vertex_grad(dz) if vertex_path else dz.T @ x
         if i > 0:
             dz = _r16((dz @ _r16(P[wn])) * masks[i - 1])
     s = 1.0 / (3.0 * B * dz_scale)

@@ -18,6 +18,15 @@ RGB_MAX, RGB_MEAN = 2e-2, 1e-3
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["ray", "vertex"])
+def eval_path(request):
+    """Every config runs on both evaluations of the two K = k contractions (InfDesc.path): per ray and per vertex."""
+    old = ops.DEFAULT_PATH
+    ops.DEFAULT_PATH = request.param
+    yield request.param
+    ops.DEFAULT_PATH = old
+
+
 def _check_no_watchdog():
     torch.cuda.synchronize()
     assert inf_b200.kernel_error_word(DEV) == 0

@@ -26,6 +26,16 @@ GRAD_REL_VIEW, GRAD_COS_VIEW = 0.2, 0.98
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["ray", "vertex"])
+def eval_path(request):
+    """Every case of this module runs on both evaluations of the two K = k contractions (InfDesc.path): per ray
+    (field_main.cu) and per vertex (vertex_project.cu / field_rays.cu / vertex_grad.cu)."""
+    old = ops.DEFAULT_PATH
+    ops.DEFAULT_PATH = request.param
+    yield request.param
+    ops.DEFAULT_PATH = old
+
+
 def _model_from(case, table_dtype="f32"):
     cfg = dict(k=case["k"], num_layers=case["num_layers"], mlp_hidden_dim=128, skip_layer_idx=case["skip"])
     mesh = None
@@ -161,7 +171,8 @@ def _check_grads_emulated(m, case, table_f16=False):
         kw = dict(view=case["view"], unit_ray_dirs=case["unit_ray_dirs"], hit_face_idxs=case["face_idxs"],
                   face_normals=case["face_normals"])
     _, _, g = O.emulated_fp16_grads(case["params"], case["table"], case["vids"], case["bary"], case["target"],
-                                    case["num_layers"], case["skip"], table_f16=table_f16, **kw)
+                                    case["num_layers"], case["skip"], table_f16=table_f16,
+                                    vertex_path=(ops.DEFAULT_PATH == "vertex"), **kw)
     return _check_grads(m, g, tol=GRAD_REL_EMULATED, cos_min=0.9999)
 
 
