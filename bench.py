@@ -264,7 +264,7 @@ def run_ours(args):
 
     faces = torus_faces(GRID, dev)
     table_dense = make_table(V, K_EIG, dev)
-    table = inf_b200.EigenTable.from_dense(table_dense, device=dev, dtype=args.table_dtype)
+    table = inf_b200.EigenTable.from_dense(table_dense, device=dev, dtype=args.table_dtype, path=args.path)
     del table_dense
     torch.manual_seed(0)
     model = inf_b200.make_model(dict(k=K_EIG, num_layers=LAYERS, mlp_hidden_dim=HID, skip_layer_idx=SKIP)).to(dev)
@@ -350,14 +350,18 @@ def run_ours(args):
     import ctypes as C
     km, kw, kr, kn = C.c_float(), C.c_float(), C.c_float(), C.c_int()
     lib.inf_profile_read(C.byref(km), C.byref(kw), C.byref(kr), C.byref(kn))
+    stage_arr = (C.c_float * _lib.PROFILE_STAGES)()
+    lib.inf_profile_read_stages(stage_arr, C.byref(kn))
+    stages = dict(zip(["incidence_lists", "vertex_project", "rays_fwd_bwd", "vertex_gather", "wgrad", "reduce_adam"],
+                      [float(x) for x in stage_arr]))
     lib.inf_profile_enable(0)
     assert inf_b200.kernel_error_word(dev) == 0, "kernel watchdog fired"
 
     _say("resident timing done")
     if args.skip_e2e:
         sampler.stop() if rank == 0 else None
-        print(json.dumps({"profiling_run": True, "ms_per_step": ms_total / args.steps,
-                          "step_kernels_ms": {"field_main": km.value, "field_wgrad": kw.value, "field_reduce": kr.value}}), flush=True)
+        print(json.dumps({"profiling_run": True, "ms_per_step": ms_total / args.steps, "rays_per_sec": B * args.steps / (ms_total / 1e3),
+                          "step_kernels_ms": stages}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -432,7 +436,7 @@ def run_ours(args):
                      # rate can exceed the DRAM rate -- and the copy peak; the DRAM side of the same launch:
                      "dram_gbs": (traffic / (main_ms / 1e3) / 1e9) if traffic else None,
                      "algorithmic_bytes_per_ray": bytes_per_ray(train),
-                     "step_kernels_ms": {"field_main": km.value, "field_wgrad": kw.value, "field_reduce": kr.value},
+                     "step_kernels_ms": stages,
                      "tensor_frac_of_sustained_bf16": rate / world * flop_per_ray(train) / (pk["bf16_tflops_sustained"] * 1e12)},
     }
     if small is not None:
@@ -463,6 +467,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--batch", type=int, default=131072, help="rays per GPU per step")
     ap.add_argument("--table-dtype", default="f32", choices=["f32", "f16"])
+    ap.add_argument("--path", default="auto", choices=["auto", "ray", "vertex"],
+                    help="evaluation of the two K = k contractions: per ray, per vertex, or the library's rule (InfDesc.path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: resident steps only (the JSON line is not a bench result)")
     ap.add_argument("--grid", type=int, default=224, help="torus grid side: V = grid^2 vertices (default: config 2)")

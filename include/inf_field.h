@@ -171,6 +171,11 @@ int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_
 size_t inf_table_image_bytes(int64_t n_rows, int32_t k_pad);
 int inf_build_table_image(const void* table, int32_t table_dtype, int64_t n_rows, int32_t k_pad, void* image, void* stream);
 
+/* The per-vertex projection on its own: out (V, 256) f16 row-major = [E W0^T | E Wy^T], i.e. layer 0's and the skip
+ * branch's pre-activations (without bias) at every VERTEX (model.py:98-104, layers.py:60-62 evaluated at bary = e_i).
+ * Needs t->table_image, t->packed and a workspace of inf_workspace_bytes(desc with n_rows set, 0). */
+int inf_project_vertices(const InfDesc* desc, const InfTensors* t, void* out, void* stream);
+
 /* fp32 master parameters -> operand images.  `params[i]` = device pointer of tensor i. */
 int inf_pack_weights(const InfDesc* desc, const float* const* params, void* packed, void* stream);
 

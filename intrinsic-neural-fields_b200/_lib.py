@@ -69,6 +69,7 @@ EXPORTS = {
                                      C.c_void_p]),
     "inf_table_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "inf_build_table_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "inf_project_vertices": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p, C.c_void_p]),
     "inf_uses_vertex_path": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors)]),
     "inf_pack_weights": (C.c_int, [C.POINTER(InfDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "inf_forward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p]),

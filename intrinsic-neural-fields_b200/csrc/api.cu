@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -22,8 +23,8 @@ cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream);
 cudaError_t launch_vertex_project(const FieldParams& p, int grid, int cluster, cudaStream_t stream);
 int vertex_project_max_grid(int cluster);
 void launch_table_image(const void* table, int table_f16, int64_t n_rows, int k_pad, void* image, cudaStream_t stream);
-cudaError_t launch_field_rays(const FieldParams& p, bool train, int grid, cudaStream_t stream);
-int field_rays_slots();
+void launch_proj_unpermute(const uint8_t* proj, int64_t n_rows, void* out, cudaStream_t stream);
+cudaError_t launch_field_rays(const FieldParams& p, bool train, int slots, int grid, cudaStream_t stream);
 cudaError_t launch_csr_build(const FieldParams& p, cudaStream_t stream);
 cudaError_t launch_vertex_gather(const FieldParams& p, int nsm, cudaStream_t stream);
 
@@ -41,7 +42,7 @@ thread_local char g_err[512] = "";
 // Environment knobs are read ONCE per process (not on every launch).  INF_DEBUG bits 1|2|4 are measurement switches
 // that skip work and produce WRONG gradients: bench.py refuses to run with them and records the value.
 struct Env {
-  int debug, prefetch, cluster, verbose, wg_cluster, force_path;
+  int debug, prefetch, cluster, verbose, wg_cluster, force_path, rays_slots, side_stream, wgrad_hid_ctas, wgrad_split;
   double wgrad_bigw;
   Env() {
     auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
@@ -50,6 +51,12 @@ struct Env {
     cluster = geti("INF_CLUSTER", 2);
     verbose = geti("INF_VERBOSE", 0);
     wg_cluster = geti("INF_WGRAD_CLUSTER", 4);
+    rays_slots = geti("INF_RAYS_SLOTS", 2) == 1 ? 1 : 2;   // flavour of the per-ray kernel (field_rays.cu)
+    // Vertex path, measured and left off: hidden-slice wgrad as its own launch, concurrent with the vertex gather on the
+    // side stream, big slices after (0.410 vs 0.394 ms/step: both kernels are bound by the same memory system)
+    wgrad_split = geti("INF_WGRAD_SPLIT", 0);
+    wgrad_hid_ctas = geti("INF_WGRAD_HID_CTAS", 0);   // vertex path: CTAs of the hidden-slice wgrad launch (0 = all SMs)
+    side_stream = geti("INF_SIDE_STREAM", 1);   // 0: incidence lists on the caller's stream
     force_path = geti("INF_PATH", 0);   // 1 = per-ray, 2 = vertex (when a table image is given): overrides InfDesc.path AUTO
     const char* b = getenv("INF_WGRAD_BIGW");
     wgrad_bigw = b ? atof(b) : 1.0;
@@ -327,6 +334,28 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   return p;
 }
 
+// The incidence lists of a training call depend on its inputs only, so they are built on a library-owned side stream,
+// forked from and joined back into the caller's stream with events (capturable: a CUDA graph records the fork/join).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+std::mutex g_side_mutex;
+SideStream g_side[16];
+SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = g_side[dev];
+  if (s.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    s.device = dev;
+  }
+  return &s;
+}
+
 // Vertex projection P = E [W0;Wy]^T: persistent CTAs in clusters of 2 (the weight stream is multicast).
 int launch_projection(const FieldParams& p, int nsm, cudaStream_t st) {
   static int max2 = -1;
@@ -342,10 +371,12 @@ int launch_projection(const FieldParams& p, int nsm, cudaStream_t st) {
   return INF_OK;
 }
 
-// CTAs of the per-ray kernel: one per SM, each walking pairs of 128-ray tiles
+// CTAs of the per-ray kernel: one per SM walking pairs of 128-ray tiles, or two per SM walking single tiles
 int rays_grid(const FieldParams& p, int nsm) {
-  const int npairs = (p.ntiles + field_rays_slots() - 1) / field_rays_slots();
-  return npairs < nsm ? npairs : nsm;
+  const int slots = env().rays_slots;
+  const int units = (p.ntiles + slots - 1) / slots;
+  const int cap = slots == 1 ? 2 * nsm : nsm;
+  return units < cap ? units : cap;
 }
 
 }  // namespace
@@ -411,6 +442,32 @@ int inf_build_table_image(const void* table, int32_t table_dtype, int64_t n_rows
   launch_table_image(table, table_dtype == INF_TABLE_F16, n_rows, k_pad, image, static_cast<cudaStream_t>(stream));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "table_image launch");
+  return INF_OK;
+}
+
+int inf_project_vertices(const InfDesc* desc, const InfTensors* t, void* out, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != INF_OK) return rc;
+  if (t == nullptr || t->table_image == nullptr || t->packed == nullptr || out == nullptr)
+    return fail(INF_ERR_BAD_ARG, "table_image / packed / out must be non-null");
+  if (desc->n_rows < 1) return fail(INF_ERR_BAD_ARG, "n_rows must be given");
+  InfDesc d = *desc;
+  d.path = INF_PATH_VERTEX;
+  d.input_mode = INF_INPUT_GATHER;
+  if (d.n_rays < 1) d.n_rays = 1;
+  const WorkspaceLayout w = workspace_layout(geo_of(&d), d.n_rays, false, d.n_rows);
+  if (t->workspace == nullptr || t->workspace_bytes < w.total)
+    return fail(INF_ERR_WORKSPACE, "workspace %zu B < required %zu B", t->workspace_bytes, w.total);
+  int nsm = 0;
+  rc = sm_count(&nsm);
+  if (rc != INF_OK) return rc;
+  FieldParams p = make_params(&d, t, false);
+  if (p.e_image == nullptr) return fail(INF_ERR_BAD_ARG, "vertex path not available for this call");
+  rc = launch_projection(p, nsm, static_cast<cudaStream_t>(stream));
+  if (rc != INF_OK) return rc;
+  launch_proj_unpermute(p.proj, d.n_rows, out, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "proj_unpermute launch");
   return INF_OK;
 }
 
@@ -484,7 +541,7 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream) {
     rc = launch_projection(p, nsm, st);
     if (rc != INF_OK) return rc;
     prof_record(slot, 2, st);
-    cudaError_t e = launch_field_rays(p, false, rays_grid(p, nsm), st);
+    cudaError_t e = launch_field_rays(p, false, env().rays_slots, rays_grid(p, nsm), st);
     if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<inference> launch");
   } else {
     prof_record(slot, 2, st);
@@ -569,53 +626,108 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   }
   // tiles a big slice walks: ray tiles, or vertex tiles on the vertex path ([dW0;dWy] = G^T E)
   const int tiles_big = vp ? p.ntiles_v : p.ntiles;
-  // bytes a CTA ingests per tile: the x panels of its 256 columns + its share of dz_0 / dz_skip
-  // (INF_WGRAD_BIGW scales the big slices' share: they also carry 2.5x the tensor work per ingested byte)
-  const double big_bytes = (2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw) * env().wgrad_bigw * tiles_big;
-  double wsum = static_cast<double>(geo.nbig) * big_bytes;
-  for (int s = 0; s < plan.nslice; ++s) wsum += static_cast<double>(plan.bytes_per_tile[s]) * p.ntiles;
   int used = 0;
   int gh[MAX_HID_SLICES] = {0, 0, 0, 0};
-  int smax = 0;
-  for (int s = 0; s < plan.nslice; ++s) {
-    int v = static_cast<int>(nsm_w * (static_cast<double>(plan.bytes_per_tile[s]) * p.ntiles / wsum));
-    if (v < 1) v = 1;
-    if (v > p.ntiles) v = p.ntiles;
-    gh[s] = v;
-    used += v;
-    if (plan.bytes_per_tile[s] > plan.bytes_per_tile[smax]) smax = s;
+  int gb = 1;
+  const bool split = vp && env().wgrad_split != 0;
+  if (split) {
+    // Two launches: the hidden slices (all SMs, no clusters) run while the vertex gradient is gathered on the side
+    // stream; the big slices follow.  Each launch splits its SMs in proportion to the bytes a slice ingests.
+    double hsum = 0;
+    for (int s = 0; s < plan.nslice; ++s) hsum += plan.bytes_per_tile[s];
+    int hid_ctas = env().wgrad_hid_ctas > 0 ? env().wgrad_hid_ctas : nsm;
+    if (hid_ctas > nsm) hid_ctas = nsm;
+    for (int s = 0; s < plan.nslice; ++s) {
+      int v = static_cast<int>(hid_ctas * (plan.bytes_per_tile[s] / hsum));
+      if (v < 1) v = 1;
+      if (v > p.ntiles) v = p.ntiles;
+      gh[s] = v;
+      used += v;
+    }
+    gb = nsm_w / geo.nbig;
+  } else {
+    // bytes a CTA ingests over the launch: the x panels of its 256 columns + its share of dz_0 / dz_skip per (ray or
+    // vertex) tile (INF_WGRAD_BIGW scales the big slices' share: they also carry 2.5x the tensor work per ingested byte)
+    const double big_bytes = (2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw) * env().wgrad_bigw * tiles_big;
+    double wsum = static_cast<double>(geo.nbig) * big_bytes;
+    for (int s = 0; s < plan.nslice; ++s) wsum += static_cast<double>(plan.bytes_per_tile[s]) * p.ntiles;
+    int smax = 0;
+    for (int s = 0; s < plan.nslice; ++s) {
+      int v = static_cast<int>(nsm_w * (static_cast<double>(plan.bytes_per_tile[s]) * p.ntiles / wsum));
+      if (v < 1) v = 1;
+      if (v > p.ntiles) v = p.ntiles;
+      gh[s] = v;
+      used += v;
+      if (plan.bytes_per_tile[s] > plan.bytes_per_tile[smax]) smax = s;
+    }
+    if (cw > 1 && used % cw != 0) {   // whole clusters only: pad the heaviest hidden slice
+      const int add = cw - used % cw;
+      if (plan.nslice > 0 && gh[smax] + add <= p.ntiles) { gh[smax] += add; used += add; }
+      else cw = 1;
+    }
+    gb = (nsm_w - used) / geo.nbig;
   }
-  if (cw > 1 && used % cw != 0) {   // whole clusters only: pad the heaviest hidden slice
-    const int add = cw - used % cw;
-    if (plan.nslice > 0 && gh[smax] + add <= p.ntiles) { gh[smax] += add; used += add; }
-    else cw = 1;
-  }
-  p.wg_cluster = cw;
-  int gb = (nsm_w - used) / geo.nbig;
   if (gb < 1) gb = 1;
   if (gb > tiles_big) gb = tiles_big;
+  p.wg_cluster = cw;
   p.groups_big = gb;
   for (int s = 0; s < MAX_HID_SLICES; ++s) p.groups_hid[s] = gh[s];
-  const int grid2 = geo.nbig * gb + used;
-  if (grid2 > MAX_CTAS) return fail(INF_ERR_UNSUPPORTED, "k_pad=%d needs %d wgrad CTAs > %d", desc->k_pad, grid2, MAX_CTAS);
+  const int grid_big = geo.nbig * gb;
+  const int grid2 = grid_big + used;
+  if (grid2 > (split ? MAX_WGRAD_CTAS : MAX_CTAS))
+    return fail(INF_ERR_UNSUPPORTED, "k_pad=%d needs %d wgrad CTAs > %d", desc->k_pad, grid2, split ? MAX_WGRAD_CTAS : MAX_CTAS);
 
   const bool f16 = desc->table_dtype == INF_TABLE_F16;
   const int slot = g_prof.n;
   cudaError_t e;
   prof_record(slot, 0, st);
   if (vp) {
-    e = launch_csr_build(p, st);
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    SideStream* side = env().side_stream ? side_stream() : nullptr;
+    if (side != nullptr) {
+      e = cudaEventRecord(side->fork, st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+      if (e == cudaSuccess) e = launch_csr_build(p, side->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(side->join, side->stream);
+    } else {
+      e = launch_csr_build(p, st);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "incidence-list (CSR) kernels launch");
     prof_record(slot, 1, st);
     rc = launch_projection(p, nsm, st);
     if (rc != INF_OK) return rc;
     prof_record(slot, 2, st);
-    e = launch_field_rays(p, true, grid1, st);
+    e = launch_field_rays(p, true, env().rays_slots, grid1, st);
     if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<train> launch");
     prof_record(slot, 3, st);
-    e = launch_vertex_gather(p, nsm, st);
+    // vertex gradient on the side stream (after the incidence lists, which are already queued there), concurrently with
+    // the hidden-slice weight gradients on the caller's stream; the big slices ([dW0;dWy] = G^T E) wait for it
+    cudaStream_t gs = st;
+    if (side != nullptr && !split) {   // the incidence lists are complete before the gather starts on the caller's stream
+      e = cudaStreamWaitEvent(st, side->join, 0);
+      if (e != cudaSuccess) return cuda_fail(e, "stream join");
+    }
+    if (side != nullptr && split) {
+      e = cudaEventRecord(side->fork, st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
+      if (e != cudaSuccess) return cuda_fail(e, "stream fork");
+      gs = side->stream;
+    }
+    e = launch_vertex_gather(p, nsm, gs);
     if (e != cudaSuccess) return cuda_fail(e, "vertex_gather_kernel launch");
+    if (split) {
+      FieldParams ph = p;
+      ph.cta_base = grid_big;
+      ph.wg_cluster = 1;
+      e = launch_field_wgrad(ph, used, st);
+      if (e != cudaSuccess) return cuda_fail(e, "field_wgrad_kernel (hidden slices) launch");
+    }
     prof_record(slot, 4, st);
+    if (side != nullptr && split) {
+      e = cudaEventRecord(side->join, side->stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
+      if (e != cudaSuccess) return cuda_fail(e, "stream join");
+    }
   } else {
     prof_record(slot, 1, st);
     prof_record(slot, 2, st);
@@ -624,7 +736,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     prof_record(slot, 3, st);
     prof_record(slot, 4, st);
   }
-  e = launch_field_wgrad(p, grid2, st);
+  e = launch_field_wgrad(p, split ? grid_big : grid2, st);   // split: the big slices only (cta_base = 0)
   prof_record(slot, 5, st);
   if (e != cudaSuccess) return cuda_fail(e, "field_wgrad_kernel launch");
 
@@ -637,7 +749,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   rp.part1 = p.part1;
   rp.flat = g->flat;
   rp.loss_sums = (t->target != nullptr) ? g->loss_sums : nullptr;
-  rp.ncta1 = vp ? grid1 * field_rays_slots() : grid1;   // rows of the forward/backward kernel's partials
+  rp.ncta1 = vp ? grid1 * env().rays_slots : grid1;   // rows of the forward/backward kernel's partials
   rp.groups_big = gb;
   int base = geo.nbig * gb;
   for (int s = 0; s < MAX_HID_SLICES; ++s) {

@@ -17,7 +17,8 @@ constexpr int HALF_PANEL = 64 * 128;          // 8 KB: 64 rows of a panel
 constexpr int DZLT_BYTES = 4096;              // [16 x 128 rays] fp16, K-major: two [16 x 64] panels
 constexpr int OUT_DIM = 3;       // RGB_COLOR_DIM, model.py:9
 constexpr float DZ_SCALE = 32.f; // backward signals are carried x32 in fp16 (range centring)
-constexpr int MAX_CTAS = 160;    // sizing bound for per-CTA partials (B200: 148 SMs)
+constexpr int MAX_CTAS = 160;    // sizing bound for per-CTA partials of one launch (B200: 148 SMs)
+constexpr int MAX_WGRAD_CTAS = 2 * MAX_CTAS;   // the vertex path runs the hidden and the big slices as two launches
 constexpr int MAX_MMA_LAYERS = 8;  // MMA layers 0..nb, nb <= 7
 constexpr int K1_PART_FLOATS = 8;  // per-CTA partials of the forward/backward kernel: gb[3], pad, loss sums[2]
 constexpr int WG_COLS = 512;     // TMEM columns = accumulator columns of a wgrad CTA
@@ -143,7 +144,7 @@ __host__ inline WorkspaceLayout workspace_layout(const Geo& g, int64_t n_rays, b
   const int64_t ntiles = (n_rays + TILE_M - 1) / TILE_M;
   if (training) {
     w.stash_off = take(static_cast<size_t>(ntiles) * stash_tile_bytes(g));
-    w.partw_off = take(static_cast<size_t>(MAX_CTAS) * WG_COLS * HID * 4);
+    w.partw_off = take(static_cast<size_t>(n_rows > 0 ? MAX_WGRAD_CTAS : MAX_CTAS) * WG_COLS * HID * 4);
     w.part1_off = take(static_cast<size_t>(2 * MAX_CTAS) * K1_PART_FLOATS * 4);
   }
   if (n_rows > 0) {
@@ -262,6 +263,7 @@ struct FieldParams {
   int64_t n_rows;                   // V
   int ntiles_v;                     // ceil(V / 128)
   size_t stash_stride;              // bytes per ray tile of the activation stash
+  int cta_base;                     // wgrad: index of this launch's first CTA in the combined (big slices, hidden slices) CTA space
   int groups_big;                   // wgrad: ray groups (CTAs) per big slice
   int groups_hid[MAX_HID_SLICES];   // wgrad: ray groups (CTAs) per hidden slice
   Geo geo;

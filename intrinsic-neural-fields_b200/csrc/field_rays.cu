@@ -9,13 +9,15 @@
 // tiles' MMAs, and the two epilogue warpgroups overlap each other and the other tile's MMA.
 //
 //   warps 0..3 / 4..7   slot 0 / slot 1: gather + interpolation of the tile's rays (lane = 16-byte chunk of a P row),
-//                       layer-0 bias + ReLU -> fp16 activation panel, zy -> fp16 panel (added in the skip layer's
+//                       layer-0 bias + ReLU -> fp16 activation image X, zy -> fp16 image Y (added in the skip layer's
 //                       epilogue); then per layer TMEM -> registers -> bias/ReLU -> next A operand; output layer,
-//                       sigmoid, L1 gradient and the dgrad epilogues as in field_main.cu; when training every h_l / dz_l
-//                       tile is bulk-stored to the stash (hidden weight gradients: field_wgrad.cu; dz_0 / dz_skip also
-//                       feed the vertex gradient G, vertex_grad.cu)
+//                       sigmoid, L1 gradient and the dgrad epilogues; the backward chain ping-pongs between X and Y so
+//                       that no step waits for the stash store of the image it overwrites
 //   warp 8              chain issuer (+ TMEM allocator): per layer step, the MMAs of both slots from one weight stage
 //   warp 9              weight loader: 32 KB hidden / view-branch operand images through a 2-stage ring
+//   warps 10 / 11       training: stash writers of slot 0 / 1 -- every h_l / dz_l image is bulk-stored to the stash
+//                       (hidden weight gradients: field_wgrad.cu; dz_0 / dz_skip also feed the vertex gradient G,
+//                       vertex_grad.cu) off the epilogue's critical path
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -23,41 +25,47 @@ namespace inf {
 
 namespace {
 
-constexpr int RY_SLOTS = 2;
-constexpr int RY_EPI_WARPS = 4 * RY_SLOTS;
-constexpr int RY_W_CH = RY_EPI_WARPS;
-constexpr int RY_W_LD = RY_EPI_WARPS + 1;
-constexpr int RY_THREADS = (RY_EPI_WARPS + 2) * 32;
+// Two flavours of the same kernel (template parameter kSlots):
+//   2  one CTA per SM running two tiles in lockstep (one weight stage feeds both tiles' MMAs), 12 warps
+//   1  two CTAs per SM, one tile each, 8 warps: the CTAs drift apart, so one's gather overlaps the other's chain
+constexpr int RY_SLOTS = 2;   // maximum (sizes the barrier table)
+__host__ __device__ constexpr int ry_threads(int slots) { return (4 * slots + 4) * 32; }
+// registers: launch value 168 x 384 (or 128 x 256, two CTAs per SM); the epilogue warpgroups grow to 200, the utility
+// warpgroup shrinks to 40
+constexpr int RY_REGS_EPI = 200, RY_REGS_UTIL = 40;
 constexpr int RY_WG_THREADS = 128;
-constexpr int RY_NSTAGE_W = 2;
 
 struct RySmem {
   uint32_t h, zy, w, dzlt, bias, wlast, red, bars, tmemptr, total;
 };
-__host__ __device__ constexpr RySmem ry_smem(bool train) {
+__host__ __device__ constexpr RySmem ry_smem(bool train, int slots) {
   RySmem s{};
-  s.h = 0;                                                   // [2] activation images (32 KB each)
-  s.zy = s.h + RY_SLOTS * BLOB_BYTES;                        // [2] skip-branch term zy as fp16 image; view: Fourier panel after the skip layer
-  s.w = s.zy + RY_SLOTS * BLOB_BYTES;                        // weight ring
-  s.dzlt = s.w + RY_NSTAGE_W * BLOB_BYTES;                   // [2] dzl^T tiles (training)
-  s.bias = s.dzlt + (train ? RY_SLOTS * DZLT_BYTES : 0u);    // f32 [MAX_MMA_LAYERS][128]
+  s.h = 0;                                                   // [slots] activation images X (32 KB each)
+  s.zy = s.h + slots * BLOB_BYTES;                           // [slots] images Y: skip-branch term zy; view: Fourier panel; backward ping-pong
+  s.w = s.zy + slots * BLOB_BYTES;                           // weight ring, `slots` stages
+  s.dzlt = s.w + slots * BLOB_BYTES;                         // [slots] dzl^T tiles (training)
+  s.bias = s.dzlt + (train ? slots * DZLT_BYTES : 0u);       // f32 [MAX_MMA_LAYERS][128]
   s.wlast = s.bias + MAX_MMA_LAYERS * HID * 4;               // f32 [3][128] + blast[4]
-  s.red = s.wlast + OUT_DIM * HID * 4 + 16;                  // f32 [2][24]
-  s.bars = s.red + RY_SLOTS * 96;
+  s.red = s.wlast + OUT_DIM * HID * 4 + 16;                  // f32 [slots][24]
+  s.bars = s.red + slots * 96;
   s.tmemptr = s.bars + 32 * 8;
   s.total = s.tmemptr + 16;
   return s;
 }
-static_assert(ry_smem(true).total <= 232448, "shared memory budget");
+static_assert(ry_smem(true, 2).total <= 232448 && 2 * (ry_smem(true, 1).total + 1024) <= 233472, "shared memory budget");
 
 constexpr int RB_ACT_READY = 0;                    // [2] activation image of the slot written (A operand of the next step)
 constexpr int RB_MMA_DONE = RB_ACT_READY + RY_SLOTS;   // [2] the slot's accumulator is complete
-constexpr int RB_H_FREE = RB_MMA_DONE + RY_SLOTS;      // [2] training: the stash store has finished reading the activation image
-constexpr int RB_W_FULL = RB_H_FREE + RY_SLOTS;        // [stages]
-constexpr int RB_W_EMPTY = RB_W_FULL + RY_NSTAGE_W;
-static_assert(RB_W_EMPTY + RY_NSTAGE_W <= 32, "barrier table overflow");
+constexpr int RB_FREE_X = RB_MMA_DONE + RY_SLOTS;      // [2] training: the stash store has finished reading image X of the slot
+constexpr int RB_FREE_Y = RB_FREE_X + RY_SLOTS;        // [2] ... image Y
+// [2][2] an image of the slot is ready to be stashed.  Requests alternate between two barriers: an mbarrier must not
+// complete two phases before its waiter has observed the first, and request i+2 is only ever posted after the image of
+// request i was handed back (FREE_X / FREE_Y), i.e. after the stash writer consumed request i.
+constexpr int RB_STASH_REQ = RB_FREE_Y + RY_SLOTS;
+constexpr int RB_W_FULL = RB_STASH_REQ + 2 * RY_SLOTS; // [stages]
+constexpr int RB_W_EMPTY = RB_W_FULL + RY_SLOTS;
+static_assert(RB_W_EMPTY + RY_SLOTS <= 32, "barrier table overflow");
 
-constexpr uint32_t RY_TMEM_COLS = 256;   // one 128-column accumulator per slot
 constexpr uint32_t RY_IDESC_N128 = umma_idesc_f16(128, 128, 0, 0);
 constexpr uint32_t RY_IDESC_N128_BMN = umma_idesc_f16(128, 128, 0, 1);
 constexpr uint32_t RY_DESC_HI = umma_desc_hi(1024);
@@ -111,28 +119,45 @@ __device__ __forceinline__ float ry_fourier(int idx, float x0, float x1, float x
   return 0.f;
 }
 
+template <int N>
+__device__ __forceinline__ void ry_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void ry_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 }  // namespace
 
-template <bool kTrain>
-__global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldParams p) {
+template <bool kTrain, int kSlots>
+__global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field_rays_kernel(const FieldParams p) {
+  constexpr int RY_THREADS = ry_threads(kSlots);
+  constexpr int RY_EPI_WARPS = 4 * kSlots;
+  constexpr int RY_W_CH = RY_EPI_WARPS, RY_W_LD = RY_EPI_WARPS + 1, RY_W_ST = RY_EPI_WARPS + 2;   // stash writer: + slot
+  constexpr int RY_NSTAGE_W = kSlots;
+  constexpr uint32_t RY_TMEM_COLS = 128u * kSlots;   // one 128-column accumulator per slot
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Geo g = p.geo;
   const bool view = g.view != INF_VIEW_NONE;
-  const RySmem sm = ry_smem(kTrain);
+  const RySmem sm = ry_smem(kTrain, kSlots);
   const int nb = g.nb, nhid = g.nhid;
   auto bar = [&](int i) -> uint32_t { return smem_base + sm.bars + 8u * static_cast<uint32_t>(i); };
+  // measurement only (INF_DEBUG & 8): per-role cycle accounting of CTA 0 (scripts/trace_rays.py)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto now = [&]() -> long long { return tracing ? clock64() : 0ll; };
+  auto put = [&](int slot_, long long v) { if (tracing) p.trace[slot_] = static_cast<unsigned long long>(v); };
 
   if ((smem_base & 1023u) != 0) {
     if (tid == 0 && p.err) atomicExch(p.err, 0xBAD00004u);
     return;
   }
   if (tid == 0) {
-    for (int s = 0; s < RY_SLOTS; ++s) {
+    for (int s = 0; s < kSlots; ++s) {
       mbar_init(bar(RB_ACT_READY + s), 1);
       mbar_init(bar(RB_MMA_DONE + s), 1);
-      mbar_init(bar(RB_H_FREE + s), 1);
+      mbar_init(bar(RB_FREE_X + s), 1);
+      mbar_init(bar(RB_FREE_Y + s), 1);
+      mbar_init(bar(RB_STASH_REQ + 2 * s), 1);
+      mbar_init(bar(RB_STASH_REQ + 2 * s + 1), 1);
     }
     for (int i = 0; i < RY_NSTAGE_W; ++i) { mbar_init(bar(RB_W_FULL + i), 1); mbar_init(bar(RB_W_EMPTY + i), 1); }
     mbar_fence_init();
@@ -154,7 +179,7 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
     }
     if (kTrain) {
       uint32_t* dz = reinterpret_cast<uint32_t*>(smem + sm.dzlt);   // rows 3..15 of both dzl^T tiles stay zero
-      for (int i = tid; i < RY_SLOTS * DZLT_BYTES / 4; i += RY_THREADS) dz[i] = 0u;
+      for (int i = tid; i < kSlots * DZLT_BYTES / 4; i += RY_THREADS) dz[i] = 0u;
     }
   }
   fence_proxy_async_smem();
@@ -164,7 +189,7 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + sm.tmemptr);
 
   const int ntiles = p.ntiles;
-  const int npairs = (ntiles + RY_SLOTS - 1) / RY_SLOTS;
+  const int npairs = (ntiles + kSlots - 1) / kSlots;
   const size_t tile_stride = p.stash_stride;
   const uint64_t stash_policy = 0ull;   // the stash is re-read by the wgrad / vertex-gradient kernels right after this launch
 
@@ -185,7 +210,9 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
     return blob_hidden(g, l);
   };
 
-  if (warp == RY_W_LD) {
+  if (warp >= RY_EPI_WARPS) {
+   ry_setmaxnreg_dec<RY_REGS_UTIL>();
+   if (warp == RY_W_LD) {
     // =========================== weight loader ==============================================
     if (lane == 0) {
       int stage = 0;
@@ -202,12 +229,14 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
         }
       }
     }
-  } else if (warp == RY_W_CH) {
+   } else if (warp == RY_W_CH) {
     // =========================== chain issuer ===============================================
     if (lane == 0) {
       int stage = 0;
       uint32_t wph = 0;
-      uint32_t aph[RY_SLOTS] = {0u, 0u};
+      uint32_t aph[2] = {0u, 0u};
+      long long t_w = 0, t_act = 0;
+      const long long t_ch0 = now();
       // D[128 x 128] (+)= A[128 x 64*npanel] * B^T, both K-major panel images
       auto mma_fwd = [&](uint32_t dcol, uint32_t abase, uint32_t bbase, int npanel, bool acc_first) {
         const uint32_t alo = umma_desc_lo(abase, 0), blo = umma_desc_lo(bbase, 0);
@@ -231,26 +260,32 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
         }
       };
       for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        const int nslot = (pair * RY_SLOTS + 1 < ntiles) ? 2 : 1;
+        const int nslot = (kSlots == 2 && pair * kSlots + 1 < ntiles) ? 2 : 1;
         for (int st = 0; st < steps_all; ++st) {
+          const long long tw0 = now();
           mbar_wait(bar(RB_W_FULL + stage), wph, p.err, 0xB1);
+          t_w += now() - tw0;
           tc_fence_after();
           const uint32_t bbase = smem_base + sm.w + static_cast<uint32_t>(stage) * BLOB_BYTES;
           const bool fourier = view && st == nhid + 1;   // second half of the view layer: no new activation, same accumulator
           const bool view_z = view && st == nhid;        // first half: the accumulator is completed by the Fourier part
           for (int s = 0; s < nslot; ++s) {
             const uint32_t dcol = tmem_base + 128u * static_cast<uint32_t>(s);
-            const uint32_t hbase = smem_base + sm.h + static_cast<uint32_t>(s) * BLOB_BYTES;
+            const uint32_t ximg = smem_base + sm.h + static_cast<uint32_t>(s) * BLOB_BYTES;
+            const uint32_t yimg = smem_base + sm.zy + static_cast<uint32_t>(s) * BLOB_BYTES;
             if (!fourier) {
+              const long long ta0 = now();
               mbar_wait(bar(RB_ACT_READY + s), aph[s], p.err, 0xB2);
+              t_act += now() - ta0;
               aph[s] ^= 1u;
               tc_fence_after();
             }
             if (st < steps_fwd) {
-              if (fourier) mma_fwd(dcol, smem_base + sm.zy + static_cast<uint32_t>(s) * BLOB_BYTES, bbase, 1, true);
-              else mma_fwd(dcol, hbase, bbase, 2, false);
+              if (fourier) mma_fwd(dcol, yimg, bbase, 1, true);
+              else mma_fwd(dcol, ximg, bbase, 2, false);
             } else {
-              mma_dgrad(dcol, hbase, bbase);
+              // the backward chain ping-pongs: dz_nb sits in Y, dz_{nb-1} in X, ...
+              mma_dgrad(dcol, ((st - steps_fwd) & 1) ? ximg : yimg, bbase);
             }
             if (!view_z) umma_commit(bar(RB_MMA_DONE + s));
           }
@@ -258,51 +293,104 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
           if (++stage == RY_NSTAGE_W) { stage = 0; wph ^= 1u; }
         }
       }
+      put(0, now() - t_ch0); put(1, t_w); put(2, t_act);
     }
+   } else if (kTrain && warp < RY_W_ST + kSlots) {
+    // =========================== stash writer of slot (warp - RY_W_ST) ==========================
+    // Mirrors the epilogue's sequence of finished images; every request is one bulk store (two where noted) whose
+    // shared-memory read is waited for HERE, then the image is handed back (FREE_X / FREE_Y).
+    if (lane == 0) {
+      const int slot = warp - RY_W_ST;
+      const uint32_t ximg = smem_base + sm.h + static_cast<uint32_t>(slot) * BLOB_BYTES;
+      const uint32_t yimg = smem_base + sm.zy + static_cast<uint32_t>(slot) * BLOB_BYTES;
+      const uint32_t dzlt = smem_base + sm.dzlt + static_cast<uint32_t>(slot) * DZLT_BYTES;
+      uint32_t nreq = 0;   // running request index: barrier nreq & 1, phase (nreq >> 1) & 1
+      auto req = [&]() { mbar_wait(bar(RB_STASH_REQ + 2 * slot + static_cast<int>(nreq & 1u)), (nreq >> 1) & 1u, p.err, 0xD0); ++nreq; };
+      auto done = [&](bool x, bool y) {
+        bulk_commit();
+        bulk_wait_read<0>();
+        if (x) mbar_arrive(bar(RB_FREE_X + slot));
+        if (y) mbar_arrive(bar(RB_FREE_Y + slot));
+      };
+      for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int tile = pair * kSlots + slot;
+        if (tile >= ntiles) break;
+        uint8_t* st = p.stash + static_cast<size_t>(tile) * tile_stride;
+        for (int l = 0; l < nb; ++l) {            // h_l from X (+ the Fourier panel from Y with the last of them)
+          req();
+          bulk_s2g_hint(st + stash_off_h(g, l), ximg, BLOB_BYTES, stash_policy);
+          const bool e = view && l == nb - 1;
+          if (e) bulk_s2g_hint(st + stash_off_e(g), yimg, PANEL_BYTES, stash_policy);
+          done(true, e);
+        }
+        req();                                      // h_nb from X, dz_nb from Y, dzl^T: one request
+        bulk_s2g_hint(st + stash_off_h(g, nb), ximg, BLOB_BYTES, stash_policy);
+        bulk_s2g_hint(st + stash_off_dz(g, nb), yimg, BLOB_BYTES, stash_policy);
+        bulk_s2g_hint(st + stash_off_dzlt(g), dzlt, DZLT_BYTES, stash_policy);
+        done(true, true);
+        for (int i = 0; i < nb; ++i) {              // dz_{nb-1-i} from X (i even) / Y (i odd)
+          req();
+          bulk_s2g_hint(st + stash_off_dz(g, nb - 1 - i), (i & 1) ? yimg : ximg, BLOB_BYTES, stash_policy);
+          done(!(i & 1), (i & 1) != 0);
+        }
+      }
+      bulk_wait<0>();   // stash stores fully written before the grid completes
+    }
+   }
   } else {
     // =========================== gather + epilogue warpgroups ==================================
+    ry_setmaxnreg_inc<RY_REGS_EPI>();
     const int slot = warp >> 2;                 // warpgroup = tile slot
     const int wq = warp & 3;                    // TMEM lane quarter of this warp
     const int r = tid - slot * RY_WG_THREADS;   // tile row == TMEM lane
     const uint32_t tb = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + 128u * static_cast<uint32_t>(slot);
-    const uint32_t himg = smem_base + sm.h + static_cast<uint32_t>(slot) * BLOB_BYTES;
-    const uint32_t zyimg = smem_base + sm.zy + static_cast<uint32_t>(slot) * BLOB_BYTES;
+    const uint32_t ximg = smem_base + sm.h + static_cast<uint32_t>(slot) * BLOB_BYTES;
+    const uint32_t yimg = smem_base + sm.zy + static_cast<uint32_t>(slot) * BLOB_BYTES;
     const uint32_t dzlt = sm.dzlt + static_cast<uint32_t>(slot) * DZLT_BYTES;
     const float* s_bias = reinterpret_cast<const float*>(smem + sm.bias);
     const float* s_wlast = reinterpret_cast<const float*>(smem + sm.wlast);
     const float* s_blast = s_wlast + OUT_DIM * HID;
     const uint32_t bar_id = 1u + static_cast<uint32_t>(slot);
-    uint32_t pdone = 0, pfree = 0;
+    uint32_t pdone = 0, pfx = 0, pfy = 0, nreq = 0;
+    bool stored_x = false, stored_y = false;   // a stash store of the image is outstanding (training)
     float loss_abs = 0.f, loss_sq = 0.f;
     float gb[3] = {0.f, 0.f, 0.f};
     uint32_t mk[MAX_MMA_LAYERS][4];   // ReLU masks of this row (local memory; indexed by layer)
 
+    long long t_done = 0, t_free = 0, t_sync = 0, t_gather = 0, t_fwd = 0, t_final = 0, t_bwd = 0;
+    const long long t_epi0 = now();
     auto wait_done = [&]() {
+      const long long t0 = now();
       mbar_wait(bar(RB_MMA_DONE + slot), pdone, p.err, 0xC0); pdone ^= 1u; tc_fence_after();
-      if (kTrain) { mbar_wait(bar(RB_H_FREE + slot), pfree, p.err, 0xC1); pfree ^= 1u; }
+      t_done += now() - t0;
+    };
+    // before an image is overwritten: its stash store (if any) has finished reading it
+    auto free_x = [&]() {
+      if (kTrain && stored_x) { const long long t0 = now(); mbar_wait(bar(RB_FREE_X + slot), pfx, p.err, 0xC1); pfx ^= 1u; stored_x = false; t_free += now() - t0; }
+    };
+    auto free_y = [&]() {
+      if (kTrain && stored_y) { const long long t0 = now(); mbar_wait(bar(RB_FREE_Y + slot), pfy, p.err, 0xC2); pfy ^= 1u; stored_y = false; t_free += now() - t0; }
     };
     auto sync_epi = [&]() {
+      const long long t0 = now();
       fence_proxy_async_smem();
       tc_fence_before();
       named_bar_sync(bar_id, RY_WG_THREADS);
+      t_sync += now() - t0;
     };
-    // thread 0 of the warpgroup: publish the activation image (stash store when training), release the MMA
-    auto publish = [&](uint8_t* dst0, uint32_t src0, uint32_t bytes0, uint8_t* dst1, uint32_t src1, uint32_t bytes1, bool arrive_act) {
+    // after sync_epi: hand the finished image(s) to the stash writer (training) and / or release the next MMA
+    auto publish = [&](bool x, bool y, bool arrive_act) {
       if (kTrain) {
-        if (dst0 != nullptr) bulk_s2g_hint(dst0, src0, bytes0, stash_policy);
-        if (dst1 != nullptr) bulk_s2g_hint(dst1, src1, bytes1, stash_policy);
-        bulk_commit();
+        stored_x = stored_x || x;
+        stored_y = stored_y || y;
+        if (r == 0) mbar_arrive(bar(RB_STASH_REQ + 2 * slot + static_cast<int>(nreq & 1u)));
+        ++nreq;
       }
-      if (arrive_act) mbar_arrive(bar(RB_ACT_READY + slot));
-      if (kTrain) {
-        bulk_wait_read<0>();   // overlaps the MMA that reads the same image
-        mbar_arrive(bar(RB_H_FREE + slot));
-      }
+      if (arrive_act && r == 0) mbar_arrive(bar(RB_ACT_READY + slot));
     };
 
-    bool first_tile = true;
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int tile = pair * RY_SLOTS + slot;
+      const int tile = pair * kSlots + slot;
       if (tile >= ntiles) break;   // odd tile count: slot 1 sits out the last pair
       const int64_t ray = static_cast<int64_t>(tile) * TILE_M + r;
       const bool valid = ray < p.n_rays;
@@ -310,11 +398,11 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
       if (valid && p.ridx != nullptr)
         src = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[ray])
                        : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[ray]);
-      uint8_t* stash_tile = kTrain ? p.stash + static_cast<size_t>(tile) * tile_stride : nullptr;
 
       // ---- gather + interpolate: [z0 | zy] = sum_j bary_j P[v_j] ------------------------------------
-      // Every lane keeps the metadata of ray 32*wq + lane; the warp then walks its 32 rays, lane = 16-byte chunk of the
-      // 512-byte P rows (fully coalesced), RU rays in flight.
+      // Every lane keeps the metadata of ray 32*wq + lane; the warp then walks its 32 rays, lane = 32-byte block of the
+      // two 512-byte plane rows of a vertex (fully coalesced), RU rays = 6 RU 16-byte loads in flight per lane.
+      const long long tg0 = now();
       uint32_t myv[3] = {0u, 0u, 0u};
       float myb[3] = {0.f, 0.f, 0.f};
       if (valid) {
@@ -326,17 +414,16 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
           myb[j] = p.bary[e];
         }
       }
-      if (kTrain && !first_tile) { mbar_wait(bar(RB_H_FREE + slot), pfree, p.err, 0xC2); pfree ^= 1u; }   // dz_0 has left the image
-      first_tile = false;
+      free_x();   // the previous tile's last dz image has left X / Y
+      free_y();
       {
-        constexpr int RU = 4;
+        constexpr int RU = 8;   // rays (= 3 RU 16-byte loads per lane) in flight: the gather is bound by bytes in flight
         const bool z0_lane = lane < 16;
-        // bias of layer 0 for this lane's 8 columns (z0 lanes only)
-        float b0[8];
+        const uint32_t blk = static_cast<uint32_t>(lane & 15);      // 8 columns of the 128-column half
+        float b0[8];   // bias of layer 0 for this lane's columns (z0 lanes only)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b0[i] = z0_lane ? s_bias[8 * lane + i] : 0.f;
-        const uint32_t dst_img = z0_lane ? himg : zyimg;
-        const uint32_t cchunk = static_cast<uint32_t>(lane & 15);   // 16-byte chunk of the 128-column half
+        for (int i = 0; i < 8; ++i) b0[i] = z0_lane ? s_bias[8 * blk + i] : 0.f;
+        const uint32_t dst_img = (z0_lane ? ximg : yimg) + (blk >> 3) * PANEL_BYTES;
         for (int rr0 = 0; rr0 < 32; rr0 += RU) {
           uint4 q[RU][3];
           float w[RU][3];
@@ -370,28 +457,29 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
 #pragma unroll
               for (int i = 0; i < 4; ++i) o[i] = pack_half2_sat(acc[2 * i], acc[2 * i + 1]);
             }
-            const int row = 32 * wq + rr0 + u;
-            const uint32_t addr = dst_img + (cchunk >> 3) * PANEL_BYTES + static_cast<uint32_t>(row) * 128u +
-                                  (((cchunk & 7u) ^ (static_cast<uint32_t>(row) & 7u)) << 4);
-            st_shared_v4(addr, o[0], o[1], o[2], o[3]);
+            const uint32_t row = static_cast<uint32_t>(32 * wq + rr0 + u);
+            st_shared_v4(dst_img + row * 128u + (((blk & 7u) ^ (row & 7u)) << 4), o[0], o[1], o[2], o[3]);
           }
         }
       }
       sync_epi();
       if (kTrain) {
-        // ReLU mask of layer 0 for this thread's row, read back from the image the warp just wrote
+        // ReLU mask of layer 0 for this thread's row, read back from the image the warps just wrote
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
           uint32_t w[16];
-          ry_load_words(himg, r, cb, w);
+          ry_load_words(ximg, r, cb, w);
           mk[0][cb] = ry_relu_mask16(w);
         }
       }
-      if (r == 0) publish(kTrain ? stash_tile + stash_off_h(g, 0) : nullptr, himg, BLOB_BYTES, nullptr, 0u, 0u, true);
+      publish(true, false, true);   // h_0
+      t_gather += now() - tg0;
+      const long long tf0 = now();
 
-      // ---- forward layers 1..nb-1: h_l = relu(z_l + b_l) -> activation image --------------------------
+      // ---- forward layers 1..nb-1: h_l = relu(z_l + b_l) -> image X -----------------------------------
       for (int l = 1; l < nb; ++l) {
         wait_done();
+        free_x();
         const bool is_skip = (l == g.skip);
         uint32_t mbits[4];
 #pragma unroll
@@ -401,7 +489,7 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
           tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(s_bias + l * HID + 32 * cb);
           uint32_t zw[16];
-          if (is_skip) ry_load_words(zyimg, r, cb, zw);   // Lx(h) + Ly(x): the interpolated zy of this row
+          if (is_skip) ry_load_words(yimg, r, cb, zw);   // Lx(h) + Ly(x): the interpolated zy of this row
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -416,13 +504,13 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
             w[2 * i + 1] = pack_half2_relu_sat(a2, a3);
           }
           if (kTrain) mbits[cb] = ry_relu_mask16(w);
-          ry_store_words(himg, r, cb, w);
+          ry_store_words(ximg, r, cb, w);
         }
         if (kTrain) { mk[l][0] = mbits[0]; mk[l][1] = mbits[1]; mk[l][2] = mbits[2]; mk[l][3] = mbits[3]; }
-        if (view && l == nb - 1) {
-          // Fourier features of this ray's view direction (model.py:175-186) -> [128 x 64] panel in the zy buffer, whose
-          // last reader was the skip layer's epilogue (an earlier iteration of this loop, or the tail below when the
-          // skip layer IS layer nb-1: then every thread has read its own zy row above, and writes only its own E row)
+        const bool fourier = view && l == nb - 1;
+        if (fourier) {
+          // Fourier features of this ray's view direction (model.py:175-186) -> [128 x 64] panel in Y, whose last reader
+          // was the skip layer's epilogue (an earlier iteration: skip < nb - 1 with the view branch)
           float x0 = 0.f, x1 = 0.f, x2 = 0.f;
           if (valid) {
             const float dx = p.dirs[src * 3 + 0], dy = p.dirs[src * 3 + 1], dz = p.dirs[src * 3 + 2];
@@ -440,7 +528,7 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
               x0 = dx; x1 = dy; x2 = dz;
             }
           }
-          const uint32_t row = zyimg + static_cast<uint32_t>(r) * 128u;
+          const uint32_t row = yimg + static_cast<uint32_t>(r) * 128u;
           for (int ch = 0; ch < 8; ++ch) {
             float f[8];
             if (8 * ch < g.edim) {
@@ -455,14 +543,15 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
           }
         }
         sync_epi();
-        if (r == 0)
-          publish(kTrain ? stash_tile + stash_off_h(g, l) : nullptr, himg, BLOB_BYTES,
-                  (kTrain && view && l == nb - 1) ? stash_tile + stash_off_e(g) : nullptr, zyimg, PANEL_BYTES, true);
+        publish(true, fourier, true);   // h_l (+ the Fourier panel)
       }
 
+      t_fwd += now() - tf0;
       // ---- layer nb epilogue + output layer (-> 3, sigmoid) on CUDA cores --------------------------------
       {
+        const long long tl0 = now();
         wait_done();
+        free_x();
         const bool is_skip = (nb == g.skip);
         float y[3] = {s_blast[0], s_blast[1], s_blast[2]};
         uint32_t mbits[4];
@@ -476,7 +565,7 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
           const float4* w1 = reinterpret_cast<const float4*>(s_wlast + 1 * HID + 32 * cb);
           const float4* w2 = reinterpret_cast<const float4*>(s_wlast + 2 * HID + 32 * cb);
           uint32_t zw[16];
-          if (is_skip) ry_load_words(zyimg, r, cb, zw);
+          if (is_skip) ry_load_words(yimg, r, cb, zw);
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -495,7 +584,7 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
           }
           if (kTrain) {
             mbits[cb] = ry_relu_mask16(w);
-            ry_store_words(himg, r, cb, w);
+            ry_store_words(ximg, r, cb, w);
           }
         }
 #pragma unroll
@@ -523,18 +612,13 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
               gb[c] += dzl[c];
             }
           }
+          // Y (zy / Fourier panel; the previous tile's dz_nb and dzl^T left with the same store) is free for dz_nb
+          free_y();
           // dzl^T tile [16 x 128 rays] (rows 3..15 stay zero): B operand of the output-layer weight gradient
 #pragma unroll
           for (int c = 0; c < 3; ++c)
             *reinterpret_cast<__half*>(smem + dzlt + static_cast<uint32_t>(r >> 6) * 2048u + sw128_off(c, r & 63)) = __float2half_rn(dzl[c]);
-          // h_nb goes to the stash, then dz_nb takes its place in the activation image
-          sync_epi();
-          if (r == 0) {
-            bulk_s2g_hint(stash_tile + stash_off_h(g, nb), himg, BLOB_BYTES, stash_policy);
-            bulk_commit();
-            bulk_wait_read<0>();
-          }
-          named_bar_sync(bar_id, RY_WG_THREADS);
+          // dz_nb = (dz_last * W_last) masked by relu' -> Y, while h_nb (X) goes to the stash
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
             const float4* w0 = reinterpret_cast<const float4*>(s_wlast + 0 * HID + 32 * cb);
@@ -551,15 +635,19 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
               w[2 * i] = ry_apply_mask(pack_half2_sat(d0, d1), mbits[cb], 2 * i);
               w[2 * i + 1] = ry_apply_mask(pack_half2_sat(d2, d3), mbits[cb], 2 * i + 1);
             }
-            ry_store_words(himg, r, cb, w);
+            ry_store_words(yimg, r, cb, w);
           }
           sync_epi();
-          if (r == 0)
-            publish(stash_tile + stash_off_dz(g, nb), himg, BLOB_BYTES, stash_tile + stash_off_dzlt(g), smem_base + dzlt, DZLT_BYTES, true);
-
-          // ---- dgrad chain: dz_l = dh_l * relu'(z_l), l = nb-1..0 ----------------------------------------
-          for (int lb = nb - 1; lb >= 0; --lb) {
+          publish(true, true, true);   // h_nb (X), dz_nb + dzl^T (Y): one stash request; releases the first dgrad MMA
+          t_final += now() - tl0;
+          const long long tb0 = now();
+          // ---- dgrad chain: dz_l = dh_l * relu'(z_l), l = nb-1..0, alternating X / Y ------------------------
+          for (int i = 0; i < nb; ++i) {
+            const int lb = nb - 1 - i;
+            const bool to_x = (i & 1) == 0;
             wait_done();
+            if (to_x) free_x(); else free_y();
+            const uint32_t dimg = to_x ? ximg : yimg;
             const uint32_t mm[4] = {mk[lb][0], mk[lb][1], mk[lb][2], mk[lb][3]};
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
@@ -568,15 +656,23 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
               tmem_ld_wait();
               uint32_t w[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                w[i] = ry_apply_mask(pack_half2_sat(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), mm[cb], i);
-              ry_store_words(himg, r, cb, w);
+              for (int q = 0; q < 16; ++q)
+                w[q] = ry_apply_mask(pack_half2_sat(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), mm[cb], q);
+              ry_store_words(dimg, r, cb, w);
             }
             sync_epi();
-            if (r == 0) publish(stash_tile + stash_off_dz(g, lb), himg, BLOB_BYTES, nullptr, 0u, 0u, lb > 0);
+            publish(to_x, !to_x, lb > 0);
           }
+          t_bwd += now() - tb0;
+        } else {
+          t_final += now() - tl0;
         }
       }
+    }
+    if (r == 0) {
+      const int o = 8 + 12 * slot;
+      put(o, now() - t_epi0); put(o + 1, t_done); put(o + 2, t_free); put(o + 3, t_sync); put(o + 4, t_gather); put(o + 5, t_fwd);
+      put(o + 6, t_final); put(o + 7, t_bwd);
     }
     if (kTrain) {
       // ---- per-warpgroup partials: output-layer bias gradient, loss sums ------------------------------
@@ -594,14 +690,13 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
       }
       named_bar_sync(bar_id, RY_WG_THREADS);
       if (r == 0) {
-        float* part = p.part1 + static_cast<size_t>(blockIdx.x * RY_SLOTS + slot) * K1_PART_FLOATS;
+        float* part = p.part1 + static_cast<size_t>(blockIdx.x * kSlots + slot) * K1_PART_FLOATS;
         part[0] = s_red[8] + s_red[9] + s_red[10] + s_red[11];
         part[1] = s_red[12] + s_red[13] + s_red[14] + s_red[15];
         part[2] = s_red[16] + s_red[17] + s_red[18] + s_red[19];
         part[3] = 0.f;
         part[4] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
         part[5] = s_red[4] + s_red[5] + s_red[6] + s_red[7];
-        bulk_wait<0>();  // stash stores fully written before the grid completes
       }
     }
     tc_fence_before();
@@ -614,16 +709,19 @@ __global__ void __launch_bounds__(RY_THREADS, 1) field_rays_kernel(const FieldPa
   }
 }
 
-cudaError_t launch_field_rays(const FieldParams& p, bool train, int grid, cudaStream_t stream) {
-  const int smem = static_cast<int>(ry_smem(train).total);
-  cudaError_t e = train ? cudaFuncSetAttribute(field_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                        : cudaFuncSetAttribute(field_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <bool kTrain, int kSlots>
+static cudaError_t launch_rays_one(const FieldParams& p, int grid, cudaStream_t stream) {
+  const int smem = static_cast<int>(ry_smem(kTrain, kSlots).total);
+  cudaError_t e = cudaFuncSetAttribute(field_rays_kernel<kTrain, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  if (train) field_rays_kernel<true><<<static_cast<unsigned>(grid), RY_THREADS, static_cast<size_t>(smem), stream>>>(p);
-  else field_rays_kernel<false><<<static_cast<unsigned>(grid), RY_THREADS, static_cast<size_t>(smem), stream>>>(p);
+  field_rays_kernel<kTrain, kSlots><<<static_cast<unsigned>(grid), ry_threads(kSlots), static_cast<size_t>(smem), stream>>>(p);
   return cudaGetLastError();
 }
 
-int field_rays_slots() { return RY_SLOTS; }
+// slots = 2: one CTA per SM, two tiles in lockstep; slots = 1: two CTAs per SM, one tile each
+cudaError_t launch_field_rays(const FieldParams& p, bool train, int slots, int grid, cudaStream_t stream) {
+  if (slots == 1) return train ? launch_rays_one<true, 1>(p, grid, stream) : launch_rays_one<false, 1>(p, grid, stream);
+  return train ? launch_rays_one<true, 2>(p, grid, stream) : launch_rays_one<false, 2>(p, grid, stream);
+}
 
 }  // namespace inf

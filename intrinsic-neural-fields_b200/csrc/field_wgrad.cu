@@ -53,17 +53,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
     return;
   }
 
-  // CTA -> (slice, ray group): big slices first (groups_big CTAs each), then the hidden slices
+  // CTA -> (slice, ray group): big slices first (groups_big CTAs each), then the hidden slices.  A launch may cover a
+  // sub-range of that CTA space (cta_base): the vertex path launches the hidden slices while the vertex gradient that the
+  // big slices need is still being gathered.
+  const int cta = static_cast<int>(blockIdx.x) + p.cta_base;
   const int nbig_ctas = g.nbig * p.groups_big;
-  const bool big = static_cast<int>(blockIdx.x) < nbig_ctas;
+  const bool big = cta < nbig_ctas;
   int slice, grp, groups;
   if (big) {
     // group-major: the CTAs of one ray group sit next to each other, so a cluster = `cw` slices of the SAME tiles
     groups = p.groups_big;
-    slice = blockIdx.x % g.nbig;
-    grp = blockIdx.x / g.nbig;
+    slice = cta % g.nbig;
+    grp = cta / g.nbig;
   } else {
-    int rel = blockIdx.x - nbig_ctas;
+    int rel = cta - nbig_ctas;
     int hs = 0;
     while (hs < p.plan.nslice - 1 && rel >= p.groups_hid[hs]) { rel -= p.groups_hid[hs]; ++hs; }
     slice = hs;
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
     mbar_wait(bar(BAR_DONE), 0, p.err, 0x80);
     tc_fence_after();
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    float* dst = p.partw + (static_cast<size_t>(blockIdx.x) * HID + tid) * WG_COLS;
+    float* dst = p.partw + (static_cast<size_t>(cta) * HID + tid) * WG_COLS;
     const int used = big ? 512 : ((p.plan.cols_used[slice] + 31) & ~31);
     for (int c0 = 0; c0 < used; c0 += 32) {
       if (big && (c0 & 255) >= ncols) continue;

@@ -8,10 +8,10 @@
 //   csr_count / csr_scan_* / csr_fill   integer atomics only -- the SET of pairs of a vertex is deterministic, their
 //                                        order inside the list is not;
 //   vertex_gather_kernel                one warp per vertex, lane = 16-byte chunk of the two stashed dz rows of a ray
-//                                        (coalesced 128-byte lines of the swizzled images field_rays.cu stored), products
-//                                        accumulated in 64-bit FIXED POINT (2^-32 quantum, far below fp16 resolution of
-//                                        the operand): integer addition is associative, so the sum -- and with it every
-//                                        gradient -- is bit-identical from run to run whatever the list order.
+//                                        (coalesced 128-byte lines of the swizzled images field_rays.cu stored).  The sum
+//                                        is made independent of the list order -- lists of <= 32 pairs are sorted in
+//                                        registers first, longer ones are accumulated in 64-bit fixed point (integer
+//                                        addition is associative) -- so every gradient is bit-identical from run to run.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -150,6 +150,9 @@ __global__ void csr_fill_kernel(const FieldParams p) {
   }
 }
 
+// Lists of up to 32 pairs (the common case: a vertex is hit ~3 B / V times) are first SORTED by (ray, weight bits) with a
+// warp-wide bitonic network and then summed in that order with plain fp32 FMAs; longer lists are summed in 64-bit fixed
+// point, where the order does not matter.  Either way the result depends on the set of pairs only.
 __global__ void __launch_bounds__(256) vertex_gather_kernel(const FieldParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -161,44 +164,85 @@ __global__ void __launch_bounds__(256) vertex_gather_kernel(const FieldParams p)
   const uint32_t panel = static_cast<uint32_t>(lane & 15) >> 3;
   const uint32_t chunk = static_cast<uint32_t>(lane) & 7u;
   const int64_t v_end = static_cast<int64_t>(p.ntiles_v) * TILE_M;
+  auto row_ptr = [&](int ray) -> const uint4* {
+    const uint32_t row = static_cast<uint32_t>(ray) & 127u;
+    return reinterpret_cast<const uint4*>(p.stash + static_cast<size_t>(ray >> 7) * p.stash_stride + blob_off + panel * PANEL_BYTES + row * 128u +
+                                          ((chunk ^ (row & 7u)) << 4));
+  };
   for (int64_t v = warp0; v < v_end; v += nwarps) {
-    long long acc[8];
+    float f[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0;
-    if (v < p.n_rows) {
-      const int beg = p.vstart[v], end = p.vstart[v + 1];
+    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+    const int beg = v < p.n_rows ? p.vstart[v] : 0, end = v < p.n_rows ? p.vstart[v + 1] : 0;
+    const int n = end - beg;
+    if (n > 0 && n <= 32) {
+      // ---- sort the list (one pair per lane; empty lanes sort to the end), then sum in order ----------------
+      int2 mine = lane < n ? pairs[beg + lane] : make_int2(0x7FFFFFFF, 0);
+      unsigned long long key = (static_cast<unsigned long long>(static_cast<uint32_t>(mine.x)) << 32) | static_cast<uint32_t>(mine.y);
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+          const bool up = (lane & k) == 0;              // ascending block
+          const bool lower = (lane & j) == 0;           // this lane keeps the smaller of the pair when ascending
+          const bool take_min = (up == lower);
+          key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+        }
+      }
+      for (int u0 = 0; u0 < n; u0 += 4) {
+        uint4 q[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned long long ku = __shfl_sync(0xffffffffu, key, (u0 + u) & 31);
+          w[u] = (u0 + u < n) ? __uint_as_float(static_cast<uint32_t>(ku)) : 0.f;
+          q[u] = (u0 + u < n) ? *row_ptr(static_cast<int>(ku >> 32)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t vv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&vv[i]));
+            f[2 * i] = fmaf(w[u], h.x, f[2 * i]);
+            f[2 * i + 1] = fmaf(w[u], h.y, f[2 * i + 1]);
+          }
+        }
+      }
+    } else if (n > 32) {
+      // ---- long list: 64-bit fixed point (2^-32 quantum, far below the fp16 resolution of the result) ---------
+      long long acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0;
       for (int e0 = beg; e0 < end; e0 += 32) {
         int2 mine = make_int2(0, 0);
         if (e0 + lane < end) mine = pairs[e0 + lane];
-        const int n = min(32, end - e0);
-        for (int u0 = 0; u0 < n; u0 += 4) {
+        const int m = min(32, end - e0);
+        for (int u0 = 0; u0 < m; u0 += 4) {
           uint4 q[4];
           float w[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int ray = __shfl_sync(0xffffffffu, mine.x, (u0 + u) & 31);
-            w[u] = (u0 + u < n) ? __int_as_float(__shfl_sync(0xffffffffu, mine.y, (u0 + u) & 31)) : 0.f;
-            const uint32_t row = static_cast<uint32_t>(ray) & 127u;
-            const uint8_t* src = p.stash + static_cast<size_t>(ray >> 7) * p.stash_stride + blob_off + panel * PANEL_BYTES + row * 128u +
-                                 ((chunk ^ (row & 7u)) << 4);
-            q[u] = (u0 + u < n) ? *reinterpret_cast<const uint4*>(src) : make_uint4(0u, 0u, 0u, 0u);
+            w[u] = (u0 + u < m) ? __int_as_float(__shfl_sync(0xffffffffu, mine.y, (u0 + u) & 31)) : 0.f;
+            q[u] = (u0 + u < m) ? *row_ptr(ray) : make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const uint32_t vv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vv[i]));
-              acc[2 * i] += __float2ll_rn(w[u] * f.x * 4294967296.f);
-              acc[2 * i + 1] += __float2ll_rn(w[u] * f.y * 4294967296.f);
+              const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&vv[i]));
+              acc[2 * i] += __float2ll_rn(w[u] * h.x * 4294967296.f);
+              acc[2 * i + 1] += __float2ll_rn(w[u] * h.y * 4294967296.f);
             }
           }
         }
       }
-    }
-    float f[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = static_cast<float>(acc[i]) * 2.3283064365386963e-10f;   // 2^-32
+      for (int i = 0; i < 8; ++i) f[i] = static_cast<float>(acc[i]) * 2.3283064365386963e-10f;   // 2^-32
+    }
     const uint32_t row = static_cast<uint32_t>(v) & 127u;
     uint8_t* dst = p.g_image + static_cast<size_t>(v >> 7) * GIMG_TILE_BYTES + (lane < 16 ? 0u : static_cast<uint32_t>(BLOB_BYTES)) +
                    panel * PANEL_BYTES + row * 128u + ((chunk ^ (row & 7u)) << 4);

@@ -280,6 +280,24 @@ __global__ void table_image_kernel(const TableT* __restrict__ table, int64_t n_r
   }
 }
 
+// P as a plain (V, 256) row-major fp16 matrix (inf_project_vertices): undo the per-row chunk permutation
+__global__ void proj_unpermute_kernel(const uint8_t* __restrict__ proj, int64_t n_rows, uint8_t* __restrict__ out) {
+  const int64_t total = n_rows * (PROJ_ROW_BYTES / 16);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t v = i >> 5;
+    const uint32_t q = static_cast<uint32_t>(i & 31);
+    *reinterpret_cast<uint4*>(out + v * PROJ_ROW_BYTES + q * 16) =
+        *reinterpret_cast<const uint4*>(proj + v * PROJ_ROW_BYTES + proj_chunk_off(static_cast<uint32_t>(v), q));
+  }
+}
+void launch_proj_unpermute(const uint8_t* proj, int64_t n_rows, void* out, cudaStream_t stream) {
+  if (n_rows == 0) return;
+  const int64_t want = (n_rows * 32 + 255) / 256;
+  proj_unpermute_kernel<<<static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(proj, n_rows,
+                                                                                                     reinterpret_cast<uint8_t*>(out));
+}
+
 void launch_table_image(const void* table, int table_f16, int64_t n_rows, int k_pad, void* image, cudaStream_t stream) {
   if (n_rows == 0) return;
   const int64_t ntv = (n_rows + TILE_M - 1) / TILE_M;

@@ -494,6 +494,22 @@ def field_adam_pack(flat_grad: torch.Tensor, packed: torch.Tensor, cfg_key: List
     _lib.check(rc, "inf_adam_pack_step")
 
 
+def project_vertices(cfg: FieldConfig, table: "EigenTable", packed: torch.Tensor) -> torch.Tensor:
+    """(V, 256) float16 = [E W0^T | E Wy^T]: layer 0's and the skip branch's pre-activations (no bias) at every vertex --
+    what the vertex path interpolates per ray (csrc/vertex_project.cu)."""
+    img = table.build_image()
+    V = table.n_rows
+    out = torch.empty((V, 2 * HIDDEN), dtype=torch.float16, device=table.device)
+    ws = _workspace(table.device, workspace_bytes(cfg, 1, False, V, _lib.PATH_VERTEX))
+    d = _desc(cfg, 1, V, table_f16=table.data.dtype == torch.float16, path=_lib.PATH_VERTEX)
+    t = _lib.InfTensors(table=table.data.data_ptr(), table_image=img.data_ptr(), packed=packed.data_ptr(),
+                        workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+    with torch.cuda.device(table.device):
+        rc = _lib.load().inf_project_vertices(C.byref(d), C.byref(t), C.c_void_p(out.data_ptr()), _stream(table.device))
+    _lib.check(rc, "inf_project_vertices")
+    return out
+
+
 def gather_interpolate_dense(table: "EigenTable", vids: torch.Tensor, bary: torch.Tensor) -> torch.Tensor:
     """get_k_eigenfunc_vec_vals (mesh.py:313-324) as one CUDA kernel: the materialised (B,k) f32 embedding.
     Only for callers that need the dense tensor; the fused path never builds it."""

@@ -283,7 +283,7 @@ def _r16(a: np.ndarray) -> np.ndarray:
 
 def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale=32.0, table_f16=False,
                         view: Optional[dict] = None, unit_ray_dirs=None, hit_face_idxs=None, face_normals=None,
-                        vertex_path: bool = False):
+                        vertex_path: bool = False, proj=None):
     """The reference's forward/backward (model.py:98-112,188-191, trainer.py:76-81) restated in float64 with the
     CUDA path's rounding points: table (optionally), interpolated embedding, weights, hidden activations, the
     Fourier view embedding and backward signals are rounded to fp16 before each matrix product; accumulation
@@ -297,7 +297,9 @@ def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale
     ``vertex_path`` selects the rounding points of the per-vertex evaluation of the two K = k contractions
     (csrc/vertex_project.cu, field_rays.cu, vertex_grad.cu): table rounded to fp16 once (the operand image),
     P = fp16(E16 [W0;Wy]16^T) per vertex, [z0|zy] interpolated from P in fp32, zy rounded to fp16 before it is added in
-    the skip layer; backward G[v] = fp16(sum bary * dz) and [dW0;dWy] = G^T E16.
+    the skip layer; backward G[v] = fp16(sum bary * dz) and [dW0;dWy] = G^T E16.  ``proj`` (V,256) replaces the
+    restated P by the one the device computed (its fp32 accumulation can land on the other side of an fp16 rounding
+    boundary in a few elements, which flips ReLU masks downstream in deep configurations).
     """
     P = {n: t.double().numpy() for n, t in p.items()}
     Ed = E.double().numpy()
@@ -333,6 +335,9 @@ def emulated_fp16_grads(p, E, vids, bary, target, num_layers=6, skip=3, dz_scale
         W0n, _ = names(0)
         Pz0 = _r16(Ed @ _r16(P[W0n]).T)                                   # (V,128) fp16 projected rows
         Pzy = _r16(Ed @ _r16(P[f"{pre}layers.{skip}.Ly.weight"]).T)
+        if proj is not None:
+            proj = np.asarray(proj, dtype=np.float64)
+            Pz0, Pzy = proj[:, :Pz0.shape[1]], proj[:, Pz0.shape[1]:]
 
         def interp(T):   # fp32: w0*t0, then two fma
             a = (b[:, 0:1] * T[vid_np[:, 0]].astype(np.float32)).astype(np.float32)

@@ -165,14 +165,24 @@ def _check_grads(m, ref_grads, tol=GRAD_REL, cos_min=GRAD_COS):
     return worst
 
 
-def _check_grads_emulated(m, case, table_f16=False):
+def _device_proj(m, tab):
+    """On the vertex path the emulation continues from the P the device computed (inf_project_vertices): its fp32
+    accumulation lands on the other side of an fp16 rounding boundary in a handful of elements, which is enough to flip
+    ReLU masks downstream in deep configurations.  P itself is checked against the restatement to one fp16 ulp."""
+    if ops.DEFAULT_PATH != "vertex":
+        return None
+    return ops.project_vertices(m.cfg, tab, m._packed_weights()).float().cpu().numpy()
+
+
+def _check_grads_emulated(m, case, table_f16=False, tab=None):
     kw = {}
     if case.get("view") is not None:
         kw = dict(view=case["view"], unit_ray_dirs=case["unit_ray_dirs"], hit_face_idxs=case["face_idxs"],
                   face_normals=case["face_normals"])
     _, _, g = O.emulated_fp16_grads(case["params"], case["table"], case["vids"], case["bary"], case["target"],
                                     case["num_layers"], case["skip"], table_f16=table_f16,
-                                    vertex_path=(ops.DEFAULT_PATH == "vertex"), **kw)
+                                    vertex_path=(ops.DEFAULT_PATH == "vertex"), proj=None if tab is None else _device_proj(m, tab),
+                                    **kw)
     return _check_grads(m, g, tol=GRAD_REL_EMULATED, cos_min=0.9999)
 
 
@@ -181,7 +191,8 @@ def _check_grads_emulated(m, case, table_f16=False):
 def test_fused_l1_step_matches_reference_golden(name, table_dtype):
     c = load_golden(name)
     m = _model_from(c)
-    sums, pred, flat = m.l1_step(_batch(c, table_dtype))
+    b = _batch(c, table_dtype)
+    sums, pred, flat = m.l1_step(b)
     _check_no_watchdog()
     B = c["target"].shape[0]
     loss = sums[0].item() / (3 * B)
@@ -192,7 +203,7 @@ def test_fused_l1_step_matches_reference_golden(name, table_dtype):
     # the deeper view-branch chain on 96-140 rays amplifies the ReLU-mask flips of a reduced-precision forward
     _check_grads(m, c["grads"], tol=GRAD_REL if c["view"] is None else GRAD_REL_VIEW,
                  cos_min=GRAD_COS if c["view"] is None else GRAD_COS_VIEW)
-    _check_grads_emulated(m, c, table_f16=(table_dtype == "f16"))
+    _check_grads_emulated(m, c, table_f16=(table_dtype == "f16"), tab=b["eigenfunction_table"])
 
 
 def test_autograd_path_matches_fused_step_and_reference():
@@ -293,55 +304,30 @@ PSNR_TOL_DB = 0.1
 
 
 def _training_problem(view, seed=0, V=1500, F_=2500, k=64, N=8192):
-    g = torch.Generator().manual_seed(seed)
-    E = torch.randn(V, k, generator=g)
-    E = (E / (E.max(0, keepdim=True).values - E.min(0, keepdim=True).values)).float()
-    faces = torch.stack([torch.randperm(V, generator=g)[:3] for _ in range(F_)])
-    fid = torch.randint(0, F_, (N,), generator=g)
-    vids = faces[fid]
-    u = torch.rand(N, 3, generator=g)
-    bary = (u / u.sum(-1, keepdim=True)).float()
-    normals = torch.nn.functional.normalize(torch.randn(F_, 3, generator=g), dim=-1)
-    dirs = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1)
-    dirs = torch.where(((-dirs * normals[fid]).sum(-1) < 0)[:, None], -dirs, dirs).float()
-    # smooth procedural colour of the hit point (+ a view-dependent tint when the branch is on)
-    x = O.gather_interpolate(E, vids, bary)
-    mix = torch.randn(k, 3, generator=g) * 1.5
-    logits = x @ mix
-    if view is not None:
-        logits = logits + 0.5 * (-dirs * normals[fid]).sum(-1, keepdim=True)
-    target = torch.sigmoid(logits)
-    return E, vids, bary, target, dirs, fid, normals
+    from psnr_protocols import problem
+    return problem(dict(view=view, V=V, F=F_, k=k, N=N), seed)
 
 
-@pytest.mark.parametrize("view_name", [None, "view_intrinsic"])
-def test_fixed_step_training_psnr_parity(view_name):
+def _psnr_ensemble(name):
+    """PSNRs (and final losses) of the fp32 reference under perturbations of its initial weights the size of fp32
+    summation-order noise (tests/golden/make_psnr_ensemble.py): the reference's own noise floor for this protocol."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    return json.load(open(os.path.join(GOLDEN_DIR, "psnr_ensemble.json")))[name]
+
+
+def _run_protocol(name, fused_adam=False):
+    """Train the protocol's model on the GPU with the committed batch index lists; returns (losses, held-out PSNR)."""
     import types
     from conftest import VIEW_CFGS
     from inf_b200 import trainer
-    view = VIEW_CFGS[view_name] if view_name else None
-    # lr = the shipped configs' 1e-4 (intrinsic_cat.yaml:33).  At 10x that lr the fp32 reference itself moves by 1-2 dB
-    # when its initial weights are perturbed by 1e-3 relative (measured), so no implementation could hold 0.1 dB there.
-    k, L, skip, B, steps, lr = 64, 6, 3, 512, 400, 1e-4
-    E, vids, bary, target, dirs, fid, normals = _training_problem(view)
-    ntrain = 4096
-    params = O.make_params(k, num_layers=L, skip=skip, view=view, seed=5)
-    gi = torch.Generator().manual_seed(9)
-    idx_lists = [torch.randperm(ntrain, generator=gi)[:B] for _ in range(steps)]   # identical batches on both sides
-    kw = dict(num_layers=L, skip=skip)
-    if view is not None:
-        kw.update(view=view, unit_ray_dirs=dirs, hit_face_idxs=fid, face_normals=normals)
-    ref_params, ref_losses = O.adam_train_steps(params, E, vids, bary, target, idx_lists, lr=lr, **kw)
-    hold = slice(ntrain, None)
-    kw_h = dict(kw)
-    if view is not None:
-        kw_h.update(unit_ray_dirs=dirs[hold], hit_face_idxs=fid[hold])
-    with torch.no_grad():
-        pr = O.field_forward(ref_params, E, vids[hold], bary[hold], **kw_h)
-    n_hold = pr.shape[0]
-    psnr_ref = O.epoch_psnr(float(((pr - target[hold]) ** 2).sum()), n_hold)
-
-    cfg = dict(k=k, num_layers=L, mlp_hidden_dim=128, skip_layer_idx=skip)
+    from psnr_protocols import PROTOCOLS, problem, index_lists
+    pr = PROTOCOLS[name]
+    view = VIEW_CFGS[pr["view"]] if pr["view"] else None
+    E, vids, bary, target, dirs, fid, normals = problem(pr)
+    params = O.make_params(pr["k"], num_layers=pr["L"], skip=pr["skip"], view=view, seed=5)
+    cfg = dict(k=pr["k"], num_layers=pr["L"], mlp_hidden_dim=128, skip_layer_idx=pr["skip"])
     mesh = None
     if view is not None:
         cfg["view_dependence"] = view
@@ -349,7 +335,7 @@ def test_fixed_step_training_psnr_parity(view_name):
     m = inf_b200.make_model(cfg, mesh=mesh)
     m.load_state_dict(params)
     m = m.to(DEV)
-    opt = torch.optim.Adam(m.parameters(), lr=lr)
+    opt = trainer.FusedFieldAdam(m, lr=pr["lr"]) if fused_adam else torch.optim.Adam(m.parameters(), lr=pr["lr"])
     tab = inf_b200.EigenTable.from_dense(E, device=DEV)
     dv, db, dt, dd, df = (t.to(DEV) for t in (vids, bary, target, dirs, fid))
 
@@ -362,16 +348,59 @@ def test_fixed_step_training_psnr_parity(view_name):
         return b
 
     losses = []
-    for idx in idx_lists:
-        loss, _ = trainer.train_step(m, opt, batch(idx.to(DEV)))                 # trainer.py:71-84
+    for idx in index_lists(pr):
+        if fused_adam:
+            loss, _ = trainer.fused_train_step_async(m, opt, batch(idx.to(DEV)))
+        else:
+            loss, _ = trainer.train_step(m, opt, batch(idx.to(DEV)))                 # trainer.py:71-84
         losses.append(loss)
+    if fused_adam:
+        losses = [float(x) for x in torch.stack(losses).cpu()]
     _check_no_watchdog()
+    hold = slice(pr["ntrain"], None)
     with torch.no_grad():
-        pg = m(batch(hold)).cpu()
-    psnr_gpu = O.epoch_psnr(float(((pg - target[hold]) ** 2).sum()), n_hold)   # trainer.py:254,263
+        pg = torch.cat([m(batch(slice(lo, min(lo + 16384, pr["N"])))).cpu() for lo in range(pr["ntrain"], pr["N"], 16384)])
+    psnr_gpu = O.epoch_psnr(float(((pg - target[hold]) ** 2).sum()), pg.shape[0])   # trainer.py:254,263
+    # per-ray RGB parity AT THE TRAINED WEIGHTS: the fp32 oracle evaluated with the weights the GPU run ended with
+    sub = torch.arange(pr["ntrain"], pr["N"], max(1, (pr["N"] - pr["ntrain"]) // 2048))
+    kw = dict(num_layers=pr["L"], skip=pr["skip"])
+    if view is not None:
+        kw.update(view=view, unit_ray_dirs=dirs[sub], hit_face_idxs=fid[sub], face_normals=normals)
+    trained = {n: t.detach().cpu() for n, t in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.field_forward(trained, E, vids[sub], bary[sub], **kw)
+    err = (pg[sub - pr["ntrain"]] - ref).abs()
+    assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN, (name, err.max().item(), err.mean().item())
+    return losses, psnr_gpu
+
+
+def _assert_psnr_parity(name, losses, psnr_gpu):
+    ens = _psnr_ensemble(name)
+    lo, hi = min(e["psnr"] for e in ens), max(e["psnr"] for e in ens)
+    base = next(e for e in ens if e["eps"] == 0.0)
     assert losses[-1] < 0.8 * losses[0]                                          # it trained
-    assert abs(losses[-1] - ref_losses[-1]) < 5e-3
-    assert abs(psnr_gpu - psnr_ref) <= PSNR_TOL_DB, (psnr_gpu, psnr_ref)
+    assert abs(losses[-1] - base["final_loss"]) < 5e-3
+    # within 0.1 dB (BASELINE.json) of what the fp32 reference itself produces under fp32-roundoff-sized perturbations
+    assert lo - PSNR_TOL_DB <= psnr_gpu <= hi + PSNR_TOL_DB, (name, psnr_gpu, lo, hi, base["psnr"])
+    return psnr_gpu - base["psnr"]
+
+
+@pytest.mark.parametrize("name", ["small_none", "small_view"])
+def test_fixed_step_training_psnr_parity(name):
+    # lr = the shipped configs' 1e-4 (intrinsic_cat.yaml:33); 400 steps of 512 rays, k = 64.  The plain model's reference
+    # ensemble spans 0.11 dB, the view-dependent model's 0.50 dB (tests/golden/psnr_ensemble.json).
+    losses, psnr_gpu = _run_protocol(name)
+    _assert_psnr_parity(name, losses, psnr_gpu)
+
+
+@pytest.mark.parametrize("name,fused_adam", [("cat_2000", False), ("cat_2000", True), ("view_2000", True)])
+def test_2000_step_training_at_config_scale_psnr_and_rgb_parity(name, fused_adam):
+    # configs[1] at its shipped sizes: k = 1023, V = 50 176, batch 4096, lr 1e-4 (intrinsic_cat.yaml), 2000 optimisation
+    # steps over identical batch index lists; the view-dependent model alike.  After ~1000 steps
+    # the weights have left their initialisation scale -- where SURVEY.md section 7.3 found all-bf16 operands to fail.
+    # Both the torch.optim.Adam step and the optimiser fused into the reduction kernel are covered.
+    losses, psnr_gpu = _run_protocol(name, fused_adam=fused_adam)
+    _assert_psnr_parity(name, losses, psnr_gpu)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -570,8 +599,9 @@ def test_shape_coverage_against_oracle(k, L, skip, view_name):
     assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN, (err.max().item(), err.mean().item())
     assert abs(sums[0].item() / (3 * B) - loss) <= 1e-3
     _check_grads(m, grads, tol=GRAD_REL_VIEW, cos_min=GRAD_COS_VIEW)
-    _, _, ge = O.emulated_fp16_grads(params, E, vids, bary, target, L, skip, **{k_: v for k_, v in kw.items()
-                                                                                  if k_ not in ("num_layers", "skip")})
+    _, _, ge = O.emulated_fp16_grads(params, E, vids, bary, target, L, skip, vertex_path=(ops.DEFAULT_PATH == "vertex"),
+                                     proj=_device_proj(m, b["eigenfunction_table"]),
+                                     **{k_: v for k_, v in kw.items() if k_ not in ("num_layers", "skip")})
     _check_grads(m, ge, tol=GRAD_REL_EMULATED, cos_min=0.9999)
 
 
@@ -789,7 +819,8 @@ def test_randomized_configurations(seed):
     assert abs(sums[0].item() / (3 * B) - loss) <= 1e-3, cs
     ekw = {k_: v for k_, v in kw.items() if k_ not in ("num_layers", "skip")}
     _, _, ge = O.emulated_fp16_grads(params, E, vids[sel], bary[sel], target[sel], L, skip,
-                                     table_f16=(cs["table_dtype"] == "f16"), **ekw)
+                                     table_f16=(cs["table_dtype"] == "f16"), vertex_path=(ops.DEFAULT_PATH == "vertex"),
+                                     proj=_device_proj(m, tab), **ekw)
     # tiny batches leave most gradient entries at a few ulps of fp16 noise: compare the whole flat vector
     got = torch.cat([p.grad.detach().cpu().reshape(-1) for p in m.parameters()])
     ref = torch.cat([torch.from_numpy(ge[n]).float().reshape(-1) for n, _ in m.named_parameters()])

@@ -94,16 +94,18 @@ def test_adam_steps_reduce_loss():
 def test_emulated_precision_restatement_tracks_reference():
     # the oracle's fp16-rounding restatement (what the CUDA kernels compute) stays within the documented
     # few-percent ReLU-kink noise of the fp32 reference gradients and reproduces loss / RGB closely
+    # (both rounding-point sets: per-ray evaluation and per-vertex evaluation of the two K = k contractions)
     for name in ("tf_k64", "tf_k1023", "tf_k100_l5s1"):
         c = load_golden(name)
-        loss, y, g = O.emulated_fp16_grads(c["params"], c["table"], c["vids"], c["bary"], c["target"],
-                                           c["num_layers"], c["skip"])
-        assert abs(loss - c["loss"]) < 1e-4
-        assert np.abs(y - c["pred"].numpy()).max() < 2e-3
-        for n, ref in c["grads"].items():
-            ref = ref.double().numpy().reshape(g[n].shape)
-            rel = np.linalg.norm(g[n] - ref) / (np.linalg.norm(ref) + 1e-12)
-            assert rel < 6e-2, (name, n, rel)
+        for vertex_path in (False, True):
+            loss, y, g = O.emulated_fp16_grads(c["params"], c["table"], c["vids"], c["bary"], c["target"],
+                                               c["num_layers"], c["skip"], vertex_path=vertex_path)
+            assert abs(loss - c["loss"]) < 1e-4
+            assert np.abs(y - c["pred"].numpy()).max() < 2e-3
+            for n, ref in c["grads"].items():
+                ref = ref.double().numpy().reshape(g[n].shape)
+                rel = np.linalg.norm(g[n] - ref) / (np.linalg.norm(ref) + 1e-12)
+                assert rel < 6e-2, (name, vertex_path, n, rel)
 
 
 def test_bake_oracle_agrees_with_the_ray_path_oracle():

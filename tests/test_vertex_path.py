@@ -1,0 +1,178 @@
+"""The per-vertex evaluation of the two K = k contractions (InfDesc.path = VERTEX; csrc/vertex_project.cu, field_rays.cu,
+vertex_grad.cu): host-side rules on the CPU, kernels on the GPU against the oracle's restatement of their rounding points.
+tests/test_gpu_parity.py and tests/test_gpu_configs.py additionally run every one of their cases on both paths."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import field_oracle as O
+
+import inf_b200
+from inf_b200 import _lib, ops
+
+DEV = "cuda:0"
+RGB_MAX, RGB_MEAN = 2e-2, 1e-3      # BASELINE.json north_star tolerances
+
+
+# ---------------------------------------------------------------------------------------------
+# host side (no GPU)
+# ---------------------------------------------------------------------------------------------
+def _uses_vertex(n_rays, n_rows, path, image=True, dense=False):
+    cfg = ops.FieldConfig(k=1023)
+    d = ops._desc(cfg, n_rays, n_rows, path=ops.PATHS[path], dense=dense)
+    t = _lib.InfTensors(table_image=0x1000 if image else None)      # only null-ness is looked at (host-only query)
+    return bool(_lib.load().inf_uses_vertex_path(C.byref(d), C.byref(t)))
+
+
+def test_auto_rule_takes_the_vertex_path_while_rows_are_at_most_twice_the_rays():
+    assert _uses_vertex(131072, 50176, "auto")            # bench workload (configs[1] at 131 072 rays per step)
+    assert not _uses_vertex(4096, 50176, "auto")          # shipped batch_size 4096: far fewer rays than vertices
+    assert not _uses_vertex(131072, 399424, "auto")       # config 4: 400k-row table
+    assert _uses_vertex(200000, 399424, "auto")
+    assert _uses_vertex(4096, 50176, "vertex")            # explicit request wins
+    assert not _uses_vertex(131072, 50176, "ray")
+    assert not _uses_vertex(131072, 50176, "auto", image=False)     # no table image: per-ray path
+    assert not _uses_vertex(131072, 50176, "vertex", dense=True)    # a materialised embedding has no vertices
+
+
+def test_workspace_grows_with_the_vertex_buffers_and_image_size_is_exact():
+    cfg = ops.FieldConfig(k=1023)
+    lib = _lib.load()
+    assert lib.inf_table_image_bytes(50176, 1024) == 392 * 16 * 16384      # 392 vertex tiles x 16 chunks x 16 KB panels
+    assert lib.inf_table_image_bytes(50177, 1024) == 393 * 16 * 16384      # ragged last tile is padded
+    assert lib.inf_table_image_bytes(100, 100) == 0                         # k_pad must be a multiple of 64
+    base_inf = ops.workspace_bytes(cfg, 4096, False)
+    assert ops.workspace_bytes(cfg, 4096, False, 50176) >= base_inf + 392 * 128 * 512          # + P (fp16, 256 columns)
+    assert ops.workspace_bytes(cfg, 4096, False, 50176, _lib.PATH_RAY) == base_inf              # path RAY never needs them
+    base_tr = ops.workspace_bytes(cfg, 4096, True)
+    assert ops.workspace_bytes(cfg, 4096, True, 50176) >= base_tr + 392 * (65536 + 65536) + 3 * 4096 * 8
+
+
+def test_bad_path_is_rejected():
+    cfg = ops.FieldConfig(k=64)
+    d = ops._desc(cfg, 0, 0, path=7)
+    assert _lib.load().inf_num_params(C.byref(d)) == -1
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------
+def _sw128(r, c):
+    return r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_table_image_is_the_fp16_panel_layout_bit_for_bit(dtype):
+    g = torch.Generator().manual_seed(1)
+    V, k = 300, 130                                     # ragged last vertex tile, padded columns
+    E = torch.randn(V, k, generator=g) / 3
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV, dtype=dtype)
+    img = tab.image.cpu().numpy().view(np.uint16)
+    kp = tab.k_pad
+    ref = np.zeros(((V + 127) // 128) * 128 * kp, dtype=np.uint16)
+    src = np.zeros((((V + 127) // 128) * 128, kp), dtype=np.float16)
+    src[:V, :k] = (E.half() if dtype == "f16" else E).numpy().astype(np.float16)
+    bits = src.view(np.uint16)
+    nch = kp // 64
+    rows, cols = np.meshgrid(np.arange(src.shape[0]), np.arange(kp), indexing="ij")
+    tile, r, c, cc = rows // 128, rows % 128, cols // 64, cols % 64
+    off = ((tile * nch + c) * 16384 + _sw128(r, cc)) // 2
+    ref[off.reshape(-1)] = bits.reshape(-1)
+    assert np.array_equal(img, ref)
+
+
+@pytest.mark.gpu
+def test_vertex_projection_matches_the_restatement_to_one_fp16_ulp():
+    c = load_golden("tf_k1023")
+    m = inf_b200.make_model(dict(k=c["k"], num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3))
+    m.load_state_dict(c["params"])
+    m = m.to(DEV)
+    g = torch.Generator().manual_seed(2)
+    V = 700                                              # six vertex tiles, the last one ragged
+    E = torch.randn(V, c["k"], generator=g) / 4
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV)
+    P = ops.project_vertices(m.cfg, tab, m._packed_weights()).float().cpu().double().numpy()
+    torch.cuda.synchronize()
+    assert inf_b200.kernel_error_word(DEV) == 0
+    E16 = E.half().double().numpy()
+    W = np.concatenate([c["params"]["layers.0.0.weight"].half().double().numpy(),
+                        c["params"]["layers.3.Ly.weight"].half().double().numpy()])
+    ref = E16 @ W.T                                      # exact products of the fp16 operands
+    ulp = np.maximum(np.abs(ref), 2.0 ** -14) * 2.0 ** -10
+    assert P.shape == (V, 256)
+    assert np.all(np.abs(P - ref) <= ulp), float(np.max(np.abs(P - ref) / ulp))
+
+
+def _l1_step(path, c, E, vids, bary, target, idx_dtype=torch.int64, ridx=None):
+    m = inf_b200.make_model(dict(k=c["k"], num_layers=c["num_layers"], mlp_hidden_dim=128, skip_layer_idx=c["skip"]))
+    m.load_state_dict(c["params"])
+    m = m.to(DEV)
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV, path=path)
+    b = {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": vids.to(DEV).to(idx_dtype), "barycentric_coords": bary.to(DEV),
+         "expected_rgbs": target.to(DEV)}
+    if ridx is not None:
+        b["ray_idxs"] = ridx.to(DEV)
+    sums, pred, flat = m.l1_step(b)
+    torch.cuda.synchronize()
+    assert inf_b200.kernel_error_word(DEV) == 0
+    return m, tab, sums.cpu(), pred.cpu(), flat.clone()
+
+
+@pytest.mark.gpu
+def test_long_incidence_lists_are_summed_in_fixed_point_and_stay_deterministic():
+    # 20 vertices, 3000 rays: every vertex is hit ~450 times, far beyond the 32-pair sorted path of vertex_gather_kernel
+    c = load_golden("tf_k100_l5s1")
+    g = torch.Generator().manual_seed(3)
+    V, B = 20, 3000
+    E = torch.randn(V, c["k"], generator=g) / 4
+    vids = torch.randint(0, V, (B, 3), generator=g)
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    m, tab, sums, pred, f1 = _l1_step("vertex", c, E, vids, bary, target)
+    _, _, _, _, f2 = _l1_step("vertex", c, E, vids, bary, target)
+    assert torch.equal(f1, f2)
+    proj = ops.project_vertices(m.cfg, tab, m._packed_weights()).float().cpu().numpy()
+    loss, y, ge = O.emulated_fp16_grads(c["params"], E, vids, bary, target, c["num_layers"], c["skip"], vertex_path=True, proj=proj)
+    assert abs(sums[0].item() / (3 * B) - loss) <= 1e-4
+    for n, p in m.named_parameters():
+        ref = torch.from_numpy(ge[n]).float().reshape(p.shape)
+        rel = (p.grad.cpu() - ref).norm().item() / (ref.norm().item() + 1e-12)
+        assert rel <= 1e-2, (n, rel)
+
+
+@pytest.mark.gpu
+def test_both_paths_agree_and_gradients_do_not_depend_on_ray_order():
+    c = load_golden("tf_k1023")
+    g = torch.Generator().manual_seed(4)
+    V, B = 900, 4000
+    E = torch.randn(V, c["k"], generator=g) / 4
+    faces = torch.randint(0, V, (1800, 3), generator=g)
+    vids = faces[torch.randint(0, 1800, (B,), generator=g)]
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    _, _, s_r, p_r, f_r = _l1_step("ray", c, E, vids, bary, target)
+    _, _, s_v, p_v, f_v = _l1_step("vertex", c, E, vids, bary, target)
+    ref = O.field_forward(c["params"], E, vids, bary, num_layers=c["num_layers"], skip=c["skip"])
+    for p in (p_r, p_v):
+        err = (p - ref).abs()
+        assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN
+    assert (p_r - p_v).abs().max().item() <= 2e-3
+    assert abs(s_r[0].item() - s_v[0].item()) <= 1e-3 * s_r[0].item()
+    rel = (f_r - f_v).norm().item() / f_r.norm().item()
+    assert rel <= 6e-2, rel                               # two sets of rounding points, same ReLU-kink noise class
+    # a permuted batch: per-ray RGB is bit-identical (rays do not interact), and the vertex gradient -- a sum over
+    # incidence lists whose order follows the atomics of the list builder -- reproduces bit for bit as well
+    perm = torch.randperm(B, generator=g)
+    _, _, _, p_perm, f_perm = _l1_step("vertex", c, E, vids[perm], bary[perm], target[perm])
+    assert torch.equal(p_perm, p_v[perm])
+    relp = (f_perm - f_v).norm().item() / f_v.norm().item()
+    assert relp <= 1e-5, relp                             # tile membership changes: fp32 re-association only
+    # the batch selection folded into the kernels (ray_idxs) on the vertex path: same arithmetic as materialised batches
+    _, _, s_i, p_i, f_i = _l1_step("vertex", c, E, vids, bary, target, idx_dtype=torch.int32, ridx=perm.to(torch.int32))
+    assert torch.equal(p_i, p_perm) and torch.equal(f_i, f_perm)
