@@ -270,6 +270,33 @@ def pack_weights(cfg: FieldConfig, params: Sequence[torch.Tensor], out: Optional
     return out
 
 
+_validated = set()
+
+
+def validate_indices(table: "EigenTable", vertex_idxs=None, face_idxs=None, n_faces: Optional[int] = None,
+                     ray_idxs=None, n_src_rays: Optional[int] = None):
+    """Range-check the index arrays of a split ONCE where it is bound (loaders, renderer, baking) -- the kernels
+    dereference them raw.  The reference's ``E[idx]`` raises IndexError for an out-of-range id and wraps negative ones
+    (mesh.py:319); negative ids are rejected here as well: every producer of the path (mesh.py:214-224) emits ids >= 0."""
+    def chk(t, hi, what):
+        if t is None or t.numel() == 0:
+            return
+        key = (what, t.data_ptr(), t.numel(), t.dtype, t._version, int(hi))
+        if key in _validated:                      # the same buffer re-bound (a renderer streaming frames from one staging area)
+            return
+        lo_v, hi_v = int(t.min()), int(t.max())
+        if lo_v < 0 or hi_v >= hi:
+            raise IndexError(f"{what} out of range: [{lo_v}, {hi_v}] not within [0, {hi})")
+        if len(_validated) > 256:
+            _validated.clear()
+        _validated.add(key)
+    chk(vertex_idxs, table.n_rows, "vertex_idxs_of_hit_faces")
+    if n_faces is not None:
+        chk(face_idxs, n_faces, "hit_face_idxs")
+    if n_src_rays is not None:
+        chk(ray_idxs, n_src_rays, "ray_idxs")
+
+
 def _check_inputs(cfg, table, vids, bary, dense, ray_idxs=None):
     """Returns (B, rows of the per-ray arrays)."""
     _require_cuda(table, "table")

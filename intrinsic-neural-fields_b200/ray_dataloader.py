@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch
 
-from .ops import EigenTable
+from .ops import EigenTable, validate_indices
 
 
 _RAY_KEYS = ("vertex_idxs_of_hit_faces", "barycentric_coords", "expected_rgbs", "unit_ray_dirs", "hit_face_idxs")
@@ -41,6 +41,7 @@ class RayDataLoader:
         self.arrays = {k: v.to(self.device) for k, v in given.items() if v is not None}      # H2D once, as :73-77
         if self.arrays["barycentric_coords"].dtype != torch.float32:
             raise TypeError("barycentric_coords must be float32 (ray_dataloader.py:132)")
+        validate_indices(self.table, self.arrays["vertex_idxs_of_hit_faces"])     # once per split, not per step
         self.shuffle, self.drop_last = bool(shuffle), bool(drop_last)
         self.materialize, self.fused_select, self.generator = materialize, fused_select, generator
         self.B = int(batch_size)
@@ -113,6 +114,8 @@ class HostRayLoader:
         self.B = batch_size
         self.shuffle, self.drop_last, self.generator = shuffle, drop_last, generator
         self.num_batches = self.N // self.B if drop_last else (self.N + self.B - 1) // self.B
+        if depth < 2:
+            raise ValueError("HostRayLoader needs depth >= 2: batch i+1 is copied while batch i is consumed")
         self.depth = depth
         self.copy_stream = torch.cuda.Stream(self.device)
         # device staging ring; each slot: tensors + "copy done" / "consumer done" events
@@ -136,6 +139,7 @@ class HostRayLoader:
                 "expected_rgbs": pin(expected_rgbs), "unit_ray_dirs": pin(unit_ray_dirs), "hit_face_idxs": pin(face_idxs)}
         host = {k: v for k, v in host.items() if v is not None}
         assert host["barycentric_coords"].dtype == torch.float32
+        validate_indices(self.table, host["vertex_idxs_of_hit_faces"])            # once per bound split
         if getattr(self, "slots", None):
             old = self.host
             assert host.keys() == old.keys() and all(host[k].dtype == old[k].dtype and host[k].shape[1:] == old[k].shape[1:]
@@ -152,6 +156,12 @@ class HostRayLoader:
         self.perm = torch.randperm(self.N, generator=self.generator) if self.shuffle else None
         self._next_issue = self._next_take = 0
         self._pending = False
+        # Slots handed out in the previous epoch may still be read by kernels the caller enqueued on the current stream
+        # (the last batch of an epoch never gets its "free" event from __next__): every copy of the new epoch waits for
+        # everything enqueued so far.
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        for slot in self.slots:
+            slot["used"] = False
         for _ in range(min(self.depth, self.num_batches)):
             self._issue()
         return self
@@ -219,9 +229,13 @@ def create_ray_dataloader(preproc_data_path, eigenfunctions_path, k, feature_str
     from . import parallel
     world = parallel.world_size(group)
     if world > 1:      # this rank's contiguous 1/W of the split and of every batch
-        each = d["expected_rgbs"].shape[0] // world        # equal shards: every rank runs the same number of steps
-        lo = parallel.rank(group) * each
-        d = {k_: v[lo:lo + each] for k_, v in d.items()}
+        n_all = d["expected_rgbs"].shape[0]
+        if shuffle:                                        # training split: equal shards, every rank runs the same number of steps
+            each = n_all // world
+            lo, hi = parallel.rank(group) * each, parallel.rank(group) * each + each
+        else:                                              # val / test: every ray is evaluated exactly once (ragged tail kept);
+            lo, hi = parallel.shard_range(n_all, group)    # the epoch metrics weight by the all-reduced ray count
+        d = {k_: v[lo:hi] for k_, v in d.items()}
         batch_size = max(1, batch_size // world)
     return RayDataLoader(table, feature_strategy, d["vertex_idxs_of_hit_faces"], d["barycentric_coords"], d["expected_rgbs"],
                          d.get("unit_ray_dirs"), d.get("face_idxs"), batch_size, shuffle, drop_last, device=device,

@@ -13,7 +13,7 @@ from typing import Optional
 
 import torch
 
-from .ops import EigenTable
+from .ops import EigenTable, validate_indices
 
 
 class FieldRenderer:
@@ -30,12 +30,18 @@ class FieldRenderer:
         self.table = eigenfunctions if isinstance(eigenfunctions, EigenTable) else EigenTable.from_dense(
             eigenfunctions.to(torch.float32), device=self.device, dtype=table_dtype)
 
+    def _validate(self, vids, face_idxs):
+        """Range-check a frame's index arrays once, where it enters (the kernels dereference them raw)."""
+        normals = getattr(self.model, "face_normals", None)
+        validate_indices(self.table, vids, face_idxs, None if normals is None else int(normals.shape[0]))
+
     @torch.no_grad()
     def predict_hits(self, vertex_idxs_of_hit_faces: torch.Tensor, barycentric_coords: torch.Tensor,
                      unit_ray_dirs: Optional[torch.Tensor] = None, face_idxs: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(M,3) vids + (M,3) bary on the host or device -> (M,3) RGB on the device, chunked."""
         self.model.eval()
         M = vertex_idxs_of_hit_faces.shape[0]
+        self._validate(vertex_idxs_of_hit_faces, face_idxs)
         out = torch.empty((M, 3), dtype=torch.float32, device=self.device)
         for lo in range(0, M, self.chunk):
             hi = min(M, lo + self.chunk)
@@ -63,6 +69,7 @@ class FieldRenderer:
             out = torch.empty((M, 3), dtype=torch.float32).pin_memory()
         if M == 0:
             return out
+        self._validate(None, face_idxs)                   # the vertex ids are checked where the loader binds them
         key = (min(chunk, M), vertex_idxs_of_hit_faces.dtype, unit_ray_dirs is not None, face_idxs is not None)
         if getattr(self, "_hl_key", None) == key and self._hl.table is self.table:
             loader = self._hl.rebind(vertex_idxs_of_hit_faces, barycentric_coords, None, unit_ray_dirs, face_idxs)

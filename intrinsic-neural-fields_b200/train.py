@@ -32,14 +32,19 @@ def run(config: dict, mesh=None, allow_checkpoint_loading: bool = False, fused_a
     out_dir = config["training"]["out_dir"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.path.exists(out_dir) and not allow_checkpoint_loading and int(os.environ.get("RANK", "0")) == 0 and os.listdir(out_dir):
-        raise RuntimeError(f"out_dir '{out_dir}' exists. Exit to not overwrite old results.")                # config.py:31-33
     if not torch.cuda.is_available():
         raise RuntimeError("the B200 path has no CPU fallback: a CUDA device is required")
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device(device))
+    # config.py:31-33, decided by rank 0 and shared: every rank leaves together instead of waiting in a collective
+    taken = torch.tensor([int(int(os.environ.get("RANK", "0")) == 0 and os.path.exists(out_dir) and not allow_checkpoint_loading
+                              and bool(os.listdir(out_dir)))], device=device)
+    if world > 1:
+        dist.broadcast(taken, src=0)
+    if int(taken.item()):
+        raise RuntimeError(f"out_dir '{out_dir}' exists. Exit to not overwrite old results.")
     seed = config.get("seed", 0)                                                                             # config.py:48-49
     _seed(seed)
     data = get_data(config, device)

@@ -53,7 +53,7 @@ def train_step_async(model, optim, batch, loss_fn=F.l1_loss, group=None, flat_gr
         loss = sums[0] / (3.0 * B * world)
     else:
         pred = model(batch)
-        loss = loss_fn(pred, batch["expected_rgbs"])
+        loss = loss_fn(pred, _targets(batch))      # the batch's own rows (the whole split's array when ray_idxs selects)
         optim.zero_grad(set_to_none=True)
         (loss / world).backward()
         if world > 1:
@@ -362,6 +362,13 @@ class Trainer:
             self.lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optim, mode="min", factor=0.2)   # trainer.py:36
         self.train_data_loader, self.val_data_loader = data["train"], data["val"]
         self.test_data_loader = data.get("test", None)
+        # the view branch reads face_normals[hit_face_idxs] raw: range-check every split once, where it is bound
+        normals = getattr(model, "face_normals", None)
+        if normals is not None:
+            for dl in (self.train_data_loader, self.val_data_loader, self.test_data_loader):
+                arrays = getattr(dl, "arrays", None) or getattr(dl, "host", None) or {}
+                if dl is not None and arrays.get("hit_face_idxs") is not None:
+                    ops.validate_indices(dl.table, None, arrays["hit_face_idxs"], int(normals.shape[0]))
         self.out_dir = tr["out_dir"]
         os.makedirs(os.path.join(self.out_dir, "logs"), exist_ok=True)
         if writer is None:

@@ -111,6 +111,26 @@ def texture_field_forward(p: Dict[str, torch.Tensor], x: torch.Tensor, num_layer
     return res
 
 
+def relu_margin_per_ray(p: Dict[str, torch.Tensor], x: torch.Tensor, num_layers: int, skip: int) -> torch.Tensor:
+    """min over every ReLU unit of |z| / rms(z of its layer), per ray, for the plain TextureField (model.py:98-112).
+
+    A reduced-precision evaluation moves every pre-activation by a few 1e-4 of its layer's scale; a unit whose |z| is
+    below that can land on the other side of the ReLU kink, which changes its mask and with it the ray's whole
+    contribution to the gradients.  Rays whose margin is well above the rounding noise have identical masks in every
+    implementation, so gradients over THOSE rays isolate the arithmetic from the kink noise."""
+    res = x
+    margin = torch.full((x.shape[0],), float("inf"))
+    for i in range(num_layers - 1):
+        if i == skip:
+            z = F.linear(res, p[f"layers.{i}.Lx.weight"], p[f"layers.{i}.Lx.bias"]) + \
+                F.linear(x, p[f"layers.{i}.Ly.weight"], p[f"layers.{i}.Ly.bias"])
+        else:
+            z = F.linear(res, p[f"layers.{i}.0.weight"], p[f"layers.{i}.0.bias"])
+        margin = torch.minimum(margin, (z.abs() / z.pow(2).mean().sqrt()).min(dim=1).values)
+        res = torch.relu(z)
+    return margin
+
+
 # --------------------------------------------------------------------------------------
 # a6: view-direction branch
 # --------------------------------------------------------------------------------------

@@ -102,9 +102,10 @@ def test_vertex_projection_matches_the_restatement_to_one_fp16_ulp():
     W = np.concatenate([c["params"]["layers.0.0.weight"].half().double().numpy(),
                         c["params"]["layers.3.Ly.weight"].half().double().numpy()])
     ref = E16 @ W.T                                      # exact products of the fp16 operands
-    ulp = np.maximum(np.abs(ref), 2.0 ** -14) * 2.0 ** -10
+    # one fp16 ulp of the value, plus the fp32 accumulation error of a 1023-term sum of O(1e-2) products
+    bound = np.abs(ref) * 2.0 ** -10 + 2e-6
     assert P.shape == (V, 256)
-    assert np.all(np.abs(P - ref) <= ulp), float(np.max(np.abs(P - ref) / ulp))
+    assert np.all(np.abs(P - ref) <= bound), float(np.max(np.abs(P - ref) / bound))
 
 
 def _l1_step(path, c, E, vids, bary, target, idx_dtype=torch.int64, ridx=None):
