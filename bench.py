@@ -1,21 +1,27 @@
 #!/usr/bin/env python
-"""Benchmark of the intrinsic-neural-field hot path (BASELINE.json metric: rays/sec, training fwd+bwd).
+"""Benchmark of the intrinsic-neural-field hot path (BASELINE.json metric: rays/sec, training fwd+bwd and inference).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--mode train|infer]
 
-A "step" is one training pass of the hot path over one batch of synthetic rays: fused gather ->
-interpolate -> MLP forward, L1 loss, backward (all parameter gradients), [N>1: one NCCL allreduce of
-the flat gradient buffer], torch.optim.Adam step and operand re-pack.  Workload = BASELINE.json
-configs[1] (cat texture reconstruction model: k=1023 eigenfunctions, 6x128 MLP, skip 3, L1, lr 1e-4) on
-a synthetic 224x224 grid-torus mesh (V=50 176, F=100 352), fp32 eigenfunction table (205 MB > L2),
-`--batch` rays per GPU per step (default 131 072; the shipped batch_size 4096 is reported alongside).
+A "step" is one pass of the hot path over one batch of synthetic rays.  Training (`--mode train`, the default): gather ->
+interpolate -> MLP forward, L1 loss, backward (all parameter gradients), [N>1: one allreduce of the flat gradient buffer],
+Adam step and operand refresh (config.py:108, trainer.py:71-84).  Inference (`--mode infer`): gather -> interpolate -> MLP
+-> RGB (renderer.py:113-118).  Workload = BASELINE.json configs[1] (cat texture reconstruction model: k=1023
+eigenfunctions, 6x128 MLP, skip 3, L1, lr 1e-4) on a synthetic 224x224 grid-torus mesh (V=50 176, F=100 352), fp32
+eigenfunction table (205 MB > L2), `--batch` rays per GPU per step (default 131 072), random hit faces.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference path
-(oracle/, kind "port": /root/reference is not present on the GPU box) on the host cores.
+Prints ONE JSON line (rank 0).  The default line carries, besides the headline arm: the other mode (`inference` /
+`training`), the shipped batch size 4096, config 4 (400k-row table, the gather-bandwidth-bound case), the first-layer
+tensor-pipe fraction, the CPU baseline and the reference's PyTorch path on the same GPU (context).
+`--impl reference` times the reference's own CPU implementation (oracle/_ref staged from /root/reference by
+oracle/make_ref.py; the oracle port if that is absent) on the host cores, at the same rays per step.
 """
 import argparse
+import ctypes as C
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -29,8 +35,11 @@ import torch  # noqa: E402
 
 # per-ray algorithmic work, k=1023 H=128 L=6 (BASELINE.md section 3 / SURVEY.md section 8d)
 K_EIG, HID, LAYERS, SKIP = 1023, 128, 6, 3
+K_PAD = 1024
 GRID = 224                       # grid-torus: V = 224*224 = 50 176 vertices, F = 100 352 faces
 LR = 1e-4                        # intrinsic_cat.yaml:33
+MODEL_CFG = dict(k=K_EIG, num_layers=LAYERS, mlp_hidden_dim=HID, skip_layer_idx=SKIP)
+STAGES = ["incidence_lists", "vertex_project", "rays_fwd_bwd", "vertex_gather", "wgrad", "reduce_adam"]
 
 
 def flop_per_ray(train: bool) -> float:
@@ -44,20 +53,22 @@ def bytes_per_ray(train: bool) -> float:
     return 3 * K_EIG * 4 + 24 + 12 + 12 + (12 if train else 0)
 
 
-def ncu_traffic(kernel_prefix: str):
-    """DRAM bytes per launch of `kernel_prefix` from the newest committed ncu summary (profiles/r*_kernels.txt), or None."""
-    import glob
-    import re
+def ncu_kernels():
+    """{kernel name: (dram bytes per launch, duration us, tensor pipe %)} from the newest committed ncu summary."""
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernels.txt")), reverse=True):
-        blocks = open(path).read().split("---")
-        for b in blocks:
-            if ("Kernel Name" in b) and (kernel_prefix in b):
-                rd = re.search(r"dram__bytes_read.sum\s+([0-9.]+) \[(\w+)\]", b)
-                wr = re.search(r"dram__bytes_write.sum\s+([0-9.]+) \[(\w+)\]", b)
-                if rd and wr:
-                    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-                    return float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)], os.path.basename(path)
-    return None, None
+        out = {}
+        for b in open(path).read().split("---"):
+            name = re.search(r"Kernel Name\s+(.+?) \[", b)
+            rd = re.search(r"dram__bytes_read.sum\s+([0-9.]+) \[(\w+)\]", b)
+            wr = re.search(r"dram__bytes_write.sum\s+([0-9.]+) \[(\w+)\]", b)
+            tp = re.search(r"sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active\s+([0-9.]+)", b)
+            if name and rd and wr:
+                out.setdefault(name.group(1).strip(), (float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)],
+                                                       float(tp.group(1)) if tp else None))
+        if out:
+            return out, os.path.basename(path)
+    return {}, None
 
 
 def peaks():
@@ -137,37 +148,47 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle's restatement of the reference path on the host cores
+# reference arm / CPU baseline: the reference's own CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(train: bool, steps: int, warmup: int, batch: int, V: int = GRID * GRID):
-    """rays/s of get_k_eigenfunc_vec_vals -> TextureField -> L1 -> backward -> Adam (trainer.py:71-84) on the CPU."""
-    from oracle import field_oracle as O
+def cpu_reference_rate(train: bool, steps: int, warmup: int, batch: int, V: int = None):
+    """rays/s of get_k_eigenfunc_vec_vals -> TextureField -> L1 -> backward -> Adam (trainer.py:71-84) on the CPU, with the
+    unmodified reference modules staged under oracle/_ref ("reference"); the oracle's restatement ("port") if absent."""
+    from oracle import ref_path
     torch.set_num_threads(os.cpu_count() or 1)
     dev = torch.device("cpu")
+    V = GRID * GRID if V is None else V
     faces = torus_faces(GRID, dev)
     table = make_table(V, K_EIG, dev)
-    params = O.make_params(K_EIG, HID, LAYERS, SKIP, seed=0)
-    q = {n: t.clone().requires_grad_(train) for n, t in params.items()}
-    opt = torch.optim.Adam(list(q.values()), lr=LR) if train else None
-    times = []
-    for s in range(warmup + steps):
-        vids, bary, target = make_rays(faces, batch, dev, seed=100 + s)
-        t0 = time.perf_counter()
-        if train:
+    kind = "reference" if ref_path.available() else "port"
+    if kind == "reference":
+        torch.manual_seed(0)
+        ref = ref_path.ReferenceStep(dict(MODEL_CFG, feature_strategy="efuncs"), table, LR, train=train)
+        step = ref.step
+    else:
+        from oracle import field_oracle as O
+        q = {n: t.clone().requires_grad_(train) for n, t in O.make_params(K_EIG, HID, LAYERS, SKIP, seed=0).items()}
+        opt = torch.optim.Adam(list(q.values()), lr=LR) if train else None
+
+        def step(vids, bary, target=None):
+            if not train:
+                with torch.no_grad():
+                    return O.field_forward(q, table, vids, bary, num_layers=LAYERS, skip=SKIP)
             pred = O.field_forward(q, table, vids, bary, num_layers=LAYERS, skip=SKIP)
             loss = O.l1_loss(pred, target)
             opt.zero_grad(set_to_none=True)
             loss.backward()
             opt.step()
-            loss.item()
-        else:
-            with torch.no_grad():
-                O.field_forward(q, table, vids, bary, num_layers=LAYERS, skip=SKIP)
+            return loss.item(), pred
+    times = []
+    for s in range(warmup + steps):
+        vids, bary, target = make_rays(faces, batch, dev, seed=100 + s)
+        t0 = time.perf_counter()
+        step(vids, bary, target if train else None)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
     total = sum(times)
-    return batch * len(times) / total, total / len(times) * 1e3
+    return batch * len(times) / total, total / len(times) * 1e3, kind
 
 
 def torch_gpu_context_rate(train: bool, dev, batch: int = 131072, steps: int = 5):
@@ -208,17 +229,19 @@ def run_reference(args):
     if rank != 0:
         return
     train = args.mode == "train"
-    batch = 16384
-    rate, ms = cpu_reference_rate(train, args.steps, args.warmup, batch)
+    batch = args.batch                      # the same rays per step as the GPU arm
+    rate, ms, kind = cpu_reference_rate(train, args.steps, args.warmup, batch)
     cores = os.cpu_count() or 1
     out = {
         "impl": "reference", "metric": "rays_per_sec_train_fwd_bwd" if train else "rays_per_sec_inference",
         "value": rate, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, batch_override=batch),
-        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} rays of the same workload (oracle/ restatement of the "
-                                   "reference PyTorch fp32 path, torch CPU, all host threads)"},
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps x {batch} rays of the same workload: "
+                                   + ("the reference's own get_k_eigenfunc_vec_vals + make_model + F.l1_loss + Adam (oracle/_ref), "
+                                      if kind == "reference" else "oracle/ restatement of the reference PyTorch fp32 path, ")
+                                   + "torch CPU, all host threads"},
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -230,7 +253,8 @@ def workload_config(args, batch_override=None):
     cfg = {"workload": f"cat_texture_recon_{args.mode}_step_torus{GRID}x{GRID}_V{GRID * GRID}_k{K_EIG}_L{LAYERS}x{HID}_skip{SKIP}",
            "rays_per_gpu_per_step": b, "table": f"{args.table_dtype} (V x 1024 padded)",
            "parallelism": f"ray-sharded dp{args.gpus}",
-           "timing": "inputs larger than L2 (205 MB table + per-step stash); 4 rotating ray batches of random hit faces"}
+           "timing": "inputs larger than L2 (205 MB table + its 103 MB operand image + per-step activation stash); "
+                     "4 rotating ray batches of random hit faces"}
     if args.mode == "train":
         cfg.update(optimizer="Adam lr 1e-4 (fused into the reduction kernel)", loss="L1")
     return cfg
@@ -244,10 +268,94 @@ def _say(msg):
         print(f"[bench r{os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
+class Timer:
+    """CUDA-event timing of K calls bracketed by barrier + synchronize on both sides, max over ranks."""
+
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def __call__(self, fn, steps):
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+
+def read_stages(lib):
+    from inf_b200 import _lib
+    arr = (C.c_float * _lib.PROFILE_STAGES)()
+    n = C.c_int()
+    lib.inf_profile_read_stages(arr, C.byref(n))
+    return dict(zip(STAGES, [float(x) for x in arr])), n.value
+
+
+def kernel_rooflines(stages, train, vertex, B, V, pk, ncu):
+    """Per-kernel rooflines of one step: what each kernel executes against the roof that binds it."""
+    tf = pk["bf16_tflops_sustained"] * 1e12
+    ntv = (V + 127) // 128
+    ker = []
+
+    def add(name, ms, flops=None, bytes_=None, bound=None, ncu_name=None, note=None):
+        if ms <= 0:
+            return
+        e = {"kernel": name, "ms": ms}
+        if flops is not None:
+            e.update(tflops=flops / (ms / 1e3) / 1e12, tensor_frac_of_sustained_bf16=flops / (ms / 1e3) / tf)
+        if bytes_ is not None:
+            e.update(gbs=bytes_ / (ms / 1e3) / 1e9, hbm_frac=bytes_ / (ms / 1e3) / 1e9 / pk["hbm_gbs"], bytes=bytes_)
+        t = ncu.get(ncu_name or name)
+        if t is not None:
+            e.update(ncu_dram_bytes=t[0], ncu_tensor_pipe_pct=t[1])
+        e["bound"] = bound
+        if note:
+            e["note"] = note
+        ker.append(e)
+    hid = (LAYERS - 2) * HID * HID * 2.0
+    if vertex:
+        add("vertex_project_kernel", stages["vertex_project"], flops=2.0 * ntv * 128 * K_PAD * 256,
+            bytes_=ntv * 128 * (K_PAD * 2 + 512), bound="tensor",
+            note="P = E [W0;Wy]^T once per vertex: the first layer + skip branch of every ray; bytes = table image in, P out")
+        add("field_rays_kernel", stages["rays_fwd_bwd"], flops=B * hid * (2 if train else 1),
+            bytes_=B * (3 * 512 + 36 + 12 + (12 + 10 * 256 + 32 if train else 0)), bound="latency",
+            note="per-ray chain; bytes = 3 P rows + inputs + RGB (+ activation stash out); neither roof binds, see DESIGN.md")
+        if train:
+            add("vertex_gather_kernel", stages["vertex_gather"], bytes_=B * 3 * 512 + ntv * 65536, bound="l2",
+                note="G[v] = sum bary * dz: 3 stashed 512 B rows per ray, G image out")
+            add("field_wgrad_kernel", stages["wgrad"], flops=B * hid + 2.0 * ntv * 128 * K_PAD * 256,
+                bytes_=B * (10 * 256 + 32) + ntv * 128 * (K_PAD * 2 + 512), bound="hbm",
+                note="hidden dW from the stash (K = rays) + [dW0;dWy] = G^T E (K = vertices); bytes = stash + table image + G")
+    else:
+        fwd = 2.0 * (2 * K_EIG * HID + (LAYERS - 2) * HID * HID + 3 * HID)
+        add("field_main_kernel", stages["rays_fwd_bwd"], flops=B * (fwd + (hid + 6.0 * HID if train else 0)),
+            bytes_=B * bytes_per_ray(train), bound="hbm", note="per-ray gather of 3 table rows fused into GEMM1 (+ dgrad chain)")
+        if train:
+            add("field_wgrad_kernel", stages["wgrad"], flops=B * fwd, bytes_=B * 4864, bound="hbm",
+                note="all weight gradients from the 4.75 KB/ray stash")
+    if train:
+        add("field_reduce_kernel", stages["reduce_adam"], bound="latency")
+    return ker
+
+
 def run_ours(args):
     import torch.distributed as dist
     import inf_b200
-    from inf_b200 import _lib, trainer, parallel
+    from inf_b200 import _lib, trainer
+    from inf_b200.ray_dataloader import HostRayLoader
+    from inf_b200.renderer import FieldRenderer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -256,18 +364,23 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    lib = _lib.load()
+    debug = lib.inf_debug_flags()
+    if debug & 7:
+        raise RuntimeError(f"INF_DEBUG={debug}: bits 1|2|4 skip work and produce wrong gradients -- refusing to benchmark")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    train = args.mode == "train"
+    headline_train = args.mode == "train"
     B = args.batch
     V = GRID * GRID
+    timed = Timer(dev, world)
 
     faces = torus_faces(GRID, dev)
     table_dense = make_table(V, K_EIG, dev)
     table = inf_b200.EigenTable.from_dense(table_dense, device=dev, dtype=args.table_dtype, path=args.path)
     del table_dense
     torch.manual_seed(0)
-    model = inf_b200.make_model(dict(k=K_EIG, num_layers=LAYERS, mlp_hidden_dim=HID, skip_layer_idx=SKIP)).to(dev)
+    model = inf_b200.make_model(MODEL_CFG).to(dev)
     # config.py:108 Adam(lr): the update + operand refresh run inside the gradient-reduction kernel (FusedFieldAdam)
     optim = trainer.FusedFieldAdam(model, lr=LR)
     graphed = trainer.GraphedTrainStep(model, optim)
@@ -279,109 +392,104 @@ def run_ours(args):
                             "expected_rgbs": target})
         # on the wire the vertex ids are int32, exactly as the reference stores them on disk (mesh.py:513-516)
         host_parts.append((vids.to(torch.int32).cpu(), bary.cpu(), target.cpu()))
+    d0 = inf_b200.ops._desc(model.cfg, B, V, path=inf_b200.ops.PATHS[args.path])
+    t0 = _lib.InfTensors(table_image=table.image.data_ptr() if table.image is not None else None)
+    vertex = bool(lib.inf_uses_vertex_path(C.byref(d0), C.byref(t0)))
 
-    def step_resident(i):
-        b = dev_batches[i % NB]
-        if train:
-            return trainer.fused_train_step_async(model, optim, b)[0]
+    from inf_b200.renderer import GraphedForward
+    gforward = GraphedForward(model)
+
+    # resident inputs: one CUDA-graph launch per step (GraphedTrainStep / GraphedForward: the kernels of a step take
+    # 0.1-0.4 ms, the eager Python path into them ~0.2 ms); the eager calls are used for the per-stage device times
+    def train_step(i):
+        return graphed.step_async(dev_batches[i % NB])[0]
+
+    def train_step_eager(i):
+        return trainer.fused_train_step_async(model, optim, dev_batches[i % NB])[0]
+
+    def infer_step(i):
+        return gforward(dev_batches[i % NB])
+
+    def infer_step_eager(i):
         with torch.no_grad():
-            return model(b)
+            return model(dev_batches[i % NB])
 
-    # end-to-end arm: every step's gather inputs start in pinned HOST memory and are copied inside the timed region
+    # end-to-end arms: every step's gather inputs start in pinned HOST memory and are copied inside the timed region
     # (HostRayLoader: copy stream, one batch ahead); the step's result is read back to the host every step
     # (training: loss.item() as trainer.py:84; inference: the (B,3) RGB as renderer.py:117).
-    from inf_b200.ray_dataloader import HostRayLoader
-    from inf_b200.renderer import FieldRenderer
     n_e2e = min(args.steps + 6, 24)      # host batches kept in pinned memory; longer runs cycle through them
     hv = torch.cat([host_parts[i % NB][0] for i in range(n_e2e)]).pin_memory()
     hb = torch.cat([host_parts[i % NB][1] for i in range(n_e2e)]).pin_memory()
-    ht = torch.cat([host_parts[i % NB][2] for i in range(n_e2e)]).pin_memory() if train else None
-    if train:
-        e2e_loader = HostRayLoader(table, hv, hb, ht, batch_size=B, device=dev)
-    else:
-        e2e_renderer = FieldRenderer(model, table, H=1, W=1, device=dev)
-        e2e_out = torch.empty((n_e2e * B, 3), dtype=torch.float32).pin_memory()
+    ht = torch.cat([host_parts[i % NB][2] for i in range(n_e2e)]).pin_memory()
+    e2e_loader = HostRayLoader(table, hv, hb, ht, batch_size=B, device=dev)
+    e2e_renderer = FieldRenderer(model, table, H=1, W=1, device=dev)
+    e2e_out = torch.empty((n_e2e * B, 3), dtype=torch.float32).pin_memory()
 
-    def run_e2e(steps):
+    def train_e2e(steps):
         done = 0
-        if train:
-            while done < steps:
-                for b in e2e_loader:                             # one pass over the pinned host split
-                    if done >= steps:
-                        break
-                    graphed.step(b)                              # one graph launch; loss.item(): D2H read every step
-                    done += 1
-        else:
-            # a stream of frames of B rays each through ONE renderer call per pass over the host split: the copies of
-            # frame i+1 (in) and i-1 (out) overlap the kernels of frame i; a call returns when the last RGB is in host memory
-            while done < steps:
-                n = min(steps - done, n_e2e)
-                e2e_renderer.predict_hits_host(hv[:n * B], hb[:n * B], chunk=B, out=e2e_out[:n * B])
-                done += n
+        while done < steps:
+            for b in e2e_loader:                             # one pass over the pinned host split
+                if done >= steps:
+                    break
+                graphed.step(b)                              # one graph launch; loss.item(): D2H read every step
+                done += 1
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def infer_e2e(steps):
+        # a stream of frames of B rays each through ONE renderer call per pass over the host split: the copies of
+        # frame i+1 (in) and i-1 (out) overlap the kernels of frame i; a call returns when the last RGB is in host memory
+        done = 0
+        while done < steps:
+            n = min(steps - done, n_e2e)
+            e2e_renderer.predict_hits_host(hv[:n * B], hb[:n * B], chunk=B, out=e2e_out[:n * B])
+            done += n
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+    def measure(train):
+        """(resident ms/step, stage ms, launches/step, e2e ms/step) of one mode."""
+        step, eager, e2e = (train_step, train_step_eager, train_e2e) if train else (infer_step, infer_step_eager, infer_e2e)
+        model.train(train)
+        for i in range(max(args.warmup, 3, 2 * NB)):     # every resident batch: one eager call, one capture
+            step(i)
+        ms = timed(step, args.steps)
+        # per-stage device times and the launch count from eager calls (a graph replay does not pass through the library)
+        for i in range(3):
+            eager(i)
+        lib.inf_profile_enable(1)
+        l0 = lib.inf_launch_count()
+        timed(eager, min(args.steps, 20))
+        launches = (lib.inf_launch_count() - l0) / min(args.steps, 20)
+        stages, _ = read_stages(lib)
+        lib.inf_profile_enable(0)
+        assert inf_b200.kernel_error_word(dev) == 0, "kernel watchdog fired"
+        if args.skip_e2e:
+            return ms / args.steps, stages, launches, None
+        e2e(6 if train else 9)       # per staging slot (2 training, 3 inference): one eager step, one graph capture, then replays
+        ms_e2e = timed(lambda i: e2e(args.steps), 1)
+        return ms / args.steps, stages, launches, ms_e2e / args.steps
 
     _say("setup done")
-    lib = _lib.load()
-    sampler = ClockSampler(local)     # 100 ms samples from here to the end of the end-to-end loop (warm-up + both timed regions)
+    sampler = ClockSampler(local)     # 100 ms samples over warm-up + every timed region
     if rank == 0:
         sampler.start()
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
-    _say("warmup done")
-    lib.inf_profile_enable(1)
-    ms_total = timed(step_resident, args.steps)
-    import ctypes as C
-    km, kw, kr, kn = C.c_float(), C.c_float(), C.c_float(), C.c_int()
-    lib.inf_profile_read(C.byref(km), C.byref(kw), C.byref(kr), C.byref(kn))
-    stage_arr = (C.c_float * _lib.PROFILE_STAGES)()
-    lib.inf_profile_read_stages(stage_arr, C.byref(kn))
-    stages = dict(zip(["incidence_lists", "vertex_project", "rays_fwd_bwd", "vertex_gather", "wgrad", "reduce_adam"],
-                      [float(x) for x in stage_arr]))
-    lib.inf_profile_enable(0)
-    assert inf_b200.kernel_error_word(dev) == 0, "kernel watchdog fired"
+    res = {}
+    modes = [headline_train] if (world > 1 or args.skip_e2e or args.headline_only) else [headline_train, not headline_train]
+    for tr in modes:
+        res[tr] = measure(tr)
+        _say(f"mode train={tr} done")
+    clocks = sampler.stop() if rank == 0 else None
 
-    _say("resident timing done")
     if args.skip_e2e:
-        sampler.stop() if rank == 0 else None
-        print(json.dumps({"profiling_run": True, "ms_per_step": ms_total / args.steps, "rays_per_sec": B * args.steps / (ms_total / 1e3),
-                          "step_kernels_ms": stages}), flush=True)
+        ms, stages, launches, _ = res[headline_train]
+        if rank == 0:
+            print(json.dumps({"profiling_run": True, "ms_per_step": ms, "rays_per_sec": B * world / (ms / 1e3), "vertex_path": vertex,
+                              "launches_per_step": launches, "step_kernels_ms": stages}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
-    run_e2e(6 if train else 2)       # per staging slot: one eager step, one graph capture, then replays
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_e2e(args.steps)
-    e1.record()
-    barrier()
-    t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    ms_e2e = t_e2e.item()
-    _say("e2e timing done")
-    clocks = sampler.stop() if rank == 0 else None
 
-    # rendering-style coherent rays: neighbouring pixels hit the same / adjacent faces
-    coherent = None
-    if (not train) and rank == 0 and world == 1:
+    extras = {}
+    if rank == 0 and world == 1 and not args.headline_only:
+        model.eval()
+        # rendering-style coherent rays (SURVEY 8d config 5 (ii)): neighbouring pixels hit the same / adjacent faces
         cb = []
         for i in range(NB):
             v, b_, _t = make_rays(faces, B, dev, seed=77 + i, coherent=True)
@@ -390,12 +498,11 @@ def run_ours(args):
             for i in range(3):
                 model(cb[i % NB])
             ms_c = timed(lambda i: model(cb[i % NB]), args.steps)
-        coherent = {"rays_per_sec": B * args.steps / (ms_c / 1e3), "ms_per_step": ms_c / args.steps,
-                    "pattern": "scanline over neighbouring faces, 8 rays per face"}
-
-    # shipped batch size (intrinsic_cat.yaml:32) for context, same model/table
-    small = None
-    if train and rank == 0 and world == 1:
+        extras["coherent_rays_inference"] = {"rays_per_sec": B * args.steps / (ms_c / 1e3), "ms_per_step": ms_c / args.steps,
+                                             "pattern": "scanline over neighbouring faces, 8 rays per face"}
+        del cb
+        # shipped batch size (intrinsic_cat.yaml:32), same model/table: eager launches and one CUDA-graph launch per step
+        model.train(True)
         vids, bary, target = make_rays(faces, 4096, dev, seed=7)
         sb = {"eigenfunction_table": table, "vertex_idxs_of_hit_faces": vids, "barycentric_coords": bary, "expected_rgbs": target}
         for _ in range(5):
@@ -404,52 +511,116 @@ def run_ours(args):
         for _ in range(4):
             graphed.step_async(sb)
         ms_small_g = timed(lambda i: graphed.step_async(sb), 50)
-        small = {"rays_per_step": 4096, "ms_per_step": ms_small / 50, "rays_per_sec": 4096 * 50 / (ms_small / 1e3),
-                 "cuda_graph_ms_per_step": ms_small_g / 50, "cuda_graph_rays_per_sec": 4096 * 50 / (ms_small_g / 1e3)}
+        extras["config_batch_4096"] = {"rays_per_step": 4096, "ms_per_step": ms_small / 50, "rays_per_sec": 4096 * 50 / (ms_small / 1e3),
+                                       "cuda_graph_ms_per_step": ms_small_g / 50,
+                                       "cuda_graph_rays_per_sec": 4096 * 50 / (ms_small_g / 1e3)}
+        # config 4 (human_cloud400k): 400k-row table, 1.64 GB, every gathered row comes from DRAM -- the gather-bandwidth case
+        try:
+            g4 = 632
+            V4 = g4 * g4
+            t4 = inf_b200.EigenTable.from_dense(make_table(V4, K_EIG, dev, seed=4), device=dev, image=False)
+            f4 = torus_faces(g4, dev)
+            m4 = inf_b200.make_model(MODEL_CFG).to(dev)
+            o4 = trainer.FusedFieldAdam(m4, lr=LR)
+            b4 = []
+            for i in range(NB):
+                v, b_, t_ = make_rays(f4, B, dev, seed=40 + i)
+                b4.append({"eigenfunction_table": t4, "vertex_idxs_of_hit_faces": v, "barycentric_coords": b_, "expected_rgbs": t_})
+            out4 = {"V": V4, "table_bytes": V4 * K_PAD * 4, "rays_per_step": B}
+            for tr in (False, True):
+                m4.train(tr)
+
+                def s4(i, tr=tr):
+                    if tr:
+                        return trainer.fused_train_step_async(m4, o4, b4[i % NB])[0]
+                    with torch.no_grad():
+                        return m4(b4[i % NB])
+                for i in range(3):
+                    s4(i)
+                lib.inf_profile_enable(1)
+                ms4 = timed(s4, args.steps)
+                st4, _ = read_stages(lib)
+                lib.inf_profile_enable(0)
+                key = "training" if tr else "inference"
+                out4[key] = {"rays_per_sec": B * args.steps / (ms4 / 1e3), "ms_per_step": ms4 / args.steps,
+                             "gather_kernel_ms": st4["rays_fwd_bwd"],
+                             "achieved_hbm_gbs": B * bytes_per_ray(tr) / (st4["rays_fwd_bwd"] / 1e3) / 1e9,
+                             "frac_of_hbm_peak": B * bytes_per_ray(tr) / (st4["rays_fwd_bwd"] / 1e3) / 1e9 / peaks()["hbm_gbs"]}
+            extras["config4_gather_bound"] = out4
+            del t4, m4, o4, b4
+            torch.cuda.empty_cache()
+        except Exception as exc:       # an extra: never fail the bench line
+            extras["config4_gather_bound"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
-    rate = B * world * args.steps / (ms_total / 1e3)
-    rate_e2e = B * world * args.steps / (ms_e2e / 1e3)
-    main_ms = km.value if kn.value else ms_total / args.steps
-    achieved = B * bytes_per_ray(train) / (main_ms / 1e3) / 1e9
-    h2d = B * (12 + 12 + (12 if train else 0))
-    # DRAM bytes of one launch of the dominant kernel from the committed ncu capture of this workload (same B, same table)
-    traffic, traffic_src = (ncu_traffic("field_main_kernel<%d, float>" % (1 if train else 0))
-                            if (args.table_dtype == "f32" and B == 131072 and GRID == 224) else (None, None))
+    ncu, ncu_src = ncu_kernels()
+    ncu = {k.replace("void ", "").replace("inf::", "").split("<")[0].split("(")[0]: v for k, v in ncu.items()}
+
+    def block(train):
+        ms, stages, launches, ms_e2e = res[train]
+        kernels_ms = sum(stages.values())
+        rate = B * world / (ms / 1e3)
+        h2d = B * (12 + 12 + (12 if train else 0))
+        ker = kernel_rooflines(stages, train, vertex, B, V, pk, ncu)
+        traffic = sum(k["ncu_dram_bytes"] for k in ker if "ncu_dram_bytes" in k) or None
+        achieved = B * bytes_per_ray(train) / (kernels_ms / 1e3) / 1e9
+        first = next((k for k in ker if k["kernel"] in ("vertex_project_kernel", "field_main_kernel")), None)
+        out = {
+            "value": rate, "unit": "rays/s", "ms_per_step": ms,
+            "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4 if train else B * 12, "ms_per_step": ms_e2e},
+            "gpu_launches": int(round(launches * args.steps)), "launches_per_step": launches,
+            "roofline": {
+                "bound": "hbm",
+                "kernel": ("whole step: the path's work is split over %d kernels (per vertex + per ray), timed with CUDA events "
+                           "on the launching stream" % round(launches)) if vertex else "field_main_kernel + field_wgrad_kernel + field_reduce_kernel",
+                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                "traffic": traffic, "traffic_source": ncu_src, "peak_source": pk["source"], "kernel_ms": kernels_ms,
+                "algorithmic_bytes_per_ray": bytes_per_ray(train),
+                "note": ("achieved = SURVEY 8(d) algorithmic bytes (3 fp32 table rows per ray, counted once) / device time of the step's "
+                         "kernels.  The vertex path does not move those bytes: it reads the table image once per contraction "
+                         "(2 x 103 MB per training step) and gathers 1.5 KB of P per ray from L2, so frac compares the path's "
+                         "throughput with what a perfect per-ray gather could do, not this implementation's DRAM traffic "
+                         "(traffic: ncu).") if vertex else "rows shared by rays are served from L2, so frac can exceed the DRAM rate",
+                "step_kernels_ms": stages, "kernels": ker,
+                "tensor_frac_of_sustained_bf16": rate / world * flop_per_ray(train) / (pk["bf16_tflops_sustained"] * 1e12)},
+            "first_layer_tensor_frac": None if first is None else {
+                "kernel": first["kernel"], "ms": first["ms"],
+                "executed_tflops": first.get("tflops"), "frac_of_sustained_bf16": first.get("tensor_frac_of_sustained_bf16"),
+                "per_ray_equivalent_tflops": B * 4.0 * K_EIG * HID / (first["ms"] / 1e3) / 1e12,
+                "note": "executed = FLOPs the kernel really performs (vertex path: 2 V k 256); per_ray_equivalent = the first-layer "
+                        "FLOPs of the reference formulation (2 B k 256) / the same time"},
+        }
+        return out
+
+    head = block(headline_train)
     out = {
-        "metric": "rays_per_sec_train_fwd_bwd" if train else "rays_per_sec_inference",
-        "value": rate, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "rays_per_sec_train_fwd_bwd" if headline_train else "rays_per_sec_inference",
+        "value": head["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 operands / f32 accumulate", "data": "synthetic", "config": workload_config(args),
-        "clocks": clocks,
-        "e2e": {"value": rate_e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if train else B * 12,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": (3 if train else 1) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "field_main_kernel<train>" if train else "field_main_kernel<infer>",
-                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"], "kernel_ms": main_ms,
-                     # rows shared by rays are served from L2 (the 205 MB table is partly resident), so the algorithmic
-                     # rate can exceed the DRAM rate -- and the copy peak; the DRAM side of the same launch:
-                     "dram_gbs": (traffic / (main_ms / 1e3) / 1e9) if traffic else None,
-                     "algorithmic_bytes_per_ray": bytes_per_ray(train),
-                     "step_kernels_ms": stages,
-                     "tensor_frac_of_sustained_bf16": rate / world * flop_per_ray(train) / (pk["bf16_tflops_sustained"] * 1e12)},
+        "clocks": clocks, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+        "first_layer_tensor_frac": head["first_layer_tensor_frac"],
+        "evaluation_path": "vertex (P = E [W0;Wy]^T per vertex, rays gather P)" if vertex else "ray (3 table rows gathered per ray)",
+        "inf_debug": debug,
     }
-    if small is not None:
-        out["config_batch_4096"] = small
-    if coherent is not None:
-        out["coherent_rays"] = coherent
+    if (not headline_train) in res:
+        other = block(not headline_train)
+        out["inference" if headline_train else "training"] = other
+    out.update(extras)
     if not args.no_cpu_baseline and world == 1:
-        cr, cms = cpu_reference_rate(train, steps=6, warmup=1, batch=16384)
-        out["cpu_baseline"] = {"value": cr, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
-                               "sample": "6 steps x 16384 rays of the same workload (oracle/ restatement, torch CPU, all threads)"}
+        cr, cms, kind = cpu_reference_rate(headline_train, steps=3, warmup=1, batch=B)
+        out["cpu_baseline"] = {"value": cr, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": kind,
+                               "sample": f"3 steps x {B} rays of the same workload ("
+                                         + ("the reference's own modules from oracle/_ref" if kind == "reference" else "oracle/ restatement")
+                                         + ", torch CPU, all host threads)"}
         try:
             out["context_reference_torch_fp32_on_this_gpu"] = {
-                "value": torch_gpu_context_rate(train, dev), "unit": "rays/s",
+                "value": torch_gpu_context_rate(headline_train, dev), "unit": "rays/s",
                 "note": "oracle restatement of the reference PyTorch path on the same B200 (TF32 off); context, not the baseline"}
         except Exception as exc:      # context only: never fail the bench line
             out["context_reference_torch_fp32_on_this_gpu"] = {"value": None, "note": f"not measured: {type(exc).__name__}"}
@@ -470,6 +641,7 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "ray", "vertex"],
                     help="evaluation of the two K = k contractions: per ray, per vertex, or the library's rule (InfDesc.path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="only the headline mode (no other mode, no extras)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: resident steps only (the JSON line is not a bench result)")
     ap.add_argument("--grid", type=int, default=224, help="torus grid side: V = grid^2 vertices (default: config 2)")
     args = ap.parse_args()

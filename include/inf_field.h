@@ -149,6 +149,11 @@ typedef struct InfAdam {
 
 /* version / errors */
 int inf_version(void);
+/* kernels of this library enqueued by the process so far (bench.py's gpu_launches is a difference of two readings;
+ * a CUDA-graph replay enqueues without passing through the library and is not counted) */
+long long inf_launch_count(void);
+/* value of the INF_DEBUG measurement knob read at first use (bits 1|2|4 skip work and produce WRONG gradients) */
+int inf_debug_flags(void);
 const char* inf_last_error(void);
 
 /* sizes (host-only, no CUDA calls) */

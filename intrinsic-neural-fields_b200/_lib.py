@@ -59,6 +59,8 @@ EXPORTS = {
     # name: (restype, argtypes)
     "inf_version": (C.c_int, []),
     "inf_last_error": (C.c_char_p, []),
+    "inf_launch_count": (C.c_longlong, []),
+    "inf_debug_flags": (C.c_int, []),
     "inf_num_params": (C.c_int64, [C.POINTER(InfDesc)]),
     "inf_num_param_tensors": (C.c_int32, [C.POINTER(InfDesc)]),
     "inf_param_info": (C.c_int, [C.POINTER(InfDesc), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),

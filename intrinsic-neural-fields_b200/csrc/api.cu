@@ -2,6 +2,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <mutex>
 #include <cstdarg>
@@ -38,6 +39,7 @@ void launch_umma_probe(int mode, int n, int k, const float* a, const float* b, f
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};   // kernels of this library enqueued so far (inf_launch_count)
 
 // Environment knobs are read ONCE per process (not on every launch).  INF_DEBUG bits 1|2|4 are measurement switches
 // that skip work and produce WRONG gradients: bench.py refuses to run with them and records the value.
@@ -388,6 +390,10 @@ extern "C" {
 
 int inf_version(void) { return INF_ABI_VERSION; }
 
+long long inf_launch_count(void) { return g_launches.load(); }
+
+int inf_debug_flags(void) { return env().debug; }
+
 const char* inf_last_error(void) { return g_err; }
 
 int64_t inf_num_params(const InfDesc* desc) {
@@ -440,6 +446,7 @@ int inf_build_table_image(const void* table, int32_t table_dtype, int64_t n_rows
   if ((reinterpret_cast<uintptr_t>(table) & 15) != 0 || (reinterpret_cast<uintptr_t>(image) & 127) != 0)
     return fail(INF_ERR_BAD_ARG, "table must be 16-byte and image 128-byte aligned");
   launch_table_image(table, table_dtype == INF_TABLE_F16, n_rows, k_pad, image, static_cast<cudaStream_t>(stream));
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "table_image launch");
   return INF_OK;
@@ -466,6 +473,7 @@ int inf_project_vertices(const InfDesc* desc, const InfTensors* t, void* out, vo
   rc = launch_projection(p, nsm, static_cast<cudaStream_t>(stream));
   if (rc != INF_OK) return rc;
   launch_proj_unpermute(p.proj, d.n_rows, out, static_cast<cudaStream_t>(stream));
+  g_launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "proj_unpermute launch");
   return INF_OK;
@@ -484,6 +492,7 @@ int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_
                 k_pad, static_cast<long long>(src_row_stride));
   if (dst_dtype != INF_TABLE_F32 && dst_dtype != INF_TABLE_F16) return fail(INF_ERR_BAD_ARG, "bad dst_dtype");
   launch_relayout(src, n_rows, k, src_row_stride, dst, k_pad, dst_dtype, static_cast<cudaStream_t>(stream));
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "relayout_table launch");
   return INF_OK;
@@ -518,6 +527,7 @@ int inf_pack_weights(const InfDesc* desc, const float* const* params, void* pack
   for (int i = 0; i < idx; ++i)
     if (params[i] == nullptr) return fail(INF_ERR_BAD_ARG, "params[%d] is null", i);
   launch_pack_weights(pp, static_cast<cudaStream_t>(stream));
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pack_weights launch");
   return INF_OK;
@@ -543,11 +553,13 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream) {
     prof_record(slot, 2, st);
     cudaError_t e = launch_field_rays(p, false, env().rays_slots, rays_grid(p, nsm), st);
     if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<inference> launch");
+    g_launches += 2;   // vertex_project, field_rays
   } else {
     prof_record(slot, 2, st);
     const int grid = pick_main_grid(desc, p.ntiles, nsm, false, &p.cluster);
     cudaError_t e = launch_field_main(p, false, desc->table_dtype == INF_TABLE_F16, grid, st);
     if (e != cudaSuccess) return cuda_fail(e, "field_main_kernel<inference> launch");
+    g_launches += 1;
   }
   for (int i = 3; i < PROF_EVENTS; ++i) prof_record(slot, i, st);
   if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
@@ -763,6 +775,8 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   rp.geo = geo;
   rp.plan = plan;
   e = launch_field_reduce(rp, st);
+  // vertex path: 5 incidence-list kernels, vertex_project, field_rays, vertex_gather, field_wgrad (x2 when split), reduce
+  g_launches += vp ? (split ? 11 : 10) : 3;
   prof_record(slot, 6, st);
   if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
   if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel launch");
@@ -801,6 +815,7 @@ int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* ada
   rp.plan = make_wplan(rp.geo);
   cudaError_t e = launch_field_reduce(rp, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel<adam> launch");
+  g_launches += 1;
   return INF_OK;
 }
 
@@ -810,6 +825,7 @@ int inf_gather_interpolate(const void* table, int32_t table_dtype, int32_t k, in
   if (n_rays > 0 && (!table || !vids || !bary || !out)) return fail(INF_ERR_BAD_ARG, "null pointer");
   launch_gather_interpolate(table, table_dtype == INF_TABLE_F16, k, k_pad, vids, idx_dtype == INF_IDX_I64, bary, n_rays, out,
                             static_cast<cudaStream_t>(stream));
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "gather_interpolate launch");
   return INF_OK;
