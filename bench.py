@@ -383,6 +383,9 @@ def run_ours(args):
     model = inf_b200.make_model(MODEL_CFG).to(dev)
     # config.py:108 Adam(lr): the update + operand refresh run inside the gradient-reduction kernel (FusedFieldAdam)
     optim = trainer.FusedFieldAdam(model, lr=LR)
+    # N > 1: the ranks' gradients are summed inside the reduction kernel over NVLink peer memory (INF_PEER_EXCHANGE=0 or
+    # --nccl: one NCCL allreduce of the flat gradient + a separate Adam launch instead)
+    exchange = optim.enable_peer_exchange() if (world > 1 and not args.nccl) else None
     graphed = trainer.GraphedTrainStep(model, optim)
     NB = 4
     dev_batches, host_parts = [], []
@@ -476,6 +479,14 @@ def run_ours(args):
         res[tr] = measure(tr)
         _say(f"mode train={tr} done")
     clocks = sampler.stop() if rank == 0 else None
+    ranks_identical = None
+    if world > 1:
+        # identical Adam steps on every rank: the weights must still agree bit for bit after all the steps above
+        mine = optim.flat.detach().clone()
+        allw = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allw, mine)
+        ranks_identical = all(torch.equal(allw[0], w) for w in allw)
+        assert ranks_identical, "rank weights diverged"
 
     if args.skip_e2e:
         ms, stages, launches, _ = res[headline_train]
@@ -606,6 +617,9 @@ def run_ours(args):
         "clocks": clocks, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
         "first_layer_tensor_frac": head["first_layer_tensor_frac"],
         "evaluation_path": "vertex (P = E [W0;Wy]^T per vertex, rays gather P)" if vertex else "ray (3 table rows gathered per ray)",
+        "gradient_exchange": None if world == 1 else ("peer memory over NVLink inside field_reduce_kernel (rank-ordered sum, Adam fused)"
+                                                      if exchange is not None else "NCCL allreduce of the flat gradient + Adam launch"),
+        "rank_weights_bit_identical": ranks_identical,
         "inf_debug": debug,
     }
     if (not headline_train) in res:
@@ -641,6 +655,7 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "ray", "vertex"],
                     help="evaluation of the two K = k contractions: per ray, per vertex, or the library's rule (InfDesc.path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL allreduce + separate Adam launch instead of the peer-memory exchange")
     ap.add_argument("--headline-only", action="store_true", help="only the headline mode (no other mode, no extras)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: resident steps only (the JSON line is not a bench result)")
     ap.add_argument("--grid", type=int, default=224, help="torus grid side: V = grid^2 vertices (default: config 2)")

@@ -147,6 +147,28 @@ typedef struct InfAdam {
   int32_t reserved0;
 } InfAdam;
 
+/* Peer-memory exchange of the multi-GPU training step (one process per GPU on one node; replaces the reference's
+ * nn.DataParallel, train.py:46-48, and the NCCL allreduce + separate optimiser launch of a plain data-parallel step).
+ * Every rank creates one exchange region (inf_comm_create: device memory + an IPC handle), the ranks swap the 64-byte
+ * handles by any means (torch.distributed all_gather_object in the Python mirror), and each opens its peers' regions
+ * (inf_comm_open).  inf_train_step_comm then sums the per-rank gradients INSIDE the reduction kernel: every rank writes
+ * its gradient into its own region, publishes a flag in every peer's region with a system-scope release store over
+ * NVLink, waits for the peers' flags, reads their slots and adds them in rank order -- so all ranks obtain bit-identical
+ * sums -- and applies Adam + the operand refresh in the same launch.  All ranks must make the same sequence of calls. */
+#define INF_MAX_PEERS 8
+#define INF_IPC_HANDLE_BYTES 64
+typedef struct InfComm {
+  int32_t world;                /* ranks on this node, 2..INF_MAX_PEERS (<= 1: no exchange)            */
+  int32_t rank;
+  void* regions[INF_MAX_PEERS]; /* regions[q]: rank q's exchange region as mapped in THIS process      */
+  size_t region_bytes;          /* >= inf_comm_region_bytes(desc)                                      */
+} InfComm;
+size_t inf_comm_region_bytes(const InfDesc* desc);
+int inf_comm_create(size_t bytes, void** region, void* ipc_handle_out /* INF_IPC_HANDLE_BYTES */);
+int inf_comm_open(const void* ipc_handle, void** mapped);
+int inf_comm_close(void* mapped);
+int inf_comm_free(void* region);
+
 /* version / errors */
 int inf_version(void);
 /* kernels of this library enqueued by the process so far (bench.py's gpu_launches is a difference of two readings;
@@ -194,6 +216,11 @@ int inf_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrad
  * all inside the gradient-reduction kernel (single-GPU training step in three launches).  g->flat still receives the
  * gradient.  `t->packed` (read by this step's forward) and `adam->packed` (written at the end) may be the same buffer. */
 int inf_train_step(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, void* stream);
+
+/* inf_train_step across the GPUs of a node: the gradient exchange runs inside the reduction kernel over peer memory
+ * (see InfComm).  g->flat and g->loss_sums receive the SUMS over ranks (desc->grad_scale carries 1/(3*B_global)). */
+int inf_train_step_comm(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, const InfComm* comm,
+                        void* stream);
 
 /* Adam + operand refresh from an already reduced gradient (multi-GPU: call after the allreduce of g->flat). */
 int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* adam, void* stream);

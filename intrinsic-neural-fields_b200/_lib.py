@@ -55,6 +55,14 @@ class InfAdam(C.Structure):
                 ("step", C.c_int32), ("reserved0", C.c_int32)]
 
 
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
+
+
+class InfComm(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("regions", C.c_void_p * MAX_PEERS), ("region_bytes", C.c_size_t)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "inf_version": (C.c_int, []),
@@ -77,6 +85,13 @@ EXPORTS = {
     "inf_forward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p]),
     "inf_forward_backward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.POINTER(InfGrads), C.c_void_p]),
     "inf_train_step": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.POINTER(InfGrads), C.POINTER(InfAdam), C.c_void_p]),
+    "inf_train_step_comm": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.POINTER(InfGrads), C.POINTER(InfAdam),
+                                      C.POINTER(InfComm), C.c_void_p]),
+    "inf_comm_region_bytes": (C.c_size_t, [C.POINTER(InfDesc)]),
+    "inf_comm_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "inf_comm_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "inf_comm_close": (C.c_int, [C.c_void_p]),
+    "inf_comm_free": (C.c_int, [C.c_void_p]),
     "inf_adam_pack_step": (C.c_int, [C.POINTER(InfDesc), C.c_void_p, C.POINTER(InfAdam), C.c_void_p]),
     "inf_gather_interpolate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]),

@@ -593,7 +593,8 @@ static AdamParams adam_params(const InfAdam* a) {
   return ap;
 }
 
-static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, void* stream) {
+static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, void* stream,
+                                const InfComm* comm = nullptr) {
   int rc = check_desc(desc);
   if (rc != INF_OK) return rc;
   rc = check_tensors(desc, t, true);
@@ -771,6 +772,13 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   }
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
   rp.do_reduce = 1;
+  rp.err = p.err;
+  if (comm != nullptr && comm->world > 1) {
+    rp.comm.world = comm->world;
+    rp.comm.rank = comm->rank;
+    for (int q = 0; q < comm->world; ++q) rp.comm.region[q] = reinterpret_cast<float*>(comm->regions[q]);
+    rp.comm.slot_floats = ((total + 2 + 31) / 32) * 32;
+  }
   rp.adam = adam_params(adam);
   rp.geo = geo;
   rp.plan = plan;
@@ -792,6 +800,67 @@ int inf_train_step(const InfDesc* desc, const InfTensors* t, const InfGrads* g, 
   int rc = check_adam(adam);
   if (rc != INF_OK) return rc;
   return run_forward_backward(desc, t, g, adam, stream);
+}
+
+int inf_train_step_comm(const InfDesc* desc, const InfTensors* t, const InfGrads* g, const InfAdam* adam, const InfComm* comm,
+                        void* stream) {
+  if (adam == nullptr) return fail(INF_ERR_BAD_ARG, "adam is null");
+  int rc = check_adam(adam);
+  if (rc != INF_OK) return rc;
+  if (comm != nullptr && comm->world > 1) {
+    if (comm->world > INF_MAX_PEERS || comm->rank < 0 || comm->rank >= comm->world) return fail(INF_ERR_BAD_ARG, "comm: bad world / rank");
+    if (check_desc(desc) != INF_OK) return INF_ERR_BAD_ARG;
+    if (comm->region_bytes < inf_comm_region_bytes(desc)) return fail(INF_ERR_WORKSPACE, "comm: exchange region too small");
+    for (int q = 0; q < comm->world; ++q)
+      if (comm->regions[q] == nullptr) return fail(INF_ERR_BAD_ARG, "comm: region of rank %d is not mapped", q);
+    if (t != nullptr && t->target == nullptr) return fail(INF_ERR_BAD_ARG, "comm: the exchanged step uses the built-in L1 loss (target)");
+  }
+  return run_forward_backward(desc, t, g, adam, stream, comm);
+}
+
+size_t inf_comm_region_bytes(const InfDesc* desc) {
+  if (check_desc(desc) != INF_OK) return 0;
+  ParamInfo pi[INF_MAX_PARAMS];
+  int64_t total = 0;
+  build_param_table(desc, pi, &total);
+  return comm_region_bytes(total);
+}
+
+int inf_comm_create(size_t bytes, void** region, void* ipc_handle_out) {
+  if (region == nullptr || ipc_handle_out == nullptr || bytes == 0) return fail(INF_ERR_BAD_ARG, "comm_create: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == INF_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc (exchange region)");
+  e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *region = p;
+  return INF_OK;
+}
+
+int inf_comm_open(const void* ipc_handle, void** mapped) {
+  if (ipc_handle == nullptr || mapped == nullptr) return fail(INF_ERR_BAD_ARG, "comm_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(mapped, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+  return INF_OK;
+}
+
+int inf_comm_close(void* mapped) {
+  cudaError_t e = cudaIpcCloseMemHandle(mapped);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+  return INF_OK;
+}
+
+int inf_comm_free(void* region) {
+  cudaError_t e = cudaFree(region);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFree");
+  return INF_OK;
 }
 
 int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* adam, void* stream) {

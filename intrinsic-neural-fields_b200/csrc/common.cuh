@@ -309,6 +309,24 @@ struct AdamParams {
   float lr, beta1, beta2, eps;
   float omb1, omb2;   // 1 - beta, rounded from double as torch does
 };
+// Peer-memory exchange of the flat gradient (multi-GPU step): every rank owns an exchange region that all
+// ranks of the node have mapped (CUDA IPC over NVLink).  A region = two gradient slots (steps alternate, so a rank may
+// run one step ahead of a peer that is still reading) followed by a control block.
+constexpr int MAX_PEERS = 8;
+constexpr int COMM_CTL_WORDS = 64;       // u32 words of the control block
+enum : int { CTL_FLAGS = 0,              // [MAX_PEERS] flags[q] = last step whose gradient rank q has published
+             CTL_SEQ = 16,               // steps this rank has completed (device-resident: a CUDA-graph replay advances it)
+             CTL_BAR = 17, CTL_DONE = 18 };   // block counters of the reduction kernel
+struct CommParams {
+  int world, rank;                       // world <= 1: no exchange
+  float* region[MAX_PEERS];              // region[q] = rank q's exchange region as mapped in this process
+  int64_t slot_floats;                   // floats per gradient slot (>= total + 2, multiple of 32)
+};
+__host__ __device__ inline size_t comm_region_bytes(int64_t total) {
+  const int64_t slot = ((total + 2 + 31) / 32) * 32;
+  return static_cast<size_t>(2 * slot) * 4 + COMM_CTL_WORDS * 4;
+}
+
 struct ReduceParams {
   ReduceSeg seg[INF_MAX_PARAMS];
   int nseg;
@@ -323,6 +341,8 @@ struct ReduceParams {
   int cta_base_hid[MAX_HID_SLICES];
   float scale;
   int do_reduce;   // 0: flat already holds the (all-reduced) gradient, only the optimiser tail runs
+  CommParams comm; // multi-GPU: exchange + sum of the per-rank gradients inside this kernel (world <= 1: none)
+  unsigned int* err;
   AdamParams adam;
   Geo geo;
   WPlan plan;

@@ -301,92 +301,184 @@ __device__ __forceinline__ void adam_update(const AdamParams& a, float step_size
   a.params[i] = p_new;
 }
 
-__device__ __forceinline__ void reduce_element(const ReduceParams& rp, int64_t i, float dev_step_size, float dev_bc2_sqrt);
+// system-scope accesses for the peer-memory exchange (peer lines are cached in L1 only: never trust a plain load)
+__device__ __forceinline__ float ld_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
+__device__ __forceinline__ float reduce_partials(const ReduceParams& rp, int64_t i, int& sidx_out);
+__device__ __forceinline__ void apply_update(const ReduceParams& rp, int64_t i, int sidx, float grad, float dev_step_size, float dev_bc2_sqrt);
+
+// One launch = partial sums -> [multi-GPU: exchange over peer memory + sum over ranks] -> flat gradient -> [Adam + refresh of the
+// operand images].  With an exchange the launch is cooperative (every block resident): the ranks' kernels meet at a flag
+// per rank, written with system-scope release stores into every peer's control block.
 __global__ void field_reduce_kernel(const ReduceParams rp) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t tid0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
   // Adam's bias corrections from the device-resident step counter: two double-precision pow() -- once per CTA, not per
   // element (FP64 transcendental code in every thread was most of this kernel's 21 us)
   __shared__ float s_bias_corr[2];
-  if (threadIdx.x == 0 && rp.adam.params != nullptr && rp.adam.step_dev != nullptr) {
-    const double t = static_cast<double>(*rp.adam.step_dev);
-    s_bias_corr[0] = static_cast<float>(static_cast<double>(rp.adam.lr) / (1.0 - pow(static_cast<double>(rp.adam.beta1), t)));
-    s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(rp.adam.beta2), t)));
+  __shared__ uint32_t s_seq;
+  const CommParams& cm = rp.comm;
+  const bool exchange = cm.world > 1 && rp.do_reduce;
+  uint32_t* ctl = exchange ? reinterpret_cast<uint32_t*>(cm.region[cm.rank] + 2 * cm.slot_floats) : nullptr;
+  if (threadIdx.x == 0) {
+    if (rp.adam.params != nullptr && rp.adam.step_dev != nullptr) {
+      const double t = static_cast<double>(*rp.adam.step_dev);
+      s_bias_corr[0] = static_cast<float>(static_cast<double>(rp.adam.lr) / (1.0 - pow(static_cast<double>(rp.adam.beta1), t)));
+      s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(rp.adam.beta2), t)));
+    }
+    if (exchange) s_seq = ld_acquire_sys_u32(ctl + CTL_SEQ) + 1u;   // this step's sequence number (advanced by the last block to leave)
   }
   __syncthreads();
-  if (i == 0 && rp.loss_sums != nullptr && rp.do_reduce) {
-    float a = 0.f, b = 0.f;
+  float loss_a = 0.f, loss_b = 0.f;
+  if (tid0 == 0 && rp.do_reduce && (rp.loss_sums != nullptr || exchange)) {
     for (int c = 0; c < rp.ncta1; ++c) {
       const float* pl = rp.part1 + static_cast<size_t>(c) * K1_PART_FLOATS;
-      a += pl[4];
-      b += pl[5];
+      loss_a += pl[4];
+      loss_b += pl[5];
     }
+    if (!exchange && rp.loss_sums != nullptr) { rp.loss_sums[0] = loss_a; rp.loss_sums[1] = loss_b; }
+  }
+  if (!exchange) {
+    // one resident wave: a CTA past the first wave would cost a whole extra pass for a handful of elements
+    for (int64_t e = tid0; e < rp.total; e += nthreads) {
+      int sidx = 0;
+      float grad;
+      if (rp.do_reduce) { grad = reduce_partials(rp, e, sidx); rp.flat[e] = grad; }
+      else {
+        for (int s = 1; s < rp.nseg; ++s) if (e >= rp.seg[s].off) sidx = s;
+        grad = rp.flat[e];
+      }
+      apply_update(rp, e, sidx, grad, s_bias_corr[0], s_bias_corr[1]);
+    }
+    return;
+  }
+  // ---- phase A: this rank's gradient into its slot of the exchange region -------------------------------------
+  const uint32_t seq = s_seq;
+  const int64_t slot = static_cast<int64_t>(seq & 1u) * cm.slot_floats;
+  float* mine = cm.region[cm.rank] + slot;
+  for (int64_t e = tid0; e < rp.total; e += nthreads) {
+    int sidx;
+    mine[e] = reduce_partials(rp, e, sidx);
+  }
+  if (tid0 == 0) { mine[rp.total] = loss_a; mine[rp.total + 1] = loss_b; }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the last block to arrive publishes: flags[rank] = seq in EVERY rank's control block (own included)
+    if (atomicAdd(ctl + CTL_BAR, 1u) == gridDim.x - 1) {
+      atomicExch(ctl + CTL_BAR, 0u);
+      __threadfence_system();
+      for (int q = 0; q < cm.world; ++q)
+        st_release_sys_u32(reinterpret_cast<uint32_t*>(cm.region[q] + 2 * cm.slot_floats) + CTL_FLAGS + cm.rank, seq);
+    }
+    // every block waits until all ranks have published this step (a peer may already be one step ahead: >=)
+    const long long t0 = clock64();
+    for (int q = 0; q < cm.world; ++q) {
+      while (static_cast<int32_t>(ld_acquire_sys_u32(ctl + CTL_FLAGS + q) - seq) < 0) {
+        if (clock64() - t0 > (1ll << 33)) {   // ~4 s: a peer died; surface it instead of hanging the GPU
+          if (rp.err) atomicExch(rp.err, 0xDEAD0C00u | static_cast<unsigned>(q));
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase B: sum over ranks in rank order (bit-identical on every rank), then the optimiser tail ------------------
+  for (int64_t e = tid0; e < rp.total; e += nthreads) {
+    float g = 0.f;
+    for (int q = 0; q < cm.world; ++q) g += ld_sys_f32(cm.region[q] + slot + e);
+    rp.flat[e] = g;
+    int sidx = 0;
+    for (int s = 1; s < rp.nseg; ++s) if (e >= rp.seg[s].off) sidx = s;
+    apply_update(rp, e, sidx, g, s_bias_corr[0], s_bias_corr[1]);
+  }
+  if (tid0 == 0 && rp.loss_sums != nullptr) {
+    float a = 0.f, b = 0.f;
+    for (int q = 0; q < cm.world; ++q) { a += ld_sys_f32(cm.region[q] + slot + rp.total); b += ld_sys_f32(cm.region[q] + slot + rp.total + 1); }
     rp.loss_sums[0] = a;
     rp.loss_sums[1] = b;
   }
-  // one resident wave: a CTA past the first wave would cost a whole extra pass for a handful of elements
-  for (int64_t e = i; e < rp.total; e += static_cast<int64_t>(gridDim.x) * blockDim.x) reduce_element(rp, e, s_bias_corr[0], s_bias_corr[1]);
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(ctl + CTL_DONE, 1u) == gridDim.x - 1) {
+    atomicExch(ctl + CTL_DONE, 0u);
+    st_release_sys_u32(ctl + CTL_SEQ, seq);   // every block has read this step's sequence number long ago
+  }
 }
 
-__device__ __forceinline__ void reduce_element(const ReduceParams& rp, const int64_t i, const float dev_step_size,
-                                               const float dev_bc2_sqrt) {
+// sum of the wgrad / forward-backward partials of flat element i, scaled; also returns its parameter segment
+__device__ __forceinline__ float reduce_partials(const ReduceParams& rp, const int64_t i, int& sidx_out) {
   int sidx = 0;
   for (int s = 1; s < rp.nseg; ++s)
     if (i >= rp.seg[s].off) sidx = s;
+  sidx_out = sidx;
   const ReduceSeg sg = rp.seg[sidx];
   const int64_t e = i - sg.off;
   const int row = static_cast<int>(e / sg.cols);
   const int col = static_cast<int>(e % sg.cols);
-  float grad;
-  if (rp.do_reduce) {
-    float acc = 0.f;
-    // (first CTA, #groups, lane, column) of the partials holding this element
-    int cta0 = 0, ng = 0, ln = row, c = 0;
-    auto from_unit = [&](int ui, int lane_, int col_) {
-      const WUnit w = rp.plan.u[ui];
-      cta0 = rp.cta_base_hid[w.slice];
-      ng = rp.groups_hid[w.slice];
-      ln = lane_;
-      c = col_;
-    };
-    int gmul = 1;   // CTAs between consecutive ray groups of the same slice
-    if (sg.kind == 0) {  // W0 / Wy: row n, column j; big CTAs are group-major (CTA = group * nbig + slice)
-      cta0 = col >> 8;
-      ng = rp.groups_big;
-      gmul = rp.geo.nbig;
-      c = (col & 255) + (sg.a ? 256 : 0);
-    } else if (sg.kind == 1) {  // hidden / view weight
-      if (col < sg.split) from_unit(sg.a, row, rp.plan.u[sg.a].col + col);
-      else from_unit(sg.b, row, rp.plan.u[sg.b].col + (col - sg.split));
-    } else if (sg.kind == 2) {  // bias (rows entries, cols == 1)
-      from_unit(sg.a, row, rp.plan.u[sg.a].bias_col);
-    } else if (sg.kind == 3) {  // output-layer weight [3][wout]: lane = input feature, column = channel
-      from_unit(sg.a, col, rp.plan.u[sg.a].col + row);
-    }
-    if (sg.kind == 4) {  // output-layer bias [3]
-      for (int k = 0; k < rp.ncta1; ++k) acc += rp.part1[static_cast<size_t>(k) * K1_PART_FLOATS + row];
-    } else {
-      // fixed summation order; loads issued eight at a time so that their latencies overlap
-      const float* src = rp.partw + (static_cast<size_t>(cta0) * HID + ln) * WG_COLS + c;
-      const size_t GSTRIDE = static_cast<size_t>(HID) * WG_COLS * static_cast<size_t>(gmul);
-      int gI = 0;
-      for (; gI + 8 <= ng; gI += 8) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = src[static_cast<size_t>(gI + q) * GSTRIDE];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc += v[q];
-      }
-      for (; gI < ng; ++gI) acc += src[static_cast<size_t>(gI) * GSTRIDE];
-    }
-    grad = acc * rp.scale;
-    rp.flat[i] = grad;
-  } else {
-    grad = rp.flat[i];
+  float acc = 0.f;
+  // (first CTA, #groups, lane, column) of the partials holding this element
+  int cta0 = 0, ng = 0, ln = row, c = 0;
+  auto from_unit = [&](int ui, int lane_, int col_) {
+    const WUnit w = rp.plan.u[ui];
+    cta0 = rp.cta_base_hid[w.slice];
+    ng = rp.groups_hid[w.slice];
+    ln = lane_;
+    c = col_;
+  };
+  int gmul = 1;   // CTAs between consecutive ray groups of the same slice
+  if (sg.kind == 0) {  // W0 / Wy: row n, column j; big CTAs are group-major (CTA = group * nbig + slice)
+    cta0 = col >> 8;
+    ng = rp.groups_big;
+    gmul = rp.geo.nbig;
+    c = (col & 255) + (sg.a ? 256 : 0);
+  } else if (sg.kind == 1) {  // hidden / view weight
+    if (col < sg.split) from_unit(sg.a, row, rp.plan.u[sg.a].col + col);
+    else from_unit(sg.b, row, rp.plan.u[sg.b].col + (col - sg.split));
+  } else if (sg.kind == 2) {  // bias (rows entries, cols == 1)
+    from_unit(sg.a, row, rp.plan.u[sg.a].bias_col);
+  } else if (sg.kind == 3) {  // output-layer weight [3][wout]: lane = input feature, column = channel
+    from_unit(sg.a, col, rp.plan.u[sg.a].col + row);
   }
+  if (sg.kind == 4) {  // output-layer bias [3]
+    for (int k = 0; k < rp.ncta1; ++k) acc += rp.part1[static_cast<size_t>(k) * K1_PART_FLOATS + row];
+  } else {
+    // fixed summation order; loads issued eight at a time so that their latencies overlap
+    const float* src = rp.partw + (static_cast<size_t>(cta0) * HID + ln) * WG_COLS + c;
+    const size_t GSTRIDE = static_cast<size_t>(HID) * WG_COLS * static_cast<size_t>(gmul);
+    int gI = 0;
+    for (; gI + 8 <= ng; gI += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = src[static_cast<size_t>(gI + q) * GSTRIDE];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += v[q];
+    }
+    for (; gI < ng; ++gI) acc += src[static_cast<size_t>(gI) * GSTRIDE];
+  }
+  return acc * rp.scale;
+}
+
+// Adam on the master parameter of flat element i, then its entry of the fp16 / f32 operand images
+__device__ __forceinline__ void apply_update(const ReduceParams& rp, const int64_t i, const int sidx, const float grad,
+                                             const float dev_step_size, const float dev_bc2_sqrt) {
   const AdamParams& ad = rp.adam;
   if (ad.params == nullptr) return;
-  // ---- Adam on the master parameter, then its entry of the fp16 / f32 operand images ----------------------------
+  const ReduceSeg sg = rp.seg[sidx];
+  const int64_t e = i - sg.off;
+  const int row = static_cast<int>(e / sg.cols);
+  const int col = static_cast<int>(e % sg.cols);
   if (sg.kind == 2 && sg.pair_off == -2) return;   // Ly.bias: handled by the thread of Lx.bias
   float step_size = ad.step_size, bc2_sqrt = ad.bc2_sqrt;
   if (ad.step_dev != nullptr) {
@@ -438,8 +530,22 @@ cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream) {
   }
   int64_t blocks = (rp.total + threads - 1) / threads;
   if (blocks > resident) blocks = resident;
-  field_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(rp);
-  return cudaGetLastError();
+  const bool exchange = rp.comm.world > 1 && rp.do_reduce;
+  if (!exchange) {
+    field_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(rp);
+    return cudaGetLastError();
+  }
+  // the blocks of a rank meet at counters and the ranks meet at flags: every block must be resident
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+  cfg.blockDim = dim3(threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, field_reduce_kernel, rp);
 }
 
 }  // namespace inf

@@ -385,7 +385,8 @@ def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps
 
 
 def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key,
-                                 dense: bool, grad_scale: float, adam=None, ray_idxs=None, table_image=None, path: int = 0):
+                                 dense: bool, grad_scale: float, adam=None, ray_idxs=None, table_image=None, path: int = 0,
+                                 comm_id: int = 0):
     cfg = FieldConfig.from_key(cfg_key)
     B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
@@ -422,7 +423,15 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
             if adam.params_flat.numel() != n_par:
                 raise ValueError("flat parameter vector does not match the model configuration")
             a = _adam_struct(*adam)
-            rc = _lib.load().inf_train_step(C.byref(d), C.byref(t), C.byref(g), C.byref(a), _stream(device))
+            if comm_id:
+                from .parallel import PeerExchange
+                comm = PeerExchange.lookup(comm_id)
+                if comm is None:
+                    raise RuntimeError(f"peer exchange {comm_id} is not open in this process")
+                rc = _lib.load().inf_train_step_comm(C.byref(d), C.byref(t), C.byref(g), C.byref(a), C.byref(comm.struct),
+                                                     _stream(device))
+            else:
+                rc = _lib.load().inf_train_step(C.byref(d), C.byref(t), C.byref(g), C.byref(a), _stream(device))
     _lib.check(rc, "inf_forward_backward" if adam is None else "inf_train_step")
     return pred, flat_full
 
@@ -489,18 +498,18 @@ def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Op
                      params_flat: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float,
                      beta2: float, eps: float, step_dev: torch.Tensor,
                      ray_idxs: Optional[torch.Tensor] = None, table_image: Optional[torch.Tensor] = None,
-                     path: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                     path: int = 0, comm_id: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Forward + L1 loss + backward + Adam + operand refresh (trainer.py:75-82); the optimiser runs inside the
-    gradient-reduction kernel."""
+    gradient-reduction kernel -- and, with ``comm_id`` (parallel.PeerExchange), so does the sum over the ranks of a node."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, None, dirs, face_idxs, face_normals, cfg_key,
                                         dense, grad_scale,
                                         adam=_AdamArgs((params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)),
-                                        ray_idxs=ray_idxs, table_image=table_image, path=path)
+                                        ray_idxs=ray_idxs, table_image=table_image, path=path, comm_id=comm_id)
 
 
 @field_train_step.register_fake
 def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, params_flat, exp_avg,
-      exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None, table_image=None, path=0):
+      exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None, table_image=None, path=0, comm_id=0):
     B = _fake_rows(table, vids, dense, ray_idxs)
     return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty((params_flat.numel() + 2,)))
 

@@ -51,3 +51,60 @@ def allreduce_module_grads(model, group=None):
 def broadcast_parameters(model, src: int = 0, group=None):
     for p in model.parameters():
         dist.broadcast(p.data, src=src, group=group)
+
+
+class PeerExchange:
+    """The multi-GPU training step's gradient exchange over NVLink peer memory (include/inf_field.h: InfComm).
+
+    Every rank creates one exchange region in the C library, the ranks swap the 64-byte CUDA IPC handles with one
+    ``all_gather_object`` (setup only -- no collective runs per step) and map each other's regions.  The fused training
+    step (``FusedFieldAdam.fused_l1_step``) then sums the per-rank gradients inside its reduction kernel, in rank order,
+    so every rank applies bit-identical updates without NCCL and without a separate optimiser launch.
+    One node only (IPC); every rank must take the same sequence of steps."""
+
+    _registry = {}
+
+    def __init__(self, cfg, device, group=None):
+        import ctypes as C
+        from . import _lib, ops
+        self.lib = lib = _lib.load()
+        self.world, self.rank = world_size(group), rank(group)
+        if not 2 <= self.world <= _lib.MAX_PEERS:
+            raise ValueError(f"PeerExchange needs 2..{_lib.MAX_PEERS} ranks on one node, got {self.world}")
+        self.device = torch.device(device)
+        nbytes = int(lib.inf_comm_region_bytes(C.byref(ops._desc(cfg, 0, 0))))
+        region, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.inf_comm_create(nbytes, C.byref(region), handle), "inf_comm_create")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            regions = (C.c_void_p * _lib.MAX_PEERS)()
+            self._mapped = []
+            for q, h in enumerate(handles):
+                if q == self.rank:
+                    regions[q] = region.value
+                else:
+                    m = C.c_void_p()
+                    _lib.check(lib.inf_comm_open(C.create_string_buffer(h, _lib.IPC_HANDLE_BYTES), C.byref(m)), "inf_comm_open")
+                    regions[q] = m.value
+                    self._mapped.append(m)
+            dist.barrier(group=group)           # every rank has mapped every region before the first step
+        self._region = region
+        self.struct = _lib.InfComm(world=self.world, rank=self.rank, regions=regions, region_bytes=nbytes)
+        self.id = len(PeerExchange._registry) + 1
+        PeerExchange._registry[self.id] = self
+
+    @staticmethod
+    def lookup(comm_id: int):
+        return PeerExchange._registry.get(comm_id)
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for m in self._mapped:
+                self.lib.inf_comm_close(m)
+            self._mapped = []
+            if self._region is not None:
+                self.lib.inf_comm_free(self._region)
+                self._region = None
+        PeerExchange._registry.pop(self.id, None)

@@ -53,6 +53,8 @@ def run(config: dict, mesh=None, allow_checkpoint_loading: bool = False, fused_a
     loss_fn = trainer.get_loss_fn(config["training"]["loss_type"])
     use_fused = fused_adam and loss_fn is torch.nn.functional.l1_loss and not config["training"].get("use_lr_scheduler", False)
     optim = trainer.FusedFieldAdam(model, lr=lr) if use_fused else torch.optim.Adam(model.parameters(), lr=lr)
+    if use_fused and world > 1:
+        optim.enable_peer_exchange()      # gradient sum over the node's GPUs inside the reduction kernel (no NCCL per step)
     _seed(seed)                                                    # again: the model's init consumed random numbers (train.py:55-57)
     t = trainer.Trainer(model, optim, loss_fn, None, data, mesh, config, device)
     t.train()

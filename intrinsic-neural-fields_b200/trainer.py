@@ -119,9 +119,18 @@ class FusedFieldAdam:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # t, on the device: a graph replay advances it
         self.layout = layout
         self.packed = ops.pack_weights(model.cfg, [p.detach() for p in params], None)     # zero padding written once
+        self.exchange = None      # parallel.PeerExchange: the multi-GPU gradient sum inside the reduction kernel
         # the operand images are refreshed by the Adam kernel only: weights written from outside (a checkpoint restored
         # after the optimiser was built, trainer.py:214-231) must be re-packed before the next forward
         model.register_load_state_dict_post_hook(lambda module, incompatible_keys: self.repack())
+
+    def enable_peer_exchange(self, group=None):
+        """Multi-GPU (one node): sum the ranks' gradients inside the reduction kernel over NVLink peer memory instead of an
+        NCCL allreduce followed by a separate optimiser launch.  Call once after ``init_process_group`` on every rank."""
+        import os
+        if parallel.world_size(group) > 1 and self.exchange is None and os.environ.get("INF_PEER_EXCHANGE", "1") != "0":
+            self.exchange = parallel.PeerExchange(self.model.cfg, self.flat.device, group)
+        return self.exchange
 
     def repack(self):
         """Rebuild the fp16 operand images from the flat fp32 parameters (in place: captured graphs keep their pointer)."""
@@ -142,7 +151,7 @@ class FusedFieldAdam:
         pred, flat_full = torch.ops.inf_b200.field_train_step(
             table, vids, bary, self.packed, target, dirs, face_idxs, normals, m.cfg.key(), dense, scale, self.flat,
             self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, ridx,
-            *m._table_extras(batch))
+            *m._table_extras(batch), self.exchange.id if self.exchange is not None else 0)
         flat, sums = ops.split_flat(flat_full)
         m._packed, m._packed_key = self.packed, None
         return sums, pred, flat
@@ -204,6 +213,8 @@ def fused_train_step_async(model, fopt: "FusedFieldAdam", batch, group=None):
     B = batch_rays(batch)
     if world == 1:
         sums, pred, _ = fopt.fused_l1_step(batch)
+    elif fopt.exchange is not None:
+        sums, pred, _ = fopt.fused_l1_step(batch, global_rays=B * world)      # the sum over ranks runs inside the step
     else:
         sums, pred, flat = fopt.backward_only(batch, B * world)
         parallel.allreduce_flat(flat, sums, group)
@@ -251,6 +262,8 @@ class GraphedTrainStep:
         if isinstance(self.optim, FusedFieldAdam):
             if world == 1:
                 return self.optim.fused_l1_step(batch)                   # includes the update
+            if self.optim.exchange is not None:
+                return self.optim.fused_l1_step(batch, global_rays=B * world)   # includes the sum over ranks and the update
             return self.optim.backward_only(batch, B * world)
         self.optim.zero_grad(set_to_none=True)
         return self.model.l1_step(batch, global_rays=B * world)          # sums, pred, flat
@@ -264,18 +277,22 @@ class GraphedTrainStep:
             self.optim.step()
         return loss
 
+    def _peer(self):
+        return isinstance(self.optim, FusedFieldAdam) and self.optim.exchange is not None
+
     def _eager(self, batch):
         world = parallel.world_size(self.group)
         sums, pred, flat = self._front(batch)
-        if world > 1:
+        nccl = world > 1 and not self._peer()
+        if nccl:
             parallel.allreduce_flat(flat, sums, self.group)
-        return self._back(sums, batch_rays(batch) * world, flat if world > 1 else None), pred
+        return self._back(sums, batch_rays(batch) * world, flat if nccl else None), pred
 
     def _capture(self, batch):
         world = parallel.world_size(self.group)
         n_global = batch_rays(batch) * world
         g1 = torch.cuda.CUDAGraph()
-        if world == 1:
+        if world == 1 or self._peer():     # no NCCL call in the step: one graph at any number of ranks
             with torch.cuda.graph(g1):
                 loss, pred = self._eager(batch)
             return (g1, None, None, None, loss, pred)
