@@ -121,6 +121,8 @@ typedef struct InfTensors {
                               /* stay in batch order                                                                */
   const void* table_image;    /* optional fp16 operand image of the table (inf_build_table_image); enables the      */
                               /* vertex path; the workspace must then be sized with desc.n_rows set                 */
+  const int8_t* col_exp;      /* optional (k_pad,) column exponents of the table (inf_column_exponents): the table  */
+                              /* holds E[:,j] * 2^col_exp[j]; `packed` must have been built with the same exponents */
   const void* packed;         /* operand images written by inf_pack_weights                         */
   float* pred;                /* (B,3) f32 out                                                      */
   void* workspace;            /* >= inf_workspace_bytes(desc, training)                             */
@@ -140,6 +142,7 @@ typedef struct InfAdam {
   float* exp_avg;     /* first moment                                                                  */
   float* exp_avg_sq;  /* second moment                                                                 */
   void* packed;       /* operand images (inf_pack_weights layout); the live entries are rewritten      */
+  const int8_t* col_exp; /* column exponents of the table these operand images are used with (null: none)        */
   const int32_t* step_dev; /* optional DEVICE counter holding t (read by the kernel; lets a CUDA graph replay   */
                       /* the step with a changing t); when null, `step` below is used                  */
   float lr, beta1, beta2, eps;
@@ -192,6 +195,20 @@ size_t inf_workspace_bytes(const InfDesc* desc, int training);
 int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride,
                        void* dst, int32_t k_pad, int32_t dst_dtype, void* stream);
 
+/* fp16 range guard.  The kernels round the interpolated embedding (and the table image) to fp16, which is harmless for
+ * the reference's default `standard` rescale (|E| <= 1, mesh.py:99-102) but loses `unscaled` / HKS / functional-map
+ * tables whose columns sit far from 1 (mesh.py:53-108): below 6e-5 they fall into fp16's subnormals, above 65504 they
+ * overflow.  inf_column_exponents writes, per column j, the power of two that brings max|E[:,j]| into [0.5, 1) when it
+ * lies outside [2^-6, 2^6] (0 otherwise: tables in the usual range stay bit for bit); inf_relayout_table_scaled stores
+ * E[:,j] * 2^col_exp[j]; inf_pack_weights_scaled stores W0[:,j] * 2^-col_exp[j] (and Wy alike) in the operand images, so
+ * every product x_j W[n,j] is unchanged -- scaling by powers of two is exact -- and the weight gradients of layer 0 / Ly
+ * are scaled back in the reduction kernel.  `scratch` = k_pad u32 of device memory. */
+int inf_column_exponents(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, int32_t k_pad, int8_t* col_exp,
+                         void* scratch, void* stream);
+int inf_relayout_table_scaled(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, const int8_t* col_exp,
+                              void* dst, int32_t k_pad, int32_t dst_dtype, void* stream);
+int inf_pack_weights_scaled(const InfDesc* desc, const float* const* params, const int8_t* col_exp, void* packed, void* stream);
+
 /* Table operand image for the vertex path: (V,k_pad) f32|f16 row-major table -> fp16 [ceil(V/128)][k_pad/64] panels of
  * [128 rows][64 columns] in the tensor core's SWIZZLE_128B layout (values rounded to fp16 once).  Built once where the
  * reference moves the table to the device (ray_dataloader.py:73, renderer.py:43). */
@@ -231,6 +248,10 @@ int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* ada
 int inf_gather_interpolate(const void* table, int32_t table_dtype, int32_t k, int32_t k_pad,
                            const void* vids, int32_t idx_dtype, const float* bary, int64_t n_rays,
                            float* out, void* stream);
+/* the same for a table stored with column exponents: the output is scaled back to the reference's values */
+int inf_gather_interpolate_scaled(const void* table, int32_t table_dtype, int32_t k, int32_t k_pad, const int8_t* col_exp,
+                                  const void* vids, int32_t idx_dtype, const float* bary, int64_t n_rays,
+                                  float* out, void* stream);
 
 /* Measurement hooks (bench.py): while enabled, inf_forward / inf_forward_backward bracket their
  * kernels with library-owned CUDA events on the launching stream (up to 256 calls, no sync);

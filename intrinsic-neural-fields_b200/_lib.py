@@ -39,7 +39,8 @@ class InfTensors(C.Structure):
     _fields_ = [
         ("table", C.c_void_p), ("vids", C.c_void_p), ("bary", C.c_void_p), ("target", C.c_void_p),
         ("grad_pred", C.c_void_p), ("unit_ray_dirs", C.c_void_p), ("face_idxs", C.c_void_p),
-        ("face_normals", C.c_void_p), ("ray_idxs", C.c_void_p), ("table_image", C.c_void_p), ("packed", C.c_void_p),
+        ("face_normals", C.c_void_p), ("ray_idxs", C.c_void_p), ("table_image", C.c_void_p), ("col_exp", C.c_void_p),
+        ("packed", C.c_void_p),
         ("pred", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
@@ -51,7 +52,7 @@ class InfGrads(C.Structure):
 
 class InfAdam(C.Structure):
     _fields_ = [("params", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("packed", C.c_void_p),
-                ("step_dev", C.c_void_p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("col_exp", C.c_void_p), ("step_dev", C.c_void_p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("step", C.c_int32), ("reserved0", C.c_int32)]
 
 
@@ -77,6 +78,12 @@ EXPORTS = {
     "inf_workspace_bytes": (C.c_size_t, [C.POINTER(InfDesc), C.c_int]),
     "inf_relayout_table": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p]),
+    "inf_column_exponents": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "inf_relayout_table_scaled": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_int32, C.c_void_p]),
+    "inf_pack_weights_scaled": (C.c_int, [C.POINTER(InfDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "inf_gather_interpolate_scaled": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "inf_table_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "inf_build_table_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "inf_project_vertices": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p, C.c_void_p]),

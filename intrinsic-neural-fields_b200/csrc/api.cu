@@ -31,9 +31,11 @@ cudaError_t launch_vertex_gather(const FieldParams& p, int nsm, cudaStream_t str
 
 void launch_pack_weights(const PackParams& pp, cudaStream_t stream);
 void launch_relayout(const float* src, int64_t n_rows, int k, int64_t src_stride, void* dst, int k_pad, int dst_dtype,
-                     cudaStream_t stream);
+                     const int8_t* col_exp, cudaStream_t stream);
+void launch_column_exponents(const float* src, int64_t n_rows, int k, int64_t src_stride, int k_pad, int8_t* col_exp,
+                             unsigned int* scratch, cudaStream_t stream);
 void launch_gather_interpolate(const void* table, int table_f16, int k, int k_pad, const void* vids, int idx64,
-                               const float* bary, int64_t n_rays, float* out, cudaStream_t stream);
+                               const float* bary, int64_t n_rays, float* out, const int8_t* col_exp, cudaStream_t stream);
 void launch_umma_probe(int mode, int n, int k, const float* a, const float* b, float* d, cudaStream_t stream);
 
 namespace {
@@ -484,26 +486,53 @@ int inf_uses_vertex_path(const InfDesc* desc, const InfTensors* t) {
   return vertex_path(desc, t) ? 1 : 0;
 }
 
+int inf_relayout_table_scaled(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, const int8_t* col_exp, void* dst,
+                              int32_t k_pad, int32_t dst_dtype, void* stream);
+
 int inf_relayout_table(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, void* dst, int32_t k_pad,
                        int32_t dst_dtype, void* stream) {
+  return inf_relayout_table_scaled(src, n_rows, k, src_row_stride, nullptr, dst, k_pad, dst_dtype, stream);
+}
+
+int inf_column_exponents(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, int32_t k_pad, int8_t* col_exp,
+                         void* scratch, void* stream) {
+  if (src == nullptr || col_exp == nullptr || scratch == nullptr) return fail(INF_ERR_BAD_ARG, "src / col_exp / scratch must be non-null");
+  if (n_rows < 0 || k < 1 || k_pad < k || k_pad % KC != 0 || src_row_stride < k) return fail(INF_ERR_BAD_ARG, "bad table shape");
+  launch_column_exponents(src, n_rows, k, src_row_stride, k_pad, col_exp, reinterpret_cast<unsigned int*>(scratch),
+                          static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "column_exponents launch");
+  g_launches += 2;
+  return INF_OK;
+}
+
+int inf_relayout_table_scaled(const float* src, int64_t n_rows, int32_t k, int64_t src_row_stride, const int8_t* col_exp, void* dst,
+                              int32_t k_pad, int32_t dst_dtype, void* stream) {
   if (src == nullptr || dst == nullptr) return fail(INF_ERR_BAD_ARG, "src / dst must be non-null");
   if (n_rows < 0 || k < 1 || k_pad < k || k_pad % KC != 0 || src_row_stride < k)
     return fail(INF_ERR_BAD_ARG, "bad table shape: rows=%lld k=%d k_pad=%d stride=%lld", static_cast<long long>(n_rows), k,
                 k_pad, static_cast<long long>(src_row_stride));
   if (dst_dtype != INF_TABLE_F32 && dst_dtype != INF_TABLE_F16) return fail(INF_ERR_BAD_ARG, "bad dst_dtype");
-  launch_relayout(src, n_rows, k, src_row_stride, dst, k_pad, dst_dtype, static_cast<cudaStream_t>(stream));
+  launch_relayout(src, n_rows, k, src_row_stride, dst, k_pad, dst_dtype, col_exp, static_cast<cudaStream_t>(stream));
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "relayout_table launch");
   return INF_OK;
 }
 
+int inf_pack_weights_scaled(const InfDesc* desc, const float* const* params, const int8_t* col_exp, void* packed, void* stream);
+
 int inf_pack_weights(const InfDesc* desc, const float* const* params, void* packed, void* stream) {
+  return inf_pack_weights_scaled(desc, params, nullptr, packed, stream);
+}
+
+int inf_pack_weights_scaled(const InfDesc* desc, const float* const* params, const int8_t* col_exp, void* packed, void* stream) {
   int rc = check_desc(desc);
   if (rc != INF_OK) return rc;
   if (params == nullptr || packed == nullptr) return fail(INF_ERR_BAD_ARG, "params / packed must be non-null");
   PackParams pp{};
   pp.geo = geo_of(desc);
+  pp.col_exp = col_exp;
   pp.packed = reinterpret_cast<uint8_t*>(packed);
   const int L = desc->num_layers;
   const bool view = desc->view_strategy != INF_VIEW_NONE;
@@ -581,6 +610,7 @@ static AdamParams adam_params(const InfAdam* a) {
   ap.params = a->params; ap.exp_avg = a->exp_avg; ap.exp_avg_sq = a->exp_avg_sq;
   ap.packed = reinterpret_cast<uint8_t*>(a->packed);
   ap.step_dev = a->step_dev;
+  ap.col_exp = a->col_exp;
   ap.lr = a->lr;
   const int tstep = a->step < 1 ? 1 : a->step;
   const double bc1 = 1.0 - pow(static_cast<double>(a->beta1), tstep);
@@ -772,7 +802,9 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   }
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
   rp.do_reduce = 1;
+  rp.col_exp = t->col_exp;
   rp.err = p.err;
+  rp.trace = p.trace;
   if (comm != nullptr && comm->world > 1) {
     rp.comm.world = comm->world;
     rp.comm.rank = comm->rank;
@@ -890,10 +922,15 @@ int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* ada
 
 int inf_gather_interpolate(const void* table, int32_t table_dtype, int32_t k, int32_t k_pad, const void* vids,
                            int32_t idx_dtype, const float* bary, int64_t n_rays, float* out, void* stream) {
+  return inf_gather_interpolate_scaled(table, table_dtype, k, k_pad, nullptr, vids, idx_dtype, bary, n_rays, out, stream);
+}
+
+int inf_gather_interpolate_scaled(const void* table, int32_t table_dtype, int32_t k, int32_t k_pad, const int8_t* col_exp,
+                                  const void* vids, int32_t idx_dtype, const float* bary, int64_t n_rays, float* out, void* stream) {
   if (n_rays < 0 || k < 1 || k_pad < k || k_pad % KC != 0) return fail(INF_ERR_BAD_ARG, "bad shape");
   if (n_rays > 0 && (!table || !vids || !bary || !out)) return fail(INF_ERR_BAD_ARG, "null pointer");
   launch_gather_interpolate(table, table_dtype == INF_TABLE_F16, k, k_pad, vids, idx_dtype == INF_IDX_I64, bary, n_rays, out,
-                            static_cast<cudaStream_t>(stream));
+                            col_exp, static_cast<cudaStream_t>(stream));
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "gather_interpolate launch");

@@ -277,6 +277,7 @@ struct PackParams {
   const float* by;                 // Ly.bias
   const float* wlast;              // output layer weight (3 x wout)
   const float* blast;              // output layer bias (3)
+  const int8_t* col_exp;           // optional column exponents of the table: W0 / Wy images hold W[:,j] * 2^-col_exp[j]
   uint8_t* packed;
   Geo geo;
 };
@@ -303,6 +304,7 @@ struct AdamParams {
   float* exp_avg;
   float* exp_avg_sq;
   uint8_t* packed;    // operand images to refresh
+  const int8_t* col_exp;     // column exponents of the table (W0 / Wy images hold W[:,j] * 2^-col_exp[j]); null = none
   const int32_t* step_dev;  // optional device-resident step count t (CUDA-graph replays); else the host values below
   float step_size;    // lr / (1 - beta1^t)
   float bc2_sqrt;     // sqrt(1 - beta2^t)
@@ -340,9 +342,11 @@ struct ReduceParams {
   int groups_hid[MAX_HID_SLICES];
   int cta_base_hid[MAX_HID_SLICES];
   float scale;
+  const int8_t* col_exp;   // column exponents of the table: the W0 / Wy gradients come out multiplied by 2^col_exp[j]
   int do_reduce;   // 0: flat already holds the (all-reduced) gradient, only the optimiser tail runs
   CommParams comm; // multi-GPU: exchange + sum of the per-rank gradients inside this kernel (world <= 1: none)
   unsigned int* err;
+  unsigned long long* trace;   // (INF_DEBUG & 8) globaltimer stamps of the exchange: start, published, peers seen, end
   AdamParams adam;
   Geo geo;
   WPlan plan;

@@ -316,6 +316,12 @@ __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ float reduce_partials(const ReduceParams& rp, int64_t i, int& sidx_out);
 __device__ __forceinline__ void apply_update(const ReduceParams& rp, int64_t i, int sidx, float grad, float dev_step_size, float dev_bc2_sqrt);
 
@@ -365,6 +371,8 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
     return;
   }
   // ---- phase A: this rank's gradient into its slot of the exchange region -------------------------------------
+  const bool tracing = rp.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tracing) rp.trace[40] = globaltimer_ns();
   const uint32_t seq = s_seq;
   const int64_t slot = static_cast<int64_t>(seq & 1u) * cm.slot_floats;
   float* mine = cm.region[cm.rank] + slot;
@@ -382,6 +390,7 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
       __threadfence_system();
       for (int q = 0; q < cm.world; ++q)
         st_release_sys_u32(reinterpret_cast<uint32_t*>(cm.region[q] + 2 * cm.slot_floats) + CTL_FLAGS + cm.rank, seq);
+      if (rp.trace != nullptr) rp.trace[41] = globaltimer_ns();
     }
     // every block waits until all ranks have published this step (a peer may already be one step ahead: >=)
     const long long t0 = clock64();
@@ -395,10 +404,15 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
     }
   }
   __syncthreads();
+  if (tracing) rp.trace[42] = globaltimer_ns();
   // ---- phase B: sum over ranks in rank order (bit-identical on every rank), then the optimiser tail ------------------
   for (int64_t e = tid0; e < rp.total; e += nthreads) {
+    float v[MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q) v[q] = q < cm.world ? ld_sys_f32(cm.region[q] + slot + e) : 0.f;   // all peer reads in flight
     float g = 0.f;
-    for (int q = 0; q < cm.world; ++q) g += ld_sys_f32(cm.region[q] + slot + e);
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q) g += v[q];
     rp.flat[e] = g;
     int sidx = 0;
     for (int s = 1; s < rp.nseg; ++s) if (e >= rp.seg[s].off) sidx = s;
@@ -414,6 +428,7 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   if (threadIdx.x == 0 && atomicAdd(ctl + CTL_DONE, 1u) == gridDim.x - 1) {
     atomicExch(ctl + CTL_DONE, 0u);
     st_release_sys_u32(ctl + CTL_SEQ, seq);   // every block has read this step's sequence number long ago
+    if (rp.trace != nullptr) rp.trace[43] = globaltimer_ns();
   }
 }
 
@@ -467,7 +482,10 @@ __device__ __forceinline__ float reduce_partials(const ReduceParams& rp, const i
     }
     for (; gI < ng; ++gI) acc += src[static_cast<size_t>(gI) * GSTRIDE];
   }
-  return acc * rp.scale;
+  acc *= rp.scale;
+  // the table holds E[:,j] * 2^e_j, so dW0 / dWy came out multiplied by 2^e_j (exact: powers of two)
+  if (sg.kind == 0 && rp.col_exp != nullptr) acc = ldexpf(acc, -static_cast<int>(rp.col_exp[col]));
+  return acc;
 }
 
 // Adam on the master parameter of flat element i, then its entry of the fp16 / f32 operand images
@@ -492,7 +510,8 @@ __device__ __forceinline__ void apply_update(const ReduceParams& rp, const int64
   const int nbias = (g.nb + 1) * HID;
   if (sg.kind == 0) {
     const uint32_t off = sw128_off(static_cast<uint32_t>(row + (sg.a ? HID : 0)), static_cast<uint32_t>(col & 63));
-    *reinterpret_cast<__half*>(ad.packed + static_cast<size_t>(col >> 6) * BLOB_BYTES + off) = __float2half_rn(pn);
+    const float img = ad.col_exp != nullptr ? ldexpf(pn, -static_cast<int>(ad.col_exp[col])) : pn;
+    *reinterpret_cast<__half*>(ad.packed + static_cast<size_t>(col >> 6) * BLOB_BYTES + off) = __float2half_rn(img);
   } else if (sg.kind == 1) {
     int blob, jj = col;
     if (g.view && sg.layer == g.nb) {

@@ -31,6 +31,7 @@ __global__ void pack_weights_kernel(const PackParams pp) {
       const int kcol = blob * KC + c;
       if (kcol < g.k) v = (row < HID) ? pp.w[0][static_cast<size_t>(row) * g.k + kcol]
                                       : pp.wy[static_cast<size_t>(row - HID) * g.k + kcol];
+      if (pp.col_exp != nullptr) v = ldexpf(v, -static_cast<int>(pp.col_exp[kcol]));   // the table holds E[:,j] * 2^e_j
       off = sw128_off(row, c);
     } else {
       // [128 rows n][128 cols j] as two 64-column panels
@@ -76,29 +77,67 @@ void launch_pack_weights(const PackParams& pp, cudaStream_t stream) {
 
 template <typename OutT>
 __global__ void relayout_table_kernel(const float* __restrict__ src, int64_t n_rows, int k, int64_t src_stride,
-                                      OutT* __restrict__ dst, int k_pad) {
+                                      OutT* __restrict__ dst, int k_pad, const int8_t* __restrict__ col_exp) {
   const int64_t total = n_rows * k_pad;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / k_pad;
     const int c = static_cast<int>(i % k_pad);
-    const float v = (c < k) ? src[r * src_stride + c] : 0.f;
+    float v = (c < k) ? src[r * src_stride + c] : 0.f;
+    if (col_exp != nullptr) v = ldexpf(v, static_cast<int>(col_exp[c]));
     if constexpr (sizeof(OutT) == 2) dst[i] = __float2half_rn(v);
     else dst[i] = v;
   }
 }
 
+// per-column max |x| as float bits (non-negative floats order like their bit patterns), then the exponent
+__global__ void __launch_bounds__(256) column_maxabs_kernel(const float* __restrict__ src, int64_t n_rows, int k, int64_t src_stride,
+                                                            unsigned int* __restrict__ maxbits) {
+  // block = 8 row lanes x 32 columns; grid.x walks column groups, grid.y row stripes
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  unsigned int m = 0u;
+  if (c < k)
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + rl; r < n_rows; r += static_cast<int64_t>(gridDim.y) * 8)
+      m = max(m, __float_as_uint(fabsf(src[r * src_stride + c])));
+  if (c < k && m != 0u) atomicMax(maxbits + c, m);
+}
+__global__ void column_exponent_kernel(const unsigned int* __restrict__ maxbits, int k, int k_pad, int8_t* __restrict__ col_exp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k_pad) return;
+  int e = 0;
+  if (c < k) {
+    const float m = __uint_as_float(maxbits[c]);
+    if (m > 0.f && isfinite(m) && (m < 0.015625f || m > 64.f)) {   // outside [2^-6, 2^6]: bring max|x| into [0.5, 1)
+      int p;
+      frexpf(m, &p);
+      e = -p;
+      e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    }
+  }
+  col_exp[c] = static_cast<int8_t>(e);
+}
+void launch_column_exponents(const float* src, int64_t n_rows, int k, int64_t src_stride, int k_pad, int8_t* col_exp,
+                             unsigned int* scratch, cudaStream_t stream) {
+  cudaMemsetAsync(scratch, 0, static_cast<size_t>(k_pad) * 4, stream);
+  if (n_rows > 0) {
+    const dim3 grid(static_cast<unsigned>((k + 31) / 32), static_cast<unsigned>(n_rows >= 8 * 64 ? 64 : (n_rows + 7) / 8));
+    column_maxabs_kernel<<<grid, 256, 0, stream>>>(src, n_rows, k, src_stride, scratch);
+  }
+  column_exponent_kernel<<<(k_pad + 255) / 256, 256, 0, stream>>>(scratch, k, k_pad, col_exp);
+}
+
 void launch_relayout(const float* src, int64_t n_rows, int k, int64_t src_stride, void* dst, int k_pad, int dst_dtype,
-                     cudaStream_t stream) {
+                     const int8_t* col_exp, cudaStream_t stream) {
   const int64_t total = n_rows * k_pad;
   if (total == 0) return;
   const int threads = 256;
   const int64_t want = (total + threads - 1) / threads;
   const unsigned blocks = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
   if (dst_dtype == INF_TABLE_F16)
-    relayout_table_kernel<__half><<<blocks, threads, 0, stream>>>(src, n_rows, k, src_stride, reinterpret_cast<__half*>(dst), k_pad);
+    relayout_table_kernel<__half><<<blocks, threads, 0, stream>>>(src, n_rows, k, src_stride, reinterpret_cast<__half*>(dst), k_pad, col_exp);
   else
-    relayout_table_kernel<float><<<blocks, threads, 0, stream>>>(src, n_rows, k, src_stride, reinterpret_cast<float*>(dst), k_pad);
+    relayout_table_kernel<float><<<blocks, threads, 0, stream>>>(src, n_rows, k, src_stride, reinterpret_cast<float*>(dst), k_pad, col_exp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -182,7 +221,8 @@ namespace inf {
 // ---------------------------------------------------------------------------------------------
 template <typename TableT>
 __global__ void gather_interpolate_kernel(const TableT* __restrict__ table, int k, int k_pad, const void* __restrict__ vids,
-                                          int idx64, const float* __restrict__ bary, int64_t n_rays, float* __restrict__ out) {
+                                          int idx64, const float* __restrict__ bary, int64_t n_rays, float* __restrict__ out,
+                                          const int8_t* __restrict__ col_exp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -214,23 +254,23 @@ __global__ void gather_interpolate_kernel(const TableT* __restrict__ table, int 
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (c0 + i < k) out[b * k + c0 + i] = acc[i];
+        if (c0 + i < k) out[b * k + c0 + i] = col_exp != nullptr ? ldexpf(acc[i], -static_cast<int>(col_exp[c0 + i])) : acc[i];
     }
   }
 }
 
 void launch_gather_interpolate(const void* table, int table_f16, int k, int k_pad, const void* vids, int idx64,
-                               const float* bary, int64_t n_rays, float* out, cudaStream_t stream) {
+                               const float* bary, int64_t n_rays, float* out, const int8_t* col_exp, cudaStream_t stream) {
   if (n_rays == 0) return;
   const int threads = 256;
   const int64_t want = (n_rays * 32 + threads - 1) / threads;
   const unsigned blocks = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
   if (table_f16)
     gather_interpolate_kernel<__half><<<blocks, threads, 0, stream>>>(reinterpret_cast<const __half*>(table), k, k_pad, vids,
-                                                                     idx64, bary, n_rays, out);
+                                                                     idx64, bary, n_rays, out, col_exp);
   else
     gather_interpolate_kernel<float><<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(table), k, k_pad, vids, idx64,
-                                                                    bary, n_rays, out);
+                                                                    bary, n_rays, out, col_exp);
 }
 
 }  // namespace inf

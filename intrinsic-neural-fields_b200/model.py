@@ -48,19 +48,19 @@ class _FieldFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, table, vids, bary, dense, dirs, face_idxs, face_normals, ray_idxs, extras, *params):
-        packed = module._packed_weights(force=True)
+        packed = module._packed_weights(force=True, col_exp=extras[2])
         ctx.module, ctx.dense, ctx.extras = module, dense, extras
         ctx.save_for_backward(table, vids, bary, dirs, face_idxs, face_normals, ray_idxs)
         return torch.ops.inf_b200.field_forward(table, vids, bary, packed, dirs, face_idxs, face_normals,
-                                                module.cfg.key(), dense, ray_idxs, extras[0], extras[1])
+                                                module.cfg.key(), dense, ray_idxs, *extras)
 
     @staticmethod
     def backward(ctx, grad_pred):
         module = ctx.module
         table, vids, bary, dirs, face_idxs, face_normals, ray_idxs = ctx.saved_tensors
         _, flat_full = torch.ops.inf_b200.field_forward_backward(
-            table, vids, bary, module._packed_weights(), None, grad_pred.contiguous().float(), dirs, face_idxs,
-            face_normals, module.cfg.key(), ctx.dense, 1.0, ray_idxs, ctx.extras[0], ctx.extras[1])
+            table, vids, bary, module._packed_weights(col_exp=ctx.extras[2]), None, grad_pred.contiguous().float(), dirs, face_idxs,
+            face_normals, module.cfg.key(), ctx.dense, 1.0, ray_idxs, *ctx.extras)
         flat, _ = ops.split_flat(flat_full)
         grads = [flat[off:off + r * c].view(p.shape) for (off, r, c), p in zip(module._layout, module._ordered_params())]
         return (None,) * 10 + tuple(grads)
@@ -83,7 +83,7 @@ class _FusedFieldBase(nn.Module):
     def _view_inputs(self, batch):
         return None, None, None
 
-    def _packed_weights(self, force: bool = False) -> torch.Tensor:
+    def _packed_weights(self, force: bool = False, col_exp: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Operand images of the current parameter values.
 
         Re-packed (one 5 us kernel) on every training-mode call: in-place optimiser kernels such as
@@ -91,10 +91,11 @@ class _FusedFieldBase(nn.Module):
         version-keyed cache would silently serve stale weights.  In eval mode the images are cached, keyed on the
         parameters' storage and version; ``train()`` / ``eval()`` and :meth:`invalidate_packed` drop the cache."""
         params = self._ordered_params()
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        # the images are specific to the table's column exponents (EigenTable.col_exp: fp16 range guard)
+        key = tuple((p.data_ptr(), p._version) for p in params) + (None if col_exp is None else col_exp.data_ptr(),)
         if force or self._packed is None or self._packed_key != key or self._packed.device != params[0].device:
             with torch.no_grad():
-                self._packed = ops.pack_weights(self.cfg, [p.detach().contiguous() for p in params], None)
+                self._packed = ops.pack_weights(self.cfg, [p.detach().contiguous() for p in params], None, col_exp)
             self._packed_key = key
         if self._layout is None:
             self._layout = ops.param_layout(self.cfg)
@@ -130,17 +131,17 @@ class _FusedFieldBase(nn.Module):
             x = batch["eigenfunctions"]
             if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.cfg.k:
                 raise ValueError(f"batch['eigenfunctions'] must be (B,{self.cfg.k}) float32")
-            return EigenTable.from_dense(x, device=x.device, dtype="f32", image=False).data, None, None, True
+            return EigenTable.from_dense(x, device=x.device, dtype="f32", image=False, range_guard=False).data, None, None, True
         raise KeyError("batch needs 'eigenfunction_table' + 'vertex_idxs_of_hit_faces' + 'barycentric_coords' "
                        "(fused path) or 'eigenfunctions' (dense path)")
 
     @staticmethod
     def _table_extras(batch):
-        """(fp16 operand image of the table or None, InfDesc.path code): what selects / enables the vertex path."""
+        """(fp16 operand image of the table or None, InfDesc.path code, column exponents or None)."""
         table = batch.get("eigenfunction_table")
         if isinstance(table, EigenTable) and "vertex_idxs_of_hit_faces" in batch:
-            return table.image, ops.PATHS[table.path]
-        return None, 0
+            return table.image, ops.PATHS[table.path], table.col_exp
+        return None, 0, None
 
     @staticmethod
     def _ray_idxs(batch):
@@ -157,8 +158,8 @@ class _FusedFieldBase(nn.Module):
         params = self._ordered_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, ridx, extras, *params)
-        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(force=self.training), dirs,
-                                                face_idxs, normals, self.cfg.key(), dense, ridx, extras[0], extras[1])
+        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(force=self.training, col_exp=extras[2]),
+                                                dirs, face_idxs, normals, self.cfg.key(), dense, ridx, *extras)
 
     # ---- fused training pass -----------------------------------------------------------------------
     def l1_step(self, batch: Dict[str, torch.Tensor], global_rays: Optional[int] = None,
@@ -176,9 +177,10 @@ class _FusedFieldBase(nn.Module):
         ridx = self._ray_idxs(batch)
         B = target.shape[0] if ridx is None else ridx.shape[0]
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
+        extras = self._table_extras(batch)
         pred, flat_full = torch.ops.inf_b200.field_forward_backward(
-            table, vids, bary, self._packed_weights(force=True), target, None, dirs, face_idxs, normals, self.cfg.key(),
-            dense, scale, ridx, *self._table_extras(batch))
+            table, vids, bary, self._packed_weights(force=True, col_exp=extras[2]), target, None, dirs, face_idxs, normals,
+            self.cfg.key(), dense, scale, ridx, *extras)
         flat, sums = ops.split_flat(flat_full)
         if flat_grad is not None:
             flat_grad.copy_(flat)

@@ -153,12 +153,16 @@ class EigenTable:
     gather traffic (values are rounded once, before interpolation).
     """
 
-    def __init__(self, data: torch.Tensor, k: int, dtype: str, image: Optional[torch.Tensor] = None, path: Optional[str] = None):
+    def __init__(self, data: torch.Tensor, k: int, dtype: str, image: Optional[torch.Tensor] = None, path: Optional[str] = None,
+                 col_exp: Optional[torch.Tensor] = None):
         path = DEFAULT_PATH if path is None else path
         if path not in PATHS:
             raise ValueError(f"path must be one of {sorted(PATHS)}")
         self.data, self.k, self.dtype = data, k, dtype
         self.image = image      # fp16 operand image of the table (vertex path), or None
+        # (k_pad,) int8 column exponents, or None: the stored table is E[:,j] * 2^col_exp[j] (fp16 range guard for
+        # unscaled / HKS / functional-map tables; all zero -- i.e. None -- for tables in the usual range)
+        self.col_exp = col_exp
         self.path = path        # "auto" | "ray" | "vertex": InfDesc.path of every call on this table
 
     def with_path(self, path: str) -> "EigenTable":
@@ -167,7 +171,7 @@ class EigenTable:
             raise ValueError(f"path must be one of {sorted(PATHS)}")
         if path == "vertex" and self.image is None:
             self.build_image()
-        return EigenTable(self.data, self.k, self.dtype, self.image, path)
+        return EigenTable(self.data, self.k, self.dtype, self.image, path, self.col_exp)
 
     def build_image(self) -> torch.Tensor:
         """fp16 tensor-core operand image of the table ([V/128][k_pad/64] panels, values rounded once): the A operand
@@ -197,7 +201,8 @@ class EigenTable:
         return self.data.device
 
     @staticmethod
-    def from_dense(E: torch.Tensor, device=None, dtype: str = "f32", image: bool = True, path: Optional[str] = None) -> "EigenTable":
+    def from_dense(E: torch.Tensor, device=None, dtype: str = "f32", image: bool = True, path: Optional[str] = None,
+                   range_guard: bool = True) -> "EigenTable":
         if E.dim() != 2 or E.dtype != torch.float32:
             raise ValueError("eigenfunction table must be a 2-D float32 tensor (mesh.py:105-108)")
         device = torch.device(device if device is not None else E.device)
@@ -209,11 +214,24 @@ class EigenTable:
         V, k = src.shape
         kp = pad_k(k)
         out = torch.empty((V, kp), device=device, dtype=torch.float16 if dtype == "f16" else torch.float32)
+        lib = _lib.load()
+        col_exp = None
         with torch.cuda.device(device):
-            rc = _lib.load().inf_relayout_table(C.c_void_p(src.data_ptr()), V, k, src.stride(0), C.c_void_p(out.data_ptr()),
-                                                kp, _lib.TABLE_F16 if dtype == "f16" else _lib.TABLE_F32, _stream(device))
-        _lib.check(rc, "inf_relayout_table")
-        t = EigenTable(out, k, dtype, None, path)
+            if range_guard and V > 0:
+                # columns whose max |E| lies outside [2^-6, 2^6] are stored times a power of two (exact), the first-layer
+                # weight images divided by it: fp16 keeps its full precision on unscaled / HKS / mapped tables
+                col_exp = torch.empty(kp, dtype=torch.int8, device=device)
+                scratch = torch.empty(kp, dtype=torch.int32, device=device)
+                _lib.check(lib.inf_column_exponents(C.c_void_p(src.data_ptr()), V, k, src.stride(0), kp, C.c_void_p(col_exp.data_ptr()),
+                                                    C.c_void_p(scratch.data_ptr()), _stream(device)), "inf_column_exponents")
+                if not bool(col_exp.any()):
+                    col_exp = None                     # the usual case ('standard' rescale): stored bit for bit
+            rc = lib.inf_relayout_table_scaled(C.c_void_p(src.data_ptr()), V, k, src.stride(0),
+                                               C.c_void_p(col_exp.data_ptr()) if col_exp is not None else None,
+                                               C.c_void_p(out.data_ptr()), kp,
+                                               _lib.TABLE_F16 if dtype == "f16" else _lib.TABLE_F32, _stream(device))
+        _lib.check(rc, "inf_relayout_table_scaled")
+        t = EigenTable(out, k, dtype, None, path, col_exp)
         if image and V > 0:
             t.build_image()
         return t
@@ -250,8 +268,9 @@ def kernel_error_word(device) -> int:
 # ------------------------------------------------------------------------------------------------
 # raw operators
 # ------------------------------------------------------------------------------------------------
-def pack_weights(cfg: FieldConfig, params: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """fp32 master parameters (state_dict order) -> tensor-core operand images."""
+def pack_weights(cfg: FieldConfig, params: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
+                 col_exp: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 master parameters (state_dict order) -> tensor-core operand images (for a table stored with ``col_exp``)."""
     lib = _lib.load()
     layout = param_layout(cfg)
     if len(params) != len(layout):
@@ -265,8 +284,9 @@ def pack_weights(cfg: FieldConfig, params: Sequence[torch.Tensor], out: Optional
         out = torch.empty(packed_bytes(cfg), dtype=torch.uint8, device=device)
     arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
     with torch.cuda.device(device):
-        rc = lib.inf_pack_weights(C.byref(_desc(cfg, 0, 0)), arr, C.c_void_p(out.data_ptr()), _stream(device))
-    _lib.check(rc, "inf_pack_weights")
+        rc = lib.inf_pack_weights_scaled(C.byref(_desc(cfg, 0, 0)), arr, C.c_void_p(_ptr(col_exp)), C.c_void_p(out.data_ptr()),
+                                         _stream(device))
+    _lib.check(rc, "inf_pack_weights_scaled")
     return out
 
 
@@ -346,7 +366,7 @@ def _check_view(cfg, B, idx64, dirs, face_idxs, face_normals):   # B = rows of t
 
 
 def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense: bool,
-                        ray_idxs=None, table_image=None, path: int = 0) -> torch.Tensor:
+                        ray_idxs=None, table_image=None, path: int = 0, col_exp=None) -> torch.Tensor:
     cfg = FieldConfig.from_key(cfg_key)
     B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
@@ -362,7 +382,7 @@ def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals
               ray_idxs=ray_idxs, n_src_rays=n_src, path=path)
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), unit_ray_dirs=_ptr(dirs),
                         face_idxs=_ptr(face_idxs), face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs),
-                        table_image=_ptr(table_image), packed=packed.data_ptr(),
+                        table_image=_ptr(table_image), col_exp=_ptr(col_exp), packed=packed.data_ptr(),
                         pred=pred.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     with torch.cuda.device(device):
         rc = _lib.load().inf_forward(C.byref(d), C.byref(t), _stream(device))
@@ -370,7 +390,7 @@ def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals
     return pred
 
 
-def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev) -> "_lib.InfAdam":
+def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev, col_exp=None) -> "_lib.InfAdam":
     n = params_flat.numel()
     for name, x in (("params_flat", params_flat), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
         _require_cuda(x, name)
@@ -380,13 +400,13 @@ def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps
     if step_dev.dtype != torch.int32 or step_dev.numel() != 1:
         raise ValueError("step_dev must be a 1-element int32 CUDA tensor holding the step count t of this update")
     return _lib.InfAdam(params=params_flat.data_ptr(), exp_avg=exp_avg.data_ptr(), exp_avg_sq=exp_avg_sq.data_ptr(),
-                        packed=packed.data_ptr(), step_dev=step_dev.data_ptr(), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
-                        step=0)
+                        packed=packed.data_ptr(), col_exp=_ptr(col_exp), step_dev=step_dev.data_ptr(), lr=lr, beta1=beta1,
+                        beta2=beta2, eps=eps, step=0)
 
 
 def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key,
                                  dense: bool, grad_scale: float, adam=None, ray_idxs=None, table_image=None, path: int = 0,
-                                 comm_id: int = 0):
+                                 comm_id: int = 0, col_exp=None):
     cfg = FieldConfig.from_key(cfg_key)
     B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
@@ -412,7 +432,7 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), target=_ptr(target),
                         grad_pred=_ptr(grad_pred), unit_ray_dirs=_ptr(dirs), face_idxs=_ptr(face_idxs),
                         face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs), table_image=_ptr(table_image),
-                        packed=packed.data_ptr(),
+                        col_exp=_ptr(col_exp), packed=packed.data_ptr(),
                         pred=pred.data_ptr(),
                         workspace=ws.data_ptr(), workspace_bytes=ws.numel())
     g = _lib.InfGrads(flat=flat.data_ptr(), loss_sums=sums.data_ptr())
@@ -422,7 +442,7 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
         else:
             if adam.params_flat.numel() != n_par:
                 raise ValueError("flat parameter vector does not match the model configuration")
-            a = _adam_struct(*adam)
+            a = _adam_struct(*adam, col_exp=col_exp)
             if comm_id:
                 from .parallel import PeerExchange
                 comm = PeerExchange.lookup(comm_id)
@@ -444,9 +464,9 @@ def field_forward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optio
                   packed: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                   face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
                   ray_idxs: Optional[torch.Tensor] = None, table_image: Optional[torch.Tensor] = None,
-                  path: int = 0) -> torch.Tensor:
+                  path: int = 0, col_exp: Optional[torch.Tensor] = None) -> torch.Tensor:
     return _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs,
-                               table_image, path)
+                               table_image, path, col_exp)
 
 
 def _fake_rows(table, vids, dense, ray_idxs):
@@ -454,7 +474,8 @@ def _fake_rows(table, vids, dense, ray_idxs):
 
 
 @field_forward.register_fake
-def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs=None, table_image=None, path=0):
+def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs=None, table_image=None, path=0,
+      col_exp=None):
     B = _fake_rows(table, vids, dense, ray_idxs)
     return table.new_empty((B, 3), dtype=torch.float32)
 
@@ -465,16 +486,18 @@ def field_forward_backward(table: torch.Tensor, vids: Optional[torch.Tensor], ba
                            dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                            face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
                            grad_scale: float, ray_idxs: Optional[torch.Tensor] = None,
-                           table_image: Optional[torch.Tensor] = None, path: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                           table_image: Optional[torch.Tensor] = None, path: int = 0,
+                           col_exp: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Returns (pred (B,3), flat (n_params + 2,)): the flat gradient followed by the two loss sums (one allocation,
     one allreduce); use :func:`split_flat`."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals,
-                                        cfg_key, dense, grad_scale, ray_idxs=ray_idxs, table_image=table_image, path=path)
+                                        cfg_key, dense, grad_scale, ray_idxs=ray_idxs, table_image=table_image, path=path,
+                                        col_exp=col_exp)
 
 
 @field_forward_backward.register_fake
 def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, ray_idxs=None,
-      table_image=None, path=0):
+      table_image=None, path=0, col_exp=None):
     B = _fake_rows(table, vids, dense, ray_idxs)
     n = num_params(FieldConfig.from_key(cfg_key))
     return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n + 2,), dtype=torch.float32))
@@ -498,18 +521,18 @@ def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Op
                      params_flat: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float,
                      beta2: float, eps: float, step_dev: torch.Tensor,
                      ray_idxs: Optional[torch.Tensor] = None, table_image: Optional[torch.Tensor] = None,
-                     path: int = 0, comm_id: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                     path: int = 0, col_exp: Optional[torch.Tensor] = None, comm_id: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Forward + L1 loss + backward + Adam + operand refresh (trainer.py:75-82); the optimiser runs inside the
     gradient-reduction kernel -- and, with ``comm_id`` (parallel.PeerExchange), so does the sum over the ranks of a node."""
     return _field_forward_backward_impl(table, vids, bary, packed, target, None, dirs, face_idxs, face_normals, cfg_key,
                                         dense, grad_scale,
                                         adam=_AdamArgs((params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)),
-                                        ray_idxs=ray_idxs, table_image=table_image, path=path, comm_id=comm_id)
+                                        ray_idxs=ray_idxs, table_image=table_image, path=path, comm_id=comm_id, col_exp=col_exp)
 
 
 @field_train_step.register_fake
 def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, params_flat, exp_avg,
-      exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None, table_image=None, path=0, comm_id=0):
+      exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None, table_image=None, path=0, col_exp=None, comm_id=0):
     B = _fake_rows(table, vids, dense, ray_idxs)
     return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty((params_flat.numel() + 2,)))
 
@@ -517,13 +540,13 @@ def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key,
 @torch.library.custom_op("inf_b200::field_adam_pack", mutates_args=("packed", "params_flat", "exp_avg", "exp_avg_sq"))
 def field_adam_pack(flat_grad: torch.Tensor, packed: torch.Tensor, cfg_key: List[int], params_flat: torch.Tensor,
                     exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float, beta1: float, beta2: float, eps: float,
-                    step_dev: torch.Tensor) -> None:
+                    step_dev: torch.Tensor, col_exp: Optional[torch.Tensor] = None) -> None:
     """Adam + operand refresh from an already (all-)reduced flat gradient."""
     cfg = FieldConfig.from_key(cfg_key)
     _require_cuda(flat_grad, "flat_grad")
     if flat_grad.dtype != torch.float32 or flat_grad.numel() != num_params(cfg) or params_flat.numel() != flat_grad.numel():
         raise ValueError("flat_grad / params_flat do not match the model configuration")
-    a = _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev)
+    a = _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev, col_exp=col_exp)
     with torch.cuda.device(flat_grad.device):
         rc = _lib.load().inf_adam_pack_step(C.byref(_desc(cfg, 0, 0)), C.c_void_p(flat_grad.data_ptr()), C.byref(a),
                                             _stream(flat_grad.device))
@@ -558,11 +581,12 @@ def gather_interpolate_dense(table: "EigenTable", vids: torch.Tensor, bary: torc
     B = vids.shape[0]
     out = torch.empty((B, table.k), dtype=torch.float32, device=table.device)
     with torch.cuda.device(table.device):
-        rc = _lib.load().inf_gather_interpolate(
+        rc = _lib.load().inf_gather_interpolate_scaled(
             C.c_void_p(table.data.data_ptr()), _lib.TABLE_F16 if table.data.dtype == torch.float16 else _lib.TABLE_F32,
-            table.k, table.k_pad, C.c_void_p(vids.data_ptr()), _lib.IDX_I64 if vids.dtype == torch.int64 else _lib.IDX_I32,
+            table.k, table.k_pad, C.c_void_p(_ptr(table.col_exp)), C.c_void_p(vids.data_ptr()),
+            _lib.IDX_I64 if vids.dtype == torch.int64 else _lib.IDX_I32,
             C.c_void_p(bary.data_ptr()), B, C.c_void_p(out.data_ptr()), _stream(table.device))
-    _lib.check(rc, "inf_gather_interpolate")
+    _lib.check(rc, "inf_gather_interpolate_scaled")
     return out
 
 

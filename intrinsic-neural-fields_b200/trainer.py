@@ -120,6 +120,7 @@ class FusedFieldAdam:
         self.layout = layout
         self.packed = ops.pack_weights(model.cfg, [p.detach() for p in params], None)     # zero padding written once
         self.exchange = None      # parallel.PeerExchange: the multi-GPU gradient sum inside the reduction kernel
+        self._col_exp = None      # column exponents (EigenTable.col_exp) the operand images were packed for
         # the operand images are refreshed by the Adam kernel only: weights written from outside (a checkpoint restored
         # after the optimiser was built, trainer.py:214-231) must be re-packed before the next forward
         model.register_load_state_dict_post_hook(lambda module, incompatible_keys: self.repack())
@@ -132,10 +133,19 @@ class FusedFieldAdam:
             self.exchange = parallel.PeerExchange(self.model.cfg, self.flat.device, group)
         return self.exchange
 
-    def repack(self):
+    def repack(self, col_exp="same"):
         """Rebuild the fp16 operand images from the flat fp32 parameters (in place: captured graphs keep their pointer)."""
-        ops.pack_weights(self.model.cfg, [p.detach() for p in self.model._ordered_params()], self.packed)
+        if col_exp != "same":
+            self._col_exp = col_exp
+        ops.pack_weights(self.model.cfg, [p.detach() for p in self.model._ordered_params()], self.packed, self._col_exp)
         self.model._packed, self.model._packed_key = self.packed, None
+
+    def _for_table(self, batch):
+        """The operand images are specific to the table's column exponents: re-pack when a batch brings another table."""
+        ce = self.model._table_extras(batch)[2]
+        if (None if ce is None else ce.data_ptr()) != (None if self._col_exp is None else self._col_exp.data_ptr()):
+            self.repack(ce)
+        return ce
 
     # ---- the two ways a step is taken ---------------------------------------------------------------------------
     def fused_l1_step(self, batch, global_rays=None):
@@ -147,6 +157,7 @@ class FusedFieldAdam:
         ridx = m._ray_idxs(batch)
         B = batch_rays(batch)
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
+        self._for_table(batch)
         self.step_dev.add_(1)
         pred, flat_full = torch.ops.inf_b200.field_train_step(
             table, vids, bary, self.packed, target, dirs, face_idxs, normals, m.cfg.key(), dense, scale, self.flat,
@@ -163,6 +174,7 @@ class FusedFieldAdam:
         dirs, face_idxs, normals = m._view_inputs(batch)
         target = batch["expected_rgbs"].contiguous()
         scale = 1.0 / (3.0 * float(global_rays))
+        self._for_table(batch)
         pred, flat_full = torch.ops.inf_b200.field_forward_backward(
             table, vids, bary, self.packed, target, None, dirs, face_idxs, normals, m.cfg.key(), dense, scale,
             m._ray_idxs(batch), *m._table_extras(batch))
@@ -173,7 +185,8 @@ class FusedFieldAdam:
         """Multi rank, second half (after the allreduce of ``flat_grad``): Adam + operand refresh in one kernel."""
         self.step_dev.add_(1)
         torch.ops.inf_b200.field_adam_pack(flat_grad, self.packed, self.model.cfg.key(), self.flat, self.exp_avg,
-                                           self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev)
+                                           self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev,
+                                           self._col_exp)
         self.model._packed, self.model._packed_key = self.packed, None
 
     # ---- torch.optim.Adam-compatible checkpoints -------------------------------------------------------------------

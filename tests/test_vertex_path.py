@@ -177,3 +177,103 @@ def test_both_paths_agree_and_gradients_do_not_depend_on_ray_order():
     # the batch selection folded into the kernels (ray_idxs) on the vertex path: same arithmetic as materialised batches
     _, _, s_i, p_i, f_i = _l1_step("vertex", c, E, vids, bary, target, idx_dtype=torch.int32, ridx=perm.to(torch.int32))
     assert torch.equal(p_i, p_perm) and torch.equal(f_i, f_perm)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp16 range guard: tables whose columns sit far from 1 (unscaled / HKS / functional-map tables, mesh.py:53-108)
+# ---------------------------------------------------------------------------------------------
+def _hks_like_table(V, k, g):
+    """Columns spanning 1e-9 .. 1e+5: heat-kernel-signature style decay plus a few huge 'unscaled' columns."""
+    base = torch.randn(V, k, generator=g)
+    mag = torch.logspace(-9, 0, k)
+    mag[::7] = 3e4 * (1 + torch.arange(len(mag[::7])))          # a few columns beyond fp16's range
+    return (base * mag).float()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["ray", "vertex"])
+def test_range_guard_keeps_fp16_precision_on_unscaled_and_hks_style_tables(path):
+    c = load_golden("tf_k100_l5s1")
+    g = torch.Generator().manual_seed(8)
+    V, B, k = 600, 900, c["k"]
+    E = _hks_like_table(V, k, g)
+    # weights sized so that every column contributes O(1) to the first layer, tiny and huge columns alike: an
+    # implementation that rounds the raw table to fp16 loses the tiny ones (subnormal / zero) and overflows on the huge ones
+    params = {n: t.clone() for n, t in c["params"].items()}
+    colmax = E.abs().amax(0)
+    for n in ("layers.0.0.weight", f"layers.{c['skip']}.Ly.weight"):
+        params[n] = params[n] / colmax[None, :] / 4
+    vids = torch.randint(0, V, (B, 3), generator=g)
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    loss, pref, grads = O.loss_and_grads(params, E, vids, bary, target, num_layers=c["num_layers"], skip=c["skip"])
+    m = inf_b200.make_model(dict(k=k, num_layers=c["num_layers"], mlp_hidden_dim=128, skip_layer_idx=c["skip"]))
+    m.load_state_dict(params)
+    m = m.to(DEV)
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV, path=path)
+    assert tab.col_exp is not None and int(tab.col_exp.abs().max()) >= 14          # the guard is active
+    # the materialising gather still returns the reference's values (mesh.py:313-324)
+    x = ops.gather_interpolate_dense(tab, vids.to(DEV), bary.to(DEV)).cpu()
+    xr = O.gather_interpolate(E, vids, bary)
+    assert ((x - xr).abs() <= 1e-6 * colmax[None, :]).all()         # relative to each column's own scale (14 decades apart)
+    b = {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": vids.to(DEV), "barycentric_coords": bary.to(DEV),
+         "expected_rgbs": target.to(DEV)}
+    sums, pred, flat = m.l1_step(b)
+    torch.cuda.synchronize()
+    assert inf_b200.kernel_error_word(DEV) == 0
+    err = (pred.cpu() - pref).abs()
+    assert err.max().item() <= RGB_MAX and err.mean().item() <= RGB_MEAN, (err.max().item(), err.mean().item())
+    assert abs(sums[0].item() / (3 * B) - loss) <= 1e-3
+    for n, p in m.named_parameters():
+        ref = grads[n]
+        rel = (p.grad.cpu() - ref).norm().item() / (ref.norm().item() + 1e-30)
+        assert rel <= 6e-2, (n, rel)                  # incl. the first-layer gradients, which span 14 decades per column
+    # without the guard the same table is outside fp16's range: the result must be visibly wrong (what the guard prevents)
+    raw = inf_b200.EigenTable.from_dense(E, device=DEV, path=path, range_guard=False)
+    with torch.no_grad():
+        bad = m(dict(b, eigenfunction_table=raw)).cpu()
+    assert not torch.isfinite(bad).all() or (bad - pref).abs().max().item() > RGB_MAX
+
+
+@pytest.mark.gpu
+def test_range_guard_leaves_tables_in_the_usual_range_bit_for_bit():
+    c = load_golden("tf_k64")
+    tab = inf_b200.EigenTable.from_dense(c["table"], device=DEV)
+    assert tab.col_exp is None
+    assert torch.equal(tab.data[:, :c["k"]].cpu(), c["table"])
+
+
+@pytest.mark.gpu
+def test_fused_adam_steps_on_a_guarded_table_match_torch_adam():
+    # the optimiser fused into the reduction kernel rewrites the first-layer operand images divided by the column scale
+    from inf_b200 import trainer
+    c = load_golden("tf_k100_l5s1")
+    g = torch.Generator().manual_seed(9)
+    V, B, k = 300, 512, c["k"]
+    E = _hks_like_table(V, k, g)
+    params = {n: t.clone() for n, t in c["params"].items()}
+    colmax = E.abs().amax(0)
+    for n in ("layers.0.0.weight", f"layers.{c['skip']}.Ly.weight"):
+        params[n] = params[n] / colmax[None, :] / 4
+    vids = torch.randint(0, V, (B, 3), generator=g)
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV)
+    b = {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": vids.to(DEV), "barycentric_coords": bary.to(DEV),
+         "expected_rgbs": target.to(DEV)}
+    cfg = dict(k=k, num_layers=c["num_layers"], mlp_hidden_dim=128, skip_layer_idx=c["skip"])
+    ma = inf_b200.make_model(cfg); ma.load_state_dict(params); ma = ma.to(DEV)
+    mb = inf_b200.make_model(cfg); mb.load_state_dict(params); mb = mb.to(DEV)
+    oa = trainer.FusedFieldAdam(ma, lr=1e-5)
+    ob = torch.optim.Adam(mb.parameters(), lr=1e-5)
+    for _ in range(5):
+        la, _ = trainer.fused_train_step(ma, oa, b)
+        lb, _ = trainer.train_step(mb, ob, b)
+        # Adam moves every weight by ~lr whatever its size, so the 1e-6-sized first-layer weights of the huge columns change
+        # by several times their value per step: an ill-conditioned trajectory on purpose.  A wrong column scale in the
+        # refreshed operand images would change the loss by O(1), not O(1e-4).
+        assert abs(la - lb) <= 5e-4, (la, lb)
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert (pa - pb).abs().max().item() <= 2e-6, n      # both took 5 steps of at most lr = 1e-5
