@@ -46,7 +46,7 @@ std::atomic<long long> g_launches{0};   // kernels of this library enqueued so f
 // Environment knobs are read ONCE per process (not on every launch).  INF_DEBUG bits 1|2|4 are measurement switches
 // that skip work and produce WRONG gradients: bench.py refuses to run with them and records the value.
 struct Env {
-  int debug, prefetch, cluster, verbose, wg_cluster, force_path, rays_slots, side_stream, wgrad_hid_ctas, wgrad_split;
+  int debug, prefetch, cluster, verbose, wg_cluster, force_path, rays_slots, side_stream, wgrad_hid_ctas, wgrad_split, wgrad_min_tiles;
   double wgrad_bigw;
   Env() {
     auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
@@ -59,6 +59,10 @@ struct Env {
     // Vertex path, measured and left off: hidden-slice wgrad as its own launch, concurrent with the vertex gather on the
     // side stream, big slices after (0.410 vs 0.394 ms/step: both kernels are bound by the same memory system)
     wgrad_split = geti("INF_WGRAD_SPLIT", 0);
+    // measured at B = 4096 (32 tiles): 1 -> wgrad 23 us + reduce 20 us; 4 -> 31 + 15; 8 -> 44 + 15: fewer, longer CTAs lose
+    // more in the wgrad kernel than the smaller partial set saves in the reduction, so no cap by default
+    wgrad_min_tiles = geti("INF_WGRAD_MIN_TILES", 1);
+    if (wgrad_min_tiles < 1) wgrad_min_tiles = 1;
     wgrad_hid_ctas = geti("INF_WGRAD_HID_CTAS", 0);   // vertex path: CTAs of the hidden-slice wgrad launch (0 = all SMs)
     side_stream = geti("INF_SIDE_STREAM", 1);   // 0: incidence lists on the caller's stream
     force_path = geti("INF_PATH", 0);   // 1 = per-ray, 2 = vertex (when a table image is given): overrides InfDesc.path AUTO
@@ -712,6 +716,27 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   }
   if (gb < 1) gb = 1;
   if (gb > tiles_big) gb = tiles_big;
+  {
+    // Small batches: every wgrad CTA dumps its whole 256 KB accumulator and the reduction reads it back, whatever it
+    // accumulated; INF_WGRAD_MIN_TILES = m makes every CTA own at least m tiles (measurement knob, see Env)
+    const int mt = env().wgrad_min_tiles;
+    const int cap_big = (tiles_big + mt - 1) / mt, cap_hid = (p.ntiles + mt - 1) / mt;
+    if (gb > cap_big) gb = cap_big;
+    int used2 = 0;
+    for (int s = 0; s < plan.nslice; ++s) {
+      if (gh[s] > cap_hid) gh[s] = cap_hid;
+      used2 += gh[s];
+    }
+    used = used2;
+    if (!split && cw > 1 && used % cw != 0) {   // whole clusters only (the big CTAs are a multiple of cw: nbig % cw == 0)
+      const int add = cw - used % cw;
+      int s_pad = -1;
+      for (int s = 0; s < plan.nslice; ++s)
+        if (gh[s] + add <= p.ntiles && (s_pad < 0 || plan.bytes_per_tile[s] > plan.bytes_per_tile[s_pad])) s_pad = s;
+      if (s_pad >= 0) { gh[s_pad] += add; used += add; }
+      else cw = 1;
+    }
+  }
   p.wg_cluster = cw;
   p.groups_big = gb;
   for (int s = 0; s < MAX_HID_SLICES; ++s) p.groups_hid[s] = gh[s];

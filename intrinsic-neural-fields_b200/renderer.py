@@ -149,9 +149,10 @@ class FieldRenderer:
         return out
 
     @torch.no_grad()
-    def render_hits(self, vertex_idxs_of_hit_faces, barycentric_coords, hit_ray_idxs, obj_mask_1d=None,
-                    unit_ray_dirs=None, face_idxs=None, eval_render: bool = False):
-        """Canvas assembly of renderer.py:119-146 on the device; returns (H,W,3) numpy (or torch + hit idxs)."""
+    def canvas_on_device(self, vertex_idxs_of_hit_faces, barycentric_coords, hit_ray_idxs, obj_mask_1d=None,
+                         unit_ray_dirs=None, face_idxs=None) -> torch.Tensor:
+        """Canvas assembly of renderer.py:119-146 on the device: (H,W,3) float32 CUDA tensor, everything enqueued
+        asynchronously on the current stream (no host synchronisation)."""
         assert obj_mask_1d is None or obj_mask_1d.size()[0] == self.H * self.W
         pred = self.predict_hits(vertex_idxs_of_hit_faces, barycentric_coords, unit_ray_dirs, face_idxs)
         fill = 1.0 if self.background == "white" else 0.0
@@ -163,7 +164,14 @@ class FieldRenderer:
             full = torch.full((self.H * self.W, 3), fill, dtype=torch.float32, device=self.device)
             full[obj_mask_1d.to(self.device)] = img
             img = full
-        img = img.reshape(self.H, self.W, 3).cpu()
+        return img.reshape(self.H, self.W, 3)
+
+    @torch.no_grad()
+    def render_hits(self, vertex_idxs_of_hit_faces, barycentric_coords, hit_ray_idxs, obj_mask_1d=None,
+                    unit_ray_dirs=None, face_idxs=None, eval_render: bool = False):
+        """Canvas assembly of renderer.py:119-146 on the device; returns (H,W,3) numpy (or torch + hit idxs)."""
+        img = self.canvas_on_device(vertex_idxs_of_hit_faces, barycentric_coords, hit_ray_idxs, obj_mask_1d,
+                                    unit_ray_dirs, face_idxs).cpu()
         if eval_render:
             return img, hit_ray_idxs
         return img.numpy()
@@ -200,9 +208,9 @@ class Renderer(FieldRenderer):
         if hasattr(self.intersect, "rebuild"):          # the reference rebuilds its intersector here (renderer.py:62)
             self.intersect.rebuild(self.mesh)
 
-    @torch.no_grad()
-    def render(self, camCv2world, K, obj_mask_1d=None, eval_render=False, distortion_coeffs=None, distortion_type=None,
-               pixel_coords=None):
+    def cast(self, camCv2world, K, obj_mask_1d=None, distortion_coeffs=None, distortion_type=None, pixel_coords=None):
+        """Host side of a frame (renderer.py:83-112): pixel rays of the masked pixels and the caller's intersector.
+        Returns the arguments of ``canvas_on_device``."""
         from .ray_store import pixel_rays
         if self.intersect is None:
             raise RuntimeError("Renderer.render needs an intersector callable (ray casting is outside this package)")
@@ -214,6 +222,57 @@ class Renderer(FieldRenderer):
         vids, bary, hit_ray_idxs, face_idxs = self.intersect(origins, dirs)
         assert vids.shape[0] > 0                                                         # renderer.py:110
         view = getattr(self.model, "cfg", None) is not None and self.model.cfg.has_view
-        return self.render_hits(vids, bary.to(torch.float32), hit_ray_idxs, obj_mask_1d,
-                                unit_ray_dirs=dirs[hit_ray_idxs] if view else None,
-                                face_idxs=face_idxs if view else None, eval_render=eval_render)
+        return dict(vertex_idxs_of_hit_faces=vids, barycentric_coords=bary.to(torch.float32), hit_ray_idxs=hit_ray_idxs,
+                    obj_mask_1d=obj_mask_1d, unit_ray_dirs=dirs[hit_ray_idxs] if view else None,
+                    face_idxs=face_idxs if view else None)
+
+    @torch.no_grad()
+    def render(self, camCv2world, K, obj_mask_1d=None, eval_render=False, distortion_coeffs=None, distortion_type=None,
+               pixel_coords=None):
+        hits = self.cast(camCv2world, K, obj_mask_1d, distortion_coeffs, distortion_type, pixel_coords)
+        return self.render_hits(eval_render=eval_render, **hits)
+
+    @torch.no_grad()
+    def render_frames(self, views):
+        """The frame loop of render_video.py:117-134 as a pipeline: yields one (H,W,3) numpy image per view, in order.
+
+        ``views`` yields ``(camCv2world, K)`` or ``(camCv2world, K, obj_mask_1d)``.  While the GPU evaluates frame n (upload
+        of the 36-68 B/ray gather inputs, the fused kernels, the canvas scatter -- all on the device) a host thread already
+        runs the caller's intersector for frame n+1, and frame n-1's canvas travels to pinned host memory on a copy
+        stream; the only host synchronisation per frame is the wait for that copy.  Every frame goes through the same
+        ``canvas_on_device`` as ``render()``, so the images are bit-identical to calling ``render()`` view by view."""
+        from concurrent.futures import ThreadPoolExecutor
+        views = iter(views)
+
+        def cast_next():
+            v = next(views, None)
+            return None if v is None else self.cast(v[0], v[1], v[2] if len(v) > 2 else None)
+
+        d2h = torch.cuda.Stream(self.device)
+        bufs = [torch.empty((self.H, self.W, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        pending = None                                   # (buffer, event) of the frame whose canvas is still on its way
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(cast_next)
+            n = 0
+            while True:
+                hits = fut.result()
+                if hits is None:
+                    break
+                fut = pool.submit(cast_next)             # frame n+1 is cast on the host while the GPU works on frame n
+                canvas = self.canvas_on_device(**hits)
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(self.device))
+                buf, ev = bufs[n % 2], torch.cuda.Event()
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(done)
+                    buf.copy_(canvas, non_blocking=True)
+                    ev.record(d2h)
+                canvas.record_stream(d2h)
+                if pending is not None:
+                    pending[1].synchronize()             # the one host wait per frame
+                    yield pending[0].numpy().copy()
+                pending = (buf, ev)
+                n += 1
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0].numpy().copy()

@@ -976,6 +976,49 @@ def test_renderer_render_matches_reference_canvas(name):
         Renderer(m, None, eigenfunctions=c["table"], feature_strategy="xyz", device=DEV, H=4, W=4)
 
 
+@pytest.mark.parametrize("name", ["tf_k1023", "view_intrinsic"])
+def test_render_frames_pipeline_is_bit_identical_to_render_per_view(name):
+    # render_video.py:117-134: a turntable of views.  render_frames overlaps the caller's intersector for frame n+1 with
+    # the GPU work of frame n and the D2H of frame n-1; the images must equal render() called view by view, bit for bit.
+    import time
+    import types
+    from inf_b200.renderer import Renderer
+    c = load_golden(name)
+    m = _model_from(c)
+    H, W = 24, 32
+    n = c["vids"].shape[0]
+    K = torch.tensor([[30.0, 0, W / 2 - 0.5], [0, 28.0, H / 2 - 0.5], [0, 0, 1]])
+    log = []
+
+    def intersect(origins, dirs):
+        # a recorded caster: which rays hit depends on the view (through the ray directions), deterministic, slow on purpose
+        g = torch.Generator().manual_seed(int(dirs[0, 0].abs().item() * 1e6) % 1000)
+        time.sleep(0.01)
+        L = origins.shape[0]
+        hits = torch.randperm(L, generator=g)[:min(L, n) - 5]
+        sel = torch.randint(0, n, (hits.numel(),), generator=g)
+        fid = c["face_idxs"][sel] if c.get("view") is not None else torch.zeros(sel.numel(), dtype=torch.int64)
+        log.append(int(hits[0]))
+        return c["vids"][sel], c["bary"][sel], hits, fid
+    mesh = types.SimpleNamespace(face_normals=c["face_normals"].numpy()) if c.get("view") is not None else None
+    r = Renderer(m, mesh, eigenfunctions=c["table"], device=DEV, H=H, W=W, intersect=intersect)
+    views = []
+    for a in np.linspace(0, 300, 6):
+        st, ct = float(np.sin(np.deg2rad(a))), float(np.cos(np.deg2rad(a)))
+        cam = torch.tensor([[ct, -st, 0, 0.1], [st, ct, 0, -0.2], [0, 0, 1, -3.0]])
+        mask = (torch.rand(H * W, generator=torch.Generator().manual_seed(int(a))) < 0.8) if int(a) % 120 == 0 else None
+        views.append((cam, K, mask))
+    frames = list(r.render_frames(iter(views)))
+    _check_no_watchdog()
+    assert len(frames) == len(views)
+    order = list(log)
+    singles = [r.render(cam, K_, obj_mask_1d=mask) for cam, K_, mask in views]
+    assert log[len(order):] == order                      # the caster saw the same views in the same order
+    for f, s_ in zip(frames, singles):
+        assert f.shape == (H, W, 3) and f.dtype == np.float32
+        assert np.array_equal(f, s_)
+
+
 def test_trainer_epoch_loop_matches_reference_loop_and_resumes(tmp_path):
     # Trainer (trainer.py:18-340): epoch metrics against the same loop run with the fp32 oracle, best-model / last-epoch /
     # checkpoint files, and a resumed run that ends bit-identical to an uninterrupted one

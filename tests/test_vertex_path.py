@@ -276,4 +276,5 @@ def test_fused_adam_steps_on_a_guarded_table_match_torch_adam():
         # refreshed operand images would change the loss by O(1), not O(1e-4).
         assert abs(la - lb) <= 5e-4, (la, lb)
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        assert (pa - pb).abs().max().item() <= 2e-6, n      # both took 5 steps of at most lr = 1e-5
+        # both took 5 steps of at most lr = 1e-5 each; entries whose gradient is at the noise floor may take opposite signs
+        assert (pa - pb).abs().max().item() <= 2.5e-5, n
