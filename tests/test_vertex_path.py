@@ -278,3 +278,52 @@ def test_fused_adam_steps_on_a_guarded_table_match_torch_adam():
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         # both took 5 steps of at most lr = 1e-5 each; entries whose gradient is at the noise floor may take opposite signs
         assert (pa - pb).abs().max().item() <= 2.5e-5, n
+
+
+# ---------------------------------------------------------------------------------------------
+# race-freedom evidence: compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer_closed.txt), so the mbarrier /
+# TMEM / bulk-copy pipelines are stressed for the symptom a race has -- run-to-run differences
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["ray", "vertex"])
+@pytest.mark.parametrize("view", [False, True])
+def test_many_tile_steps_reproduce_bit_for_bit_over_repetitions(path, view):
+    import types
+    from conftest import VIEW_CFGS
+    g = torch.Generator().manual_seed(21)
+    k, L, skip, V, B = 200, 6, 3, 2500, 40000          # 313 ray tiles: several per CTA, both pipelines' steady state
+    vcfg = VIEW_CFGS["view_intrinsic"] if view else None
+    E = torch.randn(V, k, generator=g) / 5
+    faces = torch.randint(0, V, (5000, 3), generator=g)
+    fid = torch.randint(0, 5000, (B,), generator=g)
+    vids = faces[fid]
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    normals = torch.nn.functional.normalize(torch.randn(5000, 3, generator=g), dim=-1)
+    dirs = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    cfg = dict(k=k, num_layers=L, mlp_hidden_dim=128, skip_layer_idx=skip)
+    mesh = None
+    if view:
+        cfg["view_dependence"] = vcfg
+        mesh = types.SimpleNamespace(face_normals=normals.numpy())
+    torch.manual_seed(5)
+    m = inf_b200.make_model(cfg, mesh=mesh).to(DEV)
+    b = {"eigenfunction_table": inf_b200.EigenTable.from_dense(E, device=DEV, path=path), "vertex_idxs_of_hit_faces": vids.to(DEV),
+         "barycentric_coords": bary.to(DEV), "expected_rgbs": target.to(DEV)}
+    if view:
+        b["unit_ray_dirs"], b["hit_face_idxs"] = dirs.to(DEV), fid.to(DEV)
+    first = None
+    for rep in range(12):
+        sums, pred, flat = m.l1_step(b)
+        with torch.no_grad():
+            p_inf = m(b)
+        cur = (sums.clone(), pred.clone(), flat.clone(), p_inf.clone())
+        if first is None:
+            first = cur
+        else:
+            for a, c_ in zip(first, cur):
+                assert torch.equal(a, c_), rep
+    torch.cuda.synchronize()
+    assert inf_b200.kernel_error_word(DEV) == 0
+    assert torch.equal(first[1], first[3])              # training and inference kernels agree on the RGB bit for bit
