@@ -29,14 +29,18 @@ namespace {
 //   2  one CTA per SM running two tiles in lockstep (one weight stage feeds both tiles' MMAs), 12 warps
 //   1  two CTAs per SM, one tile each, 8 warps: the CTAs drift apart, so one's gather overlaps the other's chain
 constexpr int RY_SLOTS = 2;   // maximum (sizes the barrier table)
-__host__ __device__ constexpr int ry_threads(int slots) { return (4 * slots + 4) * 32; }
-// registers: launch value 168 x 384 (or 128 x 256, two CTAs per SM); the epilogue warpgroups grow to 200, the utility
-// warpgroup shrinks to 40
-constexpr int RY_REGS_EPI = 200, RY_REGS_UTIL = 40;
-constexpr int RY_WG_THREADS = 128;
+// A tile is served by EIGHT gather/epilogue warps: warp (quarter wq, column half ch) owns TMEM lanes 32 wq .. 32 wq + 31 and
+// columns 64 ch .. 64 ch + 63 of every layer, so a layer step is two 32-column TMEM loads per thread instead of four and
+// twice as many warps hide the TMEM / shared-memory / barrier latencies of the (latency-bound) chain.
+__host__ __device__ constexpr int ry_threads(int slots) { return (8 * slots + 4) * 32; }
+// registers: launch value 96 x 640 (or 80 x 384, two CTAs per SM); the epilogue warpgroups grow, the utility warpgroup
+// shrinks to 40
+constexpr int RY_REGS_UTIL = 40;
+__host__ __device__ constexpr int ry_regs_epi(int slots) { return slots == 2 ? 104 : 96; }
+constexpr int RY_WG_THREADS = 256;
 
 struct RySmem {
-  uint32_t h, zy, w, dzlt, bias, wlast, red, bars, tmemptr, total;
+  uint32_t h, zy, w, dzlt, bias, wlast, ysum, red, bars, tmemptr, total;
 };
 __host__ __device__ constexpr RySmem ry_smem(bool train, int slots) {
   RySmem s{};
@@ -46,7 +50,8 @@ __host__ __device__ constexpr RySmem ry_smem(bool train, int slots) {
   s.dzlt = s.w + slots * BLOB_BYTES;                         // [slots] dzl^T tiles (training)
   s.bias = s.dzlt + (train ? slots * DZLT_BYTES : 0u);       // f32 [MAX_MMA_LAYERS][128]
   s.wlast = s.bias + MAX_MMA_LAYERS * HID * 4;               // f32 [3][128] + blast[4]
-  s.red = s.wlast + OUT_DIM * HID * 4 + 16;                  // f32 [slots][24]
+  s.ysum = s.wlast + OUT_DIM * HID * 4 + 16;                 // f32 [slots][2 column halves][128 rows][3]: output-layer partial sums
+  s.red = s.ysum + slots * 2 * TILE_M * OUT_DIM * 4;         // f32 [slots][24]
   s.bars = s.red + slots * 96;
   s.tmemptr = s.bars + 32 * 8;
   s.total = s.tmemptr + 16;
@@ -129,7 +134,7 @@ __device__ __forceinline__ void ry_setmaxnreg_dec() { asm volatile("setmaxnreg.d
 template <bool kTrain, int kSlots>
 __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field_rays_kernel(const FieldParams p) {
   constexpr int RY_THREADS = ry_threads(kSlots);
-  constexpr int RY_EPI_WARPS = 4 * kSlots;
+  constexpr int RY_EPI_WARPS = 8 * kSlots;
   constexpr int RY_W_CH = RY_EPI_WARPS, RY_W_LD = RY_EPI_WARPS + 1, RY_W_ST = RY_EPI_WARPS + 2;   // stash writer: + slot
   constexpr int RY_NSTAGE_W = kSlots;
   constexpr uint32_t RY_TMEM_COLS = 128u * kSlots;   // one 128-column accumulator per slot
@@ -339,10 +344,13 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
    }
   } else {
     // =========================== gather + epilogue warpgroups ==================================
-    ry_setmaxnreg_inc<RY_REGS_EPI>();
-    const int slot = warp >> 2;                 // warpgroup = tile slot
-    const int wq = warp & 3;                    // TMEM lane quarter of this warp
-    const int r = tid - slot * RY_WG_THREADS;   // tile row == TMEM lane
+    ry_setmaxnreg_inc<ry_regs_epi(kSlots)>();
+    const int slot = warp >> 3;                 // eight warps = tile slot
+    const int ws = warp & 7;
+    const int wq = ws & 3;                      // TMEM lane quarter of this warp
+    const int ch = ws >> 2;                     // column half of every layer this warp owns
+    const int r = 32 * wq + lane;               // tile row == TMEM lane
+    const bool leader = ws == 0 && lane == 0;   // one thread per slot talks to the MMA issuer / stash writer
     const uint32_t tb = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + 128u * static_cast<uint32_t>(slot);
     const uint32_t ximg = smem_base + sm.h + static_cast<uint32_t>(slot) * BLOB_BYTES;
     const uint32_t yimg = smem_base + sm.zy + static_cast<uint32_t>(slot) * BLOB_BYTES;
@@ -355,7 +363,8 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
     bool stored_x = false, stored_y = false;   // a stash store of the image is outstanding (training)
     float loss_abs = 0.f, loss_sq = 0.f;
     float gb[3] = {0.f, 0.f, 0.f};
-    uint32_t mk[MAX_MMA_LAYERS][4];   // ReLU masks of this row (local memory; indexed by layer)
+    uint32_t mk[MAX_MMA_LAYERS][2];   // ReLU masks of this row's 64 columns (local memory; indexed by layer)
+    float* s_ysum = reinterpret_cast<float*>(smem + sm.ysum) + slot * 2 * TILE_M * OUT_DIM;
 
     long long t_done = 0, t_free = 0, t_sync = 0, t_gather = 0, t_fwd = 0, t_final = 0, t_bwd = 0;
     const long long t_epi0 = now();
@@ -383,10 +392,10 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
       if (kTrain) {
         stored_x = stored_x || x;
         stored_y = stored_y || y;
-        if (r == 0) mbar_arrive(bar(RB_STASH_REQ + 2 * slot + static_cast<int>(nreq & 1u)));
+        if (leader) mbar_arrive(bar(RB_STASH_REQ + 2 * slot + static_cast<int>(nreq & 1u)));
         ++nreq;
       }
-      if (arrive_act && r == 0) mbar_arrive(bar(RB_ACT_READY + slot));
+      if (arrive_act && leader) mbar_arrive(bar(RB_ACT_READY + slot));
     };
 
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -400,31 +409,39 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
                        : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[ray]);
 
       // ---- gather + interpolate: [z0 | zy] = sum_j bary_j P[v_j] ------------------------------------
-      // Every lane keeps the metadata of ray 32*wq + lane; the warp then walks its 32 rays, lane = 32-byte block of the
-      // two 512-byte plane rows of a vertex (fully coalesced), RU rays = 6 RU 16-byte loads in flight per lane.
+      // Warp ws gathers rays 16 ws .. 16 ws + 15 of the tile: lanes 0..15 keep their metadata; the warp then walks the 16
+      // rays, lane = 16-byte chunk of the 512-byte P rows (fully coalesced), RU rays = 3 RU loads in flight per lane.
       const long long tg0 = now();
       uint32_t myv[3] = {0u, 0u, 0u};
       float myb[3] = {0.f, 0.f, 0.f};
-      if (valid) {
+      {
+        const int64_t gray = static_cast<int64_t>(tile) * TILE_M + 16 * ws + (lane & 15);
+        if (gray < p.n_rays) {
+          int64_t gsrc = gray;
+          if (p.ridx != nullptr)
+            gsrc = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[gray])
+                            : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[gray]);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int64_t e = src * 3 + j;
-          myv[j] = p.idx64 ? static_cast<uint32_t>(reinterpret_cast<const long long*>(p.vids)[e])
-                           : static_cast<uint32_t>(reinterpret_cast<const int*>(p.vids)[e]);
-          myb[j] = p.bary[e];
+          for (int j = 0; j < 3; ++j) {
+            const int64_t e = gsrc * 3 + j;
+            myv[j] = p.idx64 ? static_cast<uint32_t>(reinterpret_cast<const long long*>(p.vids)[e])
+                             : static_cast<uint32_t>(reinterpret_cast<const int*>(p.vids)[e]);
+            myb[j] = p.bary[e];
+          }
         }
       }
       free_x();   // the previous tile's last dz image has left X / Y
       free_y();
       {
-        constexpr int RU = 8;   // rays (= 3 RU 16-byte loads per lane) in flight: the gather is bound by bytes in flight
+        constexpr int RU = 4;
         const bool z0_lane = lane < 16;
         const uint32_t blk = static_cast<uint32_t>(lane & 15);      // 8 columns of the 128-column half
         float b0[8];   // bias of layer 0 for this lane's columns (z0 lanes only)
 #pragma unroll
         for (int i = 0; i < 8; ++i) b0[i] = z0_lane ? s_bias[8 * blk + i] : 0.f;
         const uint32_t dst_img = (z0_lane ? ximg : yimg) + (blk >> 3) * PANEL_BYTES;
-        for (int rr0 = 0; rr0 < 32; rr0 += RU) {
+#pragma unroll 1
+        for (int rr0 = 0; rr0 < 16; rr0 += RU) {
           uint4 q[RU][3];
           float w[RU][3];
 #pragma unroll
@@ -457,7 +474,7 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
 #pragma unroll
               for (int i = 0; i < 4; ++i) o[i] = pack_half2_sat(acc[2 * i], acc[2 * i + 1]);
             }
-            const uint32_t row = static_cast<uint32_t>(32 * wq + rr0 + u);
+            const uint32_t row = static_cast<uint32_t>(16 * ws + rr0 + u);
             st_shared_v4(dst_img + row * 128u + (((blk & 7u) ^ (row & 7u)) << 4), o[0], o[1], o[2], o[3]);
           }
         }
@@ -466,10 +483,10 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
       if (kTrain) {
         // ReLU mask of layer 0 for this thread's row, read back from the image the warps just wrote
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cq = 0; cq < 2; ++cq) {
           uint32_t w[16];
-          ry_load_words(ximg, r, cb, w);
-          mk[0][cb] = ry_relu_mask16(w);
+          ry_load_words(ximg, r, 2 * ch + cq, w);
+          mk[0][cq] = ry_relu_mask16(w);
         }
       }
       publish(true, false, true);   // h_0
@@ -481,9 +498,10 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
         wait_done();
         free_x();
         const bool is_skip = (l == g.skip);
-        uint32_t mbits[4];
+        uint32_t mbits[2];
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cq = 0; cq < 2; ++cq) {
+          const int cb = 2 * ch + cq;
           uint32_t v[32];
           tmem_ld32(tb + 32u * cb, v);
           tmem_ld_wait();
@@ -503,10 +521,10 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
             w[2 * i] = pack_half2_relu_sat(a0, a1);
             w[2 * i + 1] = pack_half2_relu_sat(a2, a3);
           }
-          if (kTrain) mbits[cb] = ry_relu_mask16(w);
+          if (kTrain) mbits[cq] = ry_relu_mask16(w);
           ry_store_words(ximg, r, cb, w);
         }
-        if (kTrain) { mk[l][0] = mbits[0]; mk[l][1] = mbits[1]; mk[l][2] = mbits[2]; mk[l][3] = mbits[3]; }
+        if (kTrain) { mk[l][0] = mbits[0]; mk[l][1] = mbits[1]; }
         const bool fourier = view && l == nb - 1;
         if (fourier) {
           // Fourier features of this ray's view direction (model.py:175-186) -> [128 x 64] panel in Y, whose last reader
@@ -529,16 +547,16 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
             }
           }
           const uint32_t row = yimg + static_cast<uint32_t>(r) * 128u;
-          for (int ch = 0; ch < 8; ++ch) {
+          for (int ck = 4 * ch; ck < 4 * ch + 4; ++ck) {      // this thread's half of the row's eight 16-byte chunks
             float f[8];
-            if (8 * ch < g.edim) {
+            if (8 * ck < g.edim) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = ry_fourier(8 * ch + i, x0, x1, x2, g.vdim, g.emb, g.include);
+              for (int i = 0; i < 8; ++i) f[i] = ry_fourier(8 * ck + i, x0, x1, x2, g.vdim, g.emb, g.include);
             } else {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = 0.f;
             }
-            st_shared_v4(row + ((static_cast<uint32_t>(ch) ^ (static_cast<uint32_t>(r) & 7u)) << 4), pack_half2(f[0], f[1]),
+            st_shared_v4(row + ((static_cast<uint32_t>(ck) ^ (static_cast<uint32_t>(r) & 7u)) << 4), pack_half2(f[0], f[1]),
                          pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
           }
         }
@@ -553,10 +571,11 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
         wait_done();
         free_x();
         const bool is_skip = (nb == g.skip);
-        float y[3] = {s_blast[0], s_blast[1], s_blast[2]};
-        uint32_t mbits[4];
+        float y[3] = {0.f, 0.f, 0.f};       // this thread's 64 columns of the output layer's dot products
+        uint32_t mbits[2];
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cq = 0; cq < 2; ++cq) {
+          const int cb = 2 * ch + cq;
           uint32_t v[32];
           tmem_ld32(tb + 32u * cb, v);
           tmem_ld_wait();
@@ -583,13 +602,18 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
             if (kTrain) { w[2 * i] = pack_half2_sat(h0, h1); w[2 * i + 1] = pack_half2_sat(h2, h3); }
           }
           if (kTrain) {
-            mbits[cb] = ry_relu_mask16(w);
+            mbits[cq] = ry_relu_mask16(w);
             ry_store_words(ximg, r, cb, w);
           }
         }
+        // the two column halves of a row meet in shared memory; both then hold the same y (same summation order)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) y[c] = ry_sigmoid(y[c]);
-        if (valid) {
+        for (int c = 0; c < 3; ++c) s_ysum[(ch * TILE_M + r) * OUT_DIM + c] = y[c];
+        named_bar_sync(bar_id, RY_WG_THREADS);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          y[c] = ry_sigmoid((s_blast[c] + s_ysum[r * OUT_DIM + c]) + s_ysum[(TILE_M + r) * OUT_DIM + c]);
+        if (valid && ch == 0) {
           p.pred[ray * 3 + 0] = y[0];
           p.pred[ray * 3 + 1] = y[1];
           p.pred[ray * 3 + 2] = y[2];
@@ -602,25 +626,30 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
               float gy;
               if (p.target != nullptr) {
                 const float d = y[c] - p.target[src * 3 + c];
-                loss_abs += fabsf(d);
-                loss_sq += d * d;
+                if (ch == 0) {      // one thread per ray counts the loss
+                  loss_abs += fabsf(d);
+                  loss_sq += d * d;
+                }
                 gy = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);  // d|d|/dd, sign(0) = 0 as F.l1_loss
               } else {
                 gy = p.grad_pred[ray * 3 + c] * p.ext_scale;
               }
               dzl[c] = gy * y[c] * (1.f - y[c]) * DZ_SCALE;
-              gb[c] += dzl[c];
+              if (ch == 0) gb[c] += dzl[c];
             }
           }
           // Y (zy / Fourier panel; the previous tile's dz_nb and dzl^T left with the same store) is free for dz_nb
           free_y();
           // dzl^T tile [16 x 128 rays] (rows 3..15 stay zero): B operand of the output-layer weight gradient
+          if (ch == 0) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            *reinterpret_cast<__half*>(smem + dzlt + static_cast<uint32_t>(r >> 6) * 2048u + sw128_off(c, r & 63)) = __float2half_rn(dzl[c]);
+            for (int c = 0; c < 3; ++c)
+              *reinterpret_cast<__half*>(smem + dzlt + static_cast<uint32_t>(r >> 6) * 2048u + sw128_off(c, r & 63)) = __float2half_rn(dzl[c]);
+          }
           // dz_nb = (dz_last * W_last) masked by relu' -> Y, while h_nb (X) goes to the stash
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
+          for (int cq = 0; cq < 2; ++cq) {
+            const int cb = 2 * ch + cq;
             const float4* w0 = reinterpret_cast<const float4*>(s_wlast + 0 * HID + 32 * cb);
             const float4* w1 = reinterpret_cast<const float4*>(s_wlast + 1 * HID + 32 * cb);
             const float4* w2 = reinterpret_cast<const float4*>(s_wlast + 2 * HID + 32 * cb);
@@ -632,8 +661,8 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
               const float d1 = fmaf(dzl[2], a2.y, fmaf(dzl[1], a1.y, dzl[0] * a0.y));
               const float d2 = fmaf(dzl[2], a2.z, fmaf(dzl[1], a1.z, dzl[0] * a0.z));
               const float d3 = fmaf(dzl[2], a2.w, fmaf(dzl[1], a1.w, dzl[0] * a0.w));
-              w[2 * i] = ry_apply_mask(pack_half2_sat(d0, d1), mbits[cb], 2 * i);
-              w[2 * i + 1] = ry_apply_mask(pack_half2_sat(d2, d3), mbits[cb], 2 * i + 1);
+              w[2 * i] = ry_apply_mask(pack_half2_sat(d0, d1), mbits[cq], 2 * i);
+              w[2 * i + 1] = ry_apply_mask(pack_half2_sat(d2, d3), mbits[cq], 2 * i + 1);
             }
             ry_store_words(yimg, r, cb, w);
           }
@@ -648,16 +677,17 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
             wait_done();
             if (to_x) free_x(); else free_y();
             const uint32_t dimg = to_x ? ximg : yimg;
-            const uint32_t mm[4] = {mk[lb][0], mk[lb][1], mk[lb][2], mk[lb][3]};
+            const uint32_t mm[2] = {mk[lb][0], mk[lb][1]};
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
+            for (int cq = 0; cq < 2; ++cq) {
+              const int cb = 2 * ch + cq;
               uint32_t v[32];
               tmem_ld32(tb + 32u * cb, v);
               tmem_ld_wait();
               uint32_t w[16];
 #pragma unroll
               for (int q = 0; q < 16; ++q)
-                w[q] = ry_apply_mask(pack_half2_sat(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), mm[cb], q);
+                w[q] = ry_apply_mask(pack_half2_sat(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), mm[cq], q);
               ry_store_words(dimg, r, cb, w);
             }
             sync_epi();
@@ -669,7 +699,7 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
         }
       }
     }
-    if (r == 0) {
+    if (leader) {
       const int o = 8 + 12 * slot;
       put(o, now() - t_epi0); put(o + 1, t_done); put(o + 2, t_free); put(o + 3, t_sync); put(o + 4, t_gather); put(o + 5, t_fwd);
       put(o + 6, t_final); put(o + 7, t_bwd);
@@ -684,12 +714,12 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
         for (int c = 0; c < 3; ++c) gb[c] += __shfl_xor_sync(0xffffffffu, gb[c], o);
       }
       float* s_red = reinterpret_cast<float*>(smem + sm.red) + slot * 24;   // [5][4]: per-warp partial sums
-      if (lane == 0) {
+      if (lane == 0 && ch == 0) {      // the column-half-0 warps carry the per-ray sums
         s_red[wq] = loss_abs; s_red[4 + wq] = loss_sq;
         s_red[8 + wq] = gb[0]; s_red[12 + wq] = gb[1]; s_red[16 + wq] = gb[2];
       }
       named_bar_sync(bar_id, RY_WG_THREADS);
-      if (r == 0) {
+      if (leader) {
         float* part = p.part1 + static_cast<size_t>(blockIdx.x * kSlots + slot) * K1_PART_FLOATS;
         part[0] = s_red[8] + s_red[9] + s_red[10] + s_red[11];
         part[1] = s_red[12] + s_red[13] + s_red[14] + s_red[15];

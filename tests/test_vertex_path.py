@@ -268,16 +268,22 @@ def test_fused_adam_steps_on_a_guarded_table_match_torch_adam():
     mb = inf_b200.make_model(cfg); mb.load_state_dict(params); mb = mb.to(DEV)
     oa = trainer.FusedFieldAdam(ma, lr=1e-5)
     ob = torch.optim.Adam(mb.parameters(), lr=1e-5)
-    for _ in range(5):
+    for it in range(5):
         la, _ = trainer.fused_train_step(ma, oa, b)
         lb, _ = trainer.train_step(mb, ob, b)
         # Adam moves every weight by ~lr whatever its size, so the 1e-6-sized first-layer weights of the huge columns change
-        # by several times their value per step: an ill-conditioned trajectory on purpose.  A wrong column scale in the
-        # refreshed operand images would change the loss by O(1), not O(1e-4).
-        assert abs(la - lb) <= 5e-4, (la, lb)
+        # by several times their value per step (the loss jumps 0.25 -> 0.41 after ONE step): an ill-conditioned trajectory
+        # on purpose.  A wrong column scale in the refreshed operand images would change the loss by O(1) at once.
+        # Measured (scripts/adam_dbg.py): the first update agrees to 1e-9 per entry; from the second step on, entries whose
+        # gradient sits at Adam's eps (|g| ~ 1e-8, dead-ReLU neighbours) amplify that 1e-9 into +-lr, and the two
+        # trajectories drift apart by 1e-7, 3e-6, 5e-5, 8e-4 in the loss -- on both evaluation paths alike.
+        assert abs(la - lb) <= (1e-6 if it == 0 else 3e-3), (it, la, lb)
+        if it == 0:
+            for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+                assert (pa - pb).abs().max().item() <= 1e-7, n
     for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         # both took 5 steps of at most lr = 1e-5 each; entries whose gradient is at the noise floor may take opposite signs
-        assert (pa - pb).abs().max().item() <= 2.5e-5, n
+        assert (pa - pb).abs().max().item() <= 5e-5, n
 
 
 # ---------------------------------------------------------------------------------------------
