@@ -296,6 +296,9 @@ struct ReduceSeg {
   int32_t layer;      // MMA layer of the tensor (kinds 0..2); -1 otherwise
   int64_t pair_off;   // kind 2, skip layer: offset of the partner bias (Lx.bias owns the update of both, its image entry
                       // is their sum); -2 marks the partner itself (Ly.bias: nothing to do here); -1 otherwise
+  int64_t item_off;   // first work item of the tensor in the reduction kernel (an item = up to 4 consecutive columns of a
+  int32_t ipr;        // row; ipr items per row) -- filled by launch_field_reduce
+  int32_t par;        // lanes sharing an item (1, 2, 4 or 8): they split the item's ray / vertex groups
 };
 // Optional optimiser tail of the reduction kernel: Adam on the flat fp32 master parameters + refresh of the fp16
 // operand images, fused with the partial sums (config.py:108 torch.optim.Adam(lr), defaults).
@@ -333,6 +336,7 @@ struct ReduceParams {
   ReduceSeg seg[INF_MAX_PARAMS];
   int nseg;
   int64_t total;
+  int64_t nitems;   // work slots (items x lanes per item, padded per tensor) of the reduction kernel (launch_field_reduce)
   const float* partw;
   const float* part1;
   float* flat;

@@ -29,6 +29,17 @@ namespace {
 //   2  one CTA per SM running two tiles in lockstep (one weight stage feeds both tiles' MMAs), 12 warps
 //   1  two CTAs per SM, one tile each, 8 warps: the CTAs drift apart, so one's gather overlaps the other's chain
 constexpr int RY_SLOTS = 2;   // maximum (sizes the barrier table)
+// measured variants: request the next tile's gather metadata one tile ahead / the L1 target at
+// the head of the tile / wait for the previous tile's last stash stores only after the first P rows are requested
+#ifndef RY_META_PF
+#define RY_META_PF 0
+#endif
+#ifndef RY_TGT_PF
+#define RY_TGT_PF 0
+#endif
+#ifndef RY_LATE_FREE
+#define RY_LATE_FREE 0
+#endif
 // A tile is served by EIGHT gather/epilogue warps: warp (quarter wq, column half ch) owns TMEM lanes 32 wq .. 32 wq + 31 and
 // columns 64 ch .. 64 ch + 63 of every layer, so a layer step is two 32-column TMEM loads per thread instead of four and
 // twice as many warps hide the TMEM / shared-memory / barrier latencies of the (latency-bound) chain.
@@ -398,6 +409,31 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
       if (arrive_act && leader) mbar_arrive(bar(RB_ACT_READY + slot));
     };
 
+    // Gather metadata of a tile (warp ws gathers rays 16 ws .. 16 ws + 15: lanes 0..15 and 16..31 hold the same ray's vertex
+    // ids and barycentrics).  It is a chain of dependent DRAM reads (ray_idxs -> vids / bary), so the NEXT tile's metadata
+    // is requested while this tile's chain runs and has long arrived when its gather starts.
+    auto load_meta = [&](int tile_, uint32_t (&mv)[3], float (&mb)[3]) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { mv[j] = 0u; mb[j] = 0.f; }
+      const int64_t gray = static_cast<int64_t>(tile_) * TILE_M + 16 * ws + (lane & 15);
+      if (tile_ < ntiles && gray < p.n_rays) {
+        int64_t gsrc = gray;
+        if (p.ridx != nullptr)
+          gsrc = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[gray])
+                          : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[gray]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int64_t e = gsrc * 3 + j;
+          mv[j] = p.idx64 ? static_cast<uint32_t>(reinterpret_cast<const long long*>(p.vids)[e])
+                          : static_cast<uint32_t>(reinterpret_cast<const int*>(p.vids)[e]);
+          mb[j] = p.bary[e];
+        }
+      }
+    };
+    uint32_t nxv[3];
+    float nxb[3];
+    if (RY_META_PF) load_meta(static_cast<int>(blockIdx.x) * kSlots + slot, nxv, nxb);
+
     for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int tile = pair * kSlots + slot;
       if (tile >= ntiles) break;   // odd tile count: slot 1 sits out the last pair
@@ -407,31 +443,29 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
       if (valid && p.ridx != nullptr)
         src = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[ray])
                        : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[ray]);
+      // the L1 target of this thread's ray: requested now (second link of a dependent DRAM chain), used after the last layer
+      float tgt[3] = {0.f, 0.f, 0.f};
+      if (RY_TGT_PF && kTrain && valid && p.target != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tgt[c] = p.target[src * 3 + c];
+      }
 
       // ---- gather + interpolate: [z0 | zy] = sum_j bary_j P[v_j] ------------------------------------
-      // Warp ws gathers rays 16 ws .. 16 ws + 15 of the tile: lanes 0..15 keep their metadata; the warp then walks the 16
-      // rays, lane = 16-byte chunk of the 512-byte P rows (fully coalesced), RU rays = 3 RU loads in flight per lane.
+      // The warp walks its 16 rays, lane = 16-byte chunk of the 512-byte P rows (fully coalesced), RU rays = 3 RU loads in
+      // flight per lane.
       const long long tg0 = now();
-      uint32_t myv[3] = {0u, 0u, 0u};
-      float myb[3] = {0.f, 0.f, 0.f};
-      {
-        const int64_t gray = static_cast<int64_t>(tile) * TILE_M + 16 * ws + (lane & 15);
-        if (gray < p.n_rays) {
-          int64_t gsrc = gray;
-          if (p.ridx != nullptr)
-            gsrc = p.ridx64 ? static_cast<int64_t>(reinterpret_cast<const long long*>(p.ridx)[gray])
-                            : static_cast<int64_t>(reinterpret_cast<const int*>(p.ridx)[gray]);
+      uint32_t myv[3];
+      float myb[3];
+      if (RY_META_PF) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int64_t e = gsrc * 3 + j;
-            myv[j] = p.idx64 ? static_cast<uint32_t>(reinterpret_cast<const long long*>(p.vids)[e])
-                             : static_cast<uint32_t>(reinterpret_cast<const int*>(p.vids)[e]);
-            myb[j] = p.bary[e];
-          }
-        }
+        for (int j = 0; j < 3; ++j) { myv[j] = nxv[j]; myb[j] = nxb[j]; }
+      } else {
+        load_meta(tile, myv, myb);
       }
-      free_x();   // the previous tile's last dz image has left X / Y
-      free_y();
+      if (!RY_LATE_FREE) {
+        free_x();   // the previous tile's last dz image has left X / Y
+        free_y();
+      }
       {
         constexpr int RU = 4;
         const bool z0_lane = lane < 16;
@@ -452,6 +486,12 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
               w[u][j] = __shfl_sync(0xffffffffu, myb[j], rr0 + u);
               q[u][j] = ldg_nc_u4(p.proj + static_cast<size_t>(v) * PROJ_ROW_BYTES + proj_chunk_off(v, static_cast<uint32_t>(lane)));
             }
+          }
+          if (RY_LATE_FREE && rr0 == 0) {
+            // the previous tile's last dz images must have left X / Y before the first store below; waiting here, with the
+            // first P rows already requested, hides the tail of that stash store behind the loads' latency
+            free_x();
+            free_y();
           }
 #pragma unroll
           for (int u = 0; u < RU; ++u) {
@@ -479,6 +519,7 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
           }
         }
       }
+      if (RY_META_PF) load_meta((pair + static_cast<int>(gridDim.x)) * kSlots + slot, nxv, nxb);   // next tile's metadata: in flight during the chain
       sync_epi();
       if (kTrain) {
         // ReLU mask of layer 0 for this thread's row, read back from the image the warps just wrote
@@ -625,7 +666,7 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
             for (int c = 0; c < 3; ++c) {
               float gy;
               if (p.target != nullptr) {
-                const float d = y[c] - p.target[src * 3 + c];
+                const float d = y[c] - (RY_TGT_PF ? tgt[c] : p.target[src * 3 + c]);
                 if (ch == 0) {      // one thread per ray counts the loss
                   loss_abs += fabsf(d);
                   loss_sq += d * d;

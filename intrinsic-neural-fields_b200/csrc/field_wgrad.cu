@@ -39,6 +39,12 @@ constexpr int BAR_DONE = 2 * NSTAGE;
 
 }  // namespace
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -244,6 +250,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
   }
 
   __syncthreads();
+  if (p.trace != nullptr && tid == 0) atomicMax(p.trace + 48, globaltimer_ns());   // measurement: last wgrad CTA done
   if (cw > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == WG_MMA_WARP) {
     tc_fence_after();
@@ -289,22 +296,37 @@ int field_wgrad_max_grid(int cluster) {
 // Partial reduction (+ optional Adam step and operand refresh): one thread per element of the flat
 // gradient vector, fixed summation order.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void adam_update(const AdamParams& a, float step_size, float bc2_sqrt, int64_t i, float g, float& p_new) {
+struct AdamState { float m, v, p; };
+__device__ __forceinline__ AdamState adam_load(const AdamParams& a, int64_t i) {
+  AdamState st;
+  st.m = a.exp_avg[i]; st.v = a.exp_avg_sq[i]; st.p = a.params[i];
+  return st;
+}
+__device__ __forceinline__ void adam_finish(const AdamParams& a, float step_size, float bc2_sqrt, int64_t i, float g, const AdamState& st,
+                                            float& p_new) {
   // torch/optim/adam.py (single-tensor math, also the fused kernel's): lerp, mul+addcmul, bias-corrected addcdiv
-  float m = a.exp_avg[i], v = a.exp_avg_sq[i];
-  m = m + (g - m) * a.omb1;
-  v = v * a.beta2 + a.omb2 * g * g;
+  const float m = st.m + (g - st.m) * a.omb1;
+  const float v = st.v * a.beta2 + a.omb2 * g * g;
   const float denom = sqrtf(v) / bc2_sqrt + a.eps;
-  p_new = a.params[i] - step_size * (m / denom);
+  p_new = st.p - step_size * (m / denom);
   a.exp_avg[i] = m;
   a.exp_avg_sq[i] = v;
   a.params[i] = p_new;
+}
+__device__ __forceinline__ void adam_update(const AdamParams& a, float step_size, float bc2_sqrt, int64_t i, float g, float& p_new) {
+  const AdamState st = adam_load(a, i);
+  adam_finish(a, step_size, bc2_sqrt, i, g, st, p_new);
 }
 
 // system-scope accesses for the peer-memory exchange (peer lines are cached in L1 only: never trust a plain load)
 __device__ __forceinline__ float ld_sys_f32(const float* p) {
   float v;
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_sys_f32x4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
@@ -316,23 +338,119 @@ __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
+
+__device__ __forceinline__ void reduce_item(const ReduceParams& rp, int sidx, uint32_t row, uint32_t c0, int nc, int p, int par, float (&g4)[4]);
+__device__ __forceinline__ void apply_update(const ReduceParams& rp, int64_t i, int sidx, float grad, float dev_step_size, float dev_bc2_sqrt,
+                                             AdamState st);
+
+// beta^t by square-and-multiply in double: <= 31 dependent multiplications instead of a pow() call (t < 2^31; the relative
+// error grows like t * 2^-53, far below what the float results below resolve)
+__device__ __forceinline__ double pow_int(double b, uint32_t t) {
+  double r = 1.0;
+  while (t != 0u) {
+    if (t & 1u) r *= b;
+    b *= b;
+    t >>= 1;
+  }
+  return r;
 }
 
-__device__ __forceinline__ float reduce_partials(const ReduceParams& rp, int64_t i, int& sidx_out);
-__device__ __forceinline__ void apply_update(const ReduceParams& rp, int64_t i, int sidx, float grad, float dev_step_size, float dev_bc2_sqrt);
+// Work slot -> (segment, row, first column, #columns, lane p of the item).  An item is up to four consecutive columns of one
+// row of one parameter tensor (the wide tensors read their partials with 16-byte loads); `par` adjacent lanes share an item
+// and split its ray / vertex groups between them (a hidden weight is the sum of ~50 CTAs' partials: one lane walking them
+// eight loads at a time was the long pole of this kernel).  Returns -1 for the padding slots between tensors.
+__device__ __forceinline__ int item_decode(const ReduceParams& rp, int64_t slot, uint32_t& row, uint32_t& c0, int& nc, int& p, int& par) {
+  int sidx = 0;
+  for (int s = 1; s < rp.nseg; ++s)
+    if (slot >= rp.seg[s].item_off) sidx = s;
+  par = rp.seg[sidx].par;
+  const uint32_t ls = static_cast<uint32_t>(slot - rp.seg[sidx].item_off);
+  const uint32_t li = ls / static_cast<uint32_t>(par);
+  p = static_cast<int>(ls - li * static_cast<uint32_t>(par));
+  const uint32_t ipr = static_cast<uint32_t>(rp.seg[sidx].ipr);
+  row = li / ipr;
+  c0 = (li - row * ipr) * 4u;
+  const int left = rp.seg[sidx].cols - static_cast<int>(c0);
+  nc = left < 4 ? left : 4;
+  return row < static_cast<uint32_t>(rp.seg[sidx].rows) ? sidx : -1;
+}
+
+// The lanes of an item add up their shares in lane order (every lane ends up with the same totals): fixed order, so the
+// gradient stays bit-identical from run to run.  Executed by all 32 lanes of the warp.
+__device__ __forceinline__ void item_combine(float (&g4)[4], int par) {
+  const int lane = threadIdx.x & 31;
+  const int base = lane & ~(par - 1);
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {   // par <= 4
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float o = __shfl_sync(0xffffffffu, g4[j], (base + q) & 31);
+      if (q < par) t[j] += o;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) g4[j] = t[j];
+}
+
+// sums of one slot's item -> flat / exchange slot `dst` -> (optionally) Adam; element j of the item is finished by lane j % par
+__device__ __forceinline__ void process_slot(const ReduceParams& rp, int64_t slot, float* dst, bool update, float step_size, float bc2_sqrt) {
+  uint32_t row = 0, c0 = 0;
+  int nc = 0, p = 0, par = 1;
+  int sidx = -1;
+  if (slot < rp.nitems) sidx = item_decode(rp, slot, row, c0, nc, p, par);
+  if (sidx >= 0 && rp.do_reduce && rp.seg[sidx].kind == 4) sidx = -1;   // block 0 did the output-layer bias
+  float g4[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t i0 = 0;
+  if (sidx >= 0) {
+    i0 = rp.seg[sidx].off + static_cast<int64_t>(row) * rp.seg[sidx].cols + c0;
+    if (rp.do_reduce) reduce_item(rp, sidx, row, c0, nc, p, par, g4);
+  }
+  if (rp.do_reduce) item_combine(g4, par);
+  if (rp.trace != nullptr && (threadIdx.x & 31) == 0) atomicMax(rp.trace + 47, globaltimer_ns());   // measurement: last sum finished
+  if (sidx < 0) return;
+  AdamState st[4];
+  const bool adam = update && rp.adam.params != nullptr;
+  const int pm = par < 4 ? par : 4;   // lanes of the item that finish elements: element j belongs to lane j % pm
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < nc && (j & (pm - 1)) == p) {
+      if (!rp.do_reduce) g4[j] = rp.flat[i0 + j];
+      if (adam) st[j] = adam_load(rp.adam, i0 + j);
+    }
+  }
+  // Rolled on purpose: every launch starts with a cold instruction cache and each warp runs its path exactly once, so this
+  // kernel is bound by its own instruction fetch (ncu: stall_no_inst is the top stall; ~11 us from block start to the last
+  // sum whatever the number of partials) -- four inlined copies of the optimiser tail were most of the executed bytes.
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    if (j < nc && (j & (pm - 1)) == p) {
+      float gj = j == 0 ? g4[0] : (j == 1 ? g4[1] : (j == 2 ? g4[2] : g4[3]));
+      if (rp.do_reduce) {
+        gj *= rp.scale;
+        // the table holds E[:,j] * 2^e_j, so dW0 / dWy came out multiplied by 2^e_j (exact: powers of two)
+        if (rp.seg[sidx].kind == 0 && rp.col_exp != nullptr) gj = ldexpf(gj, -static_cast<int>(rp.col_exp[c0 + j]));
+        dst[i0 + j] = gj;
+      }
+      if (adam) {
+        AdamState sj;
+        sj.m = j == 0 ? st[0].m : (j == 1 ? st[1].m : (j == 2 ? st[2].m : st[3].m));
+        sj.v = j == 0 ? st[0].v : (j == 1 ? st[1].v : (j == 2 ? st[2].v : st[3].v));
+        sj.p = j == 0 ? st[0].p : (j == 1 ? st[1].p : (j == 2 ? st[2].p : st[3].p));
+        apply_update(rp, i0 + j, sidx, gj, step_size, bc2_sqrt, sj);
+      }
+    }
+  }
+}
 
 // One launch = partial sums -> [multi-GPU: exchange over peer memory + sum over ranks] -> flat gradient -> [Adam + refresh of the
 // operand images].  With an exchange the launch is cooperative (every block resident): the ranks' kernels meet at a flag
 // per rank, written with system-scope release stores into every peer's control block.
-__global__ void field_reduce_kernel(const ReduceParams rp) {
+__global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams rp) {   // 4 CTAs per SM: one resident wave at the bench shape
   const int64_t tid0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  // Adam's bias corrections from the device-resident step counter: two double-precision pow() -- once per CTA, not per
-  // element (FP64 transcendental code in every thread was most of this kernel's 21 us)
+  // Adam's bias corrections from the device-resident step counter, once per CTA (FP64 transcendental code in every thread
+  // was most of this kernel's first version; a pow() call at the head of every CTA still delayed all its warps)
   __shared__ float s_bias_corr[2];
   __shared__ uint32_t s_seq;
   const CommParams& cm = rp.comm;
@@ -340,33 +458,67 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   uint32_t* ctl = exchange ? reinterpret_cast<uint32_t*>(cm.region[cm.rank] + 2 * cm.slot_floats) : nullptr;
   if (threadIdx.x == 0) {
     if (rp.adam.params != nullptr && rp.adam.step_dev != nullptr) {
-      const double t = static_cast<double>(*rp.adam.step_dev);
-      s_bias_corr[0] = static_cast<float>(static_cast<double>(rp.adam.lr) / (1.0 - pow(static_cast<double>(rp.adam.beta1), t)));
-      s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(rp.adam.beta2), t)));
+      const int32_t t = *rp.adam.step_dev;
+      const uint32_t tu = t > 0 ? static_cast<uint32_t>(t) : 0u;
+      s_bias_corr[0] = static_cast<float>(static_cast<double>(rp.adam.lr) / (1.0 - pow_int(static_cast<double>(rp.adam.beta1), tu)));
+      s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow_int(static_cast<double>(rp.adam.beta2), tu)));
     }
     if (exchange) s_seq = ld_acquire_sys_u32(ctl + CTL_SEQ) + 1u;   // this step's sequence number (advanced by the last block to leave)
   }
   __syncthreads();
+  // The forward/backward kernel's per-CTA partials (output-layer bias gradient, loss sums: ncta1 rows of 8 floats): block 0
+  // sums them as a block -- thread t takes rows t, t + 256, ..., then a fixed shuffle tree and a fixed order over the warps,
+  // so the result is deterministic.  (One thread walking the ~300 rows, four loads in flight, was 25 of this kernel's 30 us.)
+  __shared__ float s_part[5][8];
+  __shared__ float s_tot[5];   // gb[0..2] (unscaled), loss sums
   float loss_a = 0.f, loss_b = 0.f;
-  if (tid0 == 0 && rp.do_reduce && (rp.loss_sums != nullptr || exchange)) {
-    for (int c = 0; c < rp.ncta1; ++c) {
-      const float* pl = rp.part1 + static_cast<size_t>(c) * K1_PART_FLOATS;
-      loss_a += pl[4];
-      loss_b += pl[5];
+  if (blockIdx.x == 0 && rp.do_reduce) {
+    float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = threadIdx.x; c < rp.ncta1; c += blockDim.x) {
+      const float4* pl = reinterpret_cast<const float4*>(rp.part1 + static_cast<size_t>(c) * K1_PART_FLOATS);
+      const float4 lo = pl[0], hi = pl[1];
+      a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += hi.x; a[4] += hi.y;
     }
-    if (!exchange && rp.loss_sums != nullptr) { rp.loss_sums[0] = loss_a; rp.loss_sums[1] = loss_b; }
-  }
-  if (!exchange) {
-    // one resident wave: a CTA past the first wave would cost a whole extra pass for a handful of elements
-    for (int64_t e = tid0; e < rp.total; e += nthreads) {
-      int sidx = 0;
-      float grad;
-      if (rp.do_reduce) { grad = reduce_partials(rp, e, sidx); rp.flat[e] = grad; }
-      else {
-        for (int s = 1; s < rp.nseg; ++s) if (e >= rp.seg[s].off) sidx = s;
-        grad = rp.flat[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) s_part[j][threadIdx.x >> 5] = a[j];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      float t = 0.f;
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += s_part[threadIdx.x][w];
+      s_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    loss_a = s_tot[3];
+    loss_b = s_tot[4];
+    if (!exchange && threadIdx.x == 0 && rp.loss_sums != nullptr) { rp.loss_sums[0] = loss_a; rp.loss_sums[1] = loss_b; }
+    if (threadIdx.x < OUT_DIM) {   // the output-layer bias gradient (the last tensor, kind 4) is finished here
+      const int sidx = rp.nseg - 1;
+      const int64_t i = rp.seg[sidx].off + threadIdx.x;
+      const float gbias = s_tot[threadIdx.x] * rp.scale;
+      if (!exchange) {
+        rp.flat[i] = gbias;
+        if (rp.adam.params != nullptr) apply_update(rp, i, sidx, gbias, s_bias_corr[0], s_bias_corr[1], adam_load(rp.adam, i));
+      } else {
+        const uint32_t seq0 = s_seq;
+        (cm.region[cm.rank] + static_cast<int64_t>(seq0 & 1u) * cm.slot_floats)[i] = gbias;
       }
-      apply_update(rp, e, sidx, grad, s_bias_corr[0], s_bias_corr[1]);
+    }
+  }
+  const int64_t nslots32 = (rp.nitems + 31) & ~static_cast<int64_t>(31);   // whole warps walk the slots (item_combine shuffles)
+  if (!exchange) {
+    if (rp.trace != nullptr && threadIdx.x == 0) {   // measurement (INF_DEBUG & 8): earliest block start, latest block end
+      atomicMax(rp.trace + 44, (1ull << 62) - globaltimer_ns());
+      atomicMax(rp.trace + 45, globaltimer_ns());
+    }
+    for (int64_t slot = tid0; slot < nslots32; slot += nthreads) process_slot(rp, slot, rp.flat, true, s_bias_corr[0], s_bias_corr[1]);
+    if (rp.trace != nullptr) {
+      __syncthreads();
+      if (threadIdx.x == 0) atomicMax(rp.trace + 46, globaltimer_ns());
     }
     return;
   }
@@ -376,10 +528,7 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   const uint32_t seq = s_seq;
   const int64_t slot = static_cast<int64_t>(seq & 1u) * cm.slot_floats;
   float* mine = cm.region[cm.rank] + slot;
-  for (int64_t e = tid0; e < rp.total; e += nthreads) {
-    int sidx;
-    mine[e] = reduce_partials(rp, e, sidx);
-  }
+  for (int64_t slot_i = tid0; slot_i < nslots32; slot_i += nthreads) process_slot(rp, slot_i, mine, false, 0.f, 0.f);
   if (tid0 == 0) { mine[rp.total] = loss_a; mine[rp.total + 1] = loss_b; }
   __threadfence_system();
   __syncthreads();
@@ -406,17 +555,26 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   __syncthreads();
   if (tracing) rp.trace[42] = globaltimer_ns();
   // ---- phase B: sum over ranks in rank order (bit-identical on every rank), then the optimiser tail ------------------
-  for (int64_t e = tid0; e < rp.total; e += nthreads) {
-    float v[MAX_PEERS];
+  for (int64_t e = tid0 * 4; e < rp.total; e += nthreads * 4) {   // slots are padded to 32 floats: a 16-byte read never leaves one
+    float4 v[MAX_PEERS];
 #pragma unroll
-    for (int q = 0; q < MAX_PEERS; ++q) v[q] = q < cm.world ? ld_sys_f32(cm.region[q] + slot + e) : 0.f;   // all peer reads in flight
-    float g = 0.f;
+    for (int q = 0; q < MAX_PEERS; ++q) v[q] = q < cm.world ? ld_sys_f32x4(cm.region[q] + slot + e) : make_float4(0.f, 0.f, 0.f, 0.f);   // all peer reads in flight
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int q = 0; q < MAX_PEERS; ++q) g += v[q];
-    rp.flat[e] = g;
-    int sidx = 0;
-    for (int s = 1; s < rp.nseg; ++s) if (e >= rp.seg[s].off) sidx = s;
-    apply_update(rp, e, sidx, g, s_bias_corr[0], s_bias_corr[1]);
+    for (int q = 0; q < MAX_PEERS; ++q) { g[0] += v[q].x; g[1] += v[q].y; g[2] += v[q].z; g[3] += v[q].w; }
+    AdamState st[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e + j < rp.total && rp.adam.params != nullptr) st[j] = adam_load(rp.adam, e + j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (e + j < rp.total) {
+        rp.flat[e + j] = g[j];
+        int sidx = 0;
+        for (int s = 1; s < rp.nseg; ++s) if (e + j >= rp.seg[s].off) sidx = s;
+        apply_update(rp, e + j, sidx, g[j], s_bias_corr[0], s_bias_corr[1], st[j]);
+      }
+    }
   }
   if (tid0 == 0 && rp.loss_sums != nullptr) {
     float a = 0.f, b = 0.f;
@@ -432,71 +590,95 @@ __global__ void field_reduce_kernel(const ReduceParams rp) {
   }
 }
 
-// sum of the wgrad / forward-backward partials of flat element i, scaled; also returns its parameter segment
-__device__ __forceinline__ float reduce_partials(const ReduceParams& rp, const int64_t i, int& sidx_out) {
-  int sidx = 0;
-  for (int s = 1; s < rp.nseg; ++s)
-    if (i >= rp.seg[s].off) sidx = s;
-  sidx_out = sidx;
+// Lane p's share (groups p, p + par, ...) of the sums of an item's up to four consecutive columns, unscaled.  The wide tensors
+// (W0 / Wy, hidden weights) read their partials with 16-byte loads; all of a lane's loads are in flight before its first
+// addition.
+__device__ __forceinline__ void reduce_item(const ReduceParams& rp, const int sidx, const uint32_t row, const uint32_t c0, const int nc,
+                                            const int p, const int par, float (&g4)[4]) {
   const ReduceSeg sg = rp.seg[sidx];
-  const int64_t e = i - sg.off;
-  const int row = static_cast<int>(e / sg.cols);
-  const int col = static_cast<int>(e % sg.cols);
-  float acc = 0.f;
-  // (first CTA, #groups, lane, column) of the partials holding this element
-  int cta0 = 0, ng = 0, ln = row, c = 0;
-  auto from_unit = [&](int ui, int lane_, int col_) {
-    const WUnit w = rp.plan.u[ui];
-    cta0 = rp.cta_base_hid[w.slice];
-    ng = rp.groups_hid[w.slice];
-    ln = lane_;
-    c = col_;
-  };
-  int gmul = 1;   // CTAs between consecutive ray groups of the same slice
-  if (sg.kind == 0) {  // W0 / Wy: row n, column j; big CTAs are group-major (CTA = group * nbig + slice)
-    cta0 = col >> 8;
+  int cta0 = -1, ng = 0, gmul = 1, c = 0;
+  if (sg.kind == 0) {
+    cta0 = static_cast<int>(c0 >> 8);
     ng = rp.groups_big;
     gmul = rp.geo.nbig;
-    c = (col & 255) + (sg.a ? 256 : 0);
-  } else if (sg.kind == 1) {  // hidden / view weight
-    if (col < sg.split) from_unit(sg.a, row, rp.plan.u[sg.a].col + col);
-    else from_unit(sg.b, row, rp.plan.u[sg.b].col + (col - sg.split));
-  } else if (sg.kind == 2) {  // bias (rows entries, cols == 1)
-    from_unit(sg.a, row, rp.plan.u[sg.a].bias_col);
-  } else if (sg.kind == 3) {  // output-layer weight [3][wout]: lane = input feature, column = channel
-    from_unit(sg.a, col, rp.plan.u[sg.a].col + row);
-  }
-  if (sg.kind == 4) {  // output-layer bias [3]
-    for (int k = 0; k < rp.ncta1; ++k) acc += rp.part1[static_cast<size_t>(k) * K1_PART_FLOATS + row];
-  } else {
-    // fixed summation order; loads issued eight at a time so that their latencies overlap
-    const float* src = rp.partw + (static_cast<size_t>(cta0) * HID + ln) * WG_COLS + c;
-    const size_t GSTRIDE = static_cast<size_t>(HID) * WG_COLS * static_cast<size_t>(gmul);
-    int gI = 0;
-    for (; gI + 8 <= ng; gI += 8) {
-      float v[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = src[static_cast<size_t>(gI + q) * GSTRIDE];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc += v[q];
+    c = static_cast<int>(c0 & 255u) + (sg.a ? 256 : 0);
+  } else if (sg.kind == 1) {
+    const int split = sg.split;
+    const bool first = static_cast<int>(c0) + nc <= split, second = static_cast<int>(c0) >= split;
+    if (first || second) {
+      const WUnit w = rp.plan.u[first ? sg.a : sg.b];
+      const int cc = w.col + static_cast<int>(c0) - (first ? 0 : split);
+      if ((cc & 3) == 0 && cc + 4 <= WG_COLS) {
+        cta0 = rp.cta_base_hid[w.slice];
+        ng = rp.groups_hid[w.slice];
+        c = cc;
+      }
     }
-    for (; gI < ng; ++gI) acc += src[static_cast<size_t>(gI) * GSTRIDE];
   }
-  acc *= rp.scale;
-  // the table holds E[:,j] * 2^e_j, so dW0 / dWy came out multiplied by 2^e_j (exact: powers of two)
-  if (sg.kind == 0 && rp.col_exp != nullptr) acc = ldexpf(acc, -static_cast<int>(rp.col_exp[col]));
-  return acc;
+  if (cta0 < 0) {
+    // narrow tensors (biases, output-layer weight, a straddled or misaligned view-layer split): one partial address per
+    // element; the lane's loads of all (<= 4) elements are in flight together (these few warps were the kernel's long pole
+    // when they walked their elements one after the other)
+    const float* sp[4] = {rp.partw, rp.partw, rp.partw, rp.partw};
+    int ngj[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nc) continue;
+      const int col = static_cast<int>(c0) + j;
+      int ui, ln, cc;
+      if (sg.kind == 1) {
+        const bool first = col < sg.split;
+        ui = first ? sg.a : sg.b;
+        ln = static_cast<int>(row);
+        cc = rp.plan.u[ui].col + (first ? col : col - sg.split);
+      } else if (sg.kind == 2) {
+        ui = sg.a; ln = static_cast<int>(row); cc = rp.plan.u[ui].bias_col;
+      } else {   // kind 3: lane = input feature, column = channel
+        ui = sg.a; ln = col; cc = rp.plan.u[ui].col + static_cast<int>(row);
+      }
+      const int slice = rp.plan.u[ui].slice;
+      ngj[j] = rp.groups_hid[slice];
+      sp[j] = rp.partw + (static_cast<size_t>(rp.cta_base_hid[slice]) * HID + ln) * WG_COLS + cc;
+    }
+    const size_t GS = static_cast<size_t>(HID) * WG_COLS;
+    const int ngmax = max(max(ngj[0], ngj[1]), max(ngj[2], ngj[3]));
+    for (int g0 = p; g0 < ngmax; g0 += 8 * par) {
+      float v[8][4];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[q][j] = g0 + q * par < ngj[j] ? sp[j][static_cast<size_t>(g0 + q * par) * GS] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (g0 + q * par < ngj[j]) g4[j] += v[q][j];
+    }
+    return;
+  }
+  const float4* src = reinterpret_cast<const float4*>(rp.partw + (static_cast<size_t>(cta0) * HID + row) * WG_COLS + c);
+  const size_t GSTRIDE4 = static_cast<size_t>(HID) * WG_COLS * static_cast<size_t>(gmul) / 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int g0 = p; g0 < ng; g0 += 8 * par) {
+    float4 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = g0 + q * par < ng ? src[static_cast<size_t>(g0 + q * par) * GSTRIDE4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (g0 + q * par < ng) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+  }
+  g4[0] = acc.x; g4[1] = acc.y; g4[2] = acc.z; g4[3] = acc.w;
 }
 
 // Adam on the master parameter of flat element i, then its entry of the fp16 / f32 operand images
 __device__ __forceinline__ void apply_update(const ReduceParams& rp, const int64_t i, const int sidx, const float grad,
-                                             const float dev_step_size, const float dev_bc2_sqrt) {
+                                             const float dev_step_size, const float dev_bc2_sqrt, const AdamState st) {
   const AdamParams& ad = rp.adam;
   if (ad.params == nullptr) return;
   const ReduceSeg sg = rp.seg[sidx];
-  const int64_t e = i - sg.off;
-  const int row = static_cast<int>(e / sg.cols);
-  const int col = static_cast<int>(e % sg.cols);
+  const uint32_t e = static_cast<uint32_t>(i - sg.off);
+  const int row = static_cast<int>(e / static_cast<uint32_t>(sg.cols));
+  const int col = static_cast<int>(e - static_cast<uint32_t>(row) * static_cast<uint32_t>(sg.cols));
   if (sg.kind == 2 && sg.pair_off == -2) return;   // Ly.bias: handled by the thread of Lx.bias
   float step_size = ad.step_size, bc2_sqrt = ad.bc2_sqrt;
   if (ad.step_dev != nullptr) {
@@ -504,7 +686,7 @@ __device__ __forceinline__ void apply_update(const ReduceParams& rp, const int64
     bc2_sqrt = dev_bc2_sqrt;
   }
   float pn;
-  adam_update(ad, step_size, bc2_sqrt, i, grad, pn);
+  adam_finish(ad, step_size, bc2_sqrt, i, grad, st, pn);
   const Geo& g = rp.geo;
   float* f32sec = reinterpret_cast<float*>(ad.packed + packed_f32_offset(g));
   const int nbias = (g.nb + 1) * HID;
@@ -537,7 +719,8 @@ __device__ __forceinline__ void apply_update(const ReduceParams& rp, const int64
   }
 }
 
-cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream) {
+cudaError_t launch_field_reduce(const ReduceParams& rp_in, cudaStream_t stream) {
+  ReduceParams rp = rp_in;
   const int threads = 256;
   static int resident = 0;   // CTAs of one wave
   if (resident == 0) {
@@ -547,8 +730,34 @@ cudaError_t launch_field_reduce(const ReduceParams& rp, cudaStream_t stream) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, field_reduce_kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     resident = nsm * per_sm;
   }
-  int64_t blocks = (rp.total + threads - 1) / threads;
-  if (blocks > resident) blocks = resident;
+  // Work slots: items x lanes per item; a tensor's slots start at a multiple of 8 so that the lanes of an item sit in one
+  // warp.  A CTA lives ~9 us whatever it does (a handful of dependent memory round trips), so the launch must be ONE resident
+  // wave: a single CTA past it doubles the kernel.  The lanes per item are therefore capped so that the slots fit the wave.
+  int64_t blocks = 0;
+  for (int par_max = 4; par_max >= 1; par_max >>= 1) {
+    int64_t slots = 0;
+    for (int s = 0; s < rp.nseg; ++s) {
+      ReduceSeg& sg = rp.seg[s];
+      int ng = 1;
+      if (rp.do_reduce) {
+        if (sg.kind == 0) ng = rp.groups_big;
+        else if (sg.kind == 1) {
+          ng = rp.groups_hid[rp.plan.u[sg.a].slice];
+          if (sg.b >= 0 && rp.groups_hid[rp.plan.u[sg.b].slice] > ng) ng = rp.groups_hid[rp.plan.u[sg.b].slice];
+        } else if (sg.kind == 2 || sg.kind == 3) ng = rp.groups_hid[rp.plan.u[sg.a].slice];
+      }
+      sg.par = ng <= 8 ? 1 : (ng <= 16 ? 2 : 4);   // > 32 groups: two rounds of eight loads per lane
+      if (sg.par > par_max) sg.par = par_max;
+      sg.item_off = slots;
+      sg.ipr = (sg.cols + 3) / 4;
+      slots += static_cast<int64_t>(sg.rows) * sg.ipr * sg.par;
+      slots = (slots + 7) & ~static_cast<int64_t>(7);
+    }
+    rp.nitems = slots;
+    blocks = (slots + threads - 1) / threads;
+    if (blocks <= resident) break;
+  }
+  if (blocks > resident) blocks = resident;   // grid-stride beyond one wave (and an exchange needs every block resident)
   const bool exchange = rp.comm.world > 1 && rp.do_reduce;
   if (!exchange) {
     field_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(rp);

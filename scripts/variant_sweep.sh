@@ -1,11 +1,14 @@
 #!/bin/bash
-# usage: scripts/variant_sweep.sh [bench args] -- times field_main for every build/variants/libinf_field_v*.so (measurement helper;
-# overwrites the in-tree library of THIS checkout copy, so run it on the scratch copy gpurun makes)
-for lib in build/variants/libinf_field_v*.so; do
-  cp "$lib" intrinsic-neural-fields_b200/libinf_field.so
-  printf "%-44s" "$(basename $lib)"
-  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --skip-e2e "$@" 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); k=d['step_kernels_ms']
-print('step %.4f ms  main %.4f' % (d['ms_per_step'], k['field_main']))"
+# measurement helper: the training step (profiling run: per-stage device times) with each library variant in build/variants/
+L=intrinsic-neural-fields_b200/libinf_field.so
+cp $L /tmp/lib_default.so
+for v in build/variants/*.so /tmp/lib_default.so; do
+  cp $v $L
+  for slots in 2 1; do
+    echo "== $(basename $v) train vertex slots=$slots"
+    INF_RAYS_SLOTS=$slots timeout 300 python bench.py --mode train --path vertex --steps 20 --warmup 3 --skip-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print(round(d['ms_per_step'], 4), {k: round(v * 1e3, 1) for k, v in d['step_kernels_ms'].items()})"
+  done
 done
+cp /tmp/lib_default.so $L
