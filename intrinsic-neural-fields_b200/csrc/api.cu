@@ -320,6 +320,7 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
     const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training, vp ? d->n_rows : 0);
     uint8_t* ws = reinterpret_cast<uint8_t*>(t->workspace);
     p.err = reinterpret_cast<unsigned int*>(ws + w.err_off);
+    if (pdl_mode() == 1) p.debug |= DEBUG_PDL_EARLY;
     p.trace = (p.debug & 8) ? reinterpret_cast<unsigned long long*>(ws + w.err_off + 1024) : nullptr;
     if (training) {
       p.stash = ws + w.stash_off;
@@ -765,16 +766,18 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     rc = launch_projection(p, nsm, st);
     if (rc != INF_OK) return rc;
     prof_record(slot, 2, st);
-    e = launch_field_rays(p, true, env().rays_slots, grid1, st);
-    if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<train> launch");
-    prof_record(slot, 3, st);
-    // vertex gradient on the side stream (after the incidence lists, which are already queued there), concurrently with
-    // the hidden-slice weight gradients on the caller's stream; the big slices ([dW0;dWy] = G^T E) wait for it
-    cudaStream_t gs = st;
-    if (side != nullptr && !split) {   // the incidence lists are complete before the gather starts on the caller's stream
+    if (side != nullptr && !split) {
+      // The incidence lists (~25 us on the side stream, behind the ~40 us projection) join the caller's stream HERE, before
+      // the per-ray kernel, so that rays -> gather -> wgrad -> reduce is an unbroken chain of programmatic dependent launches
       e = cudaStreamWaitEvent(st, side->join, 0);
       if (e != cudaSuccess) return cuda_fail(e, "stream join");
     }
+    e = launch_field_rays(p, true, env().rays_slots, grid1, st);
+    if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<train> launch");
+    prof_record(slot, 3, st);
+    // (INF_WGRAD_SPLIT) vertex gradient on the side stream (after the incidence lists, which are already queued there),
+    // concurrently with the hidden-slice weight gradients on the caller's stream; the big slices ([dW0;dWy] = G^T E) wait for it
+    cudaStream_t gs = st;
     if (side != nullptr && split) {
       e = cudaEventRecord(side->fork, st);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(side->stream, side->fork, 0);
@@ -827,6 +830,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   }
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
   rp.do_reduce = 1;
+  rp.pdl_early = pdl_mode() == 1;
   rp.col_exp = t->col_exp;
   rp.err = p.err;
   rp.trace = p.trace;

@@ -274,6 +274,8 @@ __global__ void __launch_bounds__(NUM_THREADS_MAIN, 1) field_main_kernel(const F
     tmem_alloc(smem_base + sm.tmemptr, TMEM_COLS);
     tmem_relinquish();
   }
+  if (p.debug & DEBUG_PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();   // the operand images (previous step's Adam refresh), the stash's previous readers
   {
     // f32 section of the packed buffer -> smem (bias rows, then wlast + blast which are contiguous in both)
     const float* f32sec = reinterpret_cast<const float*>(p.packed + packed_f32_offset(g));
@@ -978,13 +980,14 @@ static cudaError_t launch_one(const FieldParams& p, int grid, cudaStream_t strea
   cfg.blockDim = dim3(NUM_THREADS_MAIN);
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(p.cluster);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  add_pdl_attr(cfg, attr);
   return cudaLaunchKernelEx(&cfg, field_main_kernel<kTrain, TableT>, p);
 }
 

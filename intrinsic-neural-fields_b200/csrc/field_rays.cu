@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(ry_threads(kSlots), kSlots == 1 ? 2 : 1) field
     tmem_alloc(smem_base + sm.tmemptr, RY_TMEM_COLS);
     tmem_relinquish();
   }
+  if (p.debug & DEBUG_PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();   // P (vertex_project), the operand images, the stash's previous readers
   {
     const float* f32sec = reinterpret_cast<const float*>(p.packed + packed_f32_offset(g));
     float* s_bias = reinterpret_cast<float*>(smem + sm.bias);
@@ -785,8 +787,14 @@ static cudaError_t launch_rays_one(const FieldParams& p, int grid, cudaStream_t 
   const int smem = static_cast<int>(ry_smem(kTrain, kSlots).total);
   cudaError_t e = cudaFuncSetAttribute(field_rays_kernel<kTrain, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  field_rays_kernel<kTrain, kSlots><<<static_cast<unsigned>(grid), ry_threads(kSlots), static_cast<size_t>(smem), stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(ry_threads(kSlots));
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  add_pdl_attr(cfg, attr);
+  return cudaLaunchKernelEx(&cfg, field_rays_kernel<kTrain, kSlots>, p);
 }
 
 // slots = 2: one CTA per SM, two tiles in lockstep; slots = 1: two CTAs per SM, one tile each

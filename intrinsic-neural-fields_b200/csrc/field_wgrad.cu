@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) field_wgrad_kernel(const FieldP
   if (cw > 1) cluster_sync_all();   // peers' barriers exist before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + SM_TMEMPTR);
+  if (p.debug & DEBUG_PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();   // the stash / vertex-gradient image of the kernels before; the partials' previous reader
 
   // Vertex-projected path: the big slices contract over VERTEX tiles -- A = the vertex-gradient image G (laid out as a
   // tile's dz_0 / dz_skip blobs), B = the table's operand image (laid out as a tile's x panels); [dW0;dWy] = G^T E.
@@ -276,8 +278,9 @@ cudaError_t launch_field_wgrad(const FieldParams& p, int grid, cudaStream_t stre
                                        static_cast<int>(SM_TOTAL));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   wgrad_launch_config(cfg, attr, grid, p.wg_cluster, stream);
+  add_pdl_attr(cfg, attr);
   return cudaLaunchKernelEx(&cfg, field_wgrad_kernel, p);
 }
 
@@ -465,6 +468,8 @@ __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams
     }
     if (exchange) s_seq = ld_acquire_sys_u32(ctl + CTL_SEQ) + 1u;   // this step's sequence number (advanced by the last block to leave)
   }
+  if (rp.pdl_early) pdl_launch_dependents();
+  pdl_wait();   // the partials (field_wgrad, and through it every kernel of the step)
   __syncthreads();
   // The forward/backward kernel's per-CTA partials (output-layer bias gradient, loss sums: ncta1 rows of 8 floats): block 0
   // sums them as a block -- thread t takes rows t, t + 256, ..., then a fixed shuffle tree and a fixed order over the warps,
@@ -760,8 +765,13 @@ cudaError_t launch_field_reduce(const ReduceParams& rp_in, cudaStream_t stream) 
   if (blocks > resident) blocks = resident;   // grid-stride beyond one wave (and an exchange needs every block resident)
   const bool exchange = rp.comm.world > 1 && rp.do_reduce;
   if (!exchange) {
-    field_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(rp);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+    cfg.blockDim = dim3(threads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    add_pdl_attr(cfg, attr);
+    return cudaLaunchKernelEx(&cfg, field_reduce_kernel, rp);
   }
   // the blocks of a rank meet at counters and the ranks meet at flags: every block must be resident
   cudaLaunchConfig_t cfg{};

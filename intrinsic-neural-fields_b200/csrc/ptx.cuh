@@ -112,6 +112,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-serialisation attribute may become
+// resident while its predecessor in the stream is still draining.  pdl_launch_dependents() lets the successor's CTAs be
+// scheduled as soon as every CTA of this grid has started; pdl_wait() returns once the predecessor grid has completed and its
+// memory is visible -- nothing that depends on (or is read by) an earlier kernel may be touched before it.  Both are no-ops for a
+// kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -153,11 +153,13 @@ __global__ void csr_fill_kernel(const FieldParams p) {
 // Lists of up to 32 pairs (the common case: a vertex is hit ~3 B / V times) are first SORTED by (ray, weight bits) with a
 // warp-wide bitonic network and then summed in that order with plain fp32 FMAs; longer lists are summed in 64-bit fixed
 // point, where the order does not matter.  Either way the result depends on the set of pairs only.
-__global__ void __launch_bounds__(256) vertex_gather_kernel(const FieldParams p) {
+__global__ void __launch_bounds__(256, 4) vertex_gather_kernel(const FieldParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const Geo g = p.geo;
+  if (p.debug & DEBUG_PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();   // the stash (field_rays); the incidence lists are ordered before this launch by an event
   const int2* pairs = reinterpret_cast<const int2*>(p.pairs);
   // lanes 0..15: dz_0 row of the ray, lanes 16..31: dz_skip row; 16-byte chunk (lane & 15) of the 128 features
   const size_t blob_off = lane < 16 ? stash_off_dz(g, 0) : stash_off_dz(g, g.skip);
@@ -169,15 +171,31 @@ __global__ void __launch_bounds__(256) vertex_gather_kernel(const FieldParams p)
     return reinterpret_cast<const uint4*>(p.stash + static_cast<size_t>(ray >> 7) * p.stash_stride + blob_off + panel * PANEL_BYTES + row * 128u +
                                           ((chunk ^ (row & 7u)) << 4));
   };
+  // A vertex is a chain of dependent reads (list bounds -> pairs -> stashed rows), so the bounds of the vertex after next and
+  // the pairs of the next vertex are requested while this vertex's rows are summed.
+  auto load_range = [&](int64_t vv, int& b, int& e) {
+    b = 0; e = 0;
+    if (vv < p.n_rows) { b = p.vstart[vv]; e = p.vstart[vv + 1]; }
+  };
+  auto load_pair = [&](int b, int e) -> int2 {
+    const int n_ = e - b;
+    return (n_ > 0 && n_ <= 32 && lane < n_) ? pairs[b + lane] : make_int2(0x7FFFFFFF, 0);
+  };
+  int beg, end, nbeg, nend;
+  load_range(warp0, beg, end);
+  load_range(warp0 + nwarps, nbeg, nend);
+  int2 cur = load_pair(beg, end);
   for (int64_t v = warp0; v < v_end; v += nwarps) {
     float f[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = 0.f;
-    const int beg = v < p.n_rows ? p.vstart[v] : 0, end = v < p.n_rows ? p.vstart[v + 1] : 0;
+    int nnbeg, nnend;
+    load_range(v + 2 * nwarps, nnbeg, nnend);
+    const int2 nxt = load_pair(nbeg, nend);
     const int n = end - beg;
     if (n > 0 && n <= 32) {
       // ---- sort the list (one pair per lane; empty lanes sort to the end), then sum in order ----------------
-      int2 mine = lane < n ? pairs[beg + lane] : make_int2(0x7FFFFFFF, 0);
+      const int2 mine = cur;
       unsigned long long key = (static_cast<unsigned long long>(static_cast<uint32_t>(mine.x)) << 32) | static_cast<uint32_t>(mine.y);
 #pragma unroll
       for (int k = 2; k <= 32; k <<= 1) {
@@ -248,6 +266,8 @@ __global__ void __launch_bounds__(256) vertex_gather_kernel(const FieldParams p)
                    panel * PANEL_BYTES + row * 128u + ((chunk ^ (row & 7u)) << 4);
     *reinterpret_cast<uint4*>(dst) = make_uint4(pack_half2_sat(f[0], f[1]), pack_half2_sat(f[2], f[3]), pack_half2_sat(f[4], f[5]),
                                                 pack_half2_sat(f[6], f[7]));
+    beg = nbeg; end = nend; cur = nxt;
+    nbeg = nnbeg; nend = nnend;
   }
 }
 
@@ -268,8 +288,13 @@ cudaError_t launch_csr_build(const FieldParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_vertex_gather(const FieldParams& p, int nsm, cudaStream_t stream) {
-  vertex_gather_kernel<<<static_cast<unsigned>(nsm * 8), 256, 0, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(nsm * 4));
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  add_pdl_attr(cfg, attr);
+  return cudaLaunchKernelEx(&cfg, vertex_gather_kernel, p);
 }
 
 }  // namespace inf

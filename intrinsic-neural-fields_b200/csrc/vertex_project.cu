@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(VP_THREADS, 1) vertex_project_kernel(const Fie
   if (cs > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + VP_SM_TMEMPTR);
+  if (p.debug & DEBUG_PDL_EARLY) pdl_launch_dependents();
+  pdl_wait();   // the operand images (previous step's Adam refresh) and P's previous readers
 
   // Vertex tiles are dealt round-robin; the CTAs of a cluster run the same number of iterations (a CTA past the end
   // recomputes the last tile and stores nothing) because they release each other's [W0;Wy] stages.
@@ -241,8 +243,9 @@ cudaError_t launch_vertex_project(const FieldParams& p, int grid, int cluster, c
   FieldParams q = p;
   q.cluster = cluster;
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   vp_launch_config(cfg, attr, grid, cluster, stream);
+  add_pdl_attr(cfg, attr);
   return cudaLaunchKernelEx(&cfg, vertex_project_kernel, q);
 }
 
