@@ -55,7 +55,7 @@ struct Env {
     cluster = geti("INF_CLUSTER", 2);
     verbose = geti("INF_VERBOSE", 0);
     wg_cluster = geti("INF_WGRAD_CLUSTER", 4);
-    rays_slots = geti("INF_RAYS_SLOTS", 2) == 1 ? 1 : 2;   // flavour of the per-ray kernel (field_rays.cu)
+    rays_slots = geti("INF_RAYS_SLOTS", 1) == 2 ? 2 : 1;   // flavour of the per-ray kernel (field_rays.cu)
     // Vertex path, measured and left off: hidden-slice wgrad as its own launch, concurrent with the vertex gather on the
     // side stream, big slices after (0.410 vs 0.394 ms/step: both kernels are bound by the same memory system)
     wgrad_split = geti("INF_WGRAD_SPLIT", 0);
@@ -838,7 +838,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     rp.comm.world = comm->world;
     rp.comm.rank = comm->rank;
     for (int q = 0; q < comm->world; ++q) rp.comm.region[q] = reinterpret_cast<float*>(comm->regions[q]);
-    rp.comm.slot_floats = ((total + 2 + 31) / 32) * 32;
+    rp.comm.slot_floats = comm_slot_floats(total);
   }
   rp.adam = adam_params(adam);
   rp.geo = geo;

@@ -317,7 +317,8 @@ struct ReduceSeg {
                       // is their sum); -2 marks the partner itself (Ly.bias: nothing to do here); -1 otherwise
   int64_t item_off;   // first work item of the tensor in the reduction kernel (an item = up to 4 consecutive columns of a
   int32_t ipr;        // row; ipr items per row) -- filled by launch_field_reduce
-  int32_t par;        // lanes sharing an item (1, 2, 4 or 8): they split the item's ray / vertex groups
+  int32_t par;        // lanes sharing an item (1, 2 or 4): they split the item's ray / vertex groups
+  int32_t cpi;        // columns per item: 4, or 1 for the narrow tensors when the table-driven kernel is used
 };
 // Optional optimiser tail of the reduction kernel: Adam on the flat fp32 master parameters + refresh of the fp16
 // operand images, fused with the partial sums (config.py:108 torch.optim.Adam(lr), defaults).
@@ -334,22 +335,66 @@ struct AdamParams {
   float omb1, omb2;   // 1 - beta, rounded from double as torch does
 };
 // Peer-memory exchange of the flat gradient (multi-GPU step): every rank owns an exchange region that all
-// ranks of the node have mapped (CUDA IPC over NVLink).  A region = two gradient slots (steps alternate, so a rank may
-// run one step ahead of a peer that is still reading) followed by a control block.
+// ranks of the node have mapped (CUDA IPC over NVLink).  A region = 2 x MAX_PEERS gradient slots -- slot (parity, q) receives
+// rank q's gradient of a step of that parity, PUSHED by rank q with posted remote stores, so that the sum over ranks reads
+// local memory only; steps alternate between the two parities, so a rank may run one step ahead of a peer that is still
+// reading -- followed by a control block.  Every element travels as an 8-byte (value, step number) pair written with one
+// store: the reader spins on the element itself until it carries this step's number, so there is no fence, no flag round
+// and no grid-wide barrier between a rank's sums and the sum over ranks (the exchange costs one NVLink store latency).
 constexpr int MAX_PEERS = 8;
 constexpr int COMM_CTL_WORDS = 64;       // u32 words of the control block
-enum : int { CTL_FLAGS = 0,              // [MAX_PEERS] flags[q] = last step whose gradient rank q has published
-             CTL_SEQ = 16,               // steps this rank has completed (device-resident: a CUDA-graph replay advances it)
-             CTL_BAR = 17, CTL_DONE = 18 };   // block counters of the reduction kernel
+enum : int { CTL_SEQ = 16,               // steps this rank has completed (device-resident: a CUDA-graph replay advances it)
+             CTL_DONE = 18 };            // block counter of the reduction kernel (the last block to leave advances CTL_SEQ)
+__host__ __device__ inline int64_t comm_slot_floats(int64_t total) { return 2 * (((total + 2 + 31) / 32) * 32); }
+// float offset of slot (parity, source rank) / of the control block inside a region
+__host__ __device__ inline int64_t comm_slot_off(int64_t slot_floats, uint32_t parity, int src) {
+  return (static_cast<int64_t>(parity) * MAX_PEERS + src) * slot_floats;
+}
+__host__ __device__ inline int64_t comm_ctl_off(int64_t slot_floats) { return 2 * MAX_PEERS * slot_floats; }
 struct CommParams {
   int world, rank;                       // world <= 1: no exchange
   float* region[MAX_PEERS];              // region[q] = rank q's exchange region as mapped in this process
-  int64_t slot_floats;                   // floats per gradient slot (>= total + 2, multiple of 32)
+  int64_t slot_floats;                   // floats per gradient slot: 2 per element (value, step number), total + 2 elements, padded
 };
 __host__ __device__ inline size_t comm_region_bytes(int64_t total) {
-  const int64_t slot = ((total + 2 + 31) / 32) * 32;
-  return static_cast<size_t>(2 * slot) * 4 + COMM_CTL_WORDS * 4;
+  return static_cast<size_t>(2 * MAX_PEERS * comm_slot_floats(total)) * 4 + COMM_CTL_WORDS * 4;
 }
+
+// Tables of the table-driven reduction kernel (field_reduce_lean_kernel), generated on the device by reduce_plan_kernel once
+// per (model geometry, wgrad CTA split) and kept by the library: what the generic kernel derives per thread from the parameter
+// block with run-time-indexed constant loads and a lot of code, the lean kernel reads with one coalesced load.
+struct ItemDesc {        // one per work slot (item x lane)
+  uint32_t src;          // float offset into the wgrad partials of (first group of this lane, first column)
+  uint32_t gstride;      // floats between consecutive groups OF THIS LANE (group stride x lanes per item)
+  uint32_t i0;           // flat index of the item's first element
+  uint16_t ng;           // groups this lane adds up
+  uint8_t nc;            // columns (1..4); 0 = padding slot
+  uint8_t flags;         // bit 0: 16-byte loads; bits 2-3: log2(lanes per item); bits 4-5: lane of the item
+};
+struct ElemDesc {        // one per flat element: where the optimiser tail writes the refreshed operand
+  uint32_t poff;         // byte offset into the packed operand buffer
+  uint32_t aux;          // bits 0-1: 0 fp16 image entry, 1 f32 entry, 2 f32 entry = this + partner (skip-layer biases), 3 nothing
+                         // bit 2: first-layer / skip-branch weight (bits 3..: its table column, for the column exponents)
+                         // type 2: bits 3..: flat index of the partner
+};
+struct LeanParams {
+  const ItemDesc* items;
+  const ElemDesc* elems;
+  int64_t nslots, total;
+  int64_t out_bias_off;   // flat index of the output-layer bias (finished by block 0)
+  const float* partw;
+  const float* part1;
+  float* flat;
+  float* loss_sums;
+  int ncta1;
+  float scale;
+  const int8_t* col_exp;
+  int pdl_early;
+  CommParams comm;
+  unsigned int* err;
+  unsigned long long* trace;
+  AdamParams adam;
+};
 
 struct ReduceParams {
   ReduceSeg seg[INF_MAX_PARAMS];

@@ -14,6 +14,10 @@
 // Ray tiles are dealt round-robin to `groups` CTAs per slice; every CTA finally dumps its
 // accumulators to a partial buffer and field_reduce_kernel sums the partials in a fixed order
 // (deterministic -> the N-GPU == 1-GPU check can be bit-stable per rank).
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -332,6 +336,16 @@ __device__ __forceinline__ float4 ld_sys_f32x4(const float* p) {
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
+// (value, step number) pairs of the exchange: one 8-byte store / load each, so a reader never sees a torn pair
+__device__ __forceinline__ void st_sys_pair(float* p, float v, uint32_t seq) {
+  asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool ld_sys_pair(const float* p, uint32_t seq, float& v) {
+  uint32_t a, b;
+  asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+  v = __uint_as_float(a);
+  return b == seq;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -371,10 +385,11 @@ __device__ __forceinline__ int item_decode(const ReduceParams& rp, int64_t slot,
   const uint32_t li = ls / static_cast<uint32_t>(par);
   p = static_cast<int>(ls - li * static_cast<uint32_t>(par));
   const uint32_t ipr = static_cast<uint32_t>(rp.seg[sidx].ipr);
+  const int cpi = rp.seg[sidx].cpi;
   row = li / ipr;
-  c0 = (li - row * ipr) * 4u;
+  c0 = (li - row * ipr) * static_cast<uint32_t>(cpi);
   const int left = rp.seg[sidx].cols - static_cast<int>(c0);
-  nc = left < 4 ? left : 4;
+  nc = left < cpi ? left : cpi;
   return row < static_cast<uint32_t>(rp.seg[sidx].rows) ? sidx : -1;
 }
 
@@ -410,7 +425,6 @@ __device__ __forceinline__ void process_slot(const ReduceParams& rp, int64_t slo
     if (rp.do_reduce) reduce_item(rp, sidx, row, c0, nc, p, par, g4);
   }
   if (rp.do_reduce) item_combine(g4, par);
-  if (rp.trace != nullptr && (threadIdx.x & 31) == 0) atomicMax(rp.trace + 47, globaltimer_ns());   // measurement: last sum finished
   if (sidx < 0) return;
   AdamState st[4];
   const bool adam = update && rp.adam.params != nullptr;
@@ -446,19 +460,15 @@ __device__ __forceinline__ void process_slot(const ReduceParams& rp, int64_t slo
   }
 }
 
-// One launch = partial sums -> [multi-GPU: exchange over peer memory + sum over ranks] -> flat gradient -> [Adam + refresh of the
-// operand images].  With an exchange the launch is cooperative (every block resident): the ranks' kernels meet at a flag
-// per rank, written with system-scope release stores into every peer's control block.
+// Generic reduction kernel: every address derived from the parameter block.  Used for the optimiser tail on an already
+// (all-)reduced gradient (inf_adam_pack_step: do_reduce = 0) and as the fallback when the tables of the table-driven kernel
+// below cannot be built (stream capture in progress, table budget exhausted); single GPU only.
 __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams rp) {   // 4 CTAs per SM: one resident wave at the bench shape
   const int64_t tid0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
   // Adam's bias corrections from the device-resident step counter, once per CTA (FP64 transcendental code in every thread
   // was most of this kernel's first version; a pow() call at the head of every CTA still delayed all its warps)
   __shared__ float s_bias_corr[2];
-  __shared__ uint32_t s_seq;
-  const CommParams& cm = rp.comm;
-  const bool exchange = cm.world > 1 && rp.do_reduce;
-  uint32_t* ctl = exchange ? reinterpret_cast<uint32_t*>(cm.region[cm.rank] + 2 * cm.slot_floats) : nullptr;
   if (threadIdx.x == 0) {
     if (rp.adam.params != nullptr && rp.adam.step_dev != nullptr) {
       const int32_t t = *rp.adam.step_dev;
@@ -466,7 +476,6 @@ __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams
       s_bias_corr[0] = static_cast<float>(static_cast<double>(rp.adam.lr) / (1.0 - pow_int(static_cast<double>(rp.adam.beta1), tu)));
       s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow_int(static_cast<double>(rp.adam.beta2), tu)));
     }
-    if (exchange) s_seq = ld_acquire_sys_u32(ctl + CTL_SEQ) + 1u;   // this step's sequence number (advanced by the last block to leave)
   }
   if (rp.pdl_early) pdl_launch_dependents();
   pdl_wait();   // the partials (field_wgrad, and through it every kernel of the step)
@@ -476,8 +485,8 @@ __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams
   // so the result is deterministic.  (One thread walking the ~300 rows, four loads in flight, was 25 of this kernel's 30 us.)
   __shared__ float s_part[5][8];
   __shared__ float s_tot[5];   // gb[0..2] (unscaled), loss sums
-  float loss_a = 0.f, loss_b = 0.f;
   if (blockIdx.x == 0 && rp.do_reduce) {
+    float loss_a, loss_b;
     float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int c = threadIdx.x; c < rp.ncta1; c += blockDim.x) {
       const float4* pl = reinterpret_cast<const float4*>(rp.part1 + static_cast<size_t>(c) * K1_PART_FLOATS);
@@ -500,99 +509,17 @@ __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams
     __syncthreads();
     loss_a = s_tot[3];
     loss_b = s_tot[4];
-    if (!exchange && threadIdx.x == 0 && rp.loss_sums != nullptr) { rp.loss_sums[0] = loss_a; rp.loss_sums[1] = loss_b; }
+    if (threadIdx.x == 0 && rp.loss_sums != nullptr) { rp.loss_sums[0] = loss_a; rp.loss_sums[1] = loss_b; }
     if (threadIdx.x < OUT_DIM) {   // the output-layer bias gradient (the last tensor, kind 4) is finished here
       const int sidx = rp.nseg - 1;
       const int64_t i = rp.seg[sidx].off + threadIdx.x;
       const float gbias = s_tot[threadIdx.x] * rp.scale;
-      if (!exchange) {
-        rp.flat[i] = gbias;
-        if (rp.adam.params != nullptr) apply_update(rp, i, sidx, gbias, s_bias_corr[0], s_bias_corr[1], adam_load(rp.adam, i));
-      } else {
-        const uint32_t seq0 = s_seq;
-        (cm.region[cm.rank] + static_cast<int64_t>(seq0 & 1u) * cm.slot_floats)[i] = gbias;
-      }
+      rp.flat[i] = gbias;
+      if (rp.adam.params != nullptr) apply_update(rp, i, sidx, gbias, s_bias_corr[0], s_bias_corr[1], adam_load(rp.adam, i));
     }
   }
   const int64_t nslots32 = (rp.nitems + 31) & ~static_cast<int64_t>(31);   // whole warps walk the slots (item_combine shuffles)
-  if (!exchange) {
-    if (rp.trace != nullptr && threadIdx.x == 0) {   // measurement (INF_DEBUG & 8): earliest block start, latest block end
-      atomicMax(rp.trace + 44, (1ull << 62) - globaltimer_ns());
-      atomicMax(rp.trace + 45, globaltimer_ns());
-    }
-    for (int64_t slot = tid0; slot < nslots32; slot += nthreads) process_slot(rp, slot, rp.flat, true, s_bias_corr[0], s_bias_corr[1]);
-    if (rp.trace != nullptr) {
-      __syncthreads();
-      if (threadIdx.x == 0) atomicMax(rp.trace + 46, globaltimer_ns());
-    }
-    return;
-  }
-  // ---- phase A: this rank's gradient into its slot of the exchange region -------------------------------------
-  const bool tracing = rp.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-  if (tracing) rp.trace[40] = globaltimer_ns();
-  const uint32_t seq = s_seq;
-  const int64_t slot = static_cast<int64_t>(seq & 1u) * cm.slot_floats;
-  float* mine = cm.region[cm.rank] + slot;
-  for (int64_t slot_i = tid0; slot_i < nslots32; slot_i += nthreads) process_slot(rp, slot_i, mine, false, 0.f, 0.f);
-  if (tid0 == 0) { mine[rp.total] = loss_a; mine[rp.total + 1] = loss_b; }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // the last block to arrive publishes: flags[rank] = seq in EVERY rank's control block (own included)
-    if (atomicAdd(ctl + CTL_BAR, 1u) == gridDim.x - 1) {
-      atomicExch(ctl + CTL_BAR, 0u);
-      __threadfence_system();
-      for (int q = 0; q < cm.world; ++q)
-        st_release_sys_u32(reinterpret_cast<uint32_t*>(cm.region[q] + 2 * cm.slot_floats) + CTL_FLAGS + cm.rank, seq);
-      if (rp.trace != nullptr) rp.trace[41] = globaltimer_ns();
-    }
-    // every block waits until all ranks have published this step (a peer may already be one step ahead: >=)
-    const long long t0 = clock64();
-    for (int q = 0; q < cm.world; ++q) {
-      while (static_cast<int32_t>(ld_acquire_sys_u32(ctl + CTL_FLAGS + q) - seq) < 0) {
-        if (clock64() - t0 > (1ll << 33)) {   // ~4 s: a peer died; surface it instead of hanging the GPU
-          if (rp.err) atomicExch(rp.err, 0xDEAD0C00u | static_cast<unsigned>(q));
-          break;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (tracing) rp.trace[42] = globaltimer_ns();
-  // ---- phase B: sum over ranks in rank order (bit-identical on every rank), then the optimiser tail ------------------
-  for (int64_t e = tid0 * 4; e < rp.total; e += nthreads * 4) {   // slots are padded to 32 floats: a 16-byte read never leaves one
-    float4 v[MAX_PEERS];
-#pragma unroll
-    for (int q = 0; q < MAX_PEERS; ++q) v[q] = q < cm.world ? ld_sys_f32x4(cm.region[q] + slot + e) : make_float4(0.f, 0.f, 0.f, 0.f);   // all peer reads in flight
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < MAX_PEERS; ++q) { g[0] += v[q].x; g[1] += v[q].y; g[2] += v[q].z; g[3] += v[q].w; }
-    AdamState st[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (e + j < rp.total && rp.adam.params != nullptr) st[j] = adam_load(rp.adam, e + j);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (e + j < rp.total) {
-        rp.flat[e + j] = g[j];
-        int sidx = 0;
-        for (int s = 1; s < rp.nseg; ++s) if (e + j >= rp.seg[s].off) sidx = s;
-        apply_update(rp, e + j, sidx, g[j], s_bias_corr[0], s_bias_corr[1], st[j]);
-      }
-    }
-  }
-  if (tid0 == 0 && rp.loss_sums != nullptr) {
-    float a = 0.f, b = 0.f;
-    for (int q = 0; q < cm.world; ++q) { a += ld_sys_f32(cm.region[q] + slot + rp.total); b += ld_sys_f32(cm.region[q] + slot + rp.total + 1); }
-    rp.loss_sums[0] = a;
-    rp.loss_sums[1] = b;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(ctl + CTL_DONE, 1u) == gridDim.x - 1) {
-    atomicExch(ctl + CTL_DONE, 0u);
-    st_release_sys_u32(ctl + CTL_SEQ, seq);   // every block has read this step's sequence number long ago
-    if (rp.trace != nullptr) rp.trace[43] = globaltimer_ns();
-  }
+  for (int64_t slot = tid0; slot < nslots32; slot += nthreads) process_slot(rp, slot, rp.flat, true, s_bias_corr[0], s_bias_corr[1]);
 }
 
 // Lane p's share (groups p, p + par, ...) of the sums of an item's up to four consecutive columns, unscaled.  The wide tensors
@@ -724,20 +651,330 @@ __device__ __forceinline__ void apply_update(const ReduceParams& rp, const int64
   }
 }
 
-cudaError_t launch_field_reduce(const ReduceParams& rp_in, cudaStream_t stream) {
-  ReduceParams rp = rp_in;
-  const int threads = 256;
-  static int resident = 0;   // CTAs of one wave
-  if (resident == 0) {
-    int dev = 0, nsm = 0, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm < 1)
-      nsm = 132;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, field_reduce_kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    resident = nsm * per_sm;
+// ---------------------------------------------------------------------------------------------
+// Table-driven reduction (the one training steps use).  The generic kernel above derives every address from the parameter
+// block: segment searches, divisions, unit / slice lookups with run-time-indexed constant loads, several inlined copies of
+// the optimiser tail -- thousands of instructions that each warp runs exactly once, on a cold instruction and constant
+// cache at every launch; measured, that (not the 25 MB of partials) is what the kernel's ~17 us were made of, twice over
+// with the two phases of the multi-GPU exchange.  Here reduce_plan_kernel evaluates the same address logic ONCE per (model
+// geometry, wgrad CTA split) into two device tables, and the per-step kernel is: one 16-byte descriptor load, the partial
+// loads, a shuffle combine, one 8-byte descriptor per element for the optimiser tail.
+// ---------------------------------------------------------------------------------------------
+__global__ void reduce_plan_kernel(const ReduceParams rp, ItemDesc* __restrict__ items, ElemDesc* __restrict__ elems) {
+  const int64_t tid0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t nslots32 = (rp.nitems + 31) & ~static_cast<int64_t>(31);
+  for (int64_t slot = tid0; slot < nslots32; slot += nthreads) {
+    ItemDesc d{};
+    uint32_t row = 0, c0 = 0;
+    int nc = 0, p = 0, par = 1;
+    int sidx = -1;
+    if (slot < rp.nitems) sidx = item_decode(rp, slot, row, c0, nc, p, par);
+    if (sidx >= 0 && rp.seg[sidx].kind != 4) {   // kind 4 (output-layer bias) is finished by block 0 of the reduction
+      const ReduceSeg sg = rp.seg[sidx];
+      size_t src = 0, gs = 0;
+      int ngt = 0;
+      bool vec = false;
+      if (sg.kind == 0) {
+        src = (static_cast<size_t>(c0 >> 8) * HID + row) * WG_COLS + (c0 & 255u) + (sg.a ? 256 : 0);
+        gs = static_cast<size_t>(HID) * WG_COLS * static_cast<size_t>(rp.geo.nbig);
+        ngt = rp.groups_big;
+        vec = true;
+      } else {
+        const int col = static_cast<int>(c0);
+        int ui, ln, cc;
+        if (sg.kind == 1) {
+          const bool first = col < sg.split;
+          ui = first ? sg.a : sg.b;
+          ln = static_cast<int>(row);
+          cc = rp.plan.u[ui].col + (first ? col : col - sg.split);
+          vec = sg.cpi == 4;   // the host vectorises a split tensor only when the split is a multiple of four
+        } else if (sg.kind == 2) {
+          ui = sg.a; ln = static_cast<int>(row); cc = rp.plan.u[ui].bias_col;
+        } else {   // kind 3: lane = input feature, column = channel
+          ui = sg.a; ln = col; cc = rp.plan.u[ui].col + static_cast<int>(row);
+        }
+        const int slice = rp.plan.u[ui].slice;
+        src = (static_cast<size_t>(rp.cta_base_hid[slice]) * HID + ln) * WG_COLS + cc;
+        gs = static_cast<size_t>(HID) * WG_COLS;
+        ngt = rp.groups_hid[slice];
+      }
+      int lg = 0;
+      while ((1 << lg) < par) ++lg;
+      d.src = static_cast<uint32_t>(src + static_cast<size_t>(p) * gs);
+      d.gstride = static_cast<uint32_t>(gs * static_cast<size_t>(par));
+      d.i0 = static_cast<uint32_t>(sg.off + static_cast<int64_t>(row) * sg.cols + c0);
+      d.ng = static_cast<uint16_t>(p < ngt ? (ngt - p + par - 1) / par : 0);
+      d.nc = static_cast<uint8_t>(nc);
+      d.flags = static_cast<uint8_t>((vec ? 1 : 0) | (lg << 2) | (p << 4));
+    }
+    items[slot] = d;
   }
-  // Work slots: items x lanes per item; a tensor's slots start at a multiple of 8 so that the lanes of an item sit in one
-  // warp.  A CTA lives ~9 us whatever it does (a handful of dependent memory round trips), so the launch must be ONE resident
-  // wave: a single CTA past it doubles the kernel.  The lanes per item are therefore capped so that the slots fit the wave.
+  const Geo& g = rp.geo;
+  const uint32_t f32off = static_cast<uint32_t>(packed_f32_offset(g));
+  const int nbias = (g.nb + 1) * HID;
+  for (int64_t i = tid0; i < rp.total; i += nthreads) {
+    int sidx = 0;
+    for (int s = 1; s < rp.nseg; ++s) if (i >= rp.seg[s].off) sidx = s;
+    const ReduceSeg sg = rp.seg[sidx];
+    const uint32_t e = static_cast<uint32_t>(i - sg.off);
+    const int row = static_cast<int>(e / static_cast<uint32_t>(sg.cols));
+    const int col = static_cast<int>(e - static_cast<uint32_t>(row) * static_cast<uint32_t>(sg.cols));
+    ElemDesc ed{};
+    if (sg.kind == 0) {
+      ed.poff = static_cast<uint32_t>(static_cast<size_t>(col >> 6) * BLOB_BYTES +
+                                      sw128_off(static_cast<uint32_t>(row + (sg.a ? HID : 0)), static_cast<uint32_t>(col & 63)));
+      ed.aux = 0u | 4u | (static_cast<uint32_t>(col) << 3);
+    } else if (sg.kind == 1) {
+      int blob, jj = col;
+      if (g.view && sg.layer == g.nb) {
+        if (col < sg.split) blob = blob_wd1z(g);
+        else { blob = blob_wd1e(g); jj = col - sg.split; }
+      } else {
+        blob = blob_hidden(g, sg.layer);
+      }
+      ed.poff = static_cast<uint32_t>(static_cast<size_t>(blob) * BLOB_BYTES + static_cast<uint32_t>(jj >> 6) * PANEL_BYTES +
+                                      sw128_off(static_cast<uint32_t>(row), static_cast<uint32_t>(jj & 63)));
+      ed.aux = 0u;
+    } else if (sg.kind == 2) {
+      ed.poff = f32off + static_cast<uint32_t>(sg.layer * HID + row) * 4u;
+      if (sg.pair_off == -2) ed.aux = 3u;
+      else if (sg.pair_off >= 0) ed.aux = 2u | (static_cast<uint32_t>(sg.pair_off + row) << 3);
+      else ed.aux = 1u;
+    } else if (sg.kind == 3) {
+      ed.poff = f32off + static_cast<uint32_t>(nbias + row * HID + col) * 4u;
+      ed.aux = 1u;
+    } else {
+      ed.poff = f32off + static_cast<uint32_t>(nbias + OUT_DIM * HID + row) * 4u;
+      ed.aux = 1u;
+    }
+    elems[i] = ed;
+  }
+}
+
+// optimiser tail of one element from its descriptor (same arithmetic as apply_update)
+__device__ __forceinline__ void lean_update(const AdamParams& ad, const ElemDesc ed, const int64_t i, const float grad, const float step_size,
+                                            const float bc2_sqrt, const AdamState st) {
+  const uint32_t type = ed.aux & 3u;
+  if (type == 3u) return;   // Ly.bias: updated by the thread of Lx.bias
+  float pn;
+  adam_finish(ad, step_size, bc2_sqrt, i, grad, st, pn);
+  if (type == 0u) {
+    const float img = ((ed.aux & 4u) && ad.col_exp != nullptr) ? ldexpf(pn, -static_cast<int>(ad.col_exp[ed.aux >> 3])) : pn;
+    *reinterpret_cast<__half*>(ad.packed + ed.poff) = __float2half_rn(img);
+  } else {
+    if (type == 2u) {   // skip layer: the image holds Lx.bias + Ly.bias; both share this gradient
+      float p2;
+      adam_update(ad, step_size, bc2_sqrt, static_cast<int64_t>(ed.aux >> 3), grad, p2);
+      pn += p2;
+    }
+    *reinterpret_cast<float*>(ad.packed + ed.poff) = pn;
+  }
+}
+
+// Sum over ranks of one element, exchanged as (value, step number) pairs: push this rank's value into slot (parity, rank) of
+// every peer's region, then add the ranks' values IN RANK ORDER (bit-identical on every rank), spinning on the local copy of a
+// peer's pair until it carries this step's number.  `i` = element index inside a slot (flat index; total, total + 1: loss sums).
+__device__ __forceinline__ void exch_push(const LeanParams& lp, const uint32_t seq, const int64_t i, const float g) {
+  const CommParams& cm = lp.comm;
+  const int64_t off = comm_slot_off(cm.slot_floats, seq & 1u, cm.rank) + 2 * i;
+  for (int q = 0; q < cm.world; ++q)
+    if (q != cm.rank) st_sys_pair(cm.region[q] + off, g, seq);   // posted store over NVLink
+}
+__device__ __forceinline__ float exch_sum(const LeanParams& lp, const uint32_t seq, const int64_t i, const float g) {
+  const CommParams& cm = lp.comm;
+  float sum = 0.f;
+  const long long t0 = clock64();
+  for (int q = 0; q < cm.world; ++q) {
+    float v = g;
+    if (q != cm.rank) {
+      const float* src = cm.region[cm.rank] + comm_slot_off(cm.slot_floats, seq & 1u, q) + 2 * i;
+      while (!ld_sys_pair(src, seq, v)) {
+        if (clock64() - t0 > (1ll << 33)) {   // ~4 s: a peer died; surface it instead of hanging the GPU
+          if (lp.err) atomicExch(lp.err, 0xDEAD0C00u | static_cast<unsigned>(q));
+          break;
+        }
+      }
+    }
+    sum += v;
+  }
+  return sum;
+}
+
+// one work slot: this lane's share of the item's sums, combined over the item's lanes, then the elements this lane finishes
+// (`seq` != 0: multi-GPU step -- the scaled gradient is summed over the ranks before it reaches flat + optimiser)
+// In a multi-GPU step the block stages its (value, index) pairs in shared memory and pushes them with consecutive threads on
+// consecutive elements: an item's lane owns up to four neighbouring elements, so pushing from the owner would put 8-byte
+// stores 32 bytes apart -- 330 k separate NVLink write requests per peer, measured at +15 us per step, whereas whole
+// 256-byte runs per warp instruction cost about what the 2.6 MB payload does.
+__device__ __forceinline__ void lean_slot(const LeanParams& lp, const int64_t slot, const uint32_t seq, const float step_size,
+                                          const float bc2_sqrt, float* s_val, int* s_idx) {
+  ItemDesc d{};
+  if (slot < lp.nslots) d = lp.items[slot];
+  if (lp.pdl_early & 2) d.ng = 0;   // measurement (INF_REDUCE_DBG bit 0): no partial loads -- wrong results
+  float g4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (d.nc != 0) {
+    const float* src = lp.partw + d.src;
+    if (d.flags & 1u) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g0 = 0; g0 < d.ng; g0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          v[q] = g0 + q < d.ng ? *reinterpret_cast<const float4*>(src + static_cast<size_t>(g0 + q) * d.gstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (g0 + q < d.ng) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+      }
+      g4[0] = acc.x; g4[1] = acc.y; g4[2] = acc.z; g4[3] = acc.w;
+    } else {
+      float a = 0.f;
+      for (int g0 = 0; g0 < d.ng; g0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = g0 + q < d.ng ? src[static_cast<size_t>(g0 + q) * d.gstride] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (g0 + q < d.ng) a += v[q];
+      }
+      g4[0] = a;
+    }
+  }
+  const int par = 1 << ((d.flags >> 2) & 3u);
+  item_combine(g4, par);
+  if (d.nc == 0 && seq == 0u) return;   // padding slot (a multi-GPU step still meets the block at the barriers below)
+  const int p = (d.flags >> 4) & 3u;
+  const bool adam = lp.adam.params != nullptr && !(lp.pdl_early & 4);   // (INF_REDUCE_DBG bit 1: no optimiser tail)
+  ElemDesc ed[4];
+  AdamState st[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < d.nc && (j & (par - 1)) == p) {
+      ed[j] = lp.elems[d.i0 + j];
+      g4[j] *= lp.scale;
+      // the table holds E[:,j] * 2^e_j, so dW0 / dWy came out multiplied by 2^e_j (exact: powers of two)
+      if ((ed[j].aux & 4u) && (ed[j].aux & 3u) == 0u && lp.col_exp != nullptr) g4[j] = ldexpf(g4[j], -static_cast<int>(lp.col_exp[ed[j].aux >> 3]));
+      if (adam) st[j] = adam_load(lp.adam, d.i0 + j);
+    }
+  }
+  if (seq != 0u) {
+    // every thread of the block is here (the slot loop's trip count is uniform per block); entries without an owner are -1
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool own = j < d.nc && (j & (par - 1)) == p;
+      s_val[threadIdx.x * 4 + j] = g4[j];
+      s_idx[threadIdx.x * 4 + j] = own ? static_cast<int>(d.i0) + j : -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = k * static_cast<int>(blockDim.x) + static_cast<int>(threadIdx.x);
+      const int i = s_idx[e];
+      if (i >= 0) exch_push(lp, seq, i, s_val[e]);   // on its way while the optimiser state arrives
+    }
+    __syncthreads();   // the staging buffers are free for the next slot
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < d.nc && (j & (par - 1)) == p) {
+      const int64_t i = static_cast<int64_t>(d.i0) + j;
+      const float g = seq != 0u ? exch_sum(lp, seq, i, g4[j]) : g4[j];
+      lp.flat[i] = g;
+      if (adam) lean_update(lp.adam, ed[j], i, g, step_size, bc2_sqrt, st[j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) field_reduce_lean_kernel(const LeanParams lp) {
+  const int64_t tid0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  __shared__ float s_bias_corr[2];
+  __shared__ uint32_t s_seq;
+  __shared__ float s_part[5][8];
+  __shared__ float s_tot[5];   // gb[0..2] (unscaled), loss sums
+  const CommParams& cm = lp.comm;
+  const bool exchange = cm.world > 1;
+  uint32_t* ctl = exchange ? reinterpret_cast<uint32_t*>(cm.region[cm.rank] + comm_ctl_off(cm.slot_floats)) : nullptr;
+  if (threadIdx.x == 0) {
+    s_bias_corr[0] = lp.adam.step_size;
+    s_bias_corr[1] = lp.adam.bc2_sqrt;
+    if (lp.adam.params != nullptr && lp.adam.step_dev != nullptr) {
+      const int32_t t = *lp.adam.step_dev;
+      const uint32_t tu = t > 0 ? static_cast<uint32_t>(t) : 0u;
+      s_bias_corr[0] = static_cast<float>(static_cast<double>(lp.adam.lr) / (1.0 - pow_int(static_cast<double>(lp.adam.beta1), tu)));
+      s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow_int(static_cast<double>(lp.adam.beta2), tu)));
+    }
+    // this step's number (> 0; advanced by the last block to leave, so every block of the launch reads the same value)
+    s_seq = exchange ? ld_acquire_sys_u32(ctl + CTL_SEQ) + 1u : 0u;
+  }
+  if (lp.pdl_early & 1) pdl_launch_dependents();
+  pdl_wait();   // the partials (field_wgrad, and through it every kernel of the step)
+  __syncthreads();
+  const float step_size = s_bias_corr[0], bc2_sqrt = s_bias_corr[1];
+  const uint32_t seq = s_seq;
+  const bool tracing = lp.trace != nullptr && threadIdx.x == 0;
+  if (tracing) {   // measurement (INF_DEBUG & 8): earliest block start, latest block start
+    atomicMax(lp.trace + 44, (1ull << 62) - globaltimer_ns());
+    atomicMax(lp.trace + 45, globaltimer_ns());
+  }
+  // block 0: the forward/backward kernel's per-CTA partials (output-layer bias gradient, loss sums) -- thread t takes rows t,
+  // t + 256, ..., then a fixed shuffle tree and a fixed order over the warps (deterministic)
+  if (blockIdx.x == 0) {
+    float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = threadIdx.x; c < lp.ncta1; c += blockDim.x) {
+      const float4* pl = reinterpret_cast<const float4*>(lp.part1 + static_cast<size_t>(c) * K1_PART_FLOATS);
+      const float4 lo = pl[0], hi = pl[1];
+      a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += hi.x; a[4] += hi.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) s_part[j][threadIdx.x >> 5] = a[j];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      float t = 0.f;
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += s_part[threadIdx.x][w];
+      s_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < OUT_DIM) {   // output-layer bias gradient (the last tensor of the flat vector)
+      const int64_t i = lp.out_bias_off + threadIdx.x;
+      float gbias = s_tot[threadIdx.x] * lp.scale;
+      if (exchange) { exch_push(lp, seq, i, gbias); gbias = exch_sum(lp, seq, i, gbias); }
+      lp.flat[i] = gbias;
+      if (lp.adam.params != nullptr) lean_update(lp.adam, lp.elems[i], i, gbias, step_size, bc2_sqrt, adam_load(lp.adam, i));
+    } else if (threadIdx.x < OUT_DIM + 2) {   // the two loss sums travel as elements total, total + 1 of the slot
+      const int j = threadIdx.x - OUT_DIM;
+      float v = s_tot[3 + j];
+      if (exchange) { exch_push(lp, seq, lp.total + j, v); v = exch_sum(lp, seq, lp.total + j, v); }
+      if (lp.loss_sums != nullptr) lp.loss_sums[j] = v;
+    }
+  }
+  // whole warps walk the slots (item_combine shuffles); whole blocks in a multi-GPU step (staged pushes)
+  __shared__ float s_val[1024];
+  __shared__ int s_idx[1024];
+  const int64_t nslots_up = (lp.nslots + 255) & ~static_cast<int64_t>(255);
+  for (int64_t slot = tid0; slot < nslots_up; slot += nthreads) lean_slot(lp, slot, seq, step_size, bc2_sqrt, s_val, s_idx);
+  if (lp.trace != nullptr || exchange) {
+    __syncthreads();
+    if (tracing) atomicMax(lp.trace + 46, globaltimer_ns());   // latest block end
+    if (exchange && threadIdx.x == 0 && atomicAdd(ctl + CTL_DONE, 1u) == gridDim.x - 1) {
+      atomicExch(ctl + CTL_DONE, 0u);
+      st_release_sys_u32(ctl + CTL_SEQ, seq);   // every block has read this step's number long ago
+    }
+  }
+}
+
+namespace {
+
+// work slots of a launch: items x lanes per item; a tensor's slots start at a multiple of 8 so that the lanes of an item sit
+// in one warp.  A CTA lives several microseconds whatever it does, so the launch should be ONE resident wave: the lanes per
+// item are capped until the slots fit it.  `narrow1`: biases / output-layer weight / a misaligned view-layer split become
+// one-column items (the table-driven kernel has no per-element fallback inside an item).
+int64_t plan_slots(ReduceParams& rp, int threads, int resident, bool narrow1) {
   int64_t blocks = 0;
   for (int par_max = 4; par_max >= 1; par_max >>= 1) {
     int64_t slots = 0;
@@ -753,8 +990,10 @@ cudaError_t launch_field_reduce(const ReduceParams& rp_in, cudaStream_t stream) 
       }
       sg.par = ng <= 8 ? 1 : (ng <= 16 ? 2 : 4);   // > 32 groups: two rounds of eight loads per lane
       if (sg.par > par_max) sg.par = par_max;
+      const bool wide = sg.kind == 0 || (sg.kind == 1 && (sg.split >= sg.cols || sg.split % 4 == 0));
+      sg.cpi = (wide || !narrow1) ? 4 : 1;
       sg.item_off = slots;
-      sg.ipr = (sg.cols + 3) / 4;
+      sg.ipr = (sg.cols + sg.cpi - 1) / sg.cpi;
       slots += static_cast<int64_t>(sg.rows) * sg.ipr * sg.par;
       slots = (slots + 7) & ~static_cast<int64_t>(7);
     }
@@ -762,27 +1001,134 @@ cudaError_t launch_field_reduce(const ReduceParams& rp_in, cudaStream_t stream) 
     blocks = (slots + threads - 1) / threads;
     if (blocks <= resident) break;
   }
-  if (blocks > resident) blocks = resident;   // grid-stride beyond one wave (and an exchange needs every block resident)
-  const bool exchange = rp.comm.world > 1 && rp.do_reduce;
-  if (!exchange) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
-    cfg.blockDim = dim3(threads);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    add_pdl_attr(cfg, attr);
-    return cudaLaunchKernelEx(&cfg, field_reduce_kernel, rp);
+  return blocks;
+}
+
+// Device tables of the table-driven kernel, keyed by everything they are computed from.  Owned by the library and never
+// freed (a captured CUDA graph may hold their addresses); capped in total size, beyond which (and while a stream capture is
+// in progress, where allocation is not allowed) the generic kernel runs instead.
+struct PlanEntry {
+  int dev;
+  std::string sig;
+  ItemDesc* items;
+  ElemDesc* elems;
+};
+std::mutex g_plan_mutex;
+std::vector<PlanEntry> g_plans;
+size_t g_plan_bytes = 0;
+constexpr size_t PLAN_BYTES_MAX = static_cast<size_t>(512) << 20;
+
+std::string plan_signature(const ReduceParams& rp) {
+  // field by field (struct padding is not part of the value)
+  std::string sig;
+  auto put = [&](int64_t v) { sig.append(reinterpret_cast<const char*>(&v), sizeof(v)); };
+  put(rp.nseg); put(rp.total); put(rp.nitems); put(rp.groups_big);
+  for (int s = 0; s < MAX_HID_SLICES; ++s) { put(rp.groups_hid[s]); put(rp.cta_base_hid[s]); }
+  for (int s = 0; s < rp.nseg; ++s) {
+    const ReduceSeg& g = rp.seg[s];
+    put(g.off); put(g.rows); put(g.cols); put(g.kind); put(g.a); put(g.b); put(g.split); put(g.layer); put(g.pair_off);
+    put(g.item_off); put(g.ipr); put(g.par); put(g.cpi);
   }
-  // the blocks of a rank meet at counters and the ranks meet at flags: every block must be resident
+  sig.append(reinterpret_cast<const char*>(&rp.geo), sizeof(rp.geo));   // all ints: no padding
+  put(rp.plan.n); put(rp.plan.nslice);
+  for (int u = 0; u < rp.plan.n; ++u) { put(rp.plan.u[u].col); put(rp.plan.u[u].bias_col); put(rp.plan.u[u].slice); put(rp.plan.u[u].layer); }
+  return sig;
+}
+
+const PlanEntry* plan_get(const ReduceParams& rp, cudaStream_t stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  const std::string sig = plan_signature(rp);
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  for (const PlanEntry& e : g_plans)
+    if (e.dev == dev && e.sig == sig) return &e;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+  const int64_t nslots32 = (rp.nitems + 31) & ~static_cast<int64_t>(31);
+  const size_t ib = static_cast<size_t>(nslots32) * sizeof(ItemDesc), eb = static_cast<size_t>(rp.total) * sizeof(ElemDesc);
+  if (g_plan_bytes + ib + eb > PLAN_BYTES_MAX) return nullptr;
+  PlanEntry e{dev, sig, nullptr, nullptr};
+  if (cudaMalloc(&e.items, ib) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMalloc(&e.elems, eb) != cudaSuccess) { cudaGetLastError(); cudaFree(e.items); return nullptr; }
+  const int64_t work = nslots32 > rp.total ? nslots32 : rp.total;
+  reduce_plan_kernel<<<static_cast<unsigned>((work + 255) / 256), 256, 0, stream>>>(rp, e.items, e.elems);
+  // once per configuration: later calls may come on other streams
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(e.items);
+    cudaFree(e.elems);
+    return nullptr;
+  }
+  g_plan_bytes += ib + eb;
+  g_plans.push_back(e);
+  return &g_plans.back();
+}
+
+bool lean_enabled() {
+  static const bool on = [] { const char* e = getenv("INF_REDUCE_LEAN"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
+
+}  // namespace
+
+cudaError_t launch_field_reduce(const ReduceParams& rp_in, cudaStream_t stream) {
+  ReduceParams rp = rp_in;
+  const int threads = 256;
+  static int resident = 0;   // CTAs of one wave (both kernels: 256 threads, 4 CTAs per SM)
+  if (resident == 0) {
+    int dev = 0, nsm = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm < 1)
+      nsm = 132;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, field_reduce_lean_kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 3;
+    int per_sm2 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, field_reduce_kernel, threads, 0) != cudaSuccess || per_sm2 < 1) per_sm2 = 3;
+    resident = nsm * (per_sm < per_sm2 ? per_sm : per_sm2);
+  }
+  const bool exchange = rp.comm.world > 1 && rp.do_reduce;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(blocks));
   cfg.blockDim = dim3(threads);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  if (exchange) {   // a block spins on its peers' data, which needs every block of every rank to run: all blocks resident
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    add_pdl_attr(cfg, attr);
+  }
+  if (rp.do_reduce && lean_enabled()) {
+    int64_t blocks = plan_slots(rp, threads, resident, true);
+    const PlanEntry* pe = plan_get(rp, stream);
+    if (pe != nullptr) {
+      if (blocks > resident) blocks = resident;   // grid-stride beyond one wave
+      LeanParams lp{};
+      lp.items = pe->items;
+      lp.elems = pe->elems;
+      lp.nslots = rp.nitems;
+      lp.total = rp.total;
+      lp.out_bias_off = rp.seg[rp.nseg - 1].off;
+      lp.partw = rp.partw;
+      lp.part1 = rp.part1;
+      lp.flat = rp.flat;
+      lp.loss_sums = rp.loss_sums;
+      lp.ncta1 = rp.ncta1;
+      lp.scale = rp.scale;
+      lp.col_exp = rp.col_exp;
+      static const int dbg = getenv("INF_REDUCE_DBG") ? atoi(getenv("INF_REDUCE_DBG")) : 0;   // measurement only
+      lp.pdl_early = (rp.pdl_early ? 1 : 0) | (dbg << 1);
+      lp.comm = rp.comm;
+      lp.err = rp.err;
+      lp.trace = rp.trace;
+      lp.adam = rp.adam;
+      cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+      return cudaLaunchKernelEx(&cfg, field_reduce_lean_kernel, lp);
+    }
+  }
+  if (exchange) return cudaErrorNotSupported;   // the exchange protocol lives in the table-driven kernel (every rank must take it)
+  int64_t blocks = plan_slots(rp, threads, resident, false);
+  if (blocks > resident) blocks = resident;   // grid-stride beyond one wave
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks));
   return cudaLaunchKernelEx(&cfg, field_reduce_kernel, rp);
 }
 

@@ -1,5 +1,5 @@
 """Measurement helper (N ranks under torchrun, INF_DEBUG=8): globaltimer stamps of the peer-memory gradient exchange
-inside field_reduce_kernel -- kernel start, flag published, all peers seen, end -- per rank, averaged over steps."""
+inside the reduction kernel -- first block start to last block end -- per rank, averaged over steps."""
 import os, sys
 os.environ["INF_DEBUG"] = os.environ.get("INF_DEBUG", "8")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,17 +26,22 @@ for i in range(5):
     o.fused_l1_step(bs[i % 4], global_rays=B * world)
 torch.cuda.synchronize()
 ws = ops._workspaces[("cuda", torch.cuda.current_device())]
-acc = torch.zeros(3, dtype=torch.float64)
+acc = torch.zeros(2, dtype=torch.float64)
 n = 20
+burst = int(os.environ.get("BURST", "1"))   # steps enqueued back to back before the stamps of the LAST one are read
 for i in range(n):
-    o.fused_l1_step(bs[i % 4], global_rays=B * world)
+    for j in range(burst):
+        if j == burst - 1:
+            ws[1024:1024 + 8 * 64].zero_()
+        o.fused_l1_step(bs[(i * burst + j) % 4], global_rays=B * world)
     torch.cuda.synchronize()
-    tr = ws[1024 + 8 * 40:1024 + 8 * 44].view(torch.int64).cpu().double()
-    acc += torch.stack([tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2]])
+    tr = ws[1024 + 8 * 44:1024 + 8 * 49].view(torch.int64).cpu().double()
+    first = float(1 << 62) - tr[0]
+    acc += torch.stack([first - tr[4], tr[2] - first])
 acc /= n * 1e3
-allv = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+allv = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
 dist.all_gather(allv, acc.to(dev))
 if rank == 0:
     for q, a in enumerate(allv):
-        print(f"rank {q}: partial sums + publish {a[0].item():7.1f} us   wait for peers {a[1].item():7.1f} us   sum over ranks + Adam + pack {a[2].item():7.1f} us")
+        print(f"burst {burst} rank {q}: last wgrad CTA done -> first reduce block {a[0].item():6.1f} us; first block start -> last block end (sums, exchange, Adam, operand refresh) {a[1].item():6.1f} us")
 dist.destroy_process_group()

@@ -1,5 +1,5 @@
 """Measurement helper (INF_DEBUG=8): globaltimer stamps around field_reduce_kernel inside a fused training step -- last wgrad
-CTA done, first reduce block started, last block started, last partial sum finished, last block finished."""
+CTA done, first reduce block started, last block started, last block finished."""
 import os, sys
 os.environ["INF_DEBUG"] = os.environ.get("INF_DEBUG", "8")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,6 +27,6 @@ for _ in range(n):
     torch.cuda.synchronize()
     tr = ws[1024 + 8 * 44:1024 + 8 * 49].view(torch.int64).cpu().double()
     first = float(1 << 62) - tr[0]
-    acc += torch.stack([first - tr[4], tr[1] - first, tr[3] - first, tr[2] - first])
+    acc += torch.stack([first - tr[4], tr[1] - first, tr[2] - first, tr[2] - first])
 acc /= n * 1e3
-print(f"B={B}: wgrad end -> first reduce block {acc[0]:.1f} us; last block start +{acc[1]:.1f}; last sum done +{acc[2]:.1f}; last block end +{acc[3]:.1f} us")
+print(f"B={B}: wgrad end -> first reduce block {acc[0]:.1f} us; last block start +{acc[1]:.1f}; last block end +{acc[3]:.1f} us")
