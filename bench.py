@@ -434,8 +434,9 @@ def run_ours(args):
             for b in e2e_loader:                             # one pass over the pinned host split
                 if done >= steps:
                     break
-                graphed.step(b)                              # one graph launch; loss.item(): D2H read every step
-                done += 1
+                graphed.step_logged(b)                       # one graph launch; the loss is read back (D2H) every step,
+                done += 1                                    # one step behind the launch (no device drain per step)
+        graphed.flush_logged()                               # the last step's loss: every step's result has reached the host
 
     def infer_e2e(steps):
         # a stream of frames of B rays each through ONE renderer call per pass over the host split: the copies of

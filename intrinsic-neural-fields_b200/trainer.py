@@ -352,6 +352,42 @@ class GraphedTrainStep:
         loss, pred = self.step_async(batch)
         return loss.item(), pred
 
+    def step_logged(self, batch):
+        """One optimisation step whose loss is read back WITHOUT draining the GPU: the scalar of this step is copied to a
+        pinned host slot behind the step's kernels (4 bytes on a copy stream) and the call returns the previous step's loss
+        -- ``loss.item()`` after every launch (trainer.py:84) leaves the device idle for a host round trip per step, a
+        training log does not need the value before the next step is enqueued.  Returns ``(loss of the previous call or
+        None, pred)``; :meth:`flush_logged` returns the last one."""
+        if not hasattr(self, "_log"):
+            dev = next(self.model.parameters()).device
+            self._log = {"host": torch.zeros(2, dtype=torch.float32).pin_memory(), "ev": [torch.cuda.Event(), torch.cuda.Event()],
+                         "stream": torch.cuda.Stream(dev), "n": 0, "done": torch.cuda.Event()}
+        lg = self._log
+        loss, pred = self.step_async(batch)
+        cur = torch.cuda.current_stream(loss.device)
+        lg["done"].record(cur)
+        slot = lg["n"] & 1
+        with torch.cuda.stream(lg["stream"]):
+            lg["stream"].wait_event(lg["done"])
+            lg["host"][slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            lg["ev"][slot].record(lg["stream"])
+        prev = None
+        if lg["n"] > 0:
+            lg["ev"][slot ^ 1].synchronize()        # the PREVIOUS step's 4 bytes: long done, the current step keeps running
+            prev = float(lg["host"][slot ^ 1])
+        # the graph's loss tensor is overwritten by the next replay: that replay must wait for this copy
+        cur.wait_event(lg["ev"][slot])
+        lg["n"] += 1
+        return prev, pred
+
+    def flush_logged(self):
+        lg = getattr(self, "_log", None)
+        if lg is None or lg["n"] == 0:
+            return None
+        slot = (lg["n"] - 1) & 1
+        lg["ev"][slot].synchronize()
+        return float(lg["host"][slot])
+
 
 class _ScalarLog:
     """Stand-in for ``tensorboardX.SummaryWriter`` (not installed in this image): keeps the scalars in memory."""

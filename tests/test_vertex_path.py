@@ -333,3 +333,41 @@ def test_many_tile_steps_reproduce_bit_for_bit_over_repetitions(path, view):
     torch.cuda.synchronize()
     assert inf_b200.kernel_error_word(DEV) == 0
     assert torch.equal(first[1], first[3])              # training and inference kernels agree on the RGB bit for bit
+
+
+# ---------------------------------------------------------------------------------------------
+# the training log without a device drain per step: same losses, one call late
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_step_logged_returns_the_previous_steps_loss_and_the_same_trajectory():
+    from inf_b200 import trainer
+    c = load_golden("tf_k100_l5s1")
+    g = torch.Generator().manual_seed(3)
+    V, B, k = 400, 640, c["k"]
+    E = torch.randn(V, k, generator=g) / 4
+    vids = torch.randint(0, V, (B, 3), generator=g)
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV)
+    b = {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": vids.to(DEV), "barycentric_coords": bary.to(DEV),
+         "expected_rgbs": target.to(DEV)}
+    cfg = dict(k=k, num_layers=c["num_layers"], mlp_hidden_dim=128, skip_layer_idx=c["skip"])
+    runs = []
+    for logged in (False, True):
+        m = inf_b200.make_model(cfg); m.load_state_dict(c["params"]); m = m.to(DEV)
+        gs = trainer.GraphedTrainStep(m, trainer.FusedFieldAdam(m, lr=1e-3))
+        losses = []
+        for _ in range(8):                       # eager call, capture, then replays
+            if logged:
+                prev, _ = gs.step_logged(b)
+                if prev is not None:
+                    losses.append(prev)
+            else:
+                losses.append(gs.step(b)[0])
+        if logged:
+            losses.append(gs.flush_logged())
+        runs.append(losses)
+    assert len(runs[0]) == len(runs[1]) == 8
+    assert runs[0] == runs[1]                    # the same kernels on the same data: bit-identical losses
+    assert runs[0][-1] < runs[0][0]
