@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define INF_ABI_VERSION 5
+#define INF_ABI_VERSION 6
 
 /* error codes */
 #define INF_OK 0
@@ -127,6 +127,11 @@ typedef struct InfTensors {
   float* pred;                /* (B,3) f32 out                                                      */
   void* workspace;            /* >= inf_workspace_bytes(desc, training)                             */
   size_t workspace_bytes;
+  const void* proj;           /* optional, inference only: the vertex projection P of THESE weights and THIS table,   */
+                              /* written by inf_project_vertices_raw (inf_projection_bytes(n_rows) bytes, the         */
+                              /* library's layout).  inf_forward then takes the vertex path whatever the batch size   */
+                              /* and launches the per-ray kernel only -- a frozen model (renderer.py:36-146,          */
+                              /* render_video.py:117-134) projects its vertices once, not once per chunk.             */
 } InfTensors;
 
 /* Gradient outputs of inf_forward_backward. */
@@ -219,6 +224,10 @@ int inf_build_table_image(const void* table, int32_t table_dtype, int64_t n_rows
  * branch's pre-activations (without bias) at every VERTEX (model.py:98-104, layers.py:60-62 evaluated at bary = e_i).
  * Needs t->table_image, t->packed and a workspace of inf_workspace_bytes(desc with n_rows set, 0). */
 int inf_project_vertices(const InfDesc* desc, const InfTensors* t, void* out, void* stream);
+/* The same projection kept in the layout the per-ray kernel gathers from (InfTensors.proj): `proj` receives
+ * inf_projection_bytes(desc->n_rows) bytes.  Needs t->table_image and t->packed; no workspace. */
+size_t inf_projection_bytes(int64_t n_rows);
+int inf_project_vertices_raw(const InfDesc* desc, const InfTensors* t, void* proj, void* stream);
 
 /* fp32 master parameters -> operand images.  `params[i]` = device pointer of tensor i. */
 int inf_pack_weights(const InfDesc* desc, const float* const* params, void* packed, void* stream);

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libinf_field.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 IDX_I32, IDX_I64 = 0, 1
 TABLE_F32, TABLE_F16 = 0, 1
 INPUT_GATHER, INPUT_DENSE = 0, 1
@@ -43,6 +43,7 @@ class InfTensors(C.Structure):
         ("packed", C.c_void_p),
         ("pred", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("proj", C.c_void_p),
     ]
 
 
@@ -87,6 +88,8 @@ EXPORTS = {
     "inf_table_image_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "inf_build_table_image": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "inf_project_vertices": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p, C.c_void_p]),
+    "inf_projection_bytes": (C.c_size_t, [C.c_int64]),
+    "inf_project_vertices_raw": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p, C.c_void_p]),
     "inf_uses_vertex_path": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors)]),
     "inf_pack_weights": (C.c_int, [C.POINTER(InfDesc), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "inf_forward": (C.c_int, [C.POINTER(InfDesc), C.POINTER(InfTensors), C.c_void_p]),

@@ -125,10 +125,12 @@ int check_desc(const InfDesc* d) {
 // ~2 V k 256 MACs + one streaming pass over the table image per contraction (forward P, backward G^T E), the per-ray
 // path ~B k 256 MACs + 12 KB of gathered rows per ray per contraction: the vertex path wins while V <= ~2 B.
 bool vertex_path(const InfDesc* d, const InfTensors* t) {
-  if (d->input_mode != INF_INPUT_GATHER || t == nullptr || t->table_image == nullptr || d->n_rows < 1 || d->n_rays < 1) return false;
+  if (d->input_mode != INF_INPUT_GATHER || t == nullptr || d->n_rows < 1 || d->n_rays < 1) return false;
   int path = d->path;
   if (path == INF_PATH_AUTO && env().force_path != 0) path = env().force_path;
   if (path == INF_PATH_RAY) return false;
+  if (t->proj != nullptr && t->target == nullptr && t->grad_pred == nullptr) return true;   // a ready projection: nothing left per vertex
+  if (t->table_image == nullptr) return false;
   if (path == INF_PATH_VERTEX) return true;
   return d->n_rows <= 2 * d->n_rays;
 }
@@ -227,9 +229,14 @@ int sm_count(int* out) {
 }
 
 int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
-  const bool vp = vertex_path(d, t);
-  if (vp && (reinterpret_cast<uintptr_t>(t->table_image) & 127) != 0) return fail(INF_ERR_BAD_ARG, "table_image must be 128-byte aligned");
   if (t == nullptr) return fail(INF_ERR_BAD_ARG, "tensors is null");
+  const bool vp = vertex_path(d, t);
+  const bool ready = vp && !training && t->proj != nullptr;   // the caller's projection: no table image, no P in the workspace
+  if (vp && !ready && (t->table_image == nullptr || (reinterpret_cast<uintptr_t>(t->table_image) & 127) != 0))
+    return fail(INF_ERR_BAD_ARG, "table_image must be non-null and 128-byte aligned");
+  if (ready && (reinterpret_cast<uintptr_t>(t->proj) & 127) != 0) return fail(INF_ERR_BAD_ARG, "proj must be 128-byte aligned");
+  if (training && t->proj != nullptr && t->table_image == nullptr)
+    return fail(INF_ERR_BAD_ARG, "proj is an inference input (the weights change every step): training needs table_image");
   if (d->n_rays == 0) return INF_OK;
   if (t->table == nullptr || t->packed == nullptr || t->pred == nullptr)
     return fail(INF_ERR_BAD_ARG, "table / packed / pred must be non-null");
@@ -252,7 +259,7 @@ int check_tensors(const InfDesc* d, const InfTensors* t, bool training) {
       return fail(INF_ERR_BAD_ARG, "exactly one of target / grad_pred must be given");
   }
   if (training || vp) {
-    const WorkspaceLayout w = workspace_layout(geo_of(d), d->n_rays, training, vp ? d->n_rows : 0);
+    const WorkspaceLayout w = workspace_layout(geo_of(d), d->n_rays, training, (vp && !ready) ? d->n_rows : 0);
     if (t->workspace == nullptr || t->workspace_bytes < w.total)
       return fail(INF_ERR_WORKSPACE, "workspace %zu B < required %zu B", t->workspace_bytes, w.total);
     if ((reinterpret_cast<uintptr_t>(t->workspace) & 255) != 0)
@@ -317,7 +324,8 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
   p.stash_stride = vp ? stash_tile_bytes_vp(p.geo) : stash_tile_bytes(p.geo);
   p.n_rows = d->n_rows;
   if (t->workspace != nullptr && t->workspace_bytes >= ERR_AREA_BYTES) {
-    const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training, vp ? d->n_rows : 0);
+    const bool ready = vp && !training && t->proj != nullptr;
+    const WorkspaceLayout w = workspace_layout(p.geo, d->n_rays, training, (vp && !ready) ? d->n_rows : 0);
     uint8_t* ws = reinterpret_cast<uint8_t*>(t->workspace);
     p.err = reinterpret_cast<unsigned int*>(ws + w.err_off);
     if (pdl_mode() == 1) p.debug |= DEBUG_PDL_EARLY;
@@ -330,7 +338,7 @@ FieldParams make_params(const InfDesc* d, const InfTensors* t, bool training) {
     if (vp) {
       p.e_image = reinterpret_cast<const uint8_t*>(t->table_image);
       p.ntiles_v = static_cast<int>((d->n_rows + TILE_M - 1) / TILE_M);
-      p.proj = ws + w.proj_off;
+      p.proj = ready ? const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(t->proj)) : ws + w.proj_off;
       if (training) {
         p.g_image = ws + w.gimg_off;
         p.vstart = reinterpret_cast<int32_t*>(ws + w.vstart_off);
@@ -486,6 +494,34 @@ int inf_project_vertices(const InfDesc* desc, const InfTensors* t, void* out, vo
   return INF_OK;
 }
 
+size_t inf_projection_bytes(int64_t n_rows) {
+  if (n_rows < 1) return 0;
+  return static_cast<size_t>((n_rows + TILE_M - 1) / TILE_M) * PROJ_TILE_BYTES;
+}
+
+int inf_project_vertices_raw(const InfDesc* desc, const InfTensors* t, void* proj, void* stream) {
+  int rc = check_desc(desc);
+  if (rc != INF_OK) return rc;
+  if (t == nullptr || t->table_image == nullptr || t->packed == nullptr || proj == nullptr)
+    return fail(INF_ERR_BAD_ARG, "table_image / packed / proj must be non-null");
+  if (desc->n_rows < 1) return fail(INF_ERR_BAD_ARG, "n_rows must be given");
+  int nsm = 0;
+  rc = sm_count(&nsm);
+  if (rc != INF_OK) return rc;
+  FieldParams p{};
+  p.packed = reinterpret_cast<const uint8_t*>(t->packed);
+  p.e_image = reinterpret_cast<const uint8_t*>(t->table_image);
+  p.n_rows = desc->n_rows;
+  p.ntiles_v = static_cast<int>((desc->n_rows + TILE_M - 1) / TILE_M);
+  p.proj = reinterpret_cast<uint8_t*>(proj);
+  p.geo = geo_of(desc);
+  if (t->workspace != nullptr && t->workspace_bytes >= ERR_AREA_BYTES) p.err = reinterpret_cast<unsigned int*>(t->workspace);
+  rc = launch_projection(p, nsm, static_cast<cudaStream_t>(stream));
+  if (rc != INF_OK) return rc;
+  g_launches += 1;
+  return INF_OK;
+}
+
 int inf_uses_vertex_path(const InfDesc* desc, const InfTensors* t) {
   if (check_desc(desc) != INF_OK) return 0;
   return vertex_path(desc, t) ? 1 : 0;
@@ -581,13 +617,16 @@ int inf_forward(const InfDesc* desc, const InfTensors* t, void* stream) {
   const int slot = g_prof.n;
   prof_record(slot, 0, st);
   prof_record(slot, 1, st);
-  if (p.e_image != nullptr) {
-    rc = launch_projection(p, nsm, st);
-    if (rc != INF_OK) return rc;
+  if (p.proj != nullptr) {
+    const bool ready = t->proj != nullptr;   // the caller's projection of these weights: the per-ray kernel only
+    if (!ready) {
+      rc = launch_projection(p, nsm, st);
+      if (rc != INF_OK) return rc;
+    }
     prof_record(slot, 2, st);
     cudaError_t e = launch_field_rays(p, false, env().rays_slots, rays_grid(p, nsm), st);
     if (e != cudaSuccess) return cuda_fail(e, "field_rays_kernel<inference> launch");
-    g_launches += 2;   // vertex_project, field_rays
+    g_launches += ready ? 1 : 2;   // [vertex_project,] field_rays
   } else {
     prof_record(slot, 2, st);
     const int grid = pick_main_grid(desc, p.ntiles, nsm, false, &p.cluster);

@@ -97,16 +97,43 @@ class _FusedFieldBase(nn.Module):
             with torch.no_grad():
                 self._packed = ops.pack_weights(self.cfg, [p.detach().contiguous() for p in params], None, col_exp)
             self._packed_key = key
+            self._pack_gen = getattr(self, "_pack_gen", 0) + 1   # every re-pack invalidates what was derived from the images
         if self._layout is None:
             self._layout = ops.param_layout(self.cfg)
         return self._packed
 
     def invalidate_packed(self):
         self._packed_key = None
+        self._proj_key = None
+
+    def _projection(self, batch, packed):
+        """Eval mode: the vertex projection P = E [W0;Wy]^T of the cached operand images, computed once per (weights, table)
+        and handed to every inference call -- a frozen model renders many chunks / frames (renderer.py:36-146,
+        render_video.py:117-134) and then launches the per-ray kernel only.  None when the call cannot use it."""
+        table = batch.get("eigenfunction_table")
+        if self.training or not isinstance(table, EigenTable) or table.image is None or table.path == "ray" \
+                or "vertex_idxs_of_hit_faces" not in batch:
+            return None
+        key = (getattr(self, "_pack_gen", 0), id(table), table.data.data_ptr())
+        if getattr(self, "_proj", None) is None or getattr(self, "_proj_key", None) != key:
+            old = getattr(self, "_proj", None)
+            if old is not None and (old.device != table.device or old.numel() != ops.projection_bytes(table.n_rows)):
+                old = None
+            self._proj = ops.project_vertices_raw(self.cfg, table, packed, out=old)   # in place when possible: same address
+            self._proj_key = key
+        return self._proj
 
     def train(self, mode: bool = True):
-        self._packed_key = None
+        if mode != self.training:          # a mode switch drops the cached operand images (see _packed_weights)
+            self._packed_key = None
         return super().train(mode)
+
+    def prepare(self, batch):
+        """(operand images, vertex projection or None) an inference call on ``batch`` would use, brought up to date."""
+        extras = self._table_extras(batch)
+        packed = self._packed_weights(force=self.training, col_exp=extras[2])
+        dense = "eigenfunctions" in batch and "eigenfunction_table" not in batch
+        return packed, (None if dense else self._projection(batch, packed))
 
     def __deepcopy__(self, memo):
         # trainer.py:67,274 deep-copies the model; cached device buffers are rebuilt lazily
@@ -115,7 +142,7 @@ class _FusedFieldBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            setattr(new, k, None if k in ("_packed", "_packed_key") else copy.deepcopy(v, memo))
+            setattr(new, k, None if k in ("_packed", "_packed_key", "_proj", "_proj_key") else copy.deepcopy(v, memo))
         return new
 
     # ---- batch decoding ----------------------------------------------------------------------------
@@ -158,8 +185,10 @@ class _FusedFieldBase(nn.Module):
         params = self._ordered_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _FieldFunction.apply(self, table, vids, bary, dense, dirs, face_idxs, normals, ridx, extras, *params)
-        return torch.ops.inf_b200.field_forward(table, vids, bary, self._packed_weights(force=self.training, col_exp=extras[2]),
-                                                dirs, face_idxs, normals, self.cfg.key(), dense, ridx, *extras)
+        packed = self._packed_weights(force=self.training, col_exp=extras[2])
+        proj = None if dense else self._projection(batch, packed)
+        return torch.ops.inf_b200.field_forward(table, vids, bary, packed, dirs, face_idxs, normals, self.cfg.key(), dense, ridx,
+                                                *extras, proj)
 
     # ---- fused training pass -----------------------------------------------------------------------
     def l1_step(self, batch: Dict[str, torch.Tensor], global_rays: Optional[int] = None,

@@ -366,7 +366,7 @@ def _check_view(cfg, B, idx64, dirs, face_idxs, face_normals):   # B = rows of t
 
 
 def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense: bool,
-                        ray_idxs=None, table_image=None, path: int = 0, col_exp=None) -> torch.Tensor:
+                        ray_idxs=None, table_image=None, path: int = 0, col_exp=None, proj=None) -> torch.Tensor:
     cfg = FieldConfig.from_key(cfg_key)
     B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
@@ -376,14 +376,18 @@ def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals
     idx64 = vids is None or vids.dtype == torch.int64
     dirs, face_idxs, face_normals, n_faces = _check_view(cfg, n_src, idx64, dirs, face_idxs, face_normals)
     if dense:
-        table_image = None
-    ws = _workspace(device, workspace_bytes(cfg, B, False, table.shape[0] if table_image is not None else 0, path))
+        table_image = proj = None
+    if proj is not None:
+        _require_cuda(proj, "proj")
+        if proj.dtype != torch.uint8 or proj.numel() != int(_lib.load().inf_projection_bytes(table.shape[0])):
+            raise ValueError("proj must be the uint8 buffer written by project_vertices_raw for this table")
+    ws = _workspace(device, workspace_bytes(cfg, B, False, table.shape[0] if (table_image is not None and proj is None) else 0, path))
     d = _desc(cfg, B, table.shape[0], idx64=idx64, table_f16=table.dtype == torch.float16, dense=dense, n_faces=n_faces,
               ray_idxs=ray_idxs, n_src_rays=n_src, path=path)
     t = _lib.InfTensors(table=table.data_ptr(), vids=_ptr(vids), bary=_ptr(bary), unit_ray_dirs=_ptr(dirs),
                         face_idxs=_ptr(face_idxs), face_normals=_ptr(face_normals), ray_idxs=_ptr(ray_idxs),
                         table_image=_ptr(table_image), col_exp=_ptr(col_exp), packed=packed.data_ptr(),
-                        pred=pred.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+                        pred=pred.data_ptr(), workspace=ws.data_ptr(), workspace_bytes=ws.numel(), proj=_ptr(proj))
     with torch.cuda.device(device):
         rc = _lib.load().inf_forward(C.byref(d), C.byref(t), _stream(device))
     _lib.check(rc, "inf_forward")
@@ -464,9 +468,9 @@ def field_forward(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optio
                   packed: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                   face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool,
                   ray_idxs: Optional[torch.Tensor] = None, table_image: Optional[torch.Tensor] = None,
-                  path: int = 0, col_exp: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  path: int = 0, col_exp: Optional[torch.Tensor] = None, proj: Optional[torch.Tensor] = None) -> torch.Tensor:
     return _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs,
-                               table_image, path, col_exp)
+                               table_image, path, col_exp, proj)
 
 
 def _fake_rows(table, vids, dense, ray_idxs):
@@ -475,7 +479,7 @@ def _fake_rows(table, vids, dense, ray_idxs):
 
 @field_forward.register_fake
 def _(table, vids, bary, packed, dirs, face_idxs, face_normals, cfg_key, dense, ray_idxs=None, table_image=None, path=0,
-      col_exp=None):
+      col_exp=None, proj=None):
     B = _fake_rows(table, vids, dense, ray_idxs)
     return table.new_empty((B, 3), dtype=torch.float32)
 
@@ -566,6 +570,32 @@ def project_vertices(cfg: FieldConfig, table: "EigenTable", packed: torch.Tensor
     with torch.cuda.device(table.device):
         rc = _lib.load().inf_project_vertices(C.byref(d), C.byref(t), C.c_void_p(out.data_ptr()), _stream(table.device))
     _lib.check(rc, "inf_project_vertices")
+    return out
+
+
+def projection_bytes(n_rows: int) -> int:
+    return int(_lib.load().inf_projection_bytes(n_rows))
+
+
+def project_vertices_raw(cfg: FieldConfig, table: "EigenTable", packed: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The vertex projection of ``packed`` (these weights) and ``table`` in the layout the per-ray kernel gathers from: a
+    uint8 buffer for ``field_forward(..., proj=...)``.  A frozen model evaluates many chunks / frames (renderer.py:36-146,
+    render_video.py:117-134) with ONE projection; ``out`` rewrites an existing buffer in place (same address: CUDA graphs
+    that read it stay valid)."""
+    img = table.build_image()
+    V = table.n_rows
+    nbytes = int(_lib.load().inf_projection_bytes(V))
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=table.device)
+    elif out.dtype != torch.uint8 or out.numel() != nbytes or out.device != table.device:
+        raise ValueError("out must be the uint8 buffer of a previous project_vertices_raw call for this table")
+    ws = _workspace(table.device, workspace_bytes(cfg, 1, False, 0, _lib.PATH_RAY))
+    d = _desc(cfg, 1, V, table_f16=table.data.dtype == torch.float16, path=_lib.PATH_VERTEX)
+    t = _lib.InfTensors(table=table.data.data_ptr(), table_image=img.data_ptr(), packed=packed.data_ptr(),
+                        workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+    with torch.cuda.device(table.device):
+        rc = _lib.load().inf_project_vertices_raw(C.byref(d), C.byref(t), C.c_void_p(out.data_ptr()), _stream(table.device))
+    _lib.check(rc, "inf_project_vertices_raw")
     return out
 
 

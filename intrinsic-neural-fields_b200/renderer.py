@@ -28,14 +28,15 @@ class GraphedForward:
     def __init__(self, model):
         self.model, self.graphs = model, {}
 
-    @staticmethod
-    def _key(batch):
+    def _key(self, batch):
+        # a re-pack of the weights (new operand images, new vertex projection) must not replay a graph of the old buffers
         return tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in sorted(batch.items()) if torch.is_tensor(v)) + \
-            (id(batch.get("eigenfunction_table")),)
+            (id(batch.get("eigenfunction_table")), getattr(self.model, "_pack_gen", 0))
 
     @torch.no_grad()
     def __call__(self, batch):
         self.model.eval()
+        self.model.prepare(batch)          # operand images / vertex projection of the current weights (cached)
         key = self._key(batch)
         ent = self.graphs.get(key)
         if ent is None:

@@ -371,3 +371,60 @@ def test_step_logged_returns_the_previous_steps_loss_and_the_same_trajectory():
     assert len(runs[0]) == len(runs[1]) == 8
     assert runs[0] == runs[1]                    # the same kernels on the same data: bit-identical losses
     assert runs[0][-1] < runs[0][0]
+
+
+# ---------------------------------------------------------------------------------------------
+# a frozen model projects its vertices once (InfTensors.proj): eval-mode inference launches the per-ray kernel only
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_eval_mode_reuses_one_vertex_projection_and_follows_weight_changes():
+    c = load_golden("tf_k100_l5s1")
+    g = torch.Generator().manual_seed(5)
+    V, k = 700, c["k"]
+    E = torch.randn(V, k, generator=g) / 4
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV)
+    cfg = dict(k=k, num_layers=c["num_layers"], mlp_hidden_dim=128, skip_layer_idx=c["skip"])
+    m = inf_b200.make_model(cfg); m.load_state_dict(c["params"]); m = m.to(DEV)
+    lib = _lib.load()
+
+    def batch(B, seed):
+        gg = torch.Generator().manual_seed(seed)
+        vids = torch.randint(0, V, (B, 3), generator=gg)
+        u = torch.rand(B, 3, generator=gg)
+        return {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": vids.to(DEV), "barycentric_coords": (u / u.sum(-1, keepdim=True)).to(DEV)}
+
+    big, small = batch(2048, 1), batch(40, 2)          # V <= 2 B (vertex path by the AUTO rule) and V >> B (per-ray path by it)
+    with torch.no_grad():
+        m.train()
+        ref_big, ref_small = m(big).clone(), m(small).clone()      # training mode: projects (or gathers table rows) in every call
+        m.eval()
+        n0 = lib.inf_launch_count()
+        out_big = m(big)                                           # projects once ...
+        n1 = lib.inf_launch_count()
+        out_small = m(small)                                       # ... and every later call is ONE launch, whatever its size
+        n2 = lib.inf_launch_count()
+        out_big2 = m(big)
+        n3 = lib.inf_launch_count()
+    assert n2 - n1 == 1 and n3 - n2 == 1 and n1 - n0 >= 2
+    assert torch.equal(out_big, ref_big) and torch.equal(out_big2, ref_big)    # same P, same per-ray kernel: bit-identical
+    # the 40-ray call took the per-ray path in training mode and the vertex path here: same tolerance as between the paths
+    assert (out_small - ref_small).abs().max().item() <= 2e-3
+    okw = dict(num_layers=c["num_layers"], skip=c["skip"])
+    want = O.field_forward(c["params"], E, small["vertex_idxs_of_hit_faces"].cpu(), small["barycentric_coords"].cpu(), **okw)
+    assert (out_small.cpu() - want).abs().max().item() <= 2e-2
+    # new weights -> new operand images -> new projection (in place, same buffer)
+    p_before = m._proj.data_ptr()
+    sd = {n: (t * 1.5 if n.endswith("weight") else t) for n, t in c["params"].items()}
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        out_new = m(small)
+    want_new = O.field_forward(sd, E, small["vertex_idxs_of_hit_faces"].cpu(), small["barycentric_coords"].cpu(), **okw)
+    assert m._proj.data_ptr() == p_before
+    assert (out_new.cpu() - want_new).abs().max().item() <= 2e-2
+    assert (out_new - out_small).abs().max().item() > 1e-3
+    # a table pinned to the per-ray path never receives a projection
+    m2 = inf_b200.make_model(cfg); m2.load_state_dict(c["params"]); m2 = m2.to(DEV).eval()
+    with torch.no_grad():
+        out_ray = m2(dict(big, eigenfunction_table=tab.with_path("ray")))
+    assert getattr(m2, "_proj", None) is None
+    assert (out_ray - ref_big).abs().max().item() <= 2e-3
