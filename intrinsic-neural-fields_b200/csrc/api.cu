@@ -878,6 +878,10 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     rp.comm.rank = comm->rank;
     for (int q = 0; q < comm->world; ++q) rp.comm.region[q] = reinterpret_cast<float*>(comm->regions[q]);
     rp.comm.slot_floats = comm_slot_floats(total);
+    {
+      static const int two_shot_min = getenv("INF_EXCH_TWO_SHOT_MIN") ? atoi(getenv("INF_EXCH_TWO_SHOT_MIN")) : 4;
+      rp.comm.own_chunk = comm->world >= two_shot_min ? (((total + comm->world - 1) / comm->world + 31) / 32) * 32 : 0;
+    }
   }
   rp.adam = adam_params(adam);
   rp.geo = geo;

@@ -347,17 +347,22 @@ enum : int { CTL_SEQ = 16,               // steps this rank has completed (devic
              CTL_DONE = 18 };            // block counter of the reduction kernel (the last block to leave advances CTL_SEQ)
 __host__ __device__ inline int64_t comm_slot_floats(int64_t total) { return 2 * (((total + 2 + 31) / 32) * 32); }
 // float offset of slot (parity, source rank) / of the control block inside a region
+// slots per parity: one per source rank (contributions) + one for the finished sums of the two-shot exchange
+constexpr int COMM_SLOTS = MAX_PEERS + 1;
+constexpr int COMM_SLOT_RESULT = MAX_PEERS;
 __host__ __device__ inline int64_t comm_slot_off(int64_t slot_floats, uint32_t parity, int src) {
-  return (static_cast<int64_t>(parity) * MAX_PEERS + src) * slot_floats;
+  return (static_cast<int64_t>(parity) * COMM_SLOTS + src) * slot_floats;
 }
-__host__ __device__ inline int64_t comm_ctl_off(int64_t slot_floats) { return 2 * MAX_PEERS * slot_floats; }
+__host__ __device__ inline int64_t comm_ctl_off(int64_t slot_floats) { return 2 * COMM_SLOTS * slot_floats; }
 struct CommParams {
   int world, rank;                       // world <= 1: no exchange
   float* region[MAX_PEERS];              // region[q] = rank q's exchange region as mapped in this process
   int64_t slot_floats;                   // floats per gradient slot: 2 per element (value, step number), total + 2 elements, padded
+  int64_t own_chunk;                     // two-shot exchange (world >= 4): rank i / own_chunk sums element i and sends the sum to
+                                         // everyone (each rank moves 2 x 7/8 of the vector instead of 7 x); 0 = one shot
 };
 __host__ __device__ inline size_t comm_region_bytes(int64_t total) {
-  return static_cast<size_t>(2 * MAX_PEERS * comm_slot_floats(total)) * 4 + COMM_CTL_WORDS * 4;
+  return static_cast<size_t>(2 * COMM_SLOTS * comm_slot_floats(total)) * 4 + COMM_CTL_WORDS * 4;
 }
 
 // Tables of the table-driven reduction kernel (field_reduce_lean_kernel), generated on the device by reduce_plan_kernel once

@@ -781,24 +781,30 @@ __device__ __forceinline__ void exch_push(const LeanParams& lp, const uint32_t s
   for (int q = 0; q < cm.world; ++q)
     if (q != cm.rank) st_sys_pair(cm.region[q] + off, g, seq);   // posted store over NVLink
 }
+// local copy of slot `src`'s pair of element i, once it carries this step's number
+__device__ __forceinline__ float exch_wait(const LeanParams& lp, const uint32_t seq, const int src, const int64_t i) {
+  const CommParams& cm = lp.comm;
+  const float* p = cm.region[cm.rank] + comm_slot_off(cm.slot_floats, seq & 1u, src) + 2 * i;
+  float v = 0.f;
+  const long long t0 = clock64();
+  while (!ld_sys_pair(p, seq, v)) {
+    if (clock64() - t0 > (1ll << 33)) {   // ~4 s: a peer died; surface it instead of hanging the GPU
+      if (lp.err) atomicExch(lp.err, 0xDEAD0C00u | static_cast<unsigned>(src));
+      break;
+    }
+  }
+  return v;
+}
 __device__ __forceinline__ float exch_sum(const LeanParams& lp, const uint32_t seq, const int64_t i, const float g) {
   const CommParams& cm = lp.comm;
   float sum = 0.f;
-  const long long t0 = clock64();
-  for (int q = 0; q < cm.world; ++q) {
-    float v = g;
-    if (q != cm.rank) {
-      const float* src = cm.region[cm.rank] + comm_slot_off(cm.slot_floats, seq & 1u, q) + 2 * i;
-      while (!ld_sys_pair(src, seq, v)) {
-        if (clock64() - t0 > (1ll << 33)) {   // ~4 s: a peer died; surface it instead of hanging the GPU
-          if (lp.err) atomicExch(lp.err, 0xDEAD0C00u | static_cast<unsigned>(q));
-          break;
-        }
-      }
-    }
-    sum += v;
-  }
+  for (int q = 0; q < cm.world; ++q) sum += q == cm.rank ? g : exch_wait(lp, seq, q, i);
   return sum;
+}
+// two-shot exchange: the rank that sums element i
+__device__ __forceinline__ int exch_owner(const CommParams& cm, const int64_t i) {
+  const int o = static_cast<int>(i / cm.own_chunk);
+  return o < cm.world ? o : cm.world - 1;
 }
 
 // one work slot: this lane's share of the item's sums, combined over the item's lanes, then the elements this lane finishes
@@ -857,6 +863,8 @@ __device__ __forceinline__ void lean_slot(const LeanParams& lp, const int64_t sl
       if (adam) st[j] = adam_load(lp.adam, d.i0 + j);
     }
   }
+  const CommParams& cm = lp.comm;
+  const bool two_shot = seq != 0u && cm.own_chunk > 0;
   if (seq != 0u) {
     // every thread of the block is here (the slot loop's trip count is uniform per block); entries without an owner are -1
 #pragma unroll
@@ -870,17 +878,58 @@ __device__ __forceinline__ void lean_slot(const LeanParams& lp, const int64_t sl
     for (int k = 0; k < 4; ++k) {
       const int e = k * static_cast<int>(blockDim.x) + static_cast<int>(threadIdx.x);
       const int i = s_idx[e];
-      if (i >= 0) exch_push(lp, seq, i, s_val[e]);   // on its way while the optimiser state arrives
+      if (i >= 0) {   // on its way while the optimiser state arrives
+        if (!two_shot) {
+          exch_push(lp, seq, i, s_val[e]);
+        } else {       // first shot: this rank's value goes to the element's summing rank only
+          const int o = exch_owner(cm, i);
+          if (o != cm.rank) st_sys_pair(cm.region[o] + comm_slot_off(cm.slot_floats, seq & 1u, cm.rank) + 2 * static_cast<int64_t>(i), s_val[e], seq);
+        }
+      }
     }
-    __syncthreads();   // the staging buffers are free for the next slot
+    __syncthreads();   // the staging buffers are free again
+  }
+  float tot[4] = {g4[0], g4[1], g4[2], g4[3]};
+  if (seq != 0u) {
+    bool mine[4] = {false, false, false, false};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < d.nc && (j & (par - 1)) == p) {
+        const int64_t i = static_cast<int64_t>(d.i0) + j;
+        mine[j] = !two_shot || exch_owner(cm, i) == cm.rank;
+        if (mine[j]) tot[j] = exch_sum(lp, seq, i, g4[j]);   // rank order: the same bits wherever the sum is made
+      }
+    }
+    if (two_shot) {
+      // second shot: the summing rank sends the finished sum to everyone (again as whole runs per warp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s_val[threadIdx.x * 4 + j] = tot[j];
+        s_idx[threadIdx.x * 4 + j] = (mine[j] && j < d.nc && (j & (par - 1)) == p) ? static_cast<int>(d.i0) + j : -1;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = k * static_cast<int>(blockDim.x) + static_cast<int>(threadIdx.x);
+        const int i = s_idx[e];
+        if (i >= 0) {
+          const int64_t off = comm_slot_off(cm.slot_floats, seq & 1u, COMM_SLOT_RESULT) + 2 * static_cast<int64_t>(i);
+          for (int q = 0; q < cm.world; ++q)
+            if (q != cm.rank) st_sys_pair(cm.region[q] + off, s_val[e], seq);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < d.nc && (j & (par - 1)) == p && !mine[j]) tot[j] = exch_wait(lp, seq, COMM_SLOT_RESULT, static_cast<int64_t>(d.i0) + j);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (j < d.nc && (j & (par - 1)) == p) {
       const int64_t i = static_cast<int64_t>(d.i0) + j;
-      const float g = seq != 0u ? exch_sum(lp, seq, i, g4[j]) : g4[j];
-      lp.flat[i] = g;
-      if (adam) lean_update(lp.adam, ed[j], i, g, step_size, bc2_sqrt, st[j]);
+      lp.flat[i] = tot[j];
+      if (adam) lean_update(lp.adam, ed[j], i, tot[j], step_size, bc2_sqrt, st[j]);
     }
   }
 }
