@@ -54,7 +54,7 @@ struct Env {
     prefetch = geti("INF_PREFETCH", 0);
     cluster = geti("INF_CLUSTER", 2);
     verbose = geti("INF_VERBOSE", 0);
-    wg_cluster = geti("INF_WGRAD_CLUSTER", 4);
+    wg_cluster = geti("INF_WGRAD_CLUSTER", 0);   // 0: 4 on the per-ray path, 2 on the vertex path (see run_forward_backward)
     rays_slots = geti("INF_RAYS_SLOTS", 1) == 2 ? 2 : 1;   // flavour of the per-ray kernel (field_rays.cu)
     // Vertex path, measured and left off: hidden-slice wgrad as its own launch, concurrent with the vertex gather on the
     // side stream, big slices after (0.410 vs 0.394 ms/step: both kernels are bound by the same memory system)
@@ -407,7 +407,11 @@ int inf_version(void) { return INF_ABI_VERSION; }
 
 long long inf_launch_count(void) { return g_launches.load(); }
 
-int inf_debug_flags(void) { return env().debug; }
+int inf_debug_flags(void) {
+  // INF_DEBUG bits 1|2|4 and INF_REDUCE_DBG (reported as bits 8, 9) skip work and produce wrong results
+  static const int rdbg = getenv("INF_REDUCE_DBG") ? atoi(getenv("INF_REDUCE_DBG")) : 0;
+  return env().debug | ((rdbg & 3) << 8);
+}
 
 const char* inf_last_error(void) { return g_err; }
 
@@ -700,7 +704,9 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   // clusters of cw big-slice CTAs share the dz_0 / dz_skip half-panels (multicast): cw = 4, 2 or 1, dividing nbig
   int cw = 4;
   {
-    const int env_cw = env().wg_cluster;
+    // per-ray path: clusters of 4 share the dz_0 / dz_skip half-panels (0.152 -> 0.127 ms, r1f); vertex path: clusters of 2 --
+    // only 33 clusters of 4 fit the 148 SMs (132 CTAs), 74 clusters of 2 use all of them (wgrad 96 -> 91.6 us, r2)
+    const int env_cw = env().wg_cluster > 0 ? env().wg_cluster : (vp ? 2 : 4);
     cw = env_cw >= 4 ? 4 : (env_cw >= 2 ? 2 : 1);
     while (cw > 1 && geo.nbig % cw != 0) cw >>= 1;
   }

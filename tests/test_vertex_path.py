@@ -428,3 +428,37 @@ def test_eval_mode_reuses_one_vertex_projection_and_follows_weight_changes():
         out_ray = m2(dict(big, eigenfunction_table=tab.with_path("ray")))
     assert getattr(m2, "_proj", None) is None
     assert (out_ray - ref_big).abs().max().item() <= 2e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# the CTA-pair (cta_group::2) variant of the projection kernel: measured slower and off by default, but kept correct
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_cta_pair_projection_kernel_matches_the_single_cta_kernel_bit_for_bit():
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import inf_b200
+from inf_b200 import ops
+torch.manual_seed(0)
+V, k = 128 * 37 + 5, 200                      # an odd number of vertex tiles: the pair's second CTA idles on the last one
+E = torch.randn(V, k) / 4
+tab = inf_b200.EigenTable.from_dense(E, device="cuda:0", path="vertex")
+m = inf_b200.make_model(dict(k=k, num_layers=6, mlp_hidden_dim=128, skip_layer_idx=3)).to("cuda:0").eval()
+packed, _ = m.prepare({"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": torch.zeros(1, 3, dtype=torch.int64, device="cuda:0"),
+                       "barycentric_coords": torch.zeros(1, 3, device="cuda:0")})
+P = ops.project_vertices(m.cfg, tab, packed)
+torch.save(P.cpu(), sys.argv[1])
+""" % root
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for flag in ("0", "1"):
+            path = os.path.join(d, f"p{flag}.pt")
+            env = dict(os.environ, INF_VP_2CTA=flag)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(torch.load(path))
+    assert outs[0].shape == outs[1].shape and outs[0].abs().max().item() > 0.1
+    assert torch.equal(outs[0], outs[1])          # same MMAs over the same operands, same fp32 accumulation order
