@@ -360,23 +360,28 @@ class GraphedTrainStep:
         None, pred)``; :meth:`flush_logged` returns the last one."""
         if not hasattr(self, "_log"):
             dev = next(self.model.parameters()).device
-            self._log = {"host": torch.zeros(2, dtype=torch.float32).pin_memory(), "ev": [torch.cuda.Event(), torch.cuda.Event()],
-                         "stream": torch.cuda.Stream(dev), "n": 0, "done": torch.cuda.Event()}
+            self._log = {"host": torch.zeros(2, dtype=torch.float32).pin_memory(), "dev": torch.zeros(2, dtype=torch.float32, device=dev),
+                         "ev": [torch.cuda.Event(), torch.cuda.Event()], "stream": torch.cuda.Stream(dev), "n": 0,
+                         "done": [torch.cuda.Event(), torch.cuda.Event()]}
         lg = self._log
         loss, pred = self.step_async(batch)
         cur = torch.cuda.current_stream(loss.device)
-        lg["done"].record(cur)
         slot = lg["n"] & 1
+        # The graph's loss tensor is overwritten by the next replay, so the scalar is first copied (4 bytes, device to device,
+        # in stream order) into a two-slot ring; the host copy then runs on its own stream and the next step never waits for it
+        # (a slot is reused two steps later: its previous host copy has long finished).
+        if lg["n"] >= 2:
+            cur.wait_event(lg["ev"][slot])
+        lg["dev"][slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        lg["done"][slot].record(cur)
         with torch.cuda.stream(lg["stream"]):
-            lg["stream"].wait_event(lg["done"])
-            lg["host"][slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            lg["stream"].wait_event(lg["done"][slot])
+            lg["host"][slot:slot + 1].copy_(lg["dev"][slot:slot + 1], non_blocking=True)
             lg["ev"][slot].record(lg["stream"])
         prev = None
         if lg["n"] > 0:
             lg["ev"][slot ^ 1].synchronize()        # the PREVIOUS step's 4 bytes: long done, the current step keeps running
             prev = float(lg["host"][slot ^ 1])
-        # the graph's loss tensor is overwritten by the next replay: that replay must wait for this copy
-        cur.wait_event(lg["ev"][slot])
         lg["n"] += 1
         return prev, pred
 
