@@ -137,22 +137,26 @@ typedef struct InfTensors {
 /* Gradient outputs of inf_forward_backward. */
 typedef struct InfGrads {
   float* flat;       /* inf_num_params(desc) f32: all parameter gradients, state_dict order   */
-  float* loss_sums;  /* 2 f32: sum|pred-target| and sum (pred-target)^2 over this call's rays */
+  float* loss_sums;  /* 3 f32: sum|pred-target|, sum (pred-target)^2 over this call's rays (over all ranks' rays after  */
+                     /* inf_train_step_comm), and the first times desc.grad_scale = the mean L1 loss when grad_scale  */
+                     /* is 1/(3 B_global) -- the training log needs no extra kernel                                    */
 } InfGrads;
 
 /* Optimiser state of inf_train_step / inf_adam_pack_step: torch.optim.Adam defaults semantics (no weight decay, no
  * amsgrad).  params / exp_avg / exp_avg_sq are flat f32 vectors of inf_num_params(desc) elements in state_dict order. */
+#define INF_ADAM_STEP_AUTOINC 1 /* step_dev counts completed updates; the kernel increments it (inf_train_step[_comm] only) */
 typedef struct InfAdam {
   float* params;      /* master parameters, updated in place                                          */
   float* exp_avg;     /* first moment                                                                  */
   float* exp_avg_sq;  /* second moment                                                                 */
   void* packed;       /* operand images (inf_pack_weights layout); the live entries are rewritten      */
   const int8_t* col_exp; /* column exponents of the table these operand images are used with (null: none)        */
-  const int32_t* step_dev; /* optional DEVICE counter holding t (read by the kernel; lets a CUDA graph replay   */
-                      /* the step with a changing t); when null, `step` below is used                  */
+  int32_t* step_dev;  /* optional DEVICE counter (lets a CUDA graph replay the step with a changing t); when null,    */
+                      /* `step` below is used.  It holds t -- or, with INF_ADAM_STEP_AUTOINC, the number of COMPLETED  */
+                      /* updates: inf_train_step[_comm] then uses t = *step_dev + 1 and writes it back itself          */
   float lr, beta1, beta2, eps;
   int32_t step;       /* 1-based step count t of THIS update (bias corrections 1 - beta^t)             */
-  int32_t reserved0;
+  int32_t flags;      /* INF_ADAM_*                                                                     */
 } InfAdam;
 
 /* Peer-memory exchange of the multi-GPU training step (one process per GPU on one node; replaces the reference's

@@ -54,7 +54,10 @@ class InfGrads(C.Structure):
 class InfAdam(C.Structure):
     _fields_ = [("params", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("packed", C.c_void_p),
                 ("col_exp", C.c_void_p), ("step_dev", C.c_void_p), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("step", C.c_int32), ("reserved0", C.c_int32)]
+                ("step", C.c_int32), ("flags", C.c_int32)]
+
+
+ADAM_STEP_AUTOINC = 1
 
 
 MAX_PEERS = 8

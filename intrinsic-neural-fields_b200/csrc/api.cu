@@ -658,6 +658,7 @@ static AdamParams adam_params(const InfAdam* a) {
   ap.params = a->params; ap.exp_avg = a->exp_avg; ap.exp_avg_sq = a->exp_avg_sq;
   ap.packed = reinterpret_cast<uint8_t*>(a->packed);
   ap.step_dev = a->step_dev;
+  ap.step_autoinc = (a->step_dev != nullptr && (a->flags & INF_ADAM_STEP_AUTOINC)) ? 1 : 0;
   ap.col_exp = a->col_exp;
   ap.lr = a->lr;
   const int tstep = a->step < 1 ? 1 : a->step;
@@ -685,7 +686,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   if (desc->n_rays == 0 && adam != nullptr) return fail(INF_ERR_BAD_ARG, "inf_train_step needs at least one ray");
   if (desc->n_rays == 0) {
     cudaError_t e = cudaMemsetAsync(g->flat, 0, static_cast<size_t>(total) * 4, st);
-    if (e == cudaSuccess && g->loss_sums) e = cudaMemsetAsync(g->loss_sums, 0, 8, st);
+    if (e == cudaSuccess && g->loss_sums) e = cudaMemsetAsync(g->loss_sums, 0, 12, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     return INF_OK;
   }
@@ -874,6 +875,7 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     base += gh[s];
   }
   rp.scale = desc->grad_scale / (DZ_SCALE * ext);
+  rp.loss_scale = desc->grad_scale;
   rp.do_reduce = 1;
   rp.pdl_early = pdl_mode() == 1;
   rp.col_exp = t->col_exp;
@@ -890,6 +892,9 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
     }
   }
   rp.adam = adam_params(adam);
+  // the block counter of the step auto-increment lives in the workspace's (zero-initialised) error area
+  rp.adam.done_ctr = p.err != nullptr ? p.err + 4 : nullptr;
+  if (rp.adam.done_ctr == nullptr) rp.adam.step_autoinc = 0;
   rp.geo = geo;
   rp.plan = plan;
   e = launch_field_reduce(rp, st);
@@ -990,6 +995,7 @@ int inf_adam_pack_step(const InfDesc* desc, float* flat_grad, const InfAdam* ada
   rp.flat = flat_grad;
   rp.do_reduce = 0;
   rp.adam = adam_params(adam);
+  if (rp.adam.step_autoinc) return fail(INF_ERR_BAD_ARG, "INF_ADAM_STEP_AUTOINC is a flag of inf_train_step[_comm]");
   rp.geo = geo_of(desc);
   rp.plan = make_wplan(rp.geo);
   cudaError_t e = launch_field_reduce(rp, static_cast<cudaStream_t>(stream));

@@ -328,7 +328,9 @@ struct AdamParams {
   float* exp_avg_sq;
   uint8_t* packed;    // operand images to refresh
   const int8_t* col_exp;     // column exponents of the table (W0 / Wy images hold W[:,j] * 2^-col_exp[j]); null = none
-  const int32_t* step_dev;  // optional device-resident step count t (CUDA-graph replays); else the host values below
+  int32_t* step_dev;        // optional device-resident step count t (CUDA-graph replays); else the host values below
+  int step_autoinc;         // step_dev counts COMPLETED updates: t = *step_dev + 1, written back by the last block to leave
+  unsigned int* done_ctr;   // block counter for that (a zero-initialised word of the workspace)
   float step_size;    // lr / (1 - beta1^t)
   float bc2_sqrt;     // sqrt(1 - beta2^t)
   float lr, beta1, beta2, eps;
@@ -393,6 +395,7 @@ struct LeanParams {
   float* loss_sums;
   int ncta1;
   float scale;
+  float loss_scale;       // loss_sums[2] = loss_sums[0] * loss_scale (desc.grad_scale: the mean L1 loss)
   const int8_t* col_exp;
   int pdl_early;
   CommParams comm;
@@ -415,6 +418,7 @@ struct ReduceParams {
   int groups_hid[MAX_HID_SLICES];
   int cta_base_hid[MAX_HID_SLICES];
   float scale;
+  float loss_scale;        // loss_sums[2] = loss_sums[0] * loss_scale (desc.grad_scale)
   const int8_t* col_exp;   // column exponents of the table: the W0 / Wy gradients come out multiplied by 2^col_exp[j]
   int pdl_early;   // call griddepcontrol.launch_dependents in the prologue (INF_PDL=1)
   int do_reduce;   // 0: flat already holds the (all-reduced) gradient, only the optimiser tail runs

@@ -303,6 +303,16 @@ int field_wgrad_max_grid(int cluster) {
 // Partial reduction (+ optional Adam step and operand refresh): one thread per element of the flat
 // gradient vector, fixed summation order.
 // ---------------------------------------------------------------------------------------------
+// INF_ADAM_STEP_AUTOINC: every block has read the step counter in its prologue; the last block to leave advances it
+__device__ __forceinline__ void step_autoinc_finish(const AdamParams& a) {
+  if (!a.step_autoinc || a.params == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(a.done_ctr, 1u) == gridDim.x - 1) {
+    atomicExch(a.done_ctr, 0u);
+    *a.step_dev = *a.step_dev + 1;
+  }
+}
+
 struct AdamState { float m, v, p; };
 __device__ __forceinline__ AdamState adam_load(const AdamParams& a, int64_t i) {
   AdamState st;
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams
   __shared__ float s_bias_corr[2];
   if (threadIdx.x == 0) {
     if (rp.adam.params != nullptr && rp.adam.step_dev != nullptr) {
-      const int32_t t = *rp.adam.step_dev;
+      const int32_t t = *rp.adam.step_dev + rp.adam.step_autoinc;
       const uint32_t tu = t > 0 ? static_cast<uint32_t>(t) : 0u;
       s_bias_corr[0] = static_cast<float>(static_cast<double>(rp.adam.lr) / (1.0 - pow_int(static_cast<double>(rp.adam.beta1), tu)));
       s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow_int(static_cast<double>(rp.adam.beta2), tu)));
@@ -509,7 +519,7 @@ __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams
     __syncthreads();
     loss_a = s_tot[3];
     loss_b = s_tot[4];
-    if (threadIdx.x == 0 && rp.loss_sums != nullptr) { rp.loss_sums[0] = loss_a; rp.loss_sums[1] = loss_b; }
+    if (threadIdx.x == 0 && rp.loss_sums != nullptr) { rp.loss_sums[0] = loss_a; rp.loss_sums[1] = loss_b; rp.loss_sums[2] = loss_a * rp.loss_scale; }
     if (threadIdx.x < OUT_DIM) {   // the output-layer bias gradient (the last tensor, kind 4) is finished here
       const int sidx = rp.nseg - 1;
       const int64_t i = rp.seg[sidx].off + threadIdx.x;
@@ -520,6 +530,7 @@ __global__ void __launch_bounds__(256, 4) field_reduce_kernel(const ReduceParams
   }
   const int64_t nslots32 = (rp.nitems + 31) & ~static_cast<int64_t>(31);   // whole warps walk the slots (item_combine shuffles)
   for (int64_t slot = tid0; slot < nslots32; slot += nthreads) process_slot(rp, slot, rp.flat, true, s_bias_corr[0], s_bias_corr[1]);
+  step_autoinc_finish(rp.adam);
 }
 
 // Lane p's share (groups p, p + par, ...) of the sums of an item's up to four consecutive columns, unscaled.  The wide tensors
@@ -948,7 +959,7 @@ __global__ void __launch_bounds__(256, 4) field_reduce_lean_kernel(const LeanPar
     s_bias_corr[0] = lp.adam.step_size;
     s_bias_corr[1] = lp.adam.bc2_sqrt;
     if (lp.adam.params != nullptr && lp.adam.step_dev != nullptr) {
-      const int32_t t = *lp.adam.step_dev;
+      const int32_t t = *lp.adam.step_dev + lp.adam.step_autoinc;
       const uint32_t tu = t > 0 ? static_cast<uint32_t>(t) : 0u;
       s_bias_corr[0] = static_cast<float>(static_cast<double>(lp.adam.lr) / (1.0 - pow_int(static_cast<double>(lp.adam.beta1), tu)));
       s_bias_corr[1] = static_cast<float>(sqrt(1.0 - pow_int(static_cast<double>(lp.adam.beta2), tu)));
@@ -999,7 +1010,10 @@ __global__ void __launch_bounds__(256, 4) field_reduce_lean_kernel(const LeanPar
       const int j = threadIdx.x - OUT_DIM;
       float v = s_tot[3 + j];
       if (exchange) { exch_push(lp, seq, lp.total + j, v); v = exch_sum(lp, seq, lp.total + j, v); }
-      if (lp.loss_sums != nullptr) lp.loss_sums[j] = v;
+      if (lp.loss_sums != nullptr) {
+        lp.loss_sums[j] = v;
+        if (j == 0) lp.loss_sums[2] = v * lp.loss_scale;
+      }
     }
   }
   // whole warps walk the slots (item_combine shuffles); whole blocks in a multi-GPU step (staged pushes)
@@ -1007,6 +1021,7 @@ __global__ void __launch_bounds__(256, 4) field_reduce_lean_kernel(const LeanPar
   __shared__ int s_idx[1024];
   const int64_t nslots_up = (lp.nslots + 255) & ~static_cast<int64_t>(255);
   for (int64_t slot = tid0; slot < nslots_up; slot += nthreads) lean_slot(lp, slot, seq, step_size, bc2_sqrt, s_val, s_idx);
+  step_autoinc_finish(lp.adam);
   if (lp.trace != nullptr || exchange) {
     __syncthreads();
     if (tracing) atomicMax(lp.trace + 46, globaltimer_ns());   // latest block end
@@ -1163,6 +1178,7 @@ cudaError_t launch_field_reduce(const ReduceParams& rp_in, cudaStream_t stream) 
       lp.loss_sums = rp.loss_sums;
       lp.ncta1 = rp.ncta1;
       lp.scale = rp.scale;
+      lp.loss_scale = rp.loss_scale;
       lp.col_exp = rp.col_exp;
       static const int dbg = getenv("INF_REDUCE_DBG") ? atoi(getenv("INF_REDUCE_DBG")) : 0;   // measurement only
       lp.pdl_early = (rp.pdl_early ? 1 : 0) | (dbg << 1);

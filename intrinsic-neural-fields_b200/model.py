@@ -196,7 +196,7 @@ class _FusedFieldBase(nn.Module):
         """Forward + mean-L1 loss + backward in one fused pass (trainer.py:75-81, config.py:117-118).
 
         Sets ``.grad`` of every parameter (views into one flat buffer, ready for a single allreduce) and
-        returns ``(loss_sums, pred, flat_grad)`` where ``loss_sums = [sum|pred-target|, sum (pred-target)^2]``
+        returns ``(loss_sums, pred, flat_grad)`` where ``loss_sums = [sum|pred-target|, sum (pred-target)^2, mean L1 loss]``
         over this call's rays; the mean L1 loss is ``loss_sums[0] / (3 * global_rays)``.
         ``global_rays`` is the number of rays of the whole (all-rank) batch; it defaults to this call's B.
         """

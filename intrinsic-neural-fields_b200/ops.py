@@ -394,7 +394,8 @@ def _field_forward_impl(table, vids, bary, packed, dirs, face_idxs, face_normals
     return pred
 
 
-def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev, col_exp=None) -> "_lib.InfAdam":
+def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps, step_dev, col_exp=None,
+                 autoinc: bool = False) -> "_lib.InfAdam":
     n = params_flat.numel()
     for name, x in (("params_flat", params_flat), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
         _require_cuda(x, name)
@@ -405,7 +406,7 @@ def _adam_struct(params_flat, exp_avg, exp_avg_sq, packed, lr, beta1, beta2, eps
         raise ValueError("step_dev must be a 1-element int32 CUDA tensor holding the step count t of this update")
     return _lib.InfAdam(params=params_flat.data_ptr(), exp_avg=exp_avg.data_ptr(), exp_avg_sq=exp_avg_sq.data_ptr(),
                         packed=packed.data_ptr(), col_exp=_ptr(col_exp), step_dev=step_dev.data_ptr(), lr=lr, beta1=beta1,
-                        beta2=beta2, eps=eps, step=0)
+                        beta2=beta2, eps=eps, step=0, flags=_lib.ADAM_STEP_AUTOINC if autoinc else 0)
 
 
 def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normals, cfg_key,
@@ -415,9 +416,10 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
     B, n_src = _check_inputs(cfg, table, vids, bary, dense, ray_idxs)
     device = table.device
     pred = torch.empty((B, 3), dtype=torch.float32, device=device)
-    # flat gradient and the two loss sums share one allocation so that a multi-rank step needs a single allreduce
+    # flat gradient and the loss sums (sum |d|, sum d^2, mean L1 loss = sum |d| * grad_scale) share one allocation so that a
+    # multi-rank step needs a single allreduce
     n_par = num_params(cfg)
-    flat_full = torch.empty(n_par + 2, dtype=torch.float32, device=device)
+    flat_full = torch.empty(n_par + N_LOSS_SUMS, dtype=torch.float32, device=device)
     flat, sums = flat_full[:n_par], flat_full[n_par:]
     if B == 0 or grad_pred is not None:
         sums.zero_()
@@ -446,7 +448,8 @@ def _field_forward_backward_impl(table, vids, bary, packed, target, grad_pred, d
         else:
             if adam.params_flat.numel() != n_par:
                 raise ValueError("flat parameter vector does not match the model configuration")
-            a = _adam_struct(*adam, col_exp=col_exp)
+            # the fused step advances the device-resident step counter itself (no separate increment kernel per step)
+            a = _adam_struct(*adam, col_exp=col_exp, autoinc=True)
             if comm_id:
                 from .parallel import PeerExchange
                 comm = PeerExchange.lookup(comm_id)
@@ -504,12 +507,16 @@ def _(table, vids, bary, packed, target, grad_pred, dirs, face_idxs, face_normal
       table_image=None, path=0, col_exp=None):
     B = _fake_rows(table, vids, dense, ray_idxs)
     n = num_params(FieldConfig.from_key(cfg_key))
-    return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n + 2,), dtype=torch.float32))
+    return (table.new_empty((B, 3), dtype=torch.float32), table.new_empty((n + N_LOSS_SUMS,), dtype=torch.float32))
+
+
+N_LOSS_SUMS = 3
 
 
 def split_flat(flat_full: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(flat gradient, [sum|pred-target|, sum (pred-target)^2]) views of the fused step's single output buffer."""
-    n = flat_full.numel() - 2
+    """(flat gradient, [sum|pred-target|, sum (pred-target)^2, mean L1 loss]) views of the fused step's single output buffer
+    (the third sum is the first times the call's grad_scale: with grad_scale = 1 / (3 B_global) the mean L1 loss)."""
+    n = flat_full.numel() - N_LOSS_SUMS
     return flat_full[:n], flat_full[n:]
 
 
@@ -518,7 +525,7 @@ class _AdamArgs(tuple):
     params_flat = property(lambda self: self[0])
 
 
-@torch.library.custom_op("inf_b200::field_train_step", mutates_args=("packed", "params_flat", "exp_avg", "exp_avg_sq"))
+@torch.library.custom_op("inf_b200::field_train_step", mutates_args=("packed", "params_flat", "exp_avg", "exp_avg_sq", "step_dev"))
 def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Optional[torch.Tensor], packed: torch.Tensor,
                      target: torch.Tensor, dirs: Optional[torch.Tensor], face_idxs: Optional[torch.Tensor],
                      face_normals: Optional[torch.Tensor], cfg_key: List[int], dense: bool, grad_scale: float,
@@ -538,7 +545,7 @@ def field_train_step(table: torch.Tensor, vids: Optional[torch.Tensor], bary: Op
 def _(table, vids, bary, packed, target, dirs, face_idxs, face_normals, cfg_key, dense, grad_scale, params_flat, exp_avg,
       exp_avg_sq, lr, beta1, beta2, eps, step_dev, ray_idxs=None, table_image=None, path=0, col_exp=None, comm_id=0):
     B = _fake_rows(table, vids, dense, ray_idxs)
-    return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty((params_flat.numel() + 2,)))
+    return (table.new_empty((B, 3), dtype=torch.float32), params_flat.new_empty((params_flat.numel() + N_LOSS_SUMS,)))
 
 
 @torch.library.custom_op("inf_b200::field_adam_pack", mutates_args=("packed", "params_flat", "exp_avg", "exp_avg_sq"))

@@ -158,7 +158,7 @@ class FusedFieldAdam:
         B = batch_rays(batch)
         scale = 1.0 / (3.0 * float(global_rays if global_rays is not None else B))
         self._for_table(batch)
-        self.step_dev.add_(1)
+        # step_dev holds the number of completed updates; the reduction kernel uses t = step_dev + 1 and advances it
         pred, flat_full = torch.ops.inf_b200.field_train_step(
             table, vids, bary, self.packed, target, dirs, face_idxs, normals, m.cfg.key(), dense, scale, self.flat,
             self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps, self.step_dev, ridx,
@@ -282,7 +282,7 @@ class GraphedTrainStep:
         return self.model.l1_step(batch, global_rays=B * world)          # sums, pred, flat
 
     def _back(self, sums, n_global, flat=None):
-        loss = sums[0] / (3.0 * n_global)
+        loss = sums[2]          # mean L1 loss = sum |d| / (3 n_global), written by the reduction kernel (no extra launch)
         if isinstance(self.optim, FusedFieldAdam):
             if flat is not None:
                 self.optim.apply(flat)
