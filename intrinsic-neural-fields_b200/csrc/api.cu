@@ -902,6 +902,9 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   g_launches += vp ? (split ? 11 : 10) : 3;
   prof_record(slot, 6, st);
   if (g_prof.on && slot < PROF_SLOTS) g_prof.n = slot + 1;
+  if (e == cudaErrorNotSupported && comm != nullptr && comm->world > 1)
+    return fail(INF_ERR_UNSUPPORTED, "the multi-GPU step needs the reduction tables, which cannot be built while a stream capture is in "
+                                     "progress (or beyond the table budget): run one eager step with this configuration first");
   if (e != cudaSuccess) return cuda_fail(e, "field_reduce_kernel launch");
   return INF_OK;
 }
