@@ -483,7 +483,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     res = {}
-    modes = [headline_train] if (world > 1 or args.skip_e2e or args.headline_only) else [headline_train, not headline_train]
+    # both halves of BASELINE.json's metric at every N (inference shards chunks / frames with no collective)
+    modes = [headline_train] if (args.skip_e2e or args.headline_only) else [headline_train, not headline_train]
     for tr in modes:
         res[tr] = measure(tr)
         _say(f"mode train={tr} done")
@@ -542,6 +543,43 @@ def run_ours(args):
         extras["config_batch_4096"] = {"rays_per_step": 4096, "ms_per_step": ms_small / 50, "rays_per_sec": 4096 * 50 / (ms_small / 1e3),
                                        "cuda_graph_ms_per_step": ms_small_g / 50,
                                        "cuda_graph_rays_per_sec": 4096 * 50 / (ms_small_g / 1e3)}
+        # config 3 (human, view-dependence branch: intrinsic angle -> Fourier features -> 2-layer directional MLP), same table
+        try:
+            import types
+            normals = torch.nn.functional.normalize(torch.randn(faces.shape[0], 3, device=dev), dim=-1)
+            vcfg = dict(MODEL_CFG, view_dependence=dict(strategy="intrinsic", in_dim_view_dir=1, include_view_dir=True, embed_size=4,
+                                                        bottleneck_vec_dim=128, directional_hidden_dim=64))
+            mv = inf_b200.make_model(vcfg, mesh=types.SimpleNamespace(face_normals=normals.cpu().numpy())).to(dev)
+            ov = trainer.FusedFieldAdam(mv, lr=LR)
+            bv = []
+            for i in range(NB):
+                gvi = torch.Generator(device=dev).manual_seed(300 + i)
+                fid = torch.randint(0, faces.shape[0], (B,), device=dev, generator=gvi)
+                u = torch.rand(B, 3, device=dev, generator=gvi)
+                dd = torch.nn.functional.normalize(torch.randn(B, 3, device=dev, generator=gvi), dim=-1)
+                dd = torch.where(((-dd * normals[fid]).sum(-1) < 0)[:, None], -dd, dd)
+                bv.append({"eigenfunction_table": table, "vertex_idxs_of_hit_faces": faces[fid].to(torch.int64).contiguous(),
+                           "barycentric_coords": (u / u.sum(-1, keepdim=True)).contiguous(),
+                           "expected_rgbs": torch.rand(B, 3, device=dev, generator=gvi), "unit_ray_dirs": dd.contiguous(),
+                           "hit_face_idxs": fid})
+            gv = trainer.GraphedTrainStep(mv, ov)
+            mv.train(True)
+            for i in range(3 * NB):
+                gv.step_async(bv[i % NB])
+            ms_vt = timed(lambda i: gv.step_async(bv[i % NB])[0], args.steps)
+            mv.eval()
+            gfv = GraphedForward(mv)
+            with torch.no_grad():
+                for i in range(3 * NB):
+                    gfv(bv[i % NB])
+                ms_vi = timed(lambda i: gfv(bv[i % NB]), args.steps)
+            extras["config3_view_dependent"] = {
+                "rays_per_step": B, "view_dependence": vcfg["view_dependence"],
+                "training": {"rays_per_sec": B * args.steps / (ms_vt / 1e3), "ms_per_step": ms_vt / args.steps},
+                "inference_frozen_weights": {"rays_per_sec": B * args.steps / (ms_vi / 1e3), "ms_per_step": ms_vi / args.steps}}
+            del mv, ov, bv, gv, gfv
+        except Exception as exc:       # an extra: never fail the bench line
+            extras["config3_view_dependent"] = {"error": f"{type(exc).__name__}: {exc}"}
         # config 4 (human_cloud400k): 400k-row table, 1.64 GB, every gathered row comes from DRAM -- the gather-bandwidth case
         try:
             g4 = 632
