@@ -300,8 +300,8 @@ int field_wgrad_max_grid(int cluster) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Partial reduction (+ optional Adam step and operand refresh): one thread per element of the flat
-// gradient vector, fixed summation order.
+// Partial reduction (+ optional multi-GPU sum, Adam step and operand refresh), fixed summation order.  Shared helpers first,
+// then the generic kernel (addresses derived per thread), then the table-driven kernel training steps use.
 // ---------------------------------------------------------------------------------------------
 // INF_ADAM_STEP_AUTOINC: every block has read the step counter in its prologue; the last block to leave advances it
 __device__ __forceinline__ void step_autoinc_finish(const AdamParams& a) {
@@ -335,26 +335,17 @@ __device__ __forceinline__ void adam_update(const AdamParams& a, float step_size
   adam_finish(a, step_size, bc2_sqrt, i, g, st, p_new);
 }
 
-// system-scope accesses for the peer-memory exchange (peer lines are cached in L1 only: never trust a plain load)
-__device__ __forceinline__ float ld_sys_f32(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_sys_f32x4(const float* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-// (value, step number) pairs of the exchange: one 8-byte store / load each, so a reader never sees a torn pair
+// system-scope accesses for the peer-memory exchange (peer lines are cached in L1 only: never trust a plain load).
+// (value, step number) pairs travel as ONE 64-bit access each -- single-copy atomic, so a reader never sees a torn pair.
 __device__ __forceinline__ void st_sys_pair(float* p, float v, uint32_t seq) {
-  asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+  const unsigned long long w = (static_cast<unsigned long long>(seq) << 32) | __float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ bool ld_sys_pair(const float* p, uint32_t seq, float& v) {
-  uint32_t a, b;
-  asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
-  v = __uint_as_float(a);
-  return b == seq;
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  v = __uint_as_float(static_cast<uint32_t>(w));
+  return static_cast<uint32_t>(w >> 32) == seq;
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
