@@ -153,7 +153,18 @@ __global__ void csr_fill_kernel(const FieldParams p) {
 // Lists of up to 32 pairs (the common case: a vertex is hit ~3 B / V times) are first SORTED by (ray, weight bits) with a
 // warp-wide bitonic network and then summed in that order with plain fp32 FMAs; longer lists are summed in 64-bit fixed
 // point, where the order does not matter.  Either way the result depends on the set of pairs only.
-__global__ void __launch_bounds__(256, 4) vertex_gather_kernel(const FieldParams p) {
+// measured variants (scripts/variant_sweep.sh; default 53 us): 8 rows in flight per warp 62-64 us, 6 CTAs per SM 62 us,
+// non-coherent no-allocate loads 59 us; one half-warp per vertex (two vertices per warp) 72 us
+#ifndef VG_BATCH
+#define VG_BATCH 4
+#endif
+#ifndef VG_MINB
+#define VG_MINB 4
+#endif
+#ifndef VG_NC
+#define VG_NC 0
+#endif
+__global__ void __launch_bounds__(256, VG_MINB) vertex_gather_kernel(const FieldParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -208,17 +219,18 @@ __global__ void __launch_bounds__(256, 4) vertex_gather_kernel(const FieldParams
           key = take_min ? (key < other ? key : other) : (key > other ? key : other);
         }
       }
-      for (int u0 = 0; u0 < n; u0 += 4) {
-        uint4 q[4];
-        float w[4];
+      for (int u0 = 0; u0 < n; u0 += VG_BATCH) {
+        uint4 q[VG_BATCH];
+        float w[VG_BATCH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < VG_BATCH; ++u) {
           const unsigned long long ku = __shfl_sync(0xffffffffu, key, (u0 + u) & 31);
           w[u] = (u0 + u < n) ? __uint_as_float(static_cast<uint32_t>(ku)) : 0.f;
-          q[u] = (u0 + u < n) ? *row_ptr(static_cast<int>(ku >> 32)) : make_uint4(0u, 0u, 0u, 0u);
+          q[u] = (u0 + u < n) ? (VG_NC ? ldg_nc_u4(row_ptr(static_cast<int>(ku >> 32))) : *row_ptr(static_cast<int>(ku >> 32)))
+                              : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < VG_BATCH; ++u) {
           const uint32_t vv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -289,7 +301,7 @@ cudaError_t launch_csr_build(const FieldParams& p, cudaStream_t stream) {
 
 cudaError_t launch_vertex_gather(const FieldParams& p, int nsm, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(nsm * 4));
+  cfg.gridDim = dim3(static_cast<unsigned>(nsm * VG_MINB));
   cfg.blockDim = dim3(256);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
