@@ -63,6 +63,21 @@ def test_production_config_sizes():
     assert ops.workspace_bytes(cfg, 4096, True) > 32 * 9 * 32768
 
 
+def test_exchange_region_and_projection_sizes():
+    import ctypes as C
+    cfg = ops.FieldConfig(k=1023, num_layers=6, skip=3)
+    lib = _lib.load()
+    # 2 parities x (8 source ranks + 1 result slot) x one slot of (value, step number) pairs for total + 2 elements, padded
+    # to 32 elements, + the 256-byte control block (csrc/common.cuh: comm_region_bytes)
+    n = ops.num_params(cfg)
+    slot_floats = 2 * ((n + 2 + 31) // 32 * 32)
+    assert int(lib.inf_comm_region_bytes(C.byref(ops._desc(cfg, 0, 0)))) == 2 * 9 * slot_floats * 4 + 64 * 4
+    # the vertex projection a frozen model keeps: 512 bytes per vertex, whole 128-vertex tiles
+    assert ops.projection_bytes(50176) == 50176 * 512
+    assert ops.projection_bytes(129) == 2 * 128 * 512
+    assert ops.N_LOSS_SUMS == 3
+
+
 def test_bad_descriptors_are_rejected():
     with pytest.raises(NotImplementedError):
         ops.num_params(ops.FieldConfig(k=64, hidden=256)) if False else _raise_for(ops.FieldConfig(k=64, hidden=256))

@@ -462,3 +462,34 @@ torch.save(P.cpu(), sys.argv[1])
             outs.append(torch.load(path))
     assert outs[0].shape == outs[1].shape and outs[0].abs().max().item() > 0.1
     assert torch.equal(outs[0], outs[1])          # same MMAs over the same operands, same fp32 accumulation order
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["ray", "vertex"])
+def test_fused_step_reports_the_mean_l1_loss_and_counts_its_own_steps(path):
+    from inf_b200 import trainer
+    c = load_golden("tf_k100_l5s1")
+    g = torch.Generator().manual_seed(12)
+    V, B, k = 500, 700, c["k"]
+    E = torch.randn(V, k, generator=g) / 4
+    vids = torch.randint(0, V, (B, 3), generator=g)
+    u = torch.rand(B, 3, generator=g)
+    bary = u / u.sum(-1, keepdim=True)
+    target = torch.rand(B, 3, generator=g)
+    tab = inf_b200.EigenTable.from_dense(E, device=DEV, path=path)
+    b = {"eigenfunction_table": tab, "vertex_idxs_of_hit_faces": vids.to(DEV), "barycentric_coords": bary.to(DEV),
+         "expected_rgbs": target.to(DEV)}
+    cfg = dict(k=k, num_layers=c["num_layers"], mlp_hidden_dim=128, skip_layer_idx=c["skip"])
+    m = inf_b200.make_model(cfg); m.load_state_dict(c["params"]); m = m.to(DEV)
+    # gradients only: the third loss sum is the first times grad_scale = the mean L1 loss
+    sums, pred, _ = m.l1_step(b)
+    want = (pred - b["expected_rgbs"]).abs().mean().item()
+    assert sums.numel() == 3
+    assert abs(sums[2].item() - want) <= 1e-5 and abs(sums[0].item() / (3 * B) - want) <= 1e-5
+    # fused optimiser: the reduction kernel advances the device-resident step counter itself, eager and inside a graph
+    opt = trainer.FusedFieldAdam(m, lr=1e-3)
+    gs = trainer.GraphedTrainStep(m, opt)
+    for i in range(5):
+        loss, _ = gs.step(b)
+        assert int(opt.step_dev.item()) == i + 1
+    assert loss < want
