@@ -11,12 +11,12 @@ import json, os, sys
 d = json.loads(sys.stdin.read()); d['args'] = os.environ['ARGS']; print(json.dumps(d))" >> "$out"
 }
 for b in 4096 32768 131072 262144 1048576; do run --batch $b; done
-for b in 4096 131072; do run --grid 632 --batch $b; done
+for b in 131072 1048576; do run --grid 632 --batch $b; done
 run --grid 632 --batch 131072 --mode infer
 run --batch 131072 --mode infer
-run --grid 632 --batch 131072 --table-dtype f16
+run --batch 1048576 --mode infer
+run --batch 131072 --path ray
 run --batch 131072 --table-dtype f16
-run --batch 131072 --table-dtype f16 --mode infer
 python - "$out" <<'PY'
 import json, re, sys
 for line in open(sys.argv[1]):
@@ -24,6 +24,7 @@ for line in open(sys.argv[1]):
     m = re.search(r"--batch (\d+)", d["args"])
     b = int(m.group(1)) if m else 131072
     k = d["step_kernels_ms"]
-    print("%-52s %8.1f M rays/s  %.4f ms/step  main %.4f  wgrad %.4f  reduce %.4f" % (
-        d["args"], b / d["ms_per_step"] / 1e3, d["ms_per_step"], k["field_main"], k["field_wgrad"], k["field_reduce"]))
+    print("%-44s %-6s %8.1f M rays/s  %.4f ms/step  project %.3f  rays/main %.3f  gather %.3f  wgrad %.3f  reduce %.3f" % (
+        d["args"], "vertex" if d.get("vertex_path") else "ray", b / d["ms_per_step"] / 1e3, d["ms_per_step"], k["vertex_project"],
+        k["rays_fwd_bwd"], k["vertex_gather"], k["wgrad"], k["reduce_adam"]))
 PY
