@@ -317,7 +317,7 @@ def kernel_rooflines(stages, train, vertex, B, V, pk, ncu):
             e.update(tflops=flops / (ms / 1e3) / 1e12, tensor_frac_of_sustained_bf16=flops / (ms / 1e3) / tf)
         if bytes_ is not None:
             e.update(gbs=bytes_ / (ms / 1e3) / 1e9, hbm_frac=bytes_ / (ms / 1e3) / 1e9 / pk["hbm_gbs"], bytes=bytes_)
-        t = ncu.get(ncu_name or name)
+        t = ncu.get(f"{ncu_name or name}<{1 if train else 0}") or ncu.get(ncu_name or name)
         if t is not None:
             e.update(ncu_dram_bytes=t[0], ncu_tensor_pipe_pct=t[1])
         e["bound"] = bound
@@ -347,7 +347,8 @@ def kernel_rooflines(stages, train, vertex, B, V, pk, ncu):
             add("field_wgrad_kernel", stages["wgrad"], flops=B * fwd, bytes_=B * 4864, bound="hbm",
                 note="all weight gradients from the 4.75 KB/ray stash")
     if train:
-        add("field_reduce_kernel", stages["reduce_adam"], bound="latency")
+        add("field_reduce_lean_kernel", stages["reduce_adam"], bound="latency",
+            note="partial sums + Adam + operand refresh (+ the N-GPU gradient exchange); the stage time includes the ~5 us launch gap")
     return ker
 
 
@@ -637,7 +638,15 @@ def run_ours(args):
         return
     pk = peaks()
     ncu, ncu_src = ncu_kernels()
-    ncu = {k.replace("void ", "").replace("inf::", "").split("<")[0].split("(")[0]: v for k, v in ncu.items()}
+    # "void inf::field_rays_kernel<1, 1>(inf::FieldParams)" -> "field_rays_kernel<1" (the first template argument is the
+    # train / inference flavour of the templated kernels) and the bare name, first capture wins
+    ncu_named = {}
+    for k, v in ncu.items():
+        base = k.replace("void ", "").replace("inf::", "").split("(")[0]
+        flav = base.split(",")[0].rstrip(">")
+        ncu_named.setdefault(flav, v)
+        ncu_named.setdefault(base.split("<")[0], v)
+    ncu = ncu_named
 
     def block(train):
         ms, stages, launches, ms_e2e = res[train]
