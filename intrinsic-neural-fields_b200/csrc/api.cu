@@ -67,6 +67,8 @@ struct Env {
     side_stream = geti("INF_SIDE_STREAM", 1);   // 0: incidence lists on the caller's stream
     force_path = geti("INF_PATH", 0);   // 1 = per-ray, 2 = vertex (when a table image is given): overrides InfDesc.path AUTO
     const char* b = getenv("INF_WGRAD_BIGW");
+    // (0.85 on the vertex path: wgrad 92 -> 88.8 us, step -1 %, within noise -- and the 2000-step view-branch PSNR protocol,
+    // a chaotic map, then lands 0.1-0.4 dB lower although one-step gradients differ by 9e-8: scripts/grad_split_check.py)
     wgrad_bigw = b ? atof(b) : 1.0;
   }
 };
@@ -742,7 +744,8 @@ static int run_forward_backward(const InfDesc* desc, const InfTensors* t, const 
   } else {
     // bytes a CTA ingests over the launch: the x panels of its 256 columns + its share of dz_0 / dz_skip per (ray or
     // vertex) tile (INF_WGRAD_BIGW scales the big slices' share: they also carry 2.5x the tensor work per ingested byte)
-    const double big_bytes = (2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw) * env().wgrad_bigw * tiles_big;
+    const double bigw = env().wgrad_bigw > 0.0 ? env().wgrad_bigw : 1.0;
+    const double big_bytes = (2.0 * BLOB_BYTES + 2.0 * BLOB_BYTES / cw) * bigw * tiles_big;
     double wsum = static_cast<double>(geo.nbig) * big_bytes;
     for (int s = 0; s < plan.nslice; ++s) wsum += static_cast<double>(plan.bytes_per_tile[s]) * p.ntiles;
     int smax = 0;

@@ -1,7 +1,8 @@
 #!/bin/bash
-# measurement helper: wgrad cluster width (dz half-panels multicast within clusters of 1 / 2 / 4 big-slice CTAs)
-q() { python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); k=d.get('step_kernels_ms') or d['roofline']['step_kernels_ms']
-print('step %.4f ms  main %.4f  wgrad %.4f' % (d['ms_per_step'], k['field_main'], k['field_wgrad']))"; }
-for cw in 1 2 4; do echo -n "INF_WGRAD_CLUSTER=$cw: "; INF_WGRAD_CLUSTER=$cw python bench.py --warmup 5 --no-cpu-baseline --steps 40 --skip-e2e "$@" 2>/dev/null | tail -1 | q; done
+# measurement helper: field_wgrad under its launch knobs on the vertex path (per-stage device times of the training step)
+for knob in ${KNOBS:-"INF_WGRAD_BIGW=0.85" "INF_WGRAD_BIGW=1.0" "INF_WGRAD_BIGW=1.15" "INF_WGRAD_BIGW=1.3" "INF_WGRAD_CLUSTER=4" "INF_WGRAD_CLUSTER=1"}; do
+  echo "== $knob"
+  env $knob timeout 120 python bench.py --mode train --path vertex --steps 20 --warmup 3 --skip-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print(round(d['ms_per_step'], 4), {k: round(v * 1e3, 1) for k, v in d['step_kernels_ms'].items()})"
+done

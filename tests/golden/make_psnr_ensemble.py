@@ -27,7 +27,8 @@ EPS = [0.0, 1e-6, -1e-6, 1e-5, -1e-5]
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "psnr_ensemble.json")
 
 
-def run(name):
+def run(name, have=()):
+    """`have`: members of an earlier run (kept; only the missing perturbations are computed)."""
     pr = PROTOCOLS[name]
     view = VIEW_CFGS[pr["view"]] if pr["view"] else None
     E, vids, bary, target, dirs, fid, normals = problem(pr)
@@ -39,8 +40,10 @@ def run(name):
     kw_h = dict(kw)
     if view is not None:
         kw_h.update(unit_ray_dirs=dirs[hold], hit_face_idxs=fid[hold])
-    out = []
+    out = [m for m in have if m["eps"] in EPS[:pr.get("members", len(EPS))]]
     for eps in EPS[:pr.get("members", len(EPS))]:
+        if any(m["eps"] == eps for m in out):
+            continue
         t0 = time.time()
         params = O.make_params(pr["k"], num_layers=pr["L"], skip=pr["skip"], view=view, seed=5)
         g = torch.Generator().manual_seed(123)
@@ -58,5 +61,5 @@ if __name__ == "__main__":
     names = sys.argv[1:] or list(PROTOCOLS)
     data = json.load(open(OUT)) if os.path.exists(OUT) else {}
     for n in names:
-        data[n] = run(n)
+        data[n] = run(n, data.get(n, ()))
         json.dump(data, open(OUT, "w"), indent=1)

@@ -13,7 +13,7 @@ PROTOCOLS = {
     "cat_2000": dict(view=None, k=1023, L=6, skip=3, B=4096, steps=2000, lr=1e-4, V=50176, F=100352, N=65536 + 16384,
                      ntrain=65536, members=3),
     "view_2000": dict(view="view_intrinsic", k=1023, L=6, skip=3, B=4096, steps=2000, lr=1e-4, V=50176, F=100352,
-                      N=65536 + 16384, ntrain=65536, members=3),
+                      N=65536 + 16384, ntrain=65536, members=5),
 }
 
 
